@@ -1,0 +1,43 @@
+"""Shared helpers for the parity tests."""
+import glob
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+OUT_NAMES = ["mel", "postnet", "pitch", "energy", "log_d", "d_rounded", "src_mask", "mel_mask", "src_lens", "mel_lens"]
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0]
+                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not p.endswith("meta.npz"))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    batch, kw, out = {}, {}, {}
+    for k in z.files:
+        a = z[k]
+        if k.startswith("in_"):
+            batch[k[3:]] = int(a) if a.ndim == 0 else torch.from_numpy(a)
+        elif k.startswith("kw_"):
+            n = k[3:]
+            if a.ndim == 0:
+                kw[n] = int(a) if n == "max_mel_len" else float(a)
+            else:
+                kw[n] = torch.from_numpy(a)
+        elif k.startswith("out_"):
+            out[k[4:]] = a
+    stride = int(z["mel_row_stride"]) if "mel_row_stride" in z.files else 1
+    return batch, kw, out, stride
+
+
+def call(fn, batch, *lead, **kw):
+    return fn(*lead, batch["speakers"], batch["emotions"], batch["arousals"], batch["valences"],
+              batch["texts"], batch["src_lens"], batch["max_src_len"], **kw)
+
+
+def valid_rows(arr, lens):
+    """Concatenate arr[b, :lens[b]] over the batch (padding rows are outside the contract)."""
+    return np.concatenate([np.asarray(arr[b, : int(lens[b])]) for b in range(len(lens))], axis=0)
