@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- mel frames/s of the FastSpeech2 inference forward on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--engine tcgen05|mma_sync] [--math tf32|bf16]
+
+A step is one forward pass over one synthetic batch of BASELINE config 2 (64 utterances of
+20-120 phonemes, mixed speakers / emotions / arousal-valence, controls 1.0) per GPU; with N > 1
+(launched by torchrun, one rank per GPU) every rank runs its own batch of that shape (utterances
+are independent: no collective on the data path, weak scaling) and rank 0 prints ONE JSON line.
+`value` is timed with inputs resident in HBM; `e2e` goes through the host-buffer entry
+(`FastSpeech2B200.synthesize_host`: pinned H2D of the int64 inputs, forward, D2H of the postnet
+mel and mel_lens) with the copies inside the timed region.  `--impl reference` times the CPU
+oracle port of the reference forward (oracle/fs2_oracle.py; the reference itself is Python and
+/root/reference does not exist on the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "mel frames/s (batch 64)"
+UNIT = "frames/s"
+CPU_SAMPLE_UTTS = 16
+FLOPS_CONV9_PER_ROW = 2 * 9 * 256 * 1024
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_burst": p["bf16_tflops"],
+                "bf16_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_cpu_run(sd, batch, n_utts, steps, warmup):
+    """The CPU oracle port of the reference forward on the first n_utts utterances, fp32, all host threads."""
+    from oracle import fs2_oracle as O
+    sub = {k: (v[:n_utts] if torch.is_tensor(v) else v) for k, v in batch.items()}
+    L = int(sub["src_lens"].max())
+    sub["texts"] = sub["texts"][:, :L].contiguous()
+    sub["max_src_len"] = L
+    args = [sub[k] for k in ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")]
+    small = [a[:2] for a in args]
+    L2 = int(small[5].max())
+    small[4] = small[4][:, :L2].contiguous()
+    for _ in range(max(warmup, 1)):
+        O.forward(sd, *small, L2, loop_lr=True)
+    times, frames = [], 0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        out = O.forward(sd, *args, L, loop_lr=True)
+        times.append(time.perf_counter() - t0)
+        frames = int(out[9].sum())
+    return frames, times
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    import fs2_b200
+    syn = fs2_b200.synthetic
+    sd = syn.synthetic_state_dict(seed=0)
+    batch = syn.config2_batch(seed=0)
+    cores = torch.get_num_threads()
+    frames, times = oracle_cpu_run(sd, batch, CPU_SAMPLE_UTTS, args.steps, args.warmup)
+    total = sum(times)
+    value = frames * len(times) / total
+    sample = (f"first {CPU_SAMPLE_UTTS} of the 64 config-2 utterances per step ({frames} frames), oracle port of "
+              f"FastSpeech2.forward, fp32, torch CPU, Python-loop LengthRegulator")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config2: batch 64, 20-120 phonemes, mixed speakers/emotions, controls 1.0",
+                       "timed_sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--engine", default=os.environ.get("FS2_ENGINE", "mma_sync"), choices=["tcgen05", "mma_sync"])
+    ap.add_argument("--math", default=os.environ.get("FS2_MATH", "tf32"), choices=["tf32", "bf16"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import fs2_b200
+    from fs2_b200 import _lib
+    syn = fs2_b200.synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    sd = syn.synthetic_state_dict(seed=0)
+    jsons = syn.write_fixture_jsons(tempfile.mkdtemp(prefix="fs2_json_"))
+    model = fs2_b200.FastSpeech2B200(fs2_b200.config.default_preprocess_config(jsons),
+                                     fs2_b200.config.default_model_config(), math_mode=args.math, engine=args.engine)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+
+    batch = syn.config2_batch(seed=rank, batch=args.batch)      # every rank: its own 64 utterances
+    names = ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")
+    dev_args = [batch[k].to(dev) for k in names]
+    host_batch = {k: batch[k].numpy() for k in names}
+    host_batch["max_src_len"] = batch["max_src_len"]
+    L = batch["max_src_len"]
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(step_fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for beg, end in evs:
+            flush.zero_()                      # evict L2 between timed iterations (outside the event pair)
+            beg.record()
+            step_fn()
+            end.record()
+        barrier()
+        return [b.elapsed_time(e) for b, e in evs]
+
+    out = None
+    for _ in range(args.warmup):
+        out = model(*dev_args, L)
+        model.synthesize_host(host_batch)
+    torch.cuda.synchronize()
+    frames = int(out[9].sum())
+    mel_lens = out[9].tolist()
+    launches = model.last_launch_count
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step_ms = timed_loop(lambda: model(*dev_args, L), args.steps)
+    clocks = sampler.stop()
+    e2e_bytes = {}
+
+    def e2e_step():
+        _, _, h2d, d2h = model.synthesize_host(host_batch)
+        e2e_bytes["h2d"], e2e_bytes["d2h"] = h2d, d2h
+
+    e2e_ms = timed_loop(e2e_step, args.steps)
+
+    # per-kernel-class CUDA-event timing (same workload, same process, after the timed region)
+    lib = _lib.load_library()
+    lib.fs2_profile_enable(model._ctx, 1)
+    prof = {}
+    PROF_RUNS = 3
+    for _ in range(PROF_RUNS):
+        flush.zero_()
+        model(*dev_args, L)
+        buf = (__import__("ctypes").c_char * 8192)()
+        lib.fs2_profile_read(model._ctx, buf, 8192)
+        for line in buf.value.decode().splitlines():
+            label, n, ms = line.split()
+            a = prof.setdefault(label, [0, 0.0])
+            a[0] += int(n)
+            a[1] += float(ms)
+    lib.fs2_profile_enable(model._ctx, 0)
+
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms, float(sum(e2e_ms)), float(frames)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, e2e_total_ms, frames_all = float(tmax[0]), float(tmax[1]), float(tsum[2])
+    else:
+        e2e_total_ms, frames_all = float(t[1]), float(frames)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        tensor_peak = peaks["bf16_sustained"] * (0.5 if args.math == "tf32" else 1.0)
+        dom = "dec.gemm_conv9"
+        n_dom, ms_dom = prof.get(dom, [0, 0.0])
+        per_launch_ms = ms_dom / max(n_dom, 1)
+        flops_per_launch = FLOPS_CONV9_PER_ROW * frames
+        achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
+        kernel_ms = {k: round(v[1] / PROF_RUNS, 4) for k, v in sorted(prof.items())}
+        line = {
+            "metric": METRIC, "value": frames_all * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.math, "data": "synthetic",
+            "config": {"workload": f"config2: batch {args.batch} per GPU, 20-120 phonemes, mixed speakers/emotions/"
+                                   "arousal-valence, controls 1.0, random-init weights (seed 0)",
+                       "frames_per_step_per_gpu": frames, "phonemes_per_step_per_gpu": int(batch["src_lens"].sum()),
+                       "engine": args.engine, "l2": "256 MB buffer written between timed iterations (L2 flushed)",
+                       "algorithmic_tflop_per_step": syn.algorithmic_flops(batch["src_lens"].tolist(), mel_lens) / 1e12},
+            "e2e": {"value": frames_all * args.steps / (e2e_total_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": e2e_bytes.get("h2d", 0), "d2h_bytes_per_step": e2e_bytes.get("d2h", 0),
+                    "ms_per_step": e2e_total_ms / args.steps},
+            "gpu_launches": launches * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": dom + " (decoder FFN Conv1d k=9 implicit GEMM, 256->1024)",
+                         "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                         "frac": achieved / tensor_peak if tensor_peak else None, "traffic": None,
+                         "per_launch_ms": per_launch_ms, "launches_per_step": n_dom // PROF_RUNS,
+                         "flops_per_launch": flops_per_launch,
+                         "peak_source": f"{peaks['source']} bf16_tflops_sustained" +
+                                        (" / 2 (TF32 runs at half the bf16 tensor rate)" if args.math == "tf32" else "")},
+            "kernel_ms_per_step": kernel_ms,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = torch.get_num_threads()
+            f_cpu, times = oracle_cpu_run(sd, syn.config2_batch(seed=0), CPU_SAMPLE_UTTS, 1, 1)
+            line["cpu_baseline"] = {"value": f_cpu * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"1 forward over the first {CPU_SAMPLE_UTTS} of the 64 utterances "
+                                              f"({f_cpu} frames, {sum(times):.1f} s), oracle port, fp32, torch CPU"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

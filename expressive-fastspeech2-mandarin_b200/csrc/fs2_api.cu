@@ -1,0 +1,797 @@
+// libfs2b200.so -- C ABI (include/fs2_b200.h) and the orchestration of the forward pass.
+// One context per device; all work is enqueued on the caller's stream.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm_mma.cuh"
+#include "gemm_tcgen05.cuh"
+#include "rowops.cuh"
+
+namespace fs2 {
+
+thread_local int g_launches = 0;
+static thread_local std::string g_create_error;
+
+struct DevTensor {
+  float* ptr = nullptr;
+  std::vector<int64_t> shape;
+  int64_t numel = 0;
+};
+
+struct FFTLayer {
+  float *wqkv, *bqkv, *wfc, *bfc, *ln1_g, *ln1_b, *w1, *b1, *w2, *b2, *ln2_g, *ln2_b;
+};
+struct Predictor {
+  float *w1, *b1, *ln1_g, *ln1_b, *w2, *b2, *ln2_g, *ln2_b, *head_w, *head_b;
+};
+struct PostConv {
+  float *w, *b;
+  int cin, cout;
+};
+
+struct RowSide {  // metadata of one packed row space (phoneme side or frame side)
+  int32_t *starts = nullptr, *lens = nullptr;       // [B+1], [B]
+  int32_t *utt = nullptr, *vpos = nullptr, *room = nullptr, *slot = nullptr;  // [rows_alloc]
+  int64_t* totals = nullptr;                         // device [3]
+  int rows_alloc = 0, batch_alloc = 0;
+  RowMeta meta() const { return RowMeta{utt, vpos, room}; }
+};
+
+struct Pool {  // activation buffers of one side
+  float* act[4] = {nullptr, nullptr, nullptr, nullptr};  // [rows,256]
+  float* qkv = nullptr;                                  // [rows,768]
+  float* hid = nullptr;                                  // [rows,1024]
+  float *mel = nullptr, *post = nullptr;                 // [rows,80]   (frame side only)
+  float* pn[2] = {nullptr, nullptr};                     // [rows,512]  (frame side only)
+  int rows = 0;
+};
+
+}  // namespace fs2
+
+using namespace fs2;
+
+struct fs2_ctx {
+  int device = 0;
+  fs2_config cfg{};
+  std::string err;
+  bool prepared = false;
+  bool debug = false;
+  std::map<std::string, DevTensor> raw;
+  std::vector<void*> owned;  // repacked weights, freed in destroy
+
+  FFTLayer enc[ENC_LAYERS], dec[DEC_LAYERS];
+  Predictor pred[3];  // duration, pitch, energy
+  PostConv post[PN_LAYERS];
+  float *mel_w = nullptr, *mel_b = nullptr;
+  float* pe_long = nullptr;  // generated sinusoid table for sequences beyond max_seq_len
+  int pe_long_rows = 0;
+
+  RowSide ps, fs;
+  Pool pp, fp;
+  int32_t* status = nullptr;
+  int32_t* cum = nullptr;       // [B, Lmax]
+  int32_t* mel_lens32 = nullptr;
+  float *raw_pitch = nullptr, *raw_energy = nullptr;  // [B, Lmax]
+  float *cond_spk = nullptr, *cond_emo = nullptr;     // [B,256]
+  int64_t scratch_bl = 0, scratch_b = 0;
+  int64_t* h_totals = nullptr;  // pinned [8]
+
+  // state carried from stage 1 to stage 2
+  bool stage1_done = false;
+  int batch = 0, max_src_len = 0, max_mel_len = 0;
+  int64_t frame_rows = 0;
+  const float* lr_input = nullptr;
+  int last_launches = 0;
+
+  std::map<std::string, std::pair<void*, std::vector<int64_t>>> taps;  // name -> (device copy, {rows, cols, elt})
+
+  // optional per-kernel-class CUDA-event timing (bench.py's roofline numbers come from here)
+  bool profiling = false;
+  struct ProfRec { const char* label; cudaEvent_t beg, end; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
+  std::string prof_text;
+};
+
+namespace fs2 {
+
+// Brackets the launches of one kernel class with CUDA events on the launching stream.
+struct ProfScope {
+  fs2_ctx* c;
+  cudaStream_t s;
+  cudaEvent_t end = nullptr;
+  ProfScope(fs2_ctx* ctx, cudaStream_t stream, const char* label) : c(ctx), s(stream) {
+    if (!c->profiling) return;
+    cudaEvent_t ev[2];
+    for (auto& e : ev) {
+      if (c->event_pool.empty()) {
+        FS2_CUDA_OK(cudaEventCreate(&e));
+      } else {
+        e = c->event_pool.back();
+        c->event_pool.pop_back();
+      }
+    }
+    FS2_CUDA_OK(cudaEventRecord(ev[0], s));
+    end = ev[1];
+    c->prof.push_back({label, ev[0], ev[1]});
+  }
+  ~ProfScope() {
+    if (end) cudaEventRecord(end, s);
+  }
+};
+
+template <typename T>
+static T* dalloc(size_t n) {
+  void* p = nullptr;
+  FS2_CUDA_OK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  return static_cast<T*>(p);
+}
+template <typename T>
+static void regrow(T*& p, size_t n) {
+  if (p) FS2_CUDA_OK(cudaFree(p));
+  p = dalloc<T>(n);
+  FS2_CUDA_OK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+}
+
+static const DevTensor& W(fs2_ctx* c, const std::string& key, std::initializer_list<int64_t> shape) {
+  auto it = c->raw.find(key);
+  require(it != c->raw.end(), FS2_ERR_INVALID, "missing weight: " + key);
+  require(it->second.shape == std::vector<int64_t>(shape), FS2_ERR_INVALID, "unexpected shape for weight: " + key);
+  return it->second;
+}
+
+static float* keep(fs2_ctx* c, size_t n) {
+  float* p = dalloc<float>(n);
+  c->owned.push_back(p);
+  return p;
+}
+
+// [Cout][Cin][k] -> [k][Cout][Cin], optional per-Cout scale, TF32-rounded operands
+static float* repack_conv(fs2_ctx* c, const float* w, int cout, int cin, int k, const float* scale, cudaStream_t s) {
+  const int64_t n = (int64_t)cout * cin * k;
+  float* out = keep(c, n);
+  repack_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, cout, cin, k, scale, 1, out);
+  FS2_LAUNCHED();
+  return out;
+}
+
+static void prepare_fft(fs2_ctx* c, const std::string& p, FFTLayer& L, cudaStream_t s) {
+  const int d = D_MODEL;
+  L.wqkv = keep(c, 3 * d * d);
+  L.bqkv = keep(c, 3 * d);
+  const char* names[3] = {"w_qs", "w_ks", "w_vs"};
+  for (int i = 0; i < 3; ++i) {
+    const auto& w = W(c, p + ".slf_attn." + names[i] + ".weight", {d, d});
+    const auto& b = W(c, p + ".slf_attn." + names[i] + ".bias", {d});
+    // Linear weight [N][K] is already K-major: repack as a 1-tap conv to round the operands
+    repack_conv_kernel<<<(d * d + 255) / 256, 256, 0, s>>>(w.ptr, d, d, 1, nullptr, 1, L.wqkv + (size_t)i * d * d);
+    FS2_LAUNCHED();
+    FS2_CUDA_OK(cudaMemcpyAsync(L.bqkv + i * d, b.ptr, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  L.wfc = repack_conv(c, W(c, p + ".slf_attn.fc.weight", {d, d}).ptr, d, d, 1, nullptr, s);
+  L.bfc = W(c, p + ".slf_attn.fc.bias", {d}).ptr;
+  L.ln1_g = W(c, p + ".slf_attn.layer_norm.weight", {d}).ptr;
+  L.ln1_b = W(c, p + ".slf_attn.layer_norm.bias", {d}).ptr;
+  L.w1 = repack_conv(c, W(c, p + ".pos_ffn.w_1.weight", {D_INNER, d, FFN_TAPS}).ptr, D_INNER, d, FFN_TAPS, nullptr, s);
+  L.b1 = W(c, p + ".pos_ffn.w_1.bias", {D_INNER}).ptr;
+  L.w2 = repack_conv(c, W(c, p + ".pos_ffn.w_2.weight", {d, D_INNER, 1}).ptr, d, D_INNER, 1, nullptr, s);
+  L.b2 = W(c, p + ".pos_ffn.w_2.bias", {d}).ptr;
+  L.ln2_g = W(c, p + ".pos_ffn.layer_norm.weight", {d}).ptr;
+  L.ln2_b = W(c, p + ".pos_ffn.layer_norm.bias", {d}).ptr;
+}
+
+static void prepare_predictor(fs2_ctx* c, const std::string& p, Predictor& P, cudaStream_t s) {
+  const int d = D_MODEL;
+  P.w1 = repack_conv(c, W(c, p + ".conv_layer.conv1d_1.conv.weight", {d, d, VP_TAPS}).ptr, d, d, VP_TAPS, nullptr, s);
+  P.b1 = W(c, p + ".conv_layer.conv1d_1.conv.bias", {d}).ptr;
+  P.ln1_g = W(c, p + ".conv_layer.layer_norm_1.weight", {d}).ptr;
+  P.ln1_b = W(c, p + ".conv_layer.layer_norm_1.bias", {d}).ptr;
+  P.w2 = repack_conv(c, W(c, p + ".conv_layer.conv1d_2.conv.weight", {d, d, VP_TAPS}).ptr, d, d, VP_TAPS, nullptr, s);
+  P.b2 = W(c, p + ".conv_layer.conv1d_2.conv.bias", {d}).ptr;
+  P.ln2_g = W(c, p + ".conv_layer.layer_norm_2.weight", {d}).ptr;
+  P.ln2_b = W(c, p + ".conv_layer.layer_norm_2.bias", {d}).ptr;
+  P.head_w = W(c, p + ".linear_layer.weight", {1, d}).ptr;
+  P.head_b = W(c, p + ".linear_layer.bias", {1}).ptr;
+}
+
+__global__ void sinusoid_kernel(float* pe, int rows) {
+  // transformer/Models.py:10-30 evaluated in float64, stored as fp32
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * D_MODEL) return;
+  const int pos = (int)(i / D_MODEL), j = (int)(i % D_MODEL);
+  const double ang = (double)pos / pow(10000.0, 2.0 * (double)(j / 2) / (double)D_MODEL);
+  pe[i] = (float)((j & 1) ? cos(ang) : sin(ang));
+}
+
+static const float* position_rows(fs2_ctx* c, const char* key, int n_rows, cudaStream_t s) {
+  // Stored table for n_rows <= max_seq_len, regenerated formula beyond (Models.py:82-91,145-162)
+  if (n_rows <= c->cfg.max_seq_len) return c->raw.at(key).ptr;
+  if (c->pe_long_rows < n_rows) {
+    const int rows = round_up(n_rows, 1024);
+    FS2_CUDA_OK(cudaStreamSynchronize(s));
+    regrow(c->pe_long, (size_t)rows * D_MODEL);
+    sinusoid_kernel<<<(unsigned)(((int64_t)rows * D_MODEL + 255) / 256), 256, 0, s>>>(c->pe_long, rows);
+    FS2_LAUNCHED();
+    c->pe_long_rows = rows;
+  }
+  return c->pe_long;
+}
+
+static void tap(fs2_ctx* c, cudaStream_t s, const char* name, const void* ptr, int64_t rows, int64_t cols, int64_t elt = 4) {
+  if (!c->debug) return;
+  auto& slot = c->taps[name];
+  if (slot.first) cudaFree(slot.first);
+  void* p = nullptr;
+  FS2_CUDA_OK(cudaMalloc(&p, std::max<int64_t>(rows * cols * elt, 1)));
+  FS2_CUDA_OK(cudaMemcpyAsync(p, ptr, rows * cols * elt, cudaMemcpyDeviceToDevice, s));
+  slot = {p, {rows, cols, elt}};
+}
+
+// ---------------------------------------------------------------------------- GEMM dispatch
+static void conv_gemm(int engine, int math, const ConvGemmArgs& a, cudaStream_t s) {
+  if (engine == FS2_ENGINE_TCGEN05) {
+    tc::launch(a, math, s);
+  } else {
+    require(math == FS2_MATH_TF32, FS2_ERR_UNSUPPORTED, "the mma.sync engine implements TF32 only");
+    mma::launch(a, s);
+  }
+}
+
+static ConvGemmArgs gemm_args(const float* A, int lda, int rows, const float* Wt, const float* bias, int taps, int K,
+                              int N, int act, float* C, int ldc) {
+  ConvGemmArgs a{};
+  a.A = A; a.lda = lda; a.rows = rows; a.W = Wt; a.bias = bias; a.taps = taps; a.pad = (taps - 1) / 2;
+  a.K = K; a.N = N; a.act = act; a.C = C; a.ldc = ldc;
+  return a;
+}
+
+static void layernorm(cudaStream_t s, const float* x, int rows, const float* g, const float* b, const RowSide* side,
+                      int extra, float* y, const float* hw = nullptr, const float* hb = nullptr, float* hout = nullptr) {
+  if (rows == 0) return;
+  layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, rows, g, b, side ? side->vpos : nullptr, side ? side->room : nullptr,
+                                                   extra, y, hw, hb, hout, side ? side->slot : nullptr);
+  FS2_LAUNCHED();
+}
+
+// One FFT block in place on x (transformer/Layers.py:21-30).  t1, t2 are [rows,256] temporaries.
+static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSide& side, Pool& pool, int rows, int batch,
+                      int max_len, float* x, float* t1, float* t2, bool frame) {
+  const int eng = c->cfg.engine, math = c->cfg.math_mode;
+  ConvGemmArgs a = gemm_args(x, D_MODEL, rows, L.wqkv, L.bqkv, 1, D_MODEL, 3 * D_MODEL, ACT_NONE, pool.qkv, 3 * D_MODEL);
+  a.live_rows = reinterpret_cast<const int32_t*>(side.totals);  // low word of totals[0] (little endian)
+  { ProfScope ps(c, s, frame ? "dec.gemm_qkv" : "enc.gemm_qkv"); conv_gemm(eng, math, a, s); }
+  { ProfScope ps(c, s, frame ? "dec.attention" : "enc.attention");
+    attn::launch(pool.qkv, side.starts, side.lens, batch, max_len, t1, s); }
+  a = gemm_args(t1, D_MODEL, rows, L.wfc, L.bfc, 1, D_MODEL, D_MODEL, ACT_NONE, t2, D_MODEL);
+  a.residual = x; a.ldr = D_MODEL; a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
+  { ProfScope ps(c, s, frame ? "dec.gemm_fc" : "enc.gemm_fc"); conv_gemm(eng, math, a, s); }
+  { ProfScope ps(c, s, frame ? "dec.layernorm" : "enc.layernorm"); layernorm(s, t2, rows, L.ln1_g, L.ln1_b, &side, 0, t1); }
+  a = gemm_args(t1, D_MODEL, rows, L.w1, L.b1, FFN_TAPS, D_MODEL, D_INNER, ACT_RELU, pool.hid, D_INNER);
+  a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
+  { ProfScope ps(c, s, frame ? "dec.gemm_conv9" : "enc.gemm_conv9"); conv_gemm(eng, math, a, s); }
+  a = gemm_args(pool.hid, D_INNER, rows, L.w2, L.b2, 1, D_INNER, D_MODEL, ACT_NONE, t2, D_MODEL);
+  a.residual = t1; a.ldr = D_MODEL; a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
+  { ProfScope ps(c, s, frame ? "dec.gemm_w2" : "enc.gemm_w2"); conv_gemm(eng, math, a, s); }
+  { ProfScope ps(c, s, frame ? "dec.layernorm" : "enc.layernorm"); layernorm(s, t2, rows, L.ln2_g, L.ln2_b, &side, 0, x); }
+}
+
+// VariancePredictor (model/modules.py:242-250) over the packed rows; head_out is [B, Lmax], pre-zeroed.
+static void predictor(fs2_ctx* c, cudaStream_t s, const Predictor& P, const RowSide& side, int rows, const float* x,
+                      float* t1, float* t2, float* head_out) {
+  ProfScope ps(c, s, "predictor");
+  const int eng = c->cfg.engine, math = c->cfg.math_mode;
+  ConvGemmArgs a = gemm_args(x, D_MODEL, rows, P.w1, P.b1, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, t1, D_MODEL);
+  a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
+  conv_gemm(eng, math, a, s);
+  layernorm(s, t1, rows, P.ln1_g, P.ln1_b, &side, 1, t2);  // the hidden row at t = L_b is live when L_b < L_max
+  a = gemm_args(t2, D_MODEL, rows, P.w2, P.b2, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, t1, D_MODEL);
+  a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
+  conv_gemm(eng, math, a, s);
+  layernorm(s, t1, rows, P.ln2_g, P.ln2_b, &side, 0, nullptr, P.head_w, P.head_b, head_out);
+}
+
+static void ensure_side(RowSide& sd, int batch, int rows) {
+  if (batch + 1 > sd.batch_alloc) {
+    regrow(sd.starts, batch + 1);
+    regrow(sd.lens, batch);
+    sd.batch_alloc = batch + 1;
+  }
+  if (rows > sd.rows_alloc) {
+    regrow(sd.utt, rows);
+    regrow(sd.vpos, rows);
+    regrow(sd.room, rows);
+    regrow(sd.slot, rows);
+    sd.rows_alloc = rows;
+  }
+  if (!sd.totals) regrow(sd.totals, 3);
+}
+
+static void ensure_pool(Pool& p, int rows, bool frame_side) {
+  if (rows <= p.rows) return;
+  for (auto& a : p.act) regrow(a, (size_t)rows * D_MODEL);
+  regrow(p.qkv, (size_t)rows * 3 * D_MODEL);
+  regrow(p.hid, (size_t)rows * D_INNER);
+  if (frame_side) {
+    regrow(p.mel, (size_t)rows * N_MEL);
+    regrow(p.post, (size_t)rows * N_MEL);
+    regrow(p.pn[0], (size_t)rows * PN_DIM);
+    regrow(p.pn[1], (size_t)rows * PN_DIM);
+  }
+  p.rows = rows;
+}
+
+static void check_status(fs2_ctx* c, int32_t st) {
+  if (st == 0) return;
+  std::string m = "invalid input:";
+  if (st & ERR_BAD_LEN) m += " src_lens outside [0, max_src_len];";
+  if (st & ERR_BAD_ID) m += " phoneme id outside the embedding table;";
+  if (st & ERR_BAD_INDEX) m += " speaker/emotion/arousal/valence index outside its table;";
+  if (st & ERR_MAXLEN_SMALL) m += " max_mel_len smaller than the longest expanded utterance;";
+  throw Error(FS2_ERR_INVALID, m);
+}
+
+static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_out* out) {
+  require(c->prepared, FS2_ERR_STATE, "fs2_forward_stage1 called before fs2_prepare");
+  require(in && out, FS2_ERR_INVALID, "null argument");
+  const int B = in->batch, L = in->max_src_len;
+  require(B > 0 && B <= 65535 && L > 0, FS2_ERR_INVALID, "batch must be in [1,65535] and max_src_len > 0");
+  require(in->speakers && in->emotions && in->arousals && in->valences && in->texts && in->src_lens, FS2_ERR_INVALID,
+          "null input tensor");
+  require(out->pitch && out->energy && out->log_d && out->d_rounded && out->src_mask && out->mel_lens, FS2_ERR_INVALID,
+          "null output tensor");
+  FS2_CUDA_OK(cudaSetDevice(c->device));
+  g_launches = 0;
+  c->stage1_done = false;
+  for (auto& r : c->prof) { c->event_pool.push_back(r.beg); c->event_pool.push_back(r.end); }
+  c->prof.clear();
+  if (c->debug) {
+    for (auto& kv : c->taps) cudaFree(kv.second.first);
+    c->taps.clear();
+  }
+
+  const int64_t bound = (int64_t)GAP_PHON + (int64_t)B * (L + GAP_PHON);
+  require(bound < (1LL << 30), FS2_ERR_INVALID, "batch * max_src_len too large");
+  const int rows = round_up((int)bound, 128);
+  ensure_side(c->ps, B, rows);
+  ensure_side(c->fs, B, 0);
+  ensure_pool(c->pp, rows, false);
+  const int64_t BL = (int64_t)B * L;
+  if (BL > c->scratch_bl) {
+    regrow(c->cum, BL);
+    regrow(c->raw_pitch, BL);
+    regrow(c->raw_energy, BL);
+    c->scratch_bl = BL;
+  }
+  if (B > c->scratch_b) {
+    regrow(c->mel_lens32, B);
+    regrow(c->cond_spk, (size_t)B * D_MODEL);
+    regrow(c->cond_emo, (size_t)B * D_MODEL);
+    c->scratch_b = B;
+  }
+
+  RowSide& ps = c->ps;
+  Pool& pp = c->pp;
+  FS2_CUDA_OK(cudaMemsetAsync(c->status, 0, sizeof(int32_t), s));
+  FS2_CUDA_OK(cudaMemsetAsync(out->pitch, 0, BL * sizeof(float), s));
+  FS2_CUDA_OK(cudaMemsetAsync(out->energy, 0, BL * sizeof(float), s));
+  FS2_CUDA_OK(cudaMemsetAsync(out->log_d, 0, BL * sizeof(float), s));
+  FS2_CUDA_OK(cudaMemsetAsync(out->d_rounded, 0, BL * sizeof(float), s));
+  FS2_CUDA_OK(cudaMemsetAsync(c->raw_pitch, 0, BL * sizeof(float), s));
+  FS2_CUDA_OK(cudaMemsetAsync(c->raw_energy, 0, BL * sizeof(float), s));
+
+  layout_scan_kernel<int64_t><<<1, 1024, 0, s>>>(in->src_lens, B, GAP_PHON, L, L, ps.starts, ps.lens, ps.totals, c->status);
+  FS2_LAUNCHED();
+  row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(ps.starts, ps.lens, B, GAP_PHON, L, nullptr, rows, ps.utt, ps.vpos,
+                                                     ps.room, ps.slot);
+  FS2_LAUNCHED();
+  src_mask_kernel<<<(unsigned)((BL + 255) / 256), 256, 0, s>>>(in->src_lens, B, L, out->src_mask);
+  FS2_LAUNCHED();
+
+  // ---- Encoder (transformer/Models.py:73-100)
+  float *x = pp.act[0], *t1 = pp.act[1], *t2 = pp.act[2], *t3 = pp.act[3];
+  const float* pe = position_rows(c, "encoder.position_enc", L, s);
+  embed_pe_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in->texts, L, c->raw.at("encoder.src_word_emb.weight").ptr,
+                                                 c->cfg.n_src_vocab, pe, ps.meta(), ps.lens, rows, x, c->status);
+  FS2_LAUNCHED();
+  tap(c, s, "p_start", ps.starts, 1, B + 1);
+  tap(c, s, "enc_in", x, rows, D_MODEL);
+  for (int i = 0; i < ENC_LAYERS; ++i) {
+    fft_block(c, s, c->enc[i], ps, pp, rows, B, L, x, t1, t2, false);
+    if (c->debug) tap(c, s, ("enc_" + std::to_string(i)).c_str(), x, rows, D_MODEL);
+  }
+
+  // ---- conditioning (model/fastspeech2.py:101-110)
+  cond_kernel<<<B, 256, 0, s>>>(in->speakers, in->emotions, in->arousals, in->valences, c->raw.at("speaker_emb.weight").ptr,
+                                c->cfg.n_speaker, c->raw.at("emotion_emb.weight").ptr, c->cfg.n_emotion,
+                                c->raw.at("arousal_emb.weight").ptr, c->cfg.n_arousal, c->raw.at("valence_emb.weight").ptr,
+                                c->cfg.n_valence, c->raw.at("emotion_linear.0.weight").ptr,
+                                c->raw.at("emotion_linear.0.bias").ptr, c->cond_spk, c->cond_emo, c->status);
+  FS2_LAUNCHED();
+  float* xc = t3;
+  add_cond_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, ps.meta(), c->cond_spk, c->cond_emo, 2, rows, xc);
+  FS2_LAUNCHED();
+  tap(c, s, "cond_x", xc, rows, D_MODEL);
+
+  // ---- VarianceAdaptor (model/modules.py:102-135)
+  predictor(c, s, c->pred[0], ps, rows, xc, t1, t2, out->log_d);
+  predictor(c, s, c->pred[1], ps, rows, xc, t1, t2, c->raw_pitch);
+  float* xe = x;  // encoder output is no longer needed
+  bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
+      xc, ps.meta(), ps.slot, 2, rows, c->raw_pitch, in->p_targets, in->p_control,
+      c->raw.at("variance_adaptor.pitch_bins").ptr, N_BINS - 1, c->raw.at("variance_adaptor.pitch_embedding.weight").ptr,
+      out->pitch, nullptr, xe);
+  FS2_LAUNCHED();
+  predictor(c, s, c->pred[2], ps, rows, xe, t1, t2, c->raw_energy);
+  float* xf = t3;
+  bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
+      xe, ps.meta(), ps.slot, 0, rows, c->raw_energy, in->e_targets, in->p_control /* sic: modules.py:123-125 */,
+      c->raw.at("variance_adaptor.energy_bins").ptr, N_BINS - 1,
+      c->raw.at("variance_adaptor.energy_embedding.weight").ptr, out->energy, nullptr, xf);
+  FS2_LAUNCHED();
+  tap(c, s, "va_x", xf, rows, D_MODEL);
+
+  const bool forced = in->d_targets != nullptr;
+  durations_kernel<<<(B + 7) / 8, 256, 0, s>>>(forced ? in->d_targets : out->log_d, forced ? 1 : 0, in->d_control,
+                                               in->src_lens, B, L, forced ? nullptr : out->d_rounded, c->cum,
+                                               out->mel_lens, c->mel_lens32);
+  FS2_LAUNCHED();
+  layout_scan_kernel<int32_t><<<1, 1024, 0, s>>>(c->mel_lens32, B, GAP_FRAME, 0, in->max_mel_len, c->fs.starts, c->fs.lens,
+                                                 c->fs.totals, c->status);
+  FS2_LAUNCHED();
+
+  // ---- the one blocking point: sizes of the frame side
+  FS2_CUDA_OK(cudaMemcpyAsync(c->h_totals, c->fs.totals, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  FS2_CUDA_OK(cudaMemcpyAsync(c->h_totals + 3, c->status, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  FS2_CUDA_OK(cudaStreamSynchronize(s));
+  check_status(c, *reinterpret_cast<int32_t*>(c->h_totals + 3));
+  c->frame_rows = c->h_totals[0];
+  c->max_mel_len = (int)c->h_totals[1];
+  out->total_frames = c->h_totals[2];
+  out->max_mel_len = c->max_mel_len;
+  require(c->frame_rows < (1LL << 30), FS2_ERR_INVALID, "expanded batch too large");
+  c->batch = B;
+  c->max_src_len = L;
+  c->lr_input = xf;
+  c->stage1_done = true;
+  c->last_launches = g_launches;
+}
+
+static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
+  require(c->stage1_done, FS2_ERR_STATE, "fs2_forward_stage2 called without a completed fs2_forward_stage1");
+  require(io && io->mel && io->postnet && io->mel_mask, FS2_ERR_INVALID, "null stage-2 output");
+  FS2_CUDA_OK(cudaSetDevice(c->device));
+  g_launches = 0;
+  const int B = c->batch, L = c->max_src_len, T = c->max_mel_len;
+  const int rows = round_up((int)c->frame_rows, 128);
+  const int eng = c->cfg.engine, math = c->cfg.math_mode;
+  ensure_side(c->fs, B, rows);
+  ensure_pool(c->fp, rows, true);
+  RowSide& fsd = c->fs;
+  Pool& fp = c->fp;
+
+  if (T > 0) {
+    row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(fsd.starts, fsd.lens, B, GAP_FRAME, T, nullptr, rows, fsd.utt,
+                                                       fsd.vpos, fsd.room, fsd.slot);
+    FS2_LAUNCHED();
+    // ---- LengthRegulator + decoder positional encoding (modules.py:167-194, Models.py:145-162)
+    float *x = fp.act[0], *t1 = fp.act[1], *t2 = fp.act[2];
+    const float* pe = position_rows(c, "decoder.position_enc", T, s);
+    {
+      ProfScope ps(c, s, "length_regulator");
+      length_regulate_kernel<<<(rows + 7) / 8, 256, 0, s>>>(c->lr_input, c->ps.starts, c->cum, L, fsd.meta(), fsd.lens, pe,
+                                                            rows, x);
+      FS2_LAUNCHED();
+    }
+    tap(c, s, "f_start", fsd.starts, 1, B + 1);
+    tap(c, s, "dec_in", x, rows, D_MODEL);
+    for (int i = 0; i < DEC_LAYERS; ++i) {
+      fft_block(c, s, c->dec[i], fsd, fp, rows, B, T, x, t1, t2, true);
+      if (c->debug) tap(c, s, ("dec_" + std::to_string(i)).c_str(), x, rows, D_MODEL);
+    }
+    // ---- mel_linear (fastspeech2.py:134); the first min(10, T_max - T_b) reserved rows get the bias
+    ConvGemmArgs a = gemm_args(x, D_MODEL, rows, c->mel_w, c->mel_b, 1, D_MODEL, N_MEL, ACT_NONE, fp.mel, N_MEL);
+    a.row_vpos = fsd.vpos; a.row_room = fsd.room; a.extra = PN_VIRTUAL;
+    { ProfScope ps(c, s, "mel_linear"); conv_gemm(eng, math, a, s); }
+    tap(c, s, "mel_p", fp.mel, rows, N_MEL);
+    // ---- PostNet (Layers.py:129-137) + residual (fastspeech2.py:136), BatchNorm folded
+    const float* src = fp.mel;
+    int ld = N_MEL;
+    for (int j = 0; j < PN_LAYERS; ++j) {
+      const PostConv& pc = c->post[j];
+      const bool last = j == PN_LAYERS - 1;
+      float* dst = last ? fp.post : fp.pn[j & 1];
+      a = gemm_args(src, ld, rows, pc.w, pc.b, PN_TAPS, pc.cin, pc.cout, last ? ACT_NONE : ACT_TANH, dst, pc.cout);
+      a.row_vpos = fsd.vpos; a.row_room = fsd.room; a.extra = PN_VIRTUAL - 2 * (j + 1);
+      if (last) { a.residual = fp.mel; a.ldr = N_MEL; }
+      { ProfScope ps(c, s, j == 0 ? "postnet.conv_80_512" : (last ? "postnet.conv_512_80" : "postnet.conv_512_512"));
+        conv_gemm(eng, math, a, s); }
+      src = dst;
+      ld = pc.cout;
+    }
+    tap(c, s, "post_p", fp.post, rows, N_MEL);
+    const int64_t out_rows = (int64_t)B * T;
+    {
+      ProfScope ps(c, s, "unpack");
+      unpack_mel_kernel<<<(unsigned)((out_rows + 7) / 8), 256, 0, s>>>(fp.mel, fp.post, fsd.starts, fsd.lens, B, T,
+                                                                       c->mel_b, io->mel, io->postnet, io->mel_mask);
+      FS2_LAUNCHED();
+    }
+  }
+  c->last_launches += g_launches;
+}
+
+static void prepare(fs2_ctx* c, cudaStream_t s) {
+  FS2_CUDA_OK(cudaSetDevice(c->device));
+  for (void* p : c->owned) cudaFree(p);
+  c->owned.clear();
+  c->prepared = false;
+  const int d = D_MODEL;
+  W(c, "encoder.src_word_emb.weight", {c->cfg.n_src_vocab, d});
+  W(c, "encoder.position_enc", {1, c->cfg.max_seq_len + 1, d});
+  W(c, "decoder.position_enc", {1, c->cfg.max_seq_len + 1, d});
+  for (int i = 0; i < ENC_LAYERS; ++i) prepare_fft(c, "encoder.layer_stack." + std::to_string(i), c->enc[i], s);
+  for (int i = 0; i < DEC_LAYERS; ++i) prepare_fft(c, "decoder.layer_stack." + std::to_string(i), c->dec[i], s);
+  const char* pn[3] = {"duration", "pitch", "energy"};
+  for (int i = 0; i < 3; ++i) prepare_predictor(c, std::string("variance_adaptor.") + pn[i] + "_predictor", c->pred[i], s);
+  W(c, "variance_adaptor.pitch_bins", {N_BINS - 1});
+  W(c, "variance_adaptor.energy_bins", {N_BINS - 1});
+  W(c, "variance_adaptor.pitch_embedding.weight", {N_BINS, d});
+  W(c, "variance_adaptor.energy_embedding.weight", {N_BINS, d});
+  W(c, "speaker_emb.weight", {c->cfg.n_speaker, d});
+  W(c, "emotion_emb.weight", {c->cfg.n_emotion, d / 2});
+  W(c, "arousal_emb.weight", {c->cfg.n_arousal, d / 4});
+  W(c, "valence_emb.weight", {c->cfg.n_valence, d / 4});
+  W(c, "emotion_linear.0.weight", {d, d});
+  W(c, "emotion_linear.0.bias", {d});
+  c->mel_w = repack_conv(c, W(c, "mel_linear.weight", {N_MEL, d}).ptr, N_MEL, d, 1, nullptr, s);
+  c->mel_b = W(c, "mel_linear.bias", {N_MEL}).ptr;
+  for (int j = 0; j < PN_LAYERS; ++j) {
+    const int cin = j == 0 ? N_MEL : PN_DIM, cout = j == PN_LAYERS - 1 ? N_MEL : PN_DIM;
+    const std::string cv = "postnet.convolutions." + std::to_string(j) + ".0.conv";
+    const std::string bn = "postnet.convolutions." + std::to_string(j) + ".1";
+    float* scale = keep(c, cout);
+    float* bias = keep(c, cout);
+    bn_fold_kernel<<<(cout + 255) / 256, 256, 0, s>>>(W(c, bn + ".weight", {cout}).ptr, W(c, bn + ".bias", {cout}).ptr,
+                                                      W(c, bn + ".running_mean", {cout}).ptr,
+                                                      W(c, bn + ".running_var", {cout}).ptr, W(c, cv + ".bias", {cout}).ptr,
+                                                      cout, scale, bias);
+    FS2_LAUNCHED();
+    c->post[j] = PostConv{repack_conv(c, W(c, cv + ".weight", {cout, cin, PN_TAPS}).ptr, cout, cin, PN_TAPS, scale, s), bias,
+                          cin, cout};
+  }
+  FS2_CUDA_OK(cudaStreamSynchronize(s));
+  c->prepared = true;
+}
+
+template <typename F>
+static int guarded(fs2_ctx* c, F&& f) {
+  try {
+    f();
+    return FS2_OK;
+  } catch (const Error& e) {
+    if (c) c->err = e.msg; else g_create_error = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    if (c) c->err = e.what(); else g_create_error = e.what();
+    return FS2_ERR_INVALID;
+  }
+}
+
+}  // namespace fs2
+
+// ============================================================================ C ABI
+extern "C" {
+
+int fs2_version(void) { return 100; }
+
+int fs2_create(const fs2_config* cfg, int device, fs2_ctx** out) {
+  return guarded(nullptr, [&] {
+    require(cfg && out, FS2_ERR_INVALID, "null argument");
+    require(cfg->math_mode == FS2_MATH_TF32 || cfg->math_mode == FS2_MATH_BF16, FS2_ERR_UNSUPPORTED, "unknown math_mode");
+    require(cfg->engine == FS2_ENGINE_MMA_SYNC || cfg->engine == FS2_ENGINE_TCGEN05, FS2_ERR_UNSUPPORTED, "unknown engine");
+    require(cfg->n_src_vocab > 0 && cfg->n_speaker > 0 && cfg->n_emotion > 0 && cfg->n_arousal > 0 && cfg->n_valence > 0 &&
+                cfg->max_seq_len > 0, FS2_ERR_INVALID, "table sizes must be positive");
+    int n_dev = 0;
+    FS2_CUDA_OK(cudaGetDeviceCount(&n_dev));
+    require(device >= 0 && device < n_dev, FS2_ERR_INVALID, "no such CUDA device");
+    FS2_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    FS2_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    require(prop.major == 10, FS2_ERR_UNSUPPORTED,
+            std::string("libfs2b200 is built for sm_100a (B200) only; device is ") + prop.name);
+    auto* c = new fs2_ctx();
+    c->device = device;
+    c->cfg = *cfg;
+    c->status = dalloc<int32_t>(1);
+    FS2_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&c->h_totals), 8 * sizeof(int64_t)));
+    *out = c;
+  });
+}
+
+void fs2_destroy(fs2_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : c->raw) cudaFree(kv.second.ptr);
+  for (void* p : c->owned) cudaFree(p);
+  for (auto& kv : c->taps) cudaFree(kv.second.first);
+  for (auto& r : c->prof) { cudaEventDestroy(r.beg); cudaEventDestroy(r.end); }
+  for (auto& e : c->event_pool) cudaEventDestroy(e);
+  for (RowSide* sd : {&c->ps, &c->fs}) {
+    cudaFree(sd->starts); cudaFree(sd->lens); cudaFree(sd->utt); cudaFree(sd->vpos); cudaFree(sd->room); cudaFree(sd->slot);
+    cudaFree(sd->totals);
+  }
+  for (Pool* p : {&c->pp, &c->fp}) {
+    for (float* a : p->act) cudaFree(a);
+    cudaFree(p->qkv); cudaFree(p->hid); cudaFree(p->mel); cudaFree(p->post); cudaFree(p->pn[0]); cudaFree(p->pn[1]);
+  }
+  cudaFree(c->status); cudaFree(c->cum); cudaFree(c->mel_lens32); cudaFree(c->raw_pitch); cudaFree(c->raw_energy);
+  cudaFree(c->cond_spk); cudaFree(c->cond_emo); cudaFree(c->pe_long);
+  cudaFreeHost(c->h_totals);
+  delete c;
+}
+
+const char* fs2_last_error(const fs2_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int fs2_set_weight(fs2_ctx* c, const char* key, const void* dev_ptr, const int64_t* shape, int ndim) {
+  if (!c) return FS2_ERR_INVALID;
+  return guarded(c, [&] {
+    require(key && dev_ptr && (shape || ndim == 0) && ndim >= 0 && ndim <= 4, FS2_ERR_INVALID, "bad fs2_set_weight argument");
+    FS2_CUDA_OK(cudaSetDevice(c->device));
+    const std::string k(key);
+    if (k.size() > 19 && k.compare(k.size() - 19, 19, "num_batches_tracked") == 0) return;  // int64 counter, unused in eval
+    DevTensor t;
+    t.numel = 1;
+    for (int i = 0; i < ndim; ++i) {
+      require(shape[i] > 0, FS2_ERR_INVALID, "non-positive dimension in " + k);
+      t.shape.push_back(shape[i]);
+      t.numel *= shape[i];
+    }
+    t.ptr = dalloc<float>(t.numel);
+    FS2_CUDA_OK(cudaMemcpy(t.ptr, dev_ptr, t.numel * sizeof(float), cudaMemcpyDeviceToDevice));
+    auto it = c->raw.find(k);
+    if (it != c->raw.end()) cudaFree(it->second.ptr);
+    c->raw[k] = t;
+    c->prepared = false;
+  });
+}
+
+int fs2_prepare(fs2_ctx* c, fs2_stream stream) {
+  if (!c) return FS2_ERR_INVALID;
+  return guarded(c, [&] { prepare(c, static_cast<cudaStream_t>(stream)); });
+}
+
+int fs2_forward_stage1(fs2_ctx* c, fs2_stream stream, const fs2_inputs* in, fs2_stage1_out* out) {
+  if (!c) return FS2_ERR_INVALID;
+  return guarded(c, [&] { stage1(c, static_cast<cudaStream_t>(stream), in, out); });
+}
+
+int fs2_forward_stage2(fs2_ctx* c, fs2_stream stream, const fs2_stage2_io* io) {
+  if (!c) return FS2_ERR_INVALID;
+  return guarded(c, [&] { stage2(c, static_cast<cudaStream_t>(stream), io); });
+}
+
+int fs2_last_launch_count(const fs2_ctx* c) { return c ? c->last_launches : 0; }
+
+int fs2_debug_enable(fs2_ctx* c, int on) {
+  if (!c) return FS2_ERR_INVALID;
+  c->debug = on != 0;
+  return FS2_OK;
+}
+
+int fs2_debug_fetch(fs2_ctx* c, const char* name, void* host_dst, int64_t max_bytes, int64_t* rows, int64_t* cols) {
+  if (!c) return FS2_ERR_INVALID;
+  return guarded(c, [&] {
+    auto it = c->taps.find(name ? name : "");
+    require(it != c->taps.end(), FS2_ERR_INVALID, std::string("no such debug tap: ") + (name ? name : "(null)"));
+    const auto& dims = it->second.second;
+    if (rows) *rows = dims[0];
+    if (cols) *cols = dims[1];
+    const int64_t bytes = dims[0] * dims[1] * dims[2];
+    if (host_dst) {
+      require(max_bytes >= bytes, FS2_ERR_INVALID, "debug_fetch: destination too small");
+      FS2_CUDA_OK(cudaSetDevice(c->device));
+      FS2_CUDA_OK(cudaDeviceSynchronize());
+      FS2_CUDA_OK(cudaMemcpy(host_dst, it->second.first, bytes, cudaMemcpyDeviceToHost));
+    }
+  });
+}
+
+int fs2_profile_enable(fs2_ctx* c, int on) {
+  if (!c) return FS2_ERR_INVALID;
+  c->profiling = on != 0;
+  return FS2_OK;
+}
+
+int fs2_profile_read(fs2_ctx* c, char* buf, int64_t buf_bytes) {
+  if (!c) return FS2_ERR_INVALID;
+  return guarded(c, [&] {
+    FS2_CUDA_OK(cudaSetDevice(c->device));
+    FS2_CUDA_OK(cudaDeviceSynchronize());
+    std::map<std::string, std::pair<int, double>> agg;
+    for (auto& r : c->prof) {
+      float ms = 0.f;
+      FS2_CUDA_OK(cudaEventElapsedTime(&ms, r.beg, r.end));
+      auto& a = agg[r.label];
+      a.first += 1;
+      a.second += ms;
+    }
+    c->prof_text.clear();
+    for (auto& kv : agg) {
+      char line[160];
+      snprintf(line, sizeof(line), "%s %d %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+      c->prof_text += line;
+    }
+    require(buf && buf_bytes > (int64_t)c->prof_text.size(), FS2_ERR_INVALID, "profile_read: buffer too small");
+    memcpy(buf, c->prof_text.c_str(), c->prof_text.size() + 1);
+  });
+}
+
+// ---------------------------------------------------------------------------- single operators
+static thread_local std::string g_op_error;
+
+int fs2_op_conv_gemm(fs2_stream stream, int engine, int math_mode, const float* A, int lda, int rows, const float* Wt,
+                     const float* bias, int taps, int pad, int K, int N, int act, const float* residual, int ldr,
+                     const int32_t* row_vpos, const int32_t* row_room, int extra, float* C, int ldc) {
+  return guarded(nullptr, [&] {
+    require(A && Wt && bias && C && rows >= 0 && taps >= 1 && K > 0 && N > 0, FS2_ERR_INVALID, "bad conv_gemm argument");
+    ConvGemmArgs a{};
+    a.A = A; a.lda = lda; a.rows = rows; a.W = Wt; a.bias = bias; a.taps = taps; a.pad = pad; a.K = K; a.N = N; a.act = act;
+    a.residual = residual; a.ldr = ldr; a.row_vpos = row_vpos; a.row_room = row_room; a.extra = extra; a.C = C; a.ldc = ldc;
+    conv_gemm(engine, math_mode, a, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int fs2_op_attention(fs2_stream stream, const float* qkv, const int32_t* starts, const int32_t* lens, int batch, int max_len,
+                     float* out) {
+  return guarded(nullptr, [&] {
+    require(qkv && starts && lens && out, FS2_ERR_INVALID, "null attention argument");
+    attn::launch(qkv, starts, lens, batch, max_len, out, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int fs2_op_layernorm(fs2_stream stream, const float* x, int rows, const float* gamma, const float* beta,
+                     const int32_t* row_vpos, const int32_t* row_room, int extra, float* y, const float* head_w,
+                     const float* head_b, float* dot) {
+  return guarded(nullptr, [&] {
+    require(x && gamma && beta && rows >= 0, FS2_ERR_INVALID, "bad layernorm argument");
+    if (rows == 0) return;
+    layernorm_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, gamma, beta, row_vpos, row_room,
+                                                                                    extra, y, head_w, head_b, dot, nullptr);
+    FS2_LAUNCHED();
+  });
+}
+
+int fs2_op_durations(fs2_stream stream, const float* d_in, int is_target, float d_control, const int64_t* src_lens,
+                     int batch, int max_src_len, float* d_rounded, int32_t* cum, int64_t* mel_lens) {
+  return guarded(nullptr, [&] {
+    require(d_in && src_lens && cum && batch > 0 && max_src_len > 0, FS2_ERR_INVALID, "bad durations argument");
+    durations_kernel<<<(batch + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_in, is_target, d_control, src_lens, batch, max_src_len, d_rounded, cum, mel_lens, nullptr);
+    FS2_LAUNCHED();
+  });
+}
+
+int fs2_op_bucketize(fs2_stream stream, const float* values, int64_t n, const float* bins, int n_bins, int32_t* idx) {
+  return guarded(nullptr, [&] {
+    require(values && bins && idx && n >= 0 && n_bins >= 0, FS2_ERR_INVALID, "bad bucketize argument");
+    if (n == 0) return;
+    bucketize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(values, n, bins, n_bins, idx);
+    FS2_LAUNCHED();
+  });
+}
+
+int fs2_op_frame_map(fs2_stream stream, const int32_t* cum, int batch, int max_src_len, int max_mel_len, int32_t* map) {
+  return guarded(nullptr, [&] {
+    require(cum && map && batch > 0 && max_src_len > 0 && max_mel_len > 0, FS2_ERR_INVALID, "bad frame_map argument");
+    const int64_t n = (int64_t)batch * max_mel_len;
+    frame_map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(cum, batch, max_src_len,
+                                                                                                max_mel_len, map);
+    FS2_LAUNCHED();
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,471 @@
+// HBM-bound kernels of the path: row layout, embedding + positional encoding, conditioning,
+// LayerNorm, bucketize + embedding add, durations + scans, length regulator, output unpack,
+// weight repack.  All activations are fp32, token-major, 256 columns unless noted; a warp owns
+// one row and moves it with 16-byte accesses.
+#pragma once
+
+#include "common.cuh"
+
+namespace fs2 {
+
+// device-side status word: nonzero => the host raises after the stage's read-back
+enum { ERR_BAD_LEN = 1, ERR_BAD_ID = 2, ERR_MAXLEN_SMALL = 4, ERR_BAD_INDEX = 8 };
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// Row layout: exclusive scan of (len + gap) over the batch.  One block.
+// totals[0] = rows in use (end of the last gap), totals[1] = max_len (max over lens, or the
+// caller's value when forced_max > 0), totals[2] = sum of lens.  (utils/tools.py:152-160 builds
+// masks from the same lengths; here they define the packed layout instead.)
+template <typename LenT>
+__global__ void layout_scan_kernel(const LenT* __restrict__ lens, int batch, int gap, int len_limit,
+                                   int forced_max, int32_t* __restrict__ starts, int32_t* __restrict__ lens32,
+                                   int64_t* __restrict__ totals, int32_t* __restrict__ status) {
+  __shared__ long long part[1024];
+  __shared__ int maxv[1024];
+  const int tid = threadIdx.x;
+  const int per = (batch + blockDim.x - 1) / blockDim.x;
+  const int lo = min(tid * per, batch), hi = min(lo + per, batch);
+  long long s = 0;
+  int mx = 0;
+  long long real = 0;
+  for (int b = lo; b < hi; ++b) {
+    long long l = (long long)lens[b];
+    if (l < 0 || (len_limit > 0 && l > len_limit)) {
+      atomicOr(status, ERR_BAD_LEN);
+      l = l < 0 ? 0 : len_limit;
+    }
+    s += l + gap;
+    real += l;
+    mx = max(mx, (int)l);
+  }
+  part[tid] = s;
+  maxv[tid] = mx;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 1024 partials
+  for (int off = 1; off < blockDim.x; off <<= 1) {
+    long long v = tid >= off ? part[tid - off] : 0;
+    int m = tid >= off ? maxv[tid - off] : 0;
+    __syncthreads();
+    part[tid] += v;
+    maxv[tid] = max(maxv[tid], m);
+    __syncthreads();
+  }
+  long long run = gap + (tid > 0 ? part[tid - 1] : 0);
+  for (int b = lo; b < hi; ++b) {
+    long long l = (long long)lens[b];
+    l = l < 0 ? 0 : ((len_limit > 0 && l > len_limit) ? len_limit : l);
+    starts[b] = (int32_t)run;
+    lens32[b] = (int32_t)l;
+    run += l + gap;
+  }
+  // sum of real lengths: second tiny reduction through shared memory
+  __syncthreads();
+  long long total_rows = gap + part[blockDim.x - 1];
+  int max_len = maxv[blockDim.x - 1];
+  __syncthreads();
+  part[tid] = real;
+  __syncthreads();
+  for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+    if (tid < off) part[tid] += part[tid + off];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (forced_max > 0) {
+      if (forced_max < max_len) atomicOr(status, ERR_MAXLEN_SMALL);
+      max_len = forced_max;
+    }
+    starts[batch] = (int32_t)total_rows;
+    totals[0] = total_rows;
+    totals[1] = max_len;
+    totals[2] = part[0];
+  }
+}
+
+// Per-row metadata from the starts.  max_len comes from a device scalar (totals[1]) when
+// max_len_dev != nullptr (frame side: T_max is only known on the device when this is enqueued).
+__global__ void row_meta_kernel(const int32_t* __restrict__ starts, const int32_t* __restrict__ lens, int batch,
+                                int gap, int max_len_host, const int64_t* __restrict__ max_len_dev, int rows_alloc,
+                                int32_t* __restrict__ utt, int32_t* __restrict__ vpos, int32_t* __restrict__ room,
+                                int32_t* __restrict__ slot) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows_alloc) return;
+  const int max_len = max_len_dev ? (int)*max_len_dev : max_len_host;
+  int u = -1, vp = VPOS_DEAD, rm = 0, sl = -1;
+  if (batch > 0 && r >= starts[0]) {
+    int lo = 0, hi = batch - 1;  // largest b with starts[b] <= r
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (starts[mid] <= r) lo = mid; else hi = mid - 1;
+    }
+    const int pos = r - starts[lo], len = lens[lo];
+    if (pos < len + gap) {
+      u = lo;
+      vp = pos - len;
+      rm = max_len - len;
+      if (pos < max_len) sl = lo * max_len + pos;
+    }
+  }
+  utt[r] = u;
+  vpos[r] = vp;
+  room[r] = rm;
+  slot[r] = sl;
+}
+
+// ---------------------------------------------------------------------------------------
+// Encoder input: src_word_emb[texts] + position_enc[:L]  (transformer/Models.py:82-91).
+__global__ void embed_pe_kernel(const int64_t* __restrict__ texts, int max_src_len, const float* __restrict__ emb,
+                                int n_vocab, const float* __restrict__ pe, RowMeta meta, const int32_t* __restrict__ lens,
+                                int rows, float* __restrict__ x, int32_t* __restrict__ status) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int u = meta.utt[row], vp = meta.vpos[row];
+  float* dst = x + (size_t)row * D_MODEL;
+  if (u < 0 || vp >= 0) {
+    st4(dst + lane * 4, make_float4(0, 0, 0, 0));
+    st4(dst + 128 + lane * 4, make_float4(0, 0, 0, 0));
+    return;
+  }
+  const int pos = vp + lens[u];
+  long long id = texts[(size_t)u * max_src_len + pos];
+  if (id < 0 || id >= n_vocab) {
+    if (lane == 0) atomicOr(status, ERR_BAD_ID);
+    id = 0;
+  }
+  const float* e = emb + (size_t)id * D_MODEL;
+  const float* p = pe + (size_t)pos * D_MODEL;
+  st4(dst + lane * 4, add4(ld4(e + lane * 4), ld4(p + lane * 4)));
+  st4(dst + 128 + lane * 4, add4(ld4(e + 128 + lane * 4), ld4(p + 128 + lane * 4)));
+}
+
+// ---------------------------------------------------------------------------------------
+// Conditioning vectors (model/fastspeech2.py:101-110): spk[b] = speaker_emb[s];
+// emo[b] = ReLU(W . cat(emotion_emb[e], arousal_emb[a], valence_emb[v]) + bias).  Block per utterance.
+__global__ void cond_kernel(const int64_t* __restrict__ speakers, const int64_t* __restrict__ emotions,
+                            const int64_t* __restrict__ arousals, const int64_t* __restrict__ valences,
+                            const float* __restrict__ spk_emb, int n_spk, const float* __restrict__ emo_emb, int n_emo,
+                            const float* __restrict__ aro_emb, int n_aro, const float* __restrict__ val_emb, int n_val,
+                            const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ spk_out,
+                            float* __restrict__ emo_out, int32_t* __restrict__ status) {
+  __shared__ float e[D_MODEL];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  long long s = speakers[b], em = emotions[b], ar = arousals[b], va = valences[b];
+  if (s < 0 || s >= n_spk || em < 0 || em >= n_emo || ar < 0 || ar >= n_aro || va < 0 || va >= n_val) {
+    if (tid == 0) atomicOr(status, ERR_BAD_INDEX);
+    s = min(max(s, 0LL), (long long)n_spk - 1);
+    em = min(max(em, 0LL), (long long)n_emo - 1);
+    ar = min(max(ar, 0LL), (long long)n_aro - 1);
+    va = min(max(va, 0LL), (long long)n_val - 1);
+  }
+  if (tid < 128) e[tid] = emo_emb[em * 128 + tid];
+  else if (tid < 192) e[tid] = aro_emb[ar * 64 + (tid - 128)];
+  else e[tid] = val_emb[va * 64 + (tid - 192)];
+  spk_out[(size_t)b * D_MODEL + tid] = spk_emb[s * D_MODEL + tid];
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int n = warp; n < D_MODEL; n += 8) {
+    const float* w = W + (size_t)n * D_MODEL;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = lane; k < D_MODEL; k += 32) acc = fmaf(w[k], e[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) emo_out[(size_t)b * D_MODEL + n] = fmaxf(acc + bias[n], 0.f);
+  }
+}
+
+// x_cond = (enc + spk[b]) + emo[b] on real rows AND on the first min(2, L_max - L_b) reserved
+// rows (the reference adds the vectors on padding rows too and the predictors read them --
+// SURVEY.md B.4); every other row is zero.
+__global__ void add_cond_kernel(const float* __restrict__ x, RowMeta meta, const float* __restrict__ spk,
+                                const float* __restrict__ emo, int extra, int rows, float* __restrict__ y) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int u = meta.utt[row];
+  float* dst = y + (size_t)row * D_MODEL;
+  if (u < 0 || !row_live(meta.vpos[row], meta.room[row], extra)) {
+    st4(dst + lane * 4, make_float4(0, 0, 0, 0));
+    st4(dst + 128 + lane * 4, make_float4(0, 0, 0, 0));
+    return;
+  }
+  const float* src = x + (size_t)row * D_MODEL;
+  const float* s = spk + (size_t)u * D_MODEL;
+  const float* e = emo + (size_t)u * D_MODEL;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = h * 128 + lane * 4;
+    st4(dst + c, add4(add4(ld4(src + c), ld4(s + c)), ld4(e + c)));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm over 256 columns (eps 1e-5, biased variance), optional row mask, optional fused
+// 256->1 head (VariancePredictor.linear_layer, model/modules.py:245-250) scattered to
+// head_out[slot[row]] for real rows.  Warp per row, two-pass in registers.
+__global__ void layernorm_kernel(const float* __restrict__ x, int rows, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, const int32_t* __restrict__ vpos,
+                                 const int32_t* __restrict__ room, int extra, float* __restrict__ y,
+                                 const float* __restrict__ head_w, const float* __restrict__ head_b,
+                                 float* __restrict__ head_out, const int32_t* __restrict__ slot) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bool live = vpos == nullptr || row_live(vpos[row], room[row], extra);
+  if (!live) {
+    if (y != nullptr) {
+      st4(y + (size_t)row * D_MODEL + lane * 4, make_float4(0, 0, 0, 0));
+      st4(y + (size_t)row * D_MODEL + 128 + lane * 4, make_float4(0, 0, 0, 0));
+    }
+    return;
+  }
+  const float* src = x + (size_t)row * D_MODEL;
+  const float4 a = ld4(src + lane * 4), b = ld4(src + 128 + lane * 4);
+  const float mean = warp_sum(a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w) * (1.f / D_MODEL);
+  float4 ca = make_float4(a.x - mean, a.y - mean, a.z - mean, a.w - mean);
+  float4 cb = make_float4(b.x - mean, b.y - mean, b.z - mean, b.w - mean);
+  const float var = warp_sum(ca.x * ca.x + ca.y * ca.y + ca.z * ca.z + ca.w * ca.w + cb.x * cb.x + cb.y * cb.y +
+                             cb.z * cb.z + cb.w * cb.w) * (1.f / D_MODEL);
+  const float rstd = 1.f / sqrtf(var + 1e-5f);
+  const float4 ga = ld4(gamma + lane * 4), gb = ld4(gamma + 128 + lane * 4);
+  const float4 ba = ld4(beta + lane * 4), bb = ld4(beta + 128 + lane * 4);
+  const float4 ya = make_float4(ca.x * rstd * ga.x + ba.x, ca.y * rstd * ga.y + ba.y, ca.z * rstd * ga.z + ba.z,
+                                ca.w * rstd * ga.w + ba.w);
+  const float4 yb = make_float4(cb.x * rstd * gb.x + bb.x, cb.y * rstd * gb.y + bb.y, cb.z * rstd * gb.z + bb.z,
+                                cb.w * rstd * gb.w + bb.w);
+  if (y != nullptr) {
+    st4(y + (size_t)row * D_MODEL + lane * 4, ya);
+    st4(y + (size_t)row * D_MODEL + 128 + lane * 4, yb);
+  }
+  if (head_out != nullptr) {
+    const float4 wa = ld4(head_w + lane * 4), wb = ld4(head_w + 128 + lane * 4);
+    float d = ya.x * wa.x + ya.y * wa.y + ya.z * wa.z + ya.w * wa.w + yb.x * wb.x + yb.y * wb.y + yb.z * wb.z +
+              yb.w * wb.w;
+    d = warp_sum(d) + head_b[0];
+    if (lane == 0) {
+      const int dst = slot ? slot[row] : row;
+      if (dst >= 0) head_out[dst] = d;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// torch.bucketize(v, bins, right=False): number of boundaries strictly below v; NaN -> n_bins.
+__device__ __forceinline__ int bucket_of(float v, const float* __restrict__ bins, int n_bins) {
+  int lo = 0, hi = n_bins;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (bins[mid] >= v) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+__global__ void bucketize_kernel(const float* __restrict__ v, int64_t n, const float* __restrict__ bins, int n_bins,
+                                 int32_t* __restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) idx[i] = bucket_of(v[i], bins, n_bins);
+}
+
+// get_pitch_embedding / get_energy_embedding (model/modules.py:80-100) + the add (:121,:126):
+// value = target ? target : raw * control; returned prediction = target ? raw : raw * control;
+// y[row] = x[row] + table[bucketize(value)].  Runs on real rows and on the `extra` virtual rows
+// (whose raw prediction is the masked 0, modules.py:248-249); other rows are zeroed.
+__global__ void bucket_embed_add_kernel(const float* __restrict__ x, RowMeta meta, const int32_t* __restrict__ slot,
+                                        int extra, int rows, const float* __restrict__ raw,
+                                        const float* __restrict__ target, float control,
+                                        const float* __restrict__ bins, int n_bins, const float* __restrict__ table,
+                                        float* __restrict__ pred_out, int32_t* __restrict__ idx_out,
+                                        float* __restrict__ y) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* dst = y + (size_t)row * D_MODEL;
+  const int sl = slot[row];
+  if (meta.utt[row] < 0 || sl < 0 || !row_live(meta.vpos[row], meta.room[row], extra)) {
+    st4(dst + lane * 4, make_float4(0, 0, 0, 0));
+    st4(dst + 128 + lane * 4, make_float4(0, 0, 0, 0));
+    return;
+  }
+  const bool real = meta.vpos[row] < 0;
+  const float r = real ? raw[sl] : 0.f;
+  const float scaled = r * control;
+  const float value = target != nullptr ? target[sl] : scaled;
+  const int idx = bucket_of(value, bins, n_bins);
+  if (lane == 0 && real) {
+    pred_out[sl] = target != nullptr ? r : scaled;
+    if (idx_out != nullptr) idx_out[sl] = idx;
+  }
+  const float* src = x + (size_t)row * D_MODEL;
+  const float* e = table + (size_t)idx * D_MODEL;
+  st4(dst + lane * 4, add4(ld4(src + lane * 4), ld4(e + lane * 4)));
+  st4(dst + 128 + lane * 4, add4(ld4(src + 128 + lane * 4), ld4(e + 128 + lane * 4)));
+}
+
+// ---------------------------------------------------------------------------------------
+// Durations (model/modules.py:132-135) -> repeat counts max(int(d),0) (modules.py:186-187) ->
+// inclusive scan per utterance.  Warp per utterance.  Padding positions expand to nothing.
+__global__ void durations_kernel(const float* __restrict__ d_in, int is_target, float d_control,
+                                 const int64_t* __restrict__ src_lens, int batch, int max_src_len,
+                                 float* __restrict__ d_rounded, int32_t* __restrict__ cum,
+                                 int64_t* __restrict__ mel_lens, int32_t* __restrict__ mel_lens32) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= batch) return;
+  long long len = src_lens[b];
+  len = len < 0 ? 0 : (len > max_src_len ? max_src_len : len);
+  int run = 0;
+  for (int j0 = 0; j0 < max_src_len; j0 += 32) {
+    const int j = j0 + lane;
+    int reps = 0;
+    if (j < max_src_len) {
+      const size_t i = (size_t)b * max_src_len + j;
+      float d;
+      if (is_target) {
+        d = d_in[i];
+      } else {
+        const float logd = j < len ? d_in[i] : 0.f;           // masked_fill(mask, 0) (modules.py:248-249)
+        d = fmaxf(rintf(expf(logd) - 1.f) * d_control, 0.f);   // round half-to-even BEFORE scaling
+        if (d_rounded != nullptr) d_rounded[i] = d;
+      }
+      if (j < len) {
+        const float t = truncf(d);
+        reps = t > 0.f ? (t < 1048576.f ? (int)t : 1048576) : 0;
+      }
+    }
+    int inc = reps;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (j < max_src_len) cum[(size_t)b * max_src_len + j] = run + inc;
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) {
+    if (mel_lens != nullptr) mel_lens[b] = run;
+    if (mel_lens32 != nullptr) mel_lens32[b] = run;
+  }
+}
+
+__device__ __forceinline__ int phoneme_of_frame(const int32_t* __restrict__ cum, int n, int t) {
+  int lo = 0, hi = n;  // first j with cum[j] > t
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cum[mid] > t) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+__global__ void frame_map_kernel(const int32_t* __restrict__ cum, int batch, int max_src_len, int max_mel_len,
+                                 int32_t* __restrict__ map) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)batch * max_mel_len) return;
+  const int b = (int)(i / max_mel_len), t = (int)(i % max_mel_len);
+  const int32_t* c = cum + (size_t)b * max_src_len;
+  map[i] = t < c[max_src_len - 1] ? phoneme_of_frame(c, max_src_len, t) : -1;
+}
+
+// LengthRegulator (model/modules.py:167-194, utils/tools.py:360-378) fused with the decoder's
+// positional-encoding add (transformer/Models.py:145-162): frame row -> phoneme row by binary
+// search in the scan, one coalesced 1 KB row copy per warp; reserved rows are zeroed.
+__global__ void length_regulate_kernel(const float* __restrict__ x, const int32_t* __restrict__ p_starts,
+                                       const int32_t* __restrict__ cum, int max_src_len, RowMeta fmeta,
+                                       const int32_t* __restrict__ f_lens, const float* __restrict__ pe, int rows,
+                                       float* __restrict__ y) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int u = fmeta.utt[row], vp = fmeta.vpos[row];
+  float* dst = y + (size_t)row * D_MODEL;
+  if (u < 0 || vp >= 0) {
+    st4(dst + lane * 4, make_float4(0, 0, 0, 0));
+    st4(dst + 128 + lane * 4, make_float4(0, 0, 0, 0));
+    return;
+  }
+  const int t = vp + f_lens[u];
+  const int j = phoneme_of_frame(cum + (size_t)u * max_src_len, max_src_len, t);
+  const float* src = x + (size_t)(p_starts[u] + j) * D_MODEL;
+  const float* p = pe + (size_t)t * D_MODEL;
+  st4(dst + lane * 4, add4(ld4(src + lane * 4), ld4(p + lane * 4)));
+  st4(dst + 128 + lane * 4, add4(ld4(src + 128 + lane * 4), ld4(p + 128 + lane * 4)));
+}
+
+// ---------------------------------------------------------------------------------------
+// Packed -> padded outputs (model/fastspeech2.py:138-149): mel / postnet [B,T_max,80] and the
+// mel mask.  Padding rows of both tensors receive mel_linear.bias (what the reference's mel has
+// there; its postnet padding rows are outside the contract).  Warp per output row.
+__global__ void unpack_mel_kernel(const float* __restrict__ mel_p, const float* __restrict__ post_p,
+                                  const int32_t* __restrict__ f_starts, const int32_t* __restrict__ f_lens, int batch,
+                                  int max_mel_len, const float* __restrict__ bias, float* __restrict__ mel,
+                                  float* __restrict__ post, uint8_t* __restrict__ mask) {
+  const int64_t o = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= (int64_t)batch * max_mel_len) return;
+  const int b = (int)(o / max_mel_len), t = (int)(o % max_mel_len);
+  const bool real = t < f_lens[b];
+  if (lane == 0 && mask != nullptr) mask[o] = real ? 0 : 1;
+  if (lane < N_MEL / 4) {
+    float4 m, p;
+    if (real) {
+      const size_t src = (size_t)(f_starts[b] + t) * N_MEL + lane * 4;
+      m = ld4(mel_p + src);
+      p = ld4(post_p + src);
+    } else {
+      m = p = ld4(bias + lane * 4);
+    }
+    st4(mel + o * N_MEL + lane * 4, m);
+    st4(post + o * N_MEL + lane * 4, p);
+  }
+}
+
+__global__ void src_mask_kernel(const int64_t* __restrict__ src_lens, int batch, int max_src_len,
+                                uint8_t* __restrict__ mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)batch * max_src_len) return;
+  mask[i] = (i % max_src_len) >= src_lens[i / max_src_len] ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Weight repack (once, in fs2_prepare).
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// Conv1d weight [Cout][Cin][k] (torch) -> [k][Cout][Cin], scaled per output channel (BatchNorm
+// folding: transformer/Layers.py:129-137 with eval-mode BatchNorm1d), operands rounded to TF32.
+__global__ void repack_conv_kernel(const float* __restrict__ w, int cout, int cin, int k,
+                                   const float* __restrict__ scale, int round_operand, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)cout * cin * k) return;
+  const int ci = (int)(i % cin);
+  const int co = (int)((i / cin) % cout);
+  const int t = (int)(i / ((int64_t)cin * cout));
+  float v = w[((size_t)co * cin + ci) * k + t];
+  if (scale != nullptr) v *= scale[co];
+  out[i] = round_operand ? round_tf32(v) : v;
+}
+
+// s = gamma / sqrt(var + eps);  b' = (b - mean) * s + beta
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var,
+                               const float* __restrict__ conv_bias, int n, float* __restrict__ scale,
+                               float* __restrict__ bias_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double s = (double)gamma[i] / sqrt((double)var[i] + 1e-5);
+  scale[i] = (float)s;
+  bias_out[i] = (float)(((double)conv_bias[i] - (double)mean[i]) * s + (double)beta[i]);
+}
+
+}  // namespace fs2

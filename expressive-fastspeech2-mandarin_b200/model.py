@@ -1,0 +1,315 @@
+"""`FastSpeech2B200` -- the host-side mirror of the reference's `FastSpeech2` module.
+
+Same constructor arguments, same 240 state-dict keys and shapes, same
+`forward` signature and 10-tuple result as model/fastspeech2.py:16-149, so
+`model.load_state_dict(ckpt["model"])` and `model(*(batch[2:]), p_control=..., ...)`
+(synthesize_chinese_pinyin.py:138-145) work unchanged.  The module only holds the
+parameters; every computation happens in libfs2b200.so (include/fs2_b200.h).  There is no
+PyTorch/CPU implementation of the forward here and none is ever selected: without the
+library, or with CPU tensors, the calls raise.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .config import N_SRC_VOCAB, POSTNET_DIM, POSTNET_KERNEL, POSTNET_LAYERS, check_supported
+from .synthetic import sinusoid_table
+
+_BUFFER_SUFFIXES = ("running_mean", "running_var", "num_batches_tracked")
+
+
+def _schema(n_speaker, n_emotion, n_arousal, n_valence, max_seq_len):
+    """(key, shape) of every tensor of the reference's state dict, in its order."""
+    d, inner = 256, 1024
+    out = [("encoder.position_enc", (1, max_seq_len + 1, d)), ("encoder.src_word_emb.weight", (N_SRC_VOCAB, d))]
+
+    def fft(prefix):
+        for w in ("w_qs", "w_ks", "w_vs"):
+            out.extend([(f"{prefix}.slf_attn.{w}.weight", (d, d)), (f"{prefix}.slf_attn.{w}.bias", (d,))])
+        out.extend([(f"{prefix}.slf_attn.layer_norm.weight", (d,)), (f"{prefix}.slf_attn.layer_norm.bias", (d,)),
+                    (f"{prefix}.slf_attn.fc.weight", (d, d)), (f"{prefix}.slf_attn.fc.bias", (d,)),
+                    (f"{prefix}.pos_ffn.w_1.weight", (inner, d, 9)), (f"{prefix}.pos_ffn.w_1.bias", (inner,)),
+                    (f"{prefix}.pos_ffn.w_2.weight", (d, inner, 1)), (f"{prefix}.pos_ffn.w_2.bias", (d,)),
+                    (f"{prefix}.pos_ffn.layer_norm.weight", (d,)), (f"{prefix}.pos_ffn.layer_norm.bias", (d,))])
+
+    for i in range(4):
+        fft(f"encoder.layer_stack.{i}")
+    va = "variance_adaptor"
+    out.extend([(f"{va}.pitch_bins", (255,)), (f"{va}.energy_bins", (255,))])
+    for name in ("duration", "pitch", "energy"):
+        p = f"{va}.{name}_predictor"
+        for n in (1, 2):
+            out.extend([(f"{p}.conv_layer.conv1d_{n}.conv.weight", (d, d, 3)), (f"{p}.conv_layer.conv1d_{n}.conv.bias", (d,)),
+                        (f"{p}.conv_layer.layer_norm_{n}.weight", (d,)), (f"{p}.conv_layer.layer_norm_{n}.bias", (d,))])
+        out.extend([(f"{p}.linear_layer.weight", (1, d)), (f"{p}.linear_layer.bias", (1,))])
+    out.extend([(f"{va}.pitch_embedding.weight", (256, d)), (f"{va}.energy_embedding.weight", (256, d))])
+    out.append(("decoder.position_enc", (1, max_seq_len + 1, d)))
+    for i in range(6):
+        fft(f"decoder.layer_stack.{i}")
+    out.extend([("mel_linear.weight", (80, d)), ("mel_linear.bias", (80,))])
+    chans = [80] + [POSTNET_DIM] * (POSTNET_LAYERS - 1) + [80]
+    for j in range(POSTNET_LAYERS):
+        c = f"postnet.convolutions.{j}"
+        out.extend([(f"{c}.0.conv.weight", (chans[j + 1], chans[j], POSTNET_KERNEL)), (f"{c}.0.conv.bias", (chans[j + 1],))])
+        for leaf in ("weight", "bias", "running_mean", "running_var"):
+            out.append((f"{c}.1.{leaf}", (chans[j + 1],)))
+        out.append((f"{c}.1.num_batches_tracked", ()))
+    out.extend([("speaker_emb.weight", (n_speaker, d)), ("emotion_emb.weight", (n_emotion, d // 2)),
+                ("arousal_emb.weight", (n_arousal, d // 4)), ("valence_emb.weight", (n_valence, d // 4)),
+                ("emotion_linear.0.weight", (d, d)), ("emotion_linear.0.bias", (d,))])
+    return out
+
+
+class FastSpeech2B200(nn.Module):
+    """Drop-in for `FastSpeech2(preprocess_config, model_config)` in eval mode on one B200."""
+
+    def __init__(self, preprocess_config, model_config, math_mode="tf32", engine="mma_sync", init_seed=0):
+        super().__init__()
+        check_supported(preprocess_config, model_config)
+        self.model_config = model_config
+        root = preprocess_config["path"]["preprocessed_path"]
+        with open(os.path.join(root, "speakers.json")) as f:       # model/fastspeech2.py:31-37
+            n_speaker = len(json.load(f))
+        with open(os.path.join(root, "emotions.json")) as f:       # model/fastspeech2.py:45-54
+            emo = json.load(f)
+        with open(os.path.join(root, "stats.json")) as f:          # model/modules.py:41-46
+            stats = json.load(f)
+        self._dims = dict(n_src_vocab=N_SRC_VOCAB, n_speaker=n_speaker, n_emotion=len(emo["emotion_dict"]),
+                          n_arousal=len(emo["arousal_dict"]), n_valence=len(emo["valence_dict"]),
+                          max_seq_len=int(model_config["max_seq_len"]))
+        self.math_mode = {"tf32": _lib.MATH_TF32, "bf16": _lib.MATH_BF16}[math_mode]
+        self.engine = {"mma_sync": _lib.ENGINE_MMA_SYNC, "tcgen05": _lib.ENGINE_TCGEN05}[engine]
+
+        # Parameter tree built from the schema; values: deterministic tables where the reference
+        # computes them (position_enc, bins), seeded random elsewhere (the reference random-inits).
+        from .synthetic import synthetic_state_dict
+        init = synthetic_state_dict(seed=init_seed, duration_bias=0.0)
+        ve = model_config["variance_embedding"]
+
+        def bins(lo, hi, kind):                                     # model/modules.py:48-71
+            if kind == "log":
+                return torch.exp(torch.linspace(np.log(lo), np.log(hi), ve["n_bins"] - 1))
+            return torch.linspace(lo, hi, ve["n_bins"] - 1)
+
+        init["variance_adaptor.pitch_bins"] = bins(stats["pitch"][0], stats["pitch"][1], ve["pitch_quantization"])
+        init["variance_adaptor.energy_bins"] = bins(stats["energy"][0], stats["energy"][1], ve["energy_quantization"])
+        pe = sinusoid_table(self._dims["max_seq_len"] + 1, 256).unsqueeze(0)
+        for key, shape in _schema(self._dims["n_speaker"], self._dims["n_emotion"], self._dims["n_arousal"],
+                                  self._dims["n_valence"], self._dims["max_seq_len"]):
+            if key.endswith("position_enc"):
+                value = pe.clone()
+            elif key in init and tuple(init[key].shape) == tuple(shape):
+                value = init[key]
+            else:  # a table whose size differs from the synthetic fixture
+                value = torch.randn(shape, generator=torch.Generator().manual_seed(init_seed)) if shape else torch.tensor(0)
+            self._attach(key, value)
+
+        self._ctx = None
+        self._ctx_device = None
+        self._dirty = True
+        self._pinned = {}
+        self.eval()
+
+    # ------------------------------------------------------------------ parameter tree
+    def _attach(self, key, value):
+        parts = key.split(".")
+        mod = self
+        for name in parts[:-1]:
+            if name not in mod._modules:
+                mod.add_module(name, nn.Module())
+            mod = mod._modules[name]
+        if parts[-1] in _BUFFER_SUFFIXES:
+            mod.register_buffer(parts[-1], value)
+        else:
+            mod.register_parameter(parts[-1], nn.Parameter(value, requires_grad=False))
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        res = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        self._dirty = True
+        return res
+
+    def _apply(self, fn, recurse=True):
+        res = super()._apply(fn, recurse)
+        self._dirty = True
+        return res
+
+    def train(self, mode=True):
+        if mode:
+            raise RuntimeError("FastSpeech2B200 is an inference engine: training mode (dropout, BatchNorm updates, "
+                               "backward) is outside the accelerated path")
+        return super().train(False)
+
+    def refresh_weights(self):
+        """Re-upload the parameters to the library (call after modifying them in place)."""
+        self._dirty = True
+
+    # ------------------------------------------------------------------ library context
+    def _device(self):
+        return self.mel_linear.weight.device
+
+    def _ensure_ctx(self):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("FastSpeech2B200 runs on a CUDA device only: call .to('cuda') first (there is no CPU path)")
+        lib = _lib.load_library()
+        if self._ctx is not None and self._ctx_device != dev:
+            lib.fs2_destroy(self._ctx)
+            self._ctx = None
+        if self._ctx is None:
+            cfg = _lib.Config(math_mode=self.math_mode, engine=self.engine, **self._dims)
+            ctx = C.c_void_p()
+            code = lib.fs2_create(C.byref(cfg), dev.index if dev.index is not None else torch.cuda.current_device(),
+                                  C.byref(ctx))
+            _lib.check(lib, None, code)
+            self._ctx, self._ctx_device, self._dirty = ctx, dev, True
+        if self._dirty:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            for key, t in self.state_dict().items():
+                if not t.is_floating_point():
+                    continue
+                t = t.detach().to(torch.float32).contiguous()
+                shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+                _lib.check(lib, self._ctx, lib.fs2_set_weight(self._ctx, key.encode(), t.data_ptr(), shape, t.dim()))
+            _lib.check(lib, self._ctx, lib.fs2_prepare(self._ctx, stream))
+            self._dirty = False
+        return lib
+
+    def __del__(self):
+        try:
+            if self._ctx is not None:
+                _lib.load_library().fs2_destroy(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass
+
+    def debug_taps(self, on=True):
+        lib = self._ensure_ctx()
+        lib.fs2_debug_enable(self._ctx, 1 if on else 0)
+
+    def fetch_tap(self, name):
+        lib = self._ensure_ctx()
+        rows, cols = C.c_int64(), C.c_int64()
+        _lib.check(lib, self._ctx, lib.fs2_debug_fetch(self._ctx, name.encode(), None, 0, C.byref(rows), C.byref(cols)))
+        dtype = np.int32 if name.endswith("_start") else np.float32
+        out = np.empty((rows.value, cols.value), dtype=dtype)
+        _lib.check(lib, self._ctx, lib.fs2_debug_fetch(self._ctx, name.encode(), out.ctypes.data, out.nbytes, None, None))
+        return out
+
+    @property
+    def last_launch_count(self):
+        return _lib.load_library().fs2_last_launch_count(self._ctx) if self._ctx is not None else 0
+
+    # ------------------------------------------------------------------ forward
+    def _idx(self, t, name, shape):
+        if not torch.is_tensor(t) or t.device != self._device():
+            raise RuntimeError(f"{name} must be a tensor on {self._device()} (got {getattr(t, 'device', type(t))})")
+        if tuple(t.shape) != tuple(shape):
+            raise RuntimeError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+        return t.to(torch.int64).contiguous()
+
+    def _target(self, t, name, shape):
+        if t is None:
+            return None
+        if not torch.is_tensor(t) or t.device != self._device():
+            raise RuntimeError(f"{name} must be a tensor on {self._device()}")
+        if tuple(t.shape) != tuple(shape):
+            raise RuntimeError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+        return t.to(torch.float32).contiguous()
+
+    @torch.no_grad()
+    def forward(self, speakers, emotions, arousals, valences, texts, src_lens, max_src_len, mels=None, mel_lens=None,
+                max_mel_len=None, p_targets=None, e_targets=None, d_targets=None, p_control=1.0, e_control=1.0,
+                d_control=1.0):
+        if self.training:
+            raise RuntimeError("FastSpeech2B200.forward is inference-only")
+        lib = self._ensure_ctx()
+        dev = self._device()
+        B, L = int(texts.shape[0]), int(max_src_len)
+        if texts.dim() != 2 or int(texts.shape[1]) != L:
+            # the reference sizes the encoder from texts.shape[1] and the masks from max_src_len and
+            # fails on a mismatch
+            raise RuntimeError(f"texts.shape[1] ({tuple(texts.shape)}) must equal max_src_len ({L})")
+        spk = self._idx(speakers, "speakers", (B,))
+        emo = self._idx(emotions, "emotions", (B,))
+        aro = self._idx(arousals, "arousals", (B,))
+        val = self._idx(valences, "valences", (B,))
+        txt = self._idx(texts, "texts", (B, L))
+        lens = self._idx(src_lens, "src_lens", (B,))
+        p_t = self._target(p_targets, "p_targets", (B, L))
+        e_t = self._target(e_targets, "e_targets", (B, L))
+        d_t = self._target(d_targets, "d_targets", (B, L))
+
+        f32 = dict(dtype=torch.float32, device=dev)
+        pitch, energy = torch.empty(B, L, **f32), torch.empty(B, L, **f32)
+        log_d, d_round = torch.empty(B, L, **f32), torch.empty(B, L, **f32)
+        src_mask = torch.empty(B, L, dtype=torch.bool, device=dev)
+        out_lens = torch.empty(B, dtype=torch.int64, device=dev)
+
+        def ptr(t):
+            return t.data_ptr() if t is not None else None
+
+        inp = _lib.Inputs(batch=B, max_src_len=L, speakers=ptr(spk), emotions=ptr(emo), arousals=ptr(aro),
+                          valences=ptr(val), texts=ptr(txt), src_lens=ptr(lens), p_targets=ptr(p_t), e_targets=ptr(e_t),
+                          d_targets=ptr(d_t), p_control=float(p_control), e_control=float(e_control),
+                          d_control=float(d_control), max_mel_len=int(max_mel_len) if max_mel_len else 0)
+        s1 = _lib.Stage1Out(pitch=ptr(pitch), energy=ptr(energy), log_d=ptr(log_d), d_rounded=ptr(d_round),
+                            src_mask=ptr(src_mask), mel_lens=ptr(out_lens))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib, self._ctx, lib.fs2_forward_stage1(self._ctx, stream, C.byref(inp), C.byref(s1)))
+        T = int(s1.max_mel_len)
+        if d_targets is not None and mel_lens is not None:
+            if not torch.equal(mel_lens.to(out_lens.device, torch.int64), out_lens):
+                raise RuntimeError("mel_lens must equal the row sums of trunc(d_targets) (inconsistent teacher forcing)")
+        mel = torch.empty(B, T, 80, **f32)
+        post = torch.empty(B, T, 80, **f32)
+        mel_mask = torch.empty(B, T, dtype=torch.bool, device=dev)
+        io = _lib.Stage2IO(mel=ptr(mel), postnet=ptr(post), mel_mask=ptr(mel_mask))
+        _lib.check(lib, self._ctx, lib.fs2_forward_stage2(self._ctx, stream, C.byref(io)))
+        self.last_total_frames = int(s1.total_frames)
+        return (mel, post, pitch, energy, log_d, d_targets if d_targets is not None else d_round, src_mask, mel_mask,
+                src_lens, out_lens)
+
+    # ------------------------------------------------------------------ host-buffer entry (what the CLI does)
+    def synthesize_host(self, batch, p_control=1.0, e_control=1.0, d_control=1.0):
+        """`to_device(batch)` (utils/tools.py:117-127) + forward + the device->host reads that
+        `synth_samples` performs (utils/tools.py:228-266), on pinned staging buffers.
+        `batch` holds host numpy arrays: speakers, emotions, arousals, valences, texts, src_lens,
+        max_src_len.  Returns (postnet_mel [B,T,80] numpy, mel_lens numpy, h2d_bytes, d2h_bytes)."""
+        dev = self._device()
+        names = ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")
+        h2d = 0
+        dev_t = {}
+        for n in names:
+            a = np.ascontiguousarray(batch[n], dtype=np.int64)
+            key = (n, a.shape)
+            if key not in self._pinned:
+                self._pinned[key] = torch.empty(a.shape, dtype=torch.int64).pin_memory()
+            self._pinned[key].numpy()[...] = a
+            dev_t[n] = self._pinned[key].to(dev, non_blocking=True)
+            h2d += a.nbytes
+        out = self.forward(dev_t["speakers"], dev_t["emotions"], dev_t["arousals"], dev_t["valences"], dev_t["texts"],
+                           dev_t["src_lens"], int(batch["max_src_len"]), p_control=p_control, e_control=e_control,
+                           d_control=d_control)
+        post, lens = out[1], out[9]
+        key = ("post", tuple(post.shape))
+        if key not in self._pinned:
+            self._pinned[key] = torch.empty(post.shape, dtype=torch.float32).pin_memory()
+            self._pinned[("lens", post.shape[0])] = torch.empty(post.shape[0], dtype=torch.int64).pin_memory()
+        hp, hl = self._pinned[key], self._pinned[("lens", post.shape[0])]
+        hp.copy_(post, non_blocking=True)
+        hl.copy_(lens, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return hp.numpy(), hl.numpy(), h2d, post.numel() * 4 + lens.numel() * 8
+
+
+def get_model(preprocess_config, model_config, state_dict=None, device="cuda", **kw):
+    """utils/model.py:11-34 without the file I/O: construct, load, move, eval."""
+    model = FastSpeech2B200(preprocess_config, model_config, **kw)
+    if state_dict is not None:
+        model.load_state_dict(state_dict)
+    return model.to(device).eval()

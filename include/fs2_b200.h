@@ -1,0 +1,172 @@
+/* fs2_b200.h -- C ABI of libfs2b200.so: the B200 (sm_100a) implementation of the
+ * FastSpeech2 acoustic-model inference forward pass.
+ *
+ * The reference (Napoliee/Expressive-FastSpeech2-Mandarin) has no FFI of its own: its
+ * boundary for this path is the Python call `FastSpeech2.forward` (model/fastspeech2.py:73-149).
+ * Each entry point below names the reference code it replaces; the ctypes binding a
+ * maintainer would add is in INTEGRATION.md and, in full, in
+ * expressive-fastspeech2-mandarin_b200/_lib.py.
+ *
+ * Conventions: every function returns 0 (FS2_OK) or a negative FS2_ERR_* code and never
+ * throws; fs2_last_error() gives the message.  All tensor memory is caller-owned and passed
+ * as raw device pointers (row-major, contiguous); the library owns only its repacked
+ * weights and a workspace that grows monotonically.  Work is enqueued on the caller's
+ * stream; the one blocking point is the size read-back at the end of fs2_forward_stage1
+ * (output shapes depend on the predicted durations).  A context is bound to one device and
+ * is not thread-safe.  There is no CPU implementation behind any of these calls.
+ */
+#ifndef FS2_B200_H
+#define FS2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fs2_ctx fs2_ctx;
+typedef void* fs2_stream; /* cudaStream_t */
+
+enum {
+  FS2_OK = 0,
+  FS2_ERR_INVALID = -1,     /* bad argument / shape / missing weight */
+  FS2_ERR_CUDA = -2,        /* a CUDA runtime or driver call failed */
+  FS2_ERR_STATE = -3,       /* call order violated (e.g. forward before prepare) */
+  FS2_ERR_UNSUPPORTED = -4  /* hyper-parameters the kernels are not compiled for */
+};
+
+/* Arithmetic of the tensor-core contractions (accumulation, LayerNorm and softmax are fp32 in both). */
+enum { FS2_MATH_TF32 = 0, FS2_MATH_BF16 = 1 };
+/* GEMM engines: the product path is TCGEN05; MMA_SYNC is the legacy-tensor-core cross-check
+ * used by the unit tests and for bring-up. */
+enum { FS2_ENGINE_MMA_SYNC = 0, FS2_ENGINE_TCGEN05 = 1 };
+
+/* Model dimensions that are data (table sizes); the layer structure is fixed to
+ * config/ESD-Chinese-Singing-MFA/model.yaml (d_model 256, 2 heads, 4+6 FFT blocks,
+ * conv 9/1 x 1024, predictors 256 k3, 256 bins, 80 mels, PostNet 5 x 512 k5). */
+typedef struct {
+  int32_t n_src_vocab;  /* transformer/Models.py:40   */
+  int32_t n_speaker;    /* model/fastspeech2.py:37-41 */
+  int32_t n_emotion;    /* model/fastspeech2.py:52    */
+  int32_t n_arousal;    /* model/fastspeech2.py:53    */
+  int32_t n_valence;    /* model/fastspeech2.py:54    */
+  int32_t max_seq_len;  /* model.yaml:27; position_enc has max_seq_len+1 rows */
+  int32_t math_mode;    /* FS2_MATH_*  */
+  int32_t engine;       /* FS2_ENGINE_* */
+} fs2_config;
+
+/* Arguments of FastSpeech2.forward (model/fastspeech2.py:73-91). */
+typedef struct {
+  int32_t batch;
+  int32_t max_src_len;     /* == texts.shape[1] */
+  const int64_t* speakers; /* device [B] */
+  const int64_t* emotions; /* device [B] */
+  const int64_t* arousals; /* device [B] */
+  const int64_t* valences; /* device [B] */
+  const int64_t* texts;    /* device [B, max_src_len] */
+  const int64_t* src_lens; /* device [B] */
+  const float* p_targets;  /* device [B, max_src_len] or NULL (model/modules.py:82-83) */
+  const float* e_targets;  /* device [B, max_src_len] or NULL (model/modules.py:93-94) */
+  const float* d_targets;  /* device [B, max_src_len] or NULL (model/modules.py:128-130) */
+  float p_control;         /* scales pitch AND energy (model/modules.py:118-125) */
+  float e_control;         /* accepted and ignored, as in the reference */
+  float d_control;         /* model/modules.py:132-135 */
+  int32_t max_mel_len;     /* 0 = max over the batch (utils/tools.py:361-364) */
+} fs2_inputs;
+
+/* Phoneme-side results; all arrays caller-allocated. */
+typedef struct {
+  float* pitch;       /* device [B, max_src_len]  output[2] */
+  float* energy;      /* device [B, max_src_len]  output[3] */
+  float* log_d;       /* device [B, max_src_len]  output[4] */
+  float* d_rounded;   /* device [B, max_src_len]  output[5] */
+  uint8_t* src_mask;  /* device [B, max_src_len]  output[6], 1 = padding */
+  int64_t* mel_lens;  /* device [B]               output[9] */
+  /* written on the host before fs2_forward_stage1 returns: */
+  int64_t total_frames; /* sum of mel_lens */
+  int32_t max_mel_len;  /* T_max the caller must allocate stage-2 outputs with */
+} fs2_stage1_out;
+
+typedef struct {
+  float* mel;         /* device [B, max_mel_len, 80]  output[0]; padding rows = mel_linear.bias */
+  float* postnet;     /* device [B, max_mel_len, 80]  output[1]; padding rows = mel_linear.bias (outside the contract) */
+  uint8_t* mel_mask;  /* device [B, max_mel_len]      output[7], 1 = padding */
+} fs2_stage2_io;
+
+/* --- lifetime ------------------------------------------------------------------------ */
+int fs2_create(const fs2_config* cfg, int device, fs2_ctx** out);
+void fs2_destroy(fs2_ctx* ctx);
+const char* fs2_last_error(const fs2_ctx* ctx); /* ctx may be NULL: last create() error */
+int fs2_version(void);
+
+/* --- weights: replaces model.load_state_dict(ckpt["model"]) (utils/model.py:16-21) ----- */
+/* `key` is the reference state-dict key; `dev_ptr` is fp32 on the context's
+ * device (int64 for num_batches_tracked, which is ignored).  The tensor is copied. */
+int fs2_set_weight(fs2_ctx* ctx, const char* key, const void* dev_ptr, const int64_t* shape, int ndim);
+/* Repack into kernel layouts: QKV concat, conv [Cout,Cin,k] -> [k][Cout][Cin], BatchNorm folded
+ * into the PostNet convs (transformer/Layers.py:129-137), operand rounding, TMA descriptors. */
+int fs2_prepare(fs2_ctx* ctx, fs2_stream stream);
+
+/* --- forward: replaces FastSpeech2.forward (model/fastspeech2.py:92-149) ---------------- */
+/* stage 1 = masks + Encoder + conditioning + VarianceAdaptor up to the durations
+ * (fastspeech2.py:92-131, modules.py:102-135); blocks until mel_lens are known. */
+int fs2_forward_stage1(fs2_ctx* ctx, fs2_stream stream, const fs2_inputs* in, fs2_stage1_out* out);
+/* stage 2 = LengthRegulator + Decoder + mel_linear + PostNet (modules.py:136-137,167-194;
+ * fastspeech2.py:133-136); asynchronous on `stream`. */
+int fs2_forward_stage2(fs2_ctx* ctx, fs2_stream stream, const fs2_stage2_io* io);
+/* Number of kernels the last stage1+stage2 pair launched. */
+int fs2_last_launch_count(const fs2_ctx* ctx);
+
+/* --- introspection for tests -------------------------------------------------------- */
+/* When enabled, intermediate activations are copied aside after each stage of the forward
+ * ("enc_in", "enc_0".."enc_3", "cond_x", "va_x", "lr_out", "dec_in", "dec_0".."dec_5", ...)
+ * in the packed row layout, together with "p_start"/"f_start" (int32 row of each utterance). */
+int fs2_debug_enable(fs2_ctx* ctx, int on);
+int fs2_debug_fetch(fs2_ctx* ctx, const char* name, void* host_dst, int64_t max_bytes,
+                    int64_t* rows, int64_t* cols);
+
+/* Per-kernel-class timing with CUDA events on the launching stream.  After a forward run with
+ * profiling enabled, fs2_profile_read writes lines "label launches total_ms\n" (NUL-terminated). */
+int fs2_profile_enable(fs2_ctx* ctx, int on);
+int fs2_profile_read(fs2_ctx* ctx, char* buf, int64_t buf_bytes);
+
+/* --- single operators (unit tests, ncu) ------------------------------------------------ */
+/* C[r,n] = act( sum_{t<taps} sum_{k<K} A[r+t-pad, k] * W[t][n][k] + bias[n] ) (+ residual[r,n]),
+ * rows outside [0,rows) read as zero; then rows with row_vpos[r] >= min(extra,row_room[r]) are
+ * zeroed when row_vpos != NULL.  act: 0 none, 1 relu, 2 tanh.  This is every Conv1d / Linear of
+ * the path in token-major layout (SubLayers.py:39-41,54,87-88; modules.py:243-247;
+ * fastspeech2.py:134; Layers.py:129-137). */
+int fs2_op_conv_gemm(fs2_stream stream, int engine, int math_mode, const float* A, int lda, int rows,
+                     const float* W, const float* bias, int taps, int pad, int K, int N, int act,
+                     const float* residual, int ldr, const int32_t* row_vpos, const int32_t* row_room,
+                     int extra, float* C, int ldc);
+/* Varlen 2-head self-attention over packed rows (SubLayers.py:42-52, Modules.py:14-25):
+ * qkv [rows,768] = [q | k | v], heads are 128-wide halves; utterance b owns rows
+ * [starts[b], starts[b]+lens[b]).  out [rows,256]. */
+int fs2_op_attention(fs2_stream stream, const float* qkv, const int32_t* starts, const int32_t* lens,
+                     int batch, int max_len, float* out);
+/* y = LayerNorm(x) * gamma + beta over 256 columns, eps 1e-5, biased variance
+ * (SubLayers.py:55,91; modules.py:224,234); masked rows -> 0; optional fused head
+ * dot[r] = y[r,:]·head_w + head_b (modules.py:245-246). */
+int fs2_op_layernorm(fs2_stream stream, const float* x, int rows, const float* gamma, const float* beta,
+                     const int32_t* row_vpos, const int32_t* row_room, int extra,
+                     float* y, const float* head_w, const float* head_b, float* dot);
+/* Durations -> repeat counts -> per-utterance inclusive scan (modules.py:132-135,186-187).
+ * d_in: log-durations (is_target=0) or target durations (is_target=1), [B,L].  Writes
+ * d_rounded [B,L] (fp32), cum [B,L] (int32 inclusive prefix sums of the repeat counts) and
+ * mel_lens [B] (int64). */
+int fs2_op_durations(fs2_stream stream, const float* d_in, int is_target, float d_control,
+                     const int64_t* src_lens, int batch, int max_src_len,
+                     float* d_rounded, int32_t* cum, int64_t* mel_lens);
+/* bucketize(v, bins[255], right=False) (modules.py:83,87,94,98): idx[i] = #{bins < v[i]}. */
+int fs2_op_bucketize(fs2_stream stream, const float* values, int64_t n, const float* bins, int n_bins,
+                     int32_t* idx);
+/* LengthRegulator index map (modules.py:182-190): for utterance b and frame t < cum[b,L-1],
+ * map[b,t] = first j with cum[b,j] > t; -1 beyond.  map is [B, max_mel_len]. */
+int fs2_op_frame_map(fs2_stream stream, const int32_t* cum, int batch, int max_src_len,
+                     int max_mel_len, int32_t* map);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FS2_B200_H */

@@ -1,0 +1,220 @@
+"""Single-operator parity on the GPU, each through its C-ABI entry point, against a plain
+torch float64 statement of the same op on the CPU (floating point) or the oracle's integer
+helpers (bit-exact)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fs2_oracle as O
+from gpu_util import DEV, lib, ptr, round_tf32, stream
+
+pytestmark = pytest.mark.gpu
+ENGINES = [0] + ([1] if os.environ.get("FS2_TEST_TCGEN05", "0") == "1" else [])
+
+
+def conv_ref(A, W, bias, pad, act, residual, vpos, room, extra):
+    """out[r] = act(sum_t A[r+t-pad] @ W[t].T + bias) (+residual), masked rows -> 0; float64."""
+    rows, K = A.shape
+    taps, N, _ = W.shape
+    A64 = torch.zeros(rows + 2 * taps, K, dtype=torch.float64)
+    A64[taps: taps + rows] = A.double()
+    out = bias.double().unsqueeze(0).repeat(rows, 1)
+    for t in range(taps):
+        lo = taps + t - pad
+        out += A64[lo: lo + rows] @ W[t].double().T
+    if act == 1:
+        out = torch.relu(out)
+    elif act == 2:
+        out = torch.tanh(out)
+    if residual is not None:
+        out = out + residual.double()
+    if vpos is not None:
+        live = vpos < torch.minimum(torch.full_like(room, extra), room)
+        out = out * live.unsqueeze(1)
+    return out
+
+
+CASES = [
+    # rows, K, N, taps, act, residual, mask, name
+    (300, 256, 768, 1, 0, False, False, "qkv"),
+    (517, 256, 1024, 9, 1, False, False, "ffn_conv9"),
+    (260, 1024, 256, 1, 0, True, False, "ffn_w2"),
+    (131, 256, 256, 3, 1, False, False, "predictor_conv3"),
+    (200, 256, 80, 1, 0, False, True, "mel_linear"),
+    (333, 80, 512, 5, 2, False, True, "postnet_first"),
+    (333, 512, 512, 5, 2, False, True, "postnet_mid"),
+    (129, 512, 80, 5, 0, True, True, "postnet_last"),
+    (5, 256, 256, 1, 0, False, False, "tiny"),
+]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("case", CASES, ids=[c[-1] for c in CASES])
+def test_conv_gemm(case, engine):
+    rows, K, N, taps, act, use_res, use_mask, _ = case
+    g = torch.Generator().manual_seed(rows * 7 + K + N + taps)
+    A = round_tf32(torch.randn(rows, K, generator=g))
+    W = round_tf32(torch.randn(taps, N, K, generator=g) / np.sqrt(K * taps))
+    bias = torch.randn(N, generator=g)
+    res = torch.randn(rows, N, generator=g) if use_res else None
+    vpos = torch.randint(-3, 4, (rows,), generator=g, dtype=torch.int32) if use_mask else None
+    room = torch.randint(0, 4, (rows,), generator=g, dtype=torch.int32) if use_mask else None
+    extra = 2
+    want = conv_ref(A, W, bias, (taps - 1) // 2, act, res, vpos, room, extra)
+
+    dA, dW, db = A.to(DEV), W.to(DEV), bias.to(DEV)
+    dres = res.to(DEV) if use_res else None
+    dv = vpos.to(DEV) if use_mask else None
+    dr = room.to(DEV) if use_mask else None
+    out = torch.full((rows, N), float("nan"), device=DEV)
+    code = lib().fs2_op_conv_gemm(stream(), engine, 0, ptr(dA), K, rows, ptr(dW), ptr(db), taps, (taps - 1) // 2, K, N,
+                                  act, ptr(dres), N, ptr(dv), ptr(dr), extra, ptr(out), N)
+    assert code == 0, lib().fs2_last_error(None)
+    torch.cuda.synchronize()
+    got = out.cpu().double()
+    assert torch.isfinite(got).all()
+    err = (got - want).abs().max().item()
+    # operands are TF32-exact, so only the fp32 accumulation order differs
+    assert err < 2e-4, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("lens", [[1], [5, 64, 65, 33], [200, 7, 129], [700]])
+def test_attention(lens):
+    g = torch.Generator().manual_seed(sum(lens))
+    gap = 4
+    starts, r = [], gap
+    for n in lens:
+        starts.append(r)
+        r += n + gap
+    rows = r
+    qkv = torch.randn(rows, 768, generator=g)
+    want = torch.zeros(rows, 256, dtype=torch.float64)
+    for s, n in zip(starts, lens):
+        x = qkv[s: s + n].double()
+        for h in range(2):
+            q, k, v = (x[:, i * 256 + h * 128: i * 256 + (h + 1) * 128] for i in range(3))
+            p = torch.softmax(q @ k.T / np.sqrt(128.0), dim=1)
+            want[s: s + n, h * 128: (h + 1) * 128] = p @ v
+    dq = qkv.to(DEV)
+    out = torch.zeros(rows, 256, device=DEV)
+    ds = torch.tensor(starts, dtype=torch.int32, device=DEV)
+    dl = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    code = lib().fs2_op_attention(stream(), ptr(dq), ptr(ds), ptr(dl), len(lens), max(lens), ptr(out))
+    assert code == 0, lib().fs2_last_error(None)
+    torch.cuda.synchronize()
+    got = out.cpu().double()
+    live = torch.zeros(rows, dtype=torch.bool)
+    for s, n in zip(starts, lens):
+        live[s: s + n] = True
+    assert (got[~live] == 0).all(), "rows outside the utterances must not be written"
+    err = (got[live] - want[live]).abs().max().item()
+    assert err < 5e-3, f"max abs err {err}"   # TF32 operands on unit-variance data, d_k = 128
+
+
+def test_layernorm_and_head():
+    g = torch.Generator().manual_seed(3)
+    rows = 77
+    x = torch.randn(rows, 256, generator=g) * 3 + 0.5
+    gamma, beta = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g)
+    hw, hb = torch.randn(256, generator=g) / 16, torch.randn(1, generator=g)
+    vpos = torch.randint(-2, 3, (rows,), generator=g, dtype=torch.int32)
+    room = torch.randint(0, 3, (rows,), generator=g, dtype=torch.int32)
+    y64 = torch.nn.functional.layer_norm(x.double(), (256,), gamma.double(), beta.double(), 1e-5)
+    live = vpos < torch.minimum(torch.full_like(room, 1), room)
+    y64 = y64 * live.unsqueeze(1)
+    dot64 = (y64 @ hw.double() + hb.double())
+    y = torch.full((rows, 256), float("nan"), device=DEV)
+    dot = torch.zeros(rows, device=DEV)
+    args = [t.to(DEV) for t in (x, gamma, beta, vpos, room, hw, hb)]
+    code = lib().fs2_op_layernorm(stream(), ptr(args[0]), rows, ptr(args[1]), ptr(args[2]), ptr(args[3]), ptr(args[4]), 1,
+                                  ptr(y), ptr(args[5]), ptr(args[6]), ptr(dot))
+    assert code == 0, lib().fs2_last_error(None)
+    torch.cuda.synchronize()
+    assert (y.cpu().double() - y64).abs().max().item() < 2e-5
+    assert (dot.cpu().double()[live] - dot64[live]).abs().max().item() < 2e-5
+    assert (dot.cpu()[~live] == 0).all()
+
+
+@pytest.mark.parametrize("d_control", [1.0, 1.5, 0.5, 2.0])
+def test_durations_bit_exact(d_control):
+    g = torch.Generator().manual_seed(11)
+    B, L = 9, 70
+    lens = torch.randint(1, L + 1, (B,), generator=g)
+    lens[0] = L
+    log_d = torch.randn(B, L, generator=g) * 0.8 + 1.2
+    # exact .5 ties and negative values
+    log_d[1, :4] = torch.log(torch.tensor([1.5, 2.5, 3.5, 0.4]))
+    pad = O.pad_mask(lens, L)
+    log_d = log_d.masked_fill(pad, 0.0)
+    want_d = O.duration_rounded(log_d, d_control)
+    want_reps = O.repeat_counts(want_d) * (~pad)
+    want_cum = torch.cumsum(want_reps, 1).to(torch.int32)
+    d_round = torch.zeros(B, L, device=DEV)
+    cum = torch.zeros(B, L, dtype=torch.int32, device=DEV)
+    mel_lens = torch.zeros(B, dtype=torch.int64, device=DEV)
+    dl, dlens = log_d.to(DEV), lens.to(DEV)
+    code = lib().fs2_op_durations(stream(), ptr(dl), 0, d_control, ptr(dlens), B, L, ptr(d_round), ptr(cum), ptr(mel_lens))
+    assert code == 0, lib().fs2_last_error(None)
+    torch.cuda.synchronize()
+    # expf on the GPU and torch.exp on the CPU may differ in the last ulp; a different integer is
+    # only tolerated (and reported) at a rounding boundary
+    got_d = d_round.cpu()
+    diff = (got_d != want_d)
+    if diff.any():
+        frac = (torch.exp(log_d.double()) - 1) % 1.0
+        assert ((frac[diff] - 0.5).abs() < 1e-5).all(), "duration mismatch away from a .5 rounding boundary"
+        print("rounding-boundary ties:", int(diff.sum()))
+    else:
+        assert torch.equal(cum.cpu(), want_cum)
+        assert torch.equal(mel_lens.cpu(), want_reps.sum(1))
+
+    # target durations (ints and fractions) expand by truncation
+    tgt = torch.randint(0, 12, (B, L), generator=g).float() * (~pad)
+    tgt[2, 0] = 2.75
+    dt = tgt.to(DEV)
+    code = lib().fs2_op_durations(stream(), ptr(dt), 1, 1.0, ptr(dlens), B, L, None, ptr(cum), ptr(mel_lens))
+    assert code == 0
+    torch.cuda.synchronize()
+    reps = O.repeat_counts(tgt)
+    assert torch.equal(cum.cpu(), torch.cumsum(reps, 1).to(torch.int32))
+    assert torch.equal(mel_lens.cpu(), reps.sum(1))
+
+
+def test_bucketize_bit_exact():
+    g = torch.Generator().manual_seed(5)
+    bins = torch.linspace(-2.5, 9.0, 255)
+    v = torch.randn(40000, generator=g) * 3 + 2
+    v[:255] = bins                       # values equal to a boundary take that boundary's index
+    v[255:510] = torch.nextafter(bins, torch.tensor(float("inf")))
+    v[510] = float("nan")
+    v[511] = float("inf")
+    v[512] = -float("inf")
+    want = O.bucket_index(v, bins).to(torch.int32)
+    dv, db = v.to(DEV), bins.to(DEV)
+    idx = torch.zeros(v.numel(), dtype=torch.int32, device=DEV)
+    code = lib().fs2_op_bucketize(stream(), ptr(dv), v.numel(), ptr(db), 255, ptr(idx))
+    assert code == 0
+    torch.cuda.synchronize()
+    assert torch.equal(idx.cpu(), want)
+
+
+def test_frame_map_bit_exact():
+    g = torch.Generator().manual_seed(8)
+    B, L = 7, 50
+    reps = torch.randint(0, 9, (B, L), generator=g)
+    reps[3] = 0
+    reps[4, 10:] = 0
+    cum = torch.cumsum(reps, 1).to(torch.int32)
+    T = int(cum[:, -1].max())
+    want = torch.full((B, T), -1, dtype=torch.int32)
+    for b in range(B):
+        m = O.frame_to_phoneme_map(reps[b].numpy())
+        want[b, : len(m)] = torch.from_numpy(m).to(torch.int32)
+    dc = cum.to(DEV)
+    out = torch.zeros(B, T, dtype=torch.int32, device=DEV)
+    code = lib().fs2_op_frame_map(stream(), ptr(dc), B, L, T, ptr(out))
+    assert code == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), want)
