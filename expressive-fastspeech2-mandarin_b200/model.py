@@ -68,7 +68,7 @@ def _schema(n_speaker, n_emotion, n_arousal, n_valence, max_seq_len):
 class FastSpeech2B200(nn.Module):
     """Drop-in for `FastSpeech2(preprocess_config, model_config)` in eval mode on one B200."""
 
-    def __init__(self, preprocess_config, model_config, math_mode="tf32", engine="mma_sync", init_seed=0):
+    def __init__(self, preprocess_config, model_config, math_mode="tf32", engine="tcgen05", init_seed=0):
         super().__init__()
         check_supported(preprocess_config, model_config)
         self.model_config = model_config

@@ -20,7 +20,7 @@ def lib():
 
 
 def model_for(sd, math_mode="tf32", engine=None, key="seed0"):
-    engine = engine or os.environ.get("FS2_ENGINE", "mma_sync")
+    engine = engine or os.environ.get("FS2_ENGINE", "tcgen05")
     k = (key, math_mode, engine)
     if k not in _MODELS:
         d = fs2_b200.synthetic.write_fixture_jsons(tempfile.mkdtemp(prefix="fs2_json_"))

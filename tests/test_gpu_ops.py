@@ -11,7 +11,7 @@ from oracle import fs2_oracle as O
 from gpu_util import DEV, lib, ptr, round_tf32, stream
 
 pytestmark = pytest.mark.gpu
-ENGINES = [0] + ([1] if os.environ.get("FS2_TEST_TCGEN05", "0") == "1" else [])
+ENGINES = [0] + ([1] if os.environ.get("FS2_TEST_TCGEN05", "1") == "1" else [])
 
 
 def conv_ref(A, W, bias, pad, act, residual, vpos, room, extra):
