@@ -1,0 +1,65 @@
+"""Multi-GPU host logic on CPU: the LPT partition and, with world_size 2 over gloo, the
+post-forward gather.  (The forward itself has no collective; each rank's shard is validated
+against the oracle on that sub-batch in the GPU tests.)"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import fs2_b200
+from fs2_b200 import partition
+
+
+def test_lpt_partition_covers_and_balances(syn):
+    lens = syn.random_lengths(512, seed=100)
+    for n in (1, 2, 4, 8):
+        parts = partition.lpt_partition(lens, n)
+        flat = sorted(i for p in parts for i in p)
+        assert flat == list(range(512))
+        loads = [sum(partition.utterance_cost(lens[i]) for i in p) for p in parts]
+        assert max(loads) / (sum(loads) / n) < 1.01, "LPT should balance 512 utterances to within 1%"
+    assert partition.lpt_partition(lens, 3) == partition.lpt_partition(list(lens), 3), "deterministic"
+
+
+def test_take_repads_to_the_shards_own_max(syn):
+    batch = syn.make_batch([30, 7, 19, 12], seed=3)
+    sub = partition.take(batch, [1, 3])
+    assert sub["max_src_len"] == 12 and tuple(sub["texts"].shape) == (2, 12)
+    assert torch.equal(sub["texts"][0, :7], batch["texts"][1, :7])
+    assert torch.equal(sub["src_lens"], torch.tensor([7, 12]))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, lens):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        parts = partition.lpt_partition(lens, world)
+        mine = parts[rank]
+        t_lens = torch.tensor([3 * lens[i] + rank for i in mine], dtype=torch.int64)
+        T = int(t_lens.max())
+        local = torch.zeros(len(mine), T, 80)
+        for j, i in enumerate(mine):
+            local[j, : t_lens[j]] = float(i + 1)
+        out, out_lens = partition.gather_padded(local, t_lens, mine, len(lens))
+        for r, p in enumerate(parts):
+            for i in p:
+                n = 3 * lens[i] + r
+                assert int(out_lens[i]) == n
+                assert torch.all(out[i, :n] == float(i + 1)) and torch.all(out[i, n:] == 0)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_over_gloo_world_size_2(syn):
+    lens = syn.random_lengths(13, lo=5, hi=40, seed=5)
+    mp.spawn(_worker, args=(2, _free_port(), lens), nprocs=2, join=True)
