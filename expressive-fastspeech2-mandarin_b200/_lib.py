@@ -52,12 +52,14 @@ SIGNATURES = {
     "fs2_last_launch_count": (C.c_int, [C.c_void_p]),
     "fs2_debug_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "fs2_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, c_i64p, c_i64p]),
+    "fs2_debug_set_flag": (C.c_int, [C.c_int, C.c_int]),
     "fs2_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "fs2_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "fs2_op_conv_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
-    "fs2_op_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "fs2_op_attention": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_void_p]),
     "fs2_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fs2_op_durations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int,

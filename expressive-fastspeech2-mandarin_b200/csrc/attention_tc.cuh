@@ -1,0 +1,315 @@
+// Varlen 2-head self-attention on tcgen05 (transformer/SubLayers.py:42-52, Modules.py:14-25).
+// One CTA = 128 queries of one (utterance, head); keys/values stream in 64-key tiles.
+//   S_j = Q K_j^T        tcgen05.mma kind::tf32, A = Q (smem, K-major), B = K_j (smem, K-major)  -> TMEM
+//   P_j = exp2(S_j*c - m) computed by 128 softmax threads (thread = query row = TMEM lane), written
+//                         back over S_j in TMEM (tcgen05.st)
+//   O_j = P_j V_j        tcgen05.mma with A = P_j FROM TMEM and B = V_j (smem, MN-major)          -> TMEM
+//   O   = O*alpha_j + O_j accumulated in registers by the softmax threads (online softmax, fp32)
+// Q/K/V are read straight out of the packed [rows,768] QKV buffer by TMA (TFLOAT32 tensor map:
+// rounded to TF32 on load); keys beyond the utterance are masked by length, never by a mask tensor.
+// S/P and O_j are double-buffered in TMEM so that Q K_{j+1}^T overlaps the softmax of tile j.
+#pragma once
+
+#include "common.cuh"
+#include "gemm_tcgen05.cuh"
+
+namespace fs2 {
+namespace attn_tc {
+
+using namespace tc;
+
+constexpr int BQ = 128, BKV = 64, THREADS = 192;
+constexpr int Q_BYTES = BQ * D_HEAD * 4;          // 64 KB: 4 sub-tiles [128 rows x 128 B]
+constexpr int K_BYTES = BKV * D_HEAD * 4;         // 32 KB: 4 sub-tiles [64 rows x 128 B]
+constexpr int KV_STAGE_BYTES = 2 * K_BYTES;
+constexpr int BAR_OFF = Q_BYTES + 2 * KV_STAGE_BYTES;
+constexpr int SMEM_TOTAL = BAR_OFF + 256 + 1024;
+constexpr int TMEM_COLS = 512;                    // S0,S1: 2 x 64 | O0,O1: 2 x 128
+constexpr int LDQKV = 3 * D_MODEL;
+
+__host__ __device__ constexpr uint32_t idesc_tf32(int m, int n, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+// MN-major descriptor for a 32-bit operand.  TF32 MN-major operands exist only in the
+// SWIZZLE_128B_BASE32B layout (cute::UMMA::Layout_MN_SW128_32B_Atom: 32-byte chunks swizzled inside
+// 128-byte rows, 4 rows per atom; TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  128-byte
+// rows run along N (the head dimension); LBO = distance between 32-column sub-tiles, SBO = distance
+// between 4-key groups.
+__device__ __forceinline__ uint64_t umma_desc_mn(const void* smem_tile, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((smem_u32(smem_tile) >> 4) & 0x3FFF);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;   // UMMA::LayoutType::SWIZZLE_128B_BASE32B
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    const __grid_constant__ CUtensorMap tmV, const int32_t* __restrict__ starts, const int32_t* __restrict__ lens, float* __restrict__ out, int dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  const int len = lens[b];
+  if (q0 >= len) return;
+  const int row0 = starts[b];
+  const int n_tiles = (len + BKV - 1) / BKV;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_s = smem;
+  uint8_t* kv_s = smem + Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* kv_full = bars + 1;       // [2]
+  uint64_t* kv_empty = bars + 3;      // [2]
+  uint64_t* s_full = bars + 5;        // [2]
+  uint64_t* p_full = bars + 7;        // [2]
+  uint64_t* o_full = bars + 9;        // [2]
+  uint64_t* o_free = bars + 11;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmKV)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
+    mbar_init(q_full, 1);
+    for (int u = 0; u < 2; ++u) {
+      mbar_init(&kv_full[u], 1);
+      mbar_init(&kv_empty[u], 1);
+      mbar_init(&s_full[u], 1);
+      mbar_init(&p_full[u], 128);
+      mbar_init(&o_full[u], 1);
+      mbar_init(&o_free[u], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;          // + u*64
+  const uint32_t tmem_o = tmem_base + 128;    // + u*128
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer: Q once, then (K_j, V_j) into the 2-stage ring
+      mbar_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+      for (int dc = 0; dc < 4; ++dc) tma_load_2d(q_s + dc * (BQ * 128), &tmQ, h * D_HEAD + dc * 32, row0 + q0, q_full);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int u = j & 1;
+        mbar_wait(&kv_empty[u], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[u], KV_STAGE_BYTES);
+        uint8_t* k_s = kv_s + u * KV_STAGE_BYTES;
+        uint8_t* v_s = k_s + K_BYTES;
+#pragma unroll
+        for (int dc = 0; dc < 4; ++dc) {
+          tma_load_2d(k_s + dc * (BKV * 128), &tmKV, D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &kv_full[u]);
+          tma_load_2d(v_s + dc * (BKV * 128), &tmV, 2 * D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &kv_full[u]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer
+      constexpr uint32_t idesc_qk = idesc_tf32(BQ, BKV, 0);
+      constexpr uint32_t idesc_pv = idesc_tf32(BQ, D_HEAD, 1);
+      auto issue_qk = [&](int j) {
+        const int u = j & 1;
+        mbar_wait(&kv_full[u], (j >> 1) & 1);
+        tc_fence_after();
+        const uint8_t* k_s = kv_s + u * KV_STAGE_BYTES;
+#pragma unroll
+        for (int dc = 0; dc < 4; ++dc) {
+          const uint64_t da = umma_desc(q_s + dc * (BQ * 128)), db = umma_desc(k_s + dc * (BKV * 128));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_tf32(tmem_s + u * BKV, da + 2 * kk, db + 2 * kk, idesc_qk, (dc | kk) != 0);
+        }
+        umma_commit(&s_full[u]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int u = j & 1;
+        const uint32_t par = (j >> 1) & 1;
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        mbar_wait(&p_full[u], par);
+        mbar_wait(&o_free[u], par ^ 1);
+        tc_fence_after();
+        const uint8_t* v_s = kv_s + u * KV_STAGE_BYTES + K_BYTES;
+        const uint64_t dv = umma_desc_mn(v_s, BKV * 128, 512);
+        if (dbg == 2) {        // A = Q[:, 0:64] from smem (K-major), B = V MN-major
+          for (int k8 = 0; k8 < BKV / 8; ++k8)
+            umma_tf32(tmem_o + u * D_HEAD, umma_desc(q_s + (k8 >> 2) * (BQ * 128)) + 2 * (k8 & 3),
+                      dv + (uint64_t)(k8 * (1024 >> 4)), idesc_pv, k8 != 0);
+        } else if (dbg == 3) { // A = P[:, 0:32] from TMEM, B = K sub-tile 0 (K-major, N = 64 keys, K = 32)
+          const uint8_t* k_s = kv_s + u * KV_STAGE_BYTES;
+          for (int k8 = 0; k8 < 4; ++k8)
+            umma_tf32_ts(tmem_o + u * D_HEAD, tmem_s + u * BKV + k8 * 8, umma_desc(k_s) + 2 * k8, idesc_qk, k8 != 0);
+        } else {
+#pragma unroll
+        for (int k8 = 0; k8 < BKV / 8; ++k8)
+          umma_tf32_ts(tmem_o + u * D_HEAD, tmem_s + u * BKV + k8 * 8, dv + (uint64_t)(k8 * (1024 >> 4)), idesc_pv, k8 != 0);
+        }
+        umma_commit(&o_full[u]);
+        umma_commit(&kv_empty[u]);
+      }
+    }
+  } else {
+    // ---- softmax + accumulation: thread = query row
+    const int q = warp & 3;
+    const int qrow = q0 + q * 32 + lane;                       // row inside the utterance
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const float c = 1.4426950408889634f / sqrtf((float)D_HEAD);  // log2(e) / temperature
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+    float o[D_HEAD];
+#pragma unroll
+    for (int i = 0; i < D_HEAD; ++i) o[i] = 0.f;
+
+    auto accumulate = [&](int j, float alpha) {
+      const int u = j & 1;
+      mbar_wait(&o_full[u], (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < D_HEAD; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_o + lane_sel + u * D_HEAD + c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c0 + i] = fmaf(o[c0 + i], alpha, v[i]);
+      }
+      tc_fence_before();
+      mbar_arrive(&o_free[u]);
+    };
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int u = j & 1;
+      mbar_wait(&s_full[u], (j >> 1) & 1);
+      tc_fence_after();
+      float s0[32], s1[32];
+      tmem_ld32(tmem_s + lane_sel + u * BKV, s0);
+      tmem_ld32(tmem_s + lane_sel + u * BKV + 32, s1);
+      const int key0 = j * BKV;
+      float mx = m;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        s0[i] = (key0 + i < len) ? s0[i] * c : -INFINITY;
+        s1[i] = (key0 + 32 + i < len) ? s1[i] * c : -INFINITY;
+        mx = fmaxf(mx, fmaxf(s0[i], s1[i]));
+      }
+      const float alpha = exp2f(m - mx);   // 0 on the first tile (m = -inf, mx finite: key0 < len)
+      m = mx;
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        s0[i] = tf32_rna(exp2f(s0[i] - m));
+        s1[i] = tf32_rna(exp2f(s1[i] - m));
+        sum += s0[i] + s1[i];
+      }
+      l = fmaf(l, alpha, sum);
+      tmem_st32(tmem_s + lane_sel + u * BKV, s0);
+      tmem_st32(tmem_s + lane_sel + u * BKV + 32, s1);
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(&p_full[u]);
+      if (j >= 1) accumulate(j - 1, alpha_prev);
+      alpha_prev = alpha;
+    }
+    accumulate(n_tiles - 1, alpha_prev);
+
+    if (dbg != 0 && qrow < len) {   // raw dumps for bring-up
+      float* dst = out + (size_t)(row0 + qrow) * D_MODEL + h * D_HEAD;
+      if (dbg == 1) {               // P of tile 0 read back from TMEM (64 values), then l
+        float v0[32], v1[32];
+        tmem_ld32(tmem_s + lane_sel, v0);
+        tmem_ld32(tmem_s + lane_sel + 32, v1);
+        for (int i = 0; i < 32; ++i) { dst[i] = v0[i]; dst[32 + i] = v1[i]; }
+        dst[64] = l;
+      } else {
+        for (int i = 0; i < D_HEAD; ++i) dst[i] = o[i];
+      }
+    } else
+    if (qrow < len) {
+      const float inv = 1.f / l;
+      float* dst = out + (size_t)(row0 + qrow) * D_MODEL + h * D_HEAD;
+#pragma unroll
+      for (int i = 0; i < D_HEAD; i += 4)
+        *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+inline int& debug_flag() {
+  static int f = 0;
+  return f;
+}
+
+inline void launch(const float* qkv, int rows, const int32_t* starts, const int32_t* lens, int batch, int max_len,
+                   float* out, cudaStream_t stream) {
+  if (batch <= 0 || max_len <= 0 || rows <= 0) return;
+  static bool configured[64] = {};
+  int dev = 0;
+  FS2_CUDA_OK(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    FS2_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    configured[dev & 63] = true;
+  }
+  const CUtensorMap tmQ = make_map(qkv, rows, LDQKV, LDQKV, BQ, true, false);
+  const CUtensorMap tmKV = make_map(qkv, rows, LDQKV, LDQKV, BKV, true, true);
+  const CUtensorMap tmV = make_map(qkv, rows, LDQKV, LDQKV, BKV, true, true, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  dim3 grid((max_len + BQ - 1) / BQ, N_HEAD, batch);
+  attention_tc_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(tmQ, tmKV, tmV, starts, lens, out, debug_flag());
+  FS2_LAUNCHED();
+}
+
+}  // namespace attn_tc
+}  // namespace fs2

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "common.cuh"
 #include "gemm_mma.cuh"
 #include "gemm_tcgen05.cuh"
@@ -240,6 +241,12 @@ static void conv_gemm(int engine, int math, const ConvGemmArgs& a, cudaStream_t 
   }
 }
 
+static void attention(int engine, const float* qkv, int rows, const int32_t* starts, const int32_t* lens, int batch,
+                      int max_len, float* out, cudaStream_t s) {
+  if (engine == FS2_ENGINE_TCGEN05) attn_tc::launch(qkv, rows, starts, lens, batch, max_len, out, s);
+  else attn::launch(qkv, starts, lens, batch, max_len, out, s);
+}
+
 static ConvGemmArgs gemm_args(const float* A, int lda, int rows, const float* Wt, const float* bias, int taps, int K,
                               int N, int act, float* C, int ldc) {
   ConvGemmArgs a{};
@@ -264,7 +271,7 @@ static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSi
   a.live_rows = reinterpret_cast<const int32_t*>(side.totals);  // low word of totals[0] (little endian)
   { ProfScope ps(c, s, frame ? "dec.gemm_qkv" : "enc.gemm_qkv"); conv_gemm(eng, math, a, s); }
   { ProfScope ps(c, s, frame ? "dec.attention" : "enc.attention");
-    attn::launch(pool.qkv, side.starts, side.lens, batch, max_len, t1, s); }
+    attention(eng, pool.qkv, rows, side.starts, side.lens, batch, max_len, t1, s); }
   a = gemm_args(t1, D_MODEL, rows, L.wfc, L.bfc, 1, D_MODEL, D_MODEL, ACT_NONE, t2, D_MODEL);
   a.residual = x; a.ldr = D_MODEL; a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
   { ProfScope ps(c, s, frame ? "dec.gemm_fc" : "enc.gemm_fc"); conv_gemm(eng, math, a, s); }
@@ -700,6 +707,11 @@ int fs2_debug_fetch(fs2_ctx* c, const char* name, void* host_dst, int64_t max_by
   });
 }
 
+int fs2_debug_set_flag(int which, int value) {
+  if (which == 0) fs2::attn_tc::debug_flag() = value;
+  return FS2_OK;
+}
+
 int fs2_profile_enable(fs2_ctx* c, int on) {
   if (!c) return FS2_ERR_INVALID;
   c->profiling = on != 0;
@@ -745,11 +757,11 @@ int fs2_op_conv_gemm(fs2_stream stream, int engine, int math_mode, const float* 
   });
 }
 
-int fs2_op_attention(fs2_stream stream, const float* qkv, const int32_t* starts, const int32_t* lens, int batch, int max_len,
-                     float* out) {
+int fs2_op_attention(fs2_stream stream, int engine, const float* qkv, int rows, const int32_t* starts, const int32_t* lens,
+                     int batch, int max_len, float* out) {
   return guarded(nullptr, [&] {
-    require(qkv && starts && lens && out, FS2_ERR_INVALID, "null attention argument");
-    attn::launch(qkv, starts, lens, batch, max_len, out, static_cast<cudaStream_t>(stream));
+    require(qkv && starts && lens && out && rows > 0, FS2_ERR_INVALID, "bad attention argument");
+    attention(engine, qkv, rows, starts, lens, batch, max_len, out, static_cast<cudaStream_t>(stream));
   });
 }
 

@@ -125,6 +125,9 @@ int fs2_debug_enable(fs2_ctx* ctx, int on);
 int fs2_debug_fetch(fs2_ctx* ctx, const char* name, void* host_dst, int64_t max_bytes,
                     int64_t* rows, int64_t* cols);
 
+/* Bring-up switches (0 = attention kernel raw-dump mode); 0 in normal operation. */
+int fs2_debug_set_flag(int which, int value);
+
 /* Per-kernel-class timing with CUDA events on the launching stream.  After a forward run with
  * profiling enabled, fs2_profile_read writes lines "label launches total_ms\n" (NUL-terminated). */
 int fs2_profile_enable(fs2_ctx* ctx, int on);
@@ -142,9 +145,9 @@ int fs2_op_conv_gemm(fs2_stream stream, int engine, int math_mode, const float* 
                      int extra, float* C, int ldc);
 /* Varlen 2-head self-attention over packed rows (SubLayers.py:42-52, Modules.py:14-25):
  * qkv [rows,768] = [q | k | v], heads are 128-wide halves; utterance b owns rows
- * [starts[b], starts[b]+lens[b]).  out [rows,256]. */
-int fs2_op_attention(fs2_stream stream, const float* qkv, const int32_t* starts, const int32_t* lens,
-                     int batch, int max_len, float* out);
+ * [starts[b], starts[b]+lens[b]); rows = rows of the qkv buffer.  out [rows,256]. */
+int fs2_op_attention(fs2_stream stream, int engine, const float* qkv, int rows, const int32_t* starts,
+                     const int32_t* lens, int batch, int max_len, float* out);
 /* y = LayerNorm(x) * gamma + beta over 256 columns, eps 1e-5, biased variance
  * (SubLayers.py:55,91; modules.py:224,234); masked rows -> 0; optional fused head
  * dot[r] = y[r,:]·head_w + head_b (modules.py:245-246). */

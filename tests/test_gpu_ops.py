@@ -80,8 +80,9 @@ def test_conv_gemm(case, engine):
     assert err < 2e-4, f"max abs err {err}"
 
 
-@pytest.mark.parametrize("lens", [[1], [5, 64, 65, 33], [200, 7, 129], [700]])
-def test_attention(lens):
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("lens", [[1], [5, 64, 65, 33], [200, 7, 129, 128, 127], [700]])
+def test_attention(lens, engine):
     g = torch.Generator().manual_seed(sum(lens))
     gap = 4
     starts, r = [], gap
@@ -101,7 +102,7 @@ def test_attention(lens):
     out = torch.zeros(rows, 256, device=DEV)
     ds = torch.tensor(starts, dtype=torch.int32, device=DEV)
     dl = torch.tensor(lens, dtype=torch.int32, device=DEV)
-    code = lib().fs2_op_attention(stream(), ptr(dq), ptr(ds), ptr(dl), len(lens), max(lens), ptr(out))
+    code = lib().fs2_op_attention(stream(), engine, ptr(dq), rows, ptr(ds), ptr(dl), len(lens), max(lens), ptr(out))
     assert code == 0, lib().fs2_last_error(None)
     torch.cuda.synchronize()
     got = out.cpu().double()

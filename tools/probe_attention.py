@@ -1,0 +1,72 @@
+"""Debug probes for the tcgen05 attention kernel (run on the GPU box)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np, torch
+from gpu_util import DEV, lib, ptr, stream
+torch.set_printoptions(precision=3, linewidth=220, sci_mode=False)
+
+def run(qkv, lens, engine=1):
+    gap = 4
+    starts, r = [], gap
+    for n in lens:
+        starts.append(r); r += n + gap
+    rows = r
+    assert qkv.shape[0] == rows
+    dq = qkv.to(DEV)
+    out = torch.zeros(rows, 256, device=DEV)
+    ds = torch.tensor(starts, dtype=torch.int32, device=DEV)
+    dl = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    code = lib().fs2_op_attention(stream(), engine, ptr(dq), rows, ptr(ds), ptr(dl), len(lens), max(lens), ptr(out))
+    assert code == 0, lib().fs2_last_error(None)
+    torch.cuda.synchronize()
+    return out.cpu(), starts
+
+n = 16
+rows = 4 + n + 4
+# probe A: Q = 0 -> uniform P; V one-hot in key k0 with values d+1  => O[d] = (d+1)/n
+for k0 in (0, 1, 7, 8, 15):
+    qkv = torch.zeros(rows, 768)
+    qkv[4 + k0, 512:640] = torch.arange(1, 129).float()
+    out, st = run(qkv, [n])
+    o = out[4, :128] * n
+    print(f"A k0={k0}: O*n first 12 = {o[:12].tolist()}  | 32..36 = {o[32:36].tolist()} | max = {float(o.max()):.2f} nnz = {int((o != 0).sum())}")
+# probe B: V[key][d] = 1 if d == key  => O[q][d] = P[q][d]; Q, K random
+g = torch.Generator().manual_seed(0)
+qkv = torch.zeros(rows, 768)
+qkv[4:4 + n, 0:128] = torch.randn(n, 128, generator=g)
+qkv[4:4 + n, 256:384] = torch.randn(n, 128, generator=g)
+for k in range(n):
+    qkv[4 + k, 512 + k] = 1.0
+out, st = run(qkv, [n])
+q, k = qkv[4:4 + n, 0:128].double(), qkv[4:4 + n, 256:384].double()
+p = torch.softmax(q @ k.T / np.sqrt(128.0), dim=1)
+print("B expected P[0,:8]", p[0, :8].tolist())
+print("B got      O[0,:8]", out[4, :8].tolist())
+print("B got      O[1,:8]", out[5, :8].tolist(), " expected", p[1, :8].tolist())
+print("B max err P", float((out[4:4 + n, :n].double() - p).abs().max()), " rowsum got", out[4:4+n, :128].sum(1)[:4].tolist())
+
+print("==== debug variants")
+g = torch.Generator().manual_seed(1)
+n = 64
+rows = 4 + n + 4
+qkv = torch.randn(rows, 768, generator=g)
+q, k, v = qkv[4:4+n, 0:128].double(), qkv[4:4+n, 256:384].double(), qkv[4:4+n, 512:640].double()
+s2 = (q @ k.T) / np.sqrt(128.0)
+p = torch.exp(s2 - s2.max(1, keepdim=True).values)     # unnormalised P relative to the row max
+lib().fs2_debug_set_flag(0, 1)
+out, _ = run(qkv, [n])
+print("dbg1 P err", float((out[4:4+n, :64].double() - p).abs().max()), " l err", float((out[4:4+n, 64].double() - p.sum(1)).abs().max()))
+print("   got P[0,:6]", out[4, :6].tolist(), "want", p[0, :6].tolist())
+lib().fs2_debug_set_flag(0, 2)
+out, _ = run(qkv, [n])
+want2 = q[:, :64] @ v[:64]
+print("dbg2 (smem A x MN-major V) err", float((out[4:4+n, :128].double() - want2).abs().max()))
+print("   got[0,:6]", out[4, :6].tolist(), "want", want2[0, :6].tolist())
+print("   got[0,32:38]", out[4, 32:38].tolist(), "want", want2[0, 32:38].tolist())
+lib().fs2_debug_set_flag(0, 3)
+out, _ = run(qkv, [n])
+want3 = p[:, :32] @ k[:, :32].T
+print("dbg3 (TMEM A x K-major) err", float((out[4:4+n, :64].double() - want3).abs().max()))
+print("   got[0,:6]", out[4, :6].tolist(), "want", want3[0, :6].tolist())
+lib().fs2_debug_set_flag(0, 0)
