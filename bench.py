@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("FS2_ENGINE", "tcgen05"), choices=["tcgen05", "mma_sync"])
+    ap.add_argument("--engine", default=os.environ.get("FS2_ENGINE", "tcgen05"), choices=["tcgen05", "tcgen05_v1", "mma_sync"])
     ap.add_argument("--math", default=os.environ.get("FS2_MATH", "tf32"), choices=["tf32", "bf16"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")

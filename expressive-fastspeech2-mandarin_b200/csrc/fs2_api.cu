@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "gemm_mma.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm_tc2.cuh"
 #include "rowops.cuh"
 
 namespace fs2 {
@@ -234,8 +235,12 @@ static void tap(fs2_ctx* c, cudaStream_t s, const char* name, const void* ptr, i
 // ---------------------------------------------------------------------------- GEMM dispatch
 static void conv_gemm(int engine, int math, const ConvGemmArgs& a, cudaStream_t s) {
   if (engine == FS2_ENGINE_TCGEN05) {
+    tc2::launch(a, math, s);
+  } else if (engine == FS2_ENGINE_TCGEN05_V1) {
+    require(a.ln_gamma == nullptr, FS2_ERR_UNSUPPORTED, "the non-persistent tcgen05 engine has no fused LayerNorm");
     tc::launch(a, math, s);
   } else {
+    require(a.ln_gamma == nullptr, FS2_ERR_UNSUPPORTED, "the mma.sync engine has no fused LayerNorm");
     require(math == FS2_MATH_TF32, FS2_ERR_UNSUPPORTED, "the mma.sync engine implements TF32 only");
     mma::launch(a, s);
   }
@@ -243,7 +248,7 @@ static void conv_gemm(int engine, int math, const ConvGemmArgs& a, cudaStream_t 
 
 static void attention(int engine, const float* qkv, int rows, const int32_t* starts, const int32_t* lens, int batch,
                       int max_len, float* out, cudaStream_t s) {
-  if (engine == FS2_ENGINE_TCGEN05) attn_tc::launch(qkv, rows, starts, lens, batch, max_len, out, s);
+  if (engine != FS2_ENGINE_MMA_SYNC) attn_tc::launch(qkv, rows, starts, lens, batch, max_len, out, s);
   else attn::launch(qkv, starts, lens, batch, max_len, out, s);
 }
 
@@ -272,6 +277,21 @@ static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSi
   { ProfScope ps(c, s, frame ? "dec.gemm_qkv" : "enc.gemm_qkv"); conv_gemm(eng, math, a, s); }
   { ProfScope ps(c, s, frame ? "dec.attention" : "enc.attention");
     attention(eng, pool.qkv, rows, side.starts, side.lens, batch, max_len, t1, s); }
+  if (eng == FS2_ENGINE_TCGEN05) {
+    // fused: LayerNorm(fc(ctx) + x) with the row mask, then LayerNorm(w2(relu(conv9(.))) + .) (SubLayers.py:54-55,87-91)
+    a = gemm_args(t1, D_MODEL, rows, L.wfc, L.bfc, 1, D_MODEL, D_MODEL, ACT_NONE, t2, D_MODEL);
+    a.residual = x; a.ldr = D_MODEL; a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
+    a.ln_gamma = L.ln1_g; a.ln_beta = L.ln1_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
+    { ProfScope ps(c, s, frame ? "dec.gemm_fc_ln" : "enc.gemm_fc_ln"); conv_gemm(eng, math, a, s); }
+    a = gemm_args(t2, D_MODEL, rows, L.w1, L.b1, FFN_TAPS, D_MODEL, D_INNER, ACT_RELU, pool.hid, D_INNER);
+    a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
+    { ProfScope ps(c, s, frame ? "dec.gemm_conv9" : "enc.gemm_conv9"); conv_gemm(eng, math, a, s); }
+    a = gemm_args(pool.hid, D_INNER, rows, L.w2, L.b2, 1, D_INNER, D_MODEL, ACT_NONE, x, D_MODEL);
+    a.residual = t2; a.ldr = D_MODEL; a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
+    a.ln_gamma = L.ln2_g; a.ln_beta = L.ln2_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
+    { ProfScope ps(c, s, frame ? "dec.gemm_w2_ln" : "enc.gemm_w2_ln"); conv_gemm(eng, math, a, s); }
+    return;
+  }
   a = gemm_args(t1, D_MODEL, rows, L.wfc, L.bfc, 1, D_MODEL, D_MODEL, ACT_NONE, t2, D_MODEL);
   a.residual = x; a.ldr = D_MODEL; a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
   { ProfScope ps(c, s, frame ? "dec.gemm_fc" : "enc.gemm_fc"); conv_gemm(eng, math, a, s); }
@@ -290,6 +310,18 @@ static void predictor(fs2_ctx* c, cudaStream_t s, const Predictor& P, const RowS
                       float* t1, float* t2, float* head_out) {
   ProfScope ps(c, s, "predictor");
   const int eng = c->cfg.engine, math = c->cfg.math_mode;
+  if (eng == FS2_ENGINE_TCGEN05) {
+    ConvGemmArgs f = gemm_args(x, D_MODEL, rows, P.w1, P.b1, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, t1, D_MODEL);
+    f.live_rows = reinterpret_cast<const int32_t*>(side.totals);
+    f.ln_gamma = P.ln1_g; f.ln_beta = P.ln1_b; f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 1;
+    conv_gemm(eng, math, f, s);
+    f = gemm_args(t1, D_MODEL, rows, P.w2, P.b2, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, nullptr, D_MODEL);
+    f.live_rows = reinterpret_cast<const int32_t*>(side.totals);
+    f.ln_gamma = P.ln2_g; f.ln_beta = P.ln2_b; f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 0;
+    f.head_w = P.head_w; f.head_b = P.head_b; f.head_out = head_out; f.slot = side.slot;
+    conv_gemm(eng, math, f, s);
+    return;
+  }
   ConvGemmArgs a = gemm_args(x, D_MODEL, rows, P.w1, P.b1, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, t1, D_MODEL);
   a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
   conv_gemm(eng, math, a, s);
@@ -598,7 +630,8 @@ int fs2_create(const fs2_config* cfg, int device, fs2_ctx** out) {
   return guarded(nullptr, [&] {
     require(cfg && out, FS2_ERR_INVALID, "null argument");
     require(cfg->math_mode == FS2_MATH_TF32 || cfg->math_mode == FS2_MATH_BF16, FS2_ERR_UNSUPPORTED, "unknown math_mode");
-    require(cfg->engine == FS2_ENGINE_MMA_SYNC || cfg->engine == FS2_ENGINE_TCGEN05, FS2_ERR_UNSUPPORTED, "unknown engine");
+    require(cfg->engine == FS2_ENGINE_MMA_SYNC || cfg->engine == FS2_ENGINE_TCGEN05 ||
+                cfg->engine == FS2_ENGINE_TCGEN05_V1, FS2_ERR_UNSUPPORTED, "unknown engine");
     require(cfg->n_src_vocab > 0 && cfg->n_speaker > 0 && cfg->n_emotion > 0 && cfg->n_arousal > 0 && cfg->n_valence > 0 &&
                 cfg->max_seq_len > 0, FS2_ERR_INVALID, "table sizes must be positive");
     int n_dev = 0;
@@ -754,6 +787,20 @@ int fs2_op_conv_gemm(fs2_stream stream, int engine, int math_mode, const float* 
     a.A = A; a.lda = lda; a.rows = rows; a.W = Wt; a.bias = bias; a.taps = taps; a.pad = pad; a.K = K; a.N = N; a.act = act;
     a.residual = residual; a.ldr = ldr; a.row_vpos = row_vpos; a.row_room = row_room; a.extra = extra; a.C = C; a.ldc = ldc;
     conv_gemm(engine, math_mode, a, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int fs2_op_conv_gemm_ln(fs2_stream stream, int engine, const float* A, int lda, int rows, const float* Wt, const float* bias,
+                        int taps, int pad, int K, int act, const float* residual, int ldr, const float* gamma,
+                        const float* beta, const int32_t* row_vpos, const int32_t* row_room, int extra, float* C, int ldc,
+                        const float* head_w, const float* head_b, float* head_out) {
+  return guarded(nullptr, [&] {
+    require(A && Wt && bias && gamma && beta && rows >= 0 && taps >= 1 && K > 0, FS2_ERR_INVALID, "bad conv_gemm_ln argument");
+    ConvGemmArgs a{};
+    a.A = A; a.lda = lda; a.rows = rows; a.W = Wt; a.bias = bias; a.taps = taps; a.pad = pad; a.K = K; a.N = D_MODEL; a.act = act;
+    a.residual = residual; a.ldr = ldr; a.row_vpos = row_vpos; a.row_room = row_room; a.extra = extra; a.C = C; a.ldc = ldc;
+    a.ln_gamma = gamma; a.ln_beta = beta; a.head_w = head_w; a.head_b = head_b; a.head_out = head_out;
+    conv_gemm(engine, FS2_MATH_TF32, a, static_cast<cudaStream_t>(stream));
   });
 }
 

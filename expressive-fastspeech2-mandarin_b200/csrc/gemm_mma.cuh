@@ -26,6 +26,16 @@ struct ConvGemmArgs {
   float* C;
   int ldc;
   const int32_t* live_rows;  // optional device scalar: tiles at or beyond *live_rows exit early
+  // Fused LayerNorm epilogue (persistent tcgen05 engine only; requires N == 256):
+  //   y = LayerNorm(act(acc + bias) + residual) * ln_gamma + ln_beta, non-live rows -> 0,
+  //   optional head: head_out[slot ? slot[row] : row] = y . head_w + head_b[0] on live rows.
+  // C may be nullptr when only the head output is wanted.
+  const float* ln_gamma;
+  const float* ln_beta;
+  const float* head_w;
+  const float* head_b;
+  float* head_out;
+  const int32_t* slot;
 };
 
 namespace mma {

@@ -1,0 +1,391 @@
+// Persistent implicit-GEMM Conv1d / Linear on tcgen05 with fused epilogues (the product engine).
+//
+// One CTA per SM loops over output tiles (128 rows x BN columns).  Three pipelines run
+// concurrently:
+//   warp 0      TMA producer: A (activations, tap = row offset) and B (weights) into a smem ring;
+//   warp 1      MMA issuer:   tcgen05.mma kind::tf32 into one of TWO TMEM accumulators, so the
+//                             main loop of tile i+1 overlaps the epilogue of tile i;
+//   warps 2..5  epilogue:     tcgen05.ld (thread = output row) -> bias / ReLU / tanh / residual /
+//                             row mask, or the full post-LN of the FFT block and the predictors
+//                             (LayerNorm over the 256-wide row held in TMEM, optional 256->1 head)
+//                             -> swizzled smem staging -> TMA store (coalesced, asynchronous).
+// Residual tiles are fetched by TMA into smem (never by per-thread strided loads).
+#pragma once
+
+#include "common.cuh"
+#include "gemm_mma.cuh"
+#include "tc_ptx.cuh"
+
+namespace fs2 {
+namespace tc2 {
+
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int BK = 32;
+constexpr int THREADS = 192;
+constexpr int CHUNK_BYTES = BM * 128;   // one [128 rows x 32 fp32] swizzled sub-tile
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = BN > 128 ? 3 : 4;
+  static constexpr int A_BYTES = BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OFF_CST = STAGES * STAGE_BYTES;      // 2 output staging chunks
+  static constexpr int OFF_RES = OFF_CST + 2 * CHUNK_BYTES; // 2 residual chunks
+  static constexpr int OFF_PAR = OFF_RES + 2 * CHUNK_BYTES; // bias | gamma | beta | head_w (256 floats each)
+  static constexpr int OFF_BAR = OFF_PAR + 4096;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static constexpr int NCHUNK = (BN + 31) / 32;
+  static_assert(B_BYTES % 1024 == 0, "stages must stay 1024-byte aligned (SWIZZLE_128B)");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
+  static_assert(TOTAL <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+
+// byte offset of (row r, 16-byte chunk cc) inside a [128 x 128 B] SWIZZLE_128B sub-tile
+__device__ __forceinline__ int swz_off(int r, int cc) { return r * 128 + ((cc ^ (r & 7)) << 4); }
+
+template <int BN, bool LN>
+__global__ void __launch_bounds__(THREADS, 1)
+conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, ConvGemmArgs p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* cst = smem + C::OFF_CST;
+  uint8_t* res = smem + C::OFF_RES;
+  float* bias_s = reinterpret_cast<float*>(smem + C::OFF_PAR);
+  float* gamma_s = bias_s + 256;
+  float* beta_s = bias_s + 512;
+  float* headw_s = bias_s + 768;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* acc_full = empty + C::STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint64_t* res_full = acc_empty + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = (p.K + BK - 1) / BK;
+  const int iters = p.taps * kchunks;
+  const int n_tiles_n = (p.N + BN - 1) / BN;
+  int rows_live = p.rows;
+  if (p.live_rows != nullptr) rows_live = min(rows_live, *p.live_rows);
+  const int total_tiles = ((rows_live + BM - 1) / BM) * n_tiles_n;
+  if ((int)blockIdx.x >= total_tiles) return;
+  const bool has_res = p.residual != nullptr;
+  const bool has_out = p.C != nullptr;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    if (has_out) asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+    if (has_res) asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int u = 0; u < 2; ++u) {
+      mbar_init(&acc_full[u], 1);
+      mbar_init(&acc_empty[u], 128);
+      mbar_init(&res_full[u], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles_n) * BM, n0 = (t % n_tiles_n) * BN;
+        for (int i = 0; i < iters; ++i, ++it) {
+          const int s = it % C::STAGES;
+          mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full[s], C::STAGE_BYTES);
+          const int tap = i / kchunks, kc = i - tap * kchunks;
+          uint8_t* a_s = smem + s * C::STAGE_BYTES;
+          tma_load_2d(a_s, &tmA, kc * BK, m0 + tap - p.pad, &full[s]);
+          tma_load_2d(a_s + C::A_BYTES, &tmW, kc * BK, tap * p.N + n0, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer
+      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        const int u = lt & 1;
+        mbar_wait(&acc_empty[u], ((lt >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + u * C::ACC_COLS;
+        for (int i = 0; i < iters; ++i, ++it) {
+          const int s = it % C::STAGES;
+          mbar_wait(&full[s], (it / C::STAGES) & 1);
+          tc_fence_after();
+          const uint8_t* a_s = smem + s * C::STAGE_BYTES;
+          const uint64_t da = umma_desc(a_s), db = umma_desc(a_s + C::A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) umma_tf32(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[u]);
+      }
+    }
+  } else {
+    // ---------------- epilogue (128 threads; thread = one accumulator row)
+    const int et = threadIdx.x - 64;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                     // row inside the tile
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    if (LN) {
+      for (int i = et; i < 256; i += 128) {
+        gamma_s[i] = p.ln_gamma[i];
+        beta_s[i] = p.ln_beta[i];
+        headw_s[i] = p.head_w != nullptr ? p.head_w[i] : 0.f;
+      }
+    }
+    int g_res = 0;   // residual chunks consumed so far (buffer = g & 1, parity = (g >> 1) & 1)
+    int g_st = 0;    // staging chunks produced so far
+    if (has_res && et == 0) {  // first residual chunk of the first tile
+      const int t = blockIdx.x;
+      mbar_expect_tx(&res_full[0], CHUNK_BYTES);
+      tma_load_2d(res, &tmR, (t % n_tiles_n) * BN, (t / n_tiles_n) * BM, &res_full[0]);
+    }
+    int lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      const int m0 = (t / n_tiles_n) * BM, n0 = (t % n_tiles_n) * BN;
+      const int u = lt & 1;
+      const int row = m0 + r;
+      const bool in_range = row < p.rows;
+      bool live = in_range;
+      if (in_range && p.row_vpos != nullptr) live = row_live(p.row_vpos[row], p.row_room[row], p.extra);
+      epi_barrier();   // previous tile's readers of bias_s are done
+      for (int i = et; i < BN; i += 128) bias_s[i] = (n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+      epi_barrier();
+      mbar_wait(&acc_full[u], (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + lane_sel + u * C::ACC_COLS;
+      const int t_next = t + gridDim.x;
+
+      // residual prefetch of the chunk after (tile t, chunk c): next chunk of this tile or chunk 0 of the next tile
+      auto prefetch_res = [&](int c) {
+        if (!has_res || et != 0) return;
+        int tt = t, cc = c + 1;
+        if (cc >= C::NCHUNK) { tt = t_next; cc = 0; }
+        if (tt >= total_tiles) return;
+        const int buf = (g_res + 1) & 1;
+        mbar_expect_tx(&res_full[buf], CHUNK_BYTES);
+        tma_load_2d(res + buf * CHUNK_BYTES, &tmR, (tt % n_tiles_n) * BN + cc * 32, (tt / n_tiles_n) * BM, &res_full[buf]);
+      };
+      // v = act(acc + bias) (+ residual from the smem chunk)
+      auto finish = [&](float (&v)[32], int c0, int width) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j < width) {
+            float x = v[j] + bias_s[c0 + j];
+            if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
+            else if (p.act == ACT_TANH) x = tanhf(x);
+            v[j] = x;
+          }
+        }
+        if (has_res) {
+          mbar_wait(&res_full[g_res & 1], (g_res >> 1) & 1);
+          const uint8_t* rb = res + (g_res & 1) * CHUNK_BYTES;
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) {
+            if (cc * 4 < width) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rb + swz_off(r, cc));
+              v[cc * 4 + 0] += r4.x; v[cc * 4 + 1] += r4.y; v[cc * 4 + 2] += r4.z; v[cc * 4 + 3] += r4.w;
+            }
+          }
+        }
+      };
+      // staging chunk -> TMA store
+      auto stage_out = [&](const float (&v)[32], int c0, int width) {
+        if (et == 0) bulk_wait_read<1>();     // the store that used this staging buffer two chunks ago is done
+        epi_barrier();
+        uint8_t* sb = cst + (g_st & 1) * CHUNK_BYTES;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          if (cc * 4 < width)
+            *reinterpret_cast<float4*>(sb + swz_off(r, cc)) = make_float4(v[cc * 4], v[cc * 4 + 1], v[cc * 4 + 2], v[cc * 4 + 3]);
+        }
+        fence_async_smem();
+        epi_barrier();
+        if (et == 0) {
+          tma_store_2d(&tmC, sb, n0 + c0, m0);
+          bulk_commit();
+        }
+        ++g_st;
+      };
+
+      if (!LN) {
+#pragma unroll 1
+        for (int c = 0; c < C::NCHUNK; ++c) {
+          const int c0 = c * 32;
+          const int width = (BN - c0) >= 32 ? 32 : 16;
+          float v[32];
+          if (width == 32) tmem_ld32(acc + c0, v); else tmem_ld16(acc + c0, v);
+          if (has_res) {
+            epi_barrier();          // everyone finished reading the other residual buffer
+            prefetch_res(c);
+          }
+          finish(v, c0, width);
+          if (has_res) ++g_res;
+          if (!live) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (c == C::NCHUNK - 1) {   // all TMEM reads of this tile are done: release the accumulator
+            tc_fence_before();
+            mbar_arrive(&acc_empty[u]);
+          }
+          stage_out(v, c0, width);
+        }
+      } else {
+        // ---- LayerNorm over the 256-wide row held in TMEM (eps 1e-5, biased variance, two-pass)
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < C::NCHUNK; ++c) {
+          float v[32];
+          tmem_ld32(acc + c * 32, v);
+          if (has_res) {
+            epi_barrier();
+            prefetch_res(c);
+          }
+          finish(v, c * 32, 32);
+          if (has_res) ++g_res;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum += v[j];
+          tmem_st32(acc + c * 32, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        const float mean = sum * (1.f / 256.f);
+        float var = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < C::NCHUNK; ++c) {
+          float v[32];
+          tmem_ld32(acc + c * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = v[j] - mean;
+            var = fmaf(d, d, var);
+          }
+        }
+        const float rstd = 1.f / sqrtf(var * (1.f / 256.f) + 1e-5f);
+        float dot = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < C::NCHUNK; ++c) {
+          float v[32];
+          tmem_ld32(acc + c * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float y = (v[j] - mean) * rstd * gamma_s[c * 32 + j] + beta_s[c * 32 + j];
+            dot = fmaf(y, headw_s[c * 32 + j], dot);
+            v[j] = live ? y : 0.f;
+          }
+          if (c == C::NCHUNK - 1) {
+            tc_fence_before();
+            mbar_arrive(&acc_empty[u]);
+          }
+          if (has_out) stage_out(v, c * 32, 32);
+        }
+        if (p.head_out != nullptr && live) {
+          const int dst = p.slot != nullptr ? p.slot[row] : row;
+          if (dst >= 0) p.head_out[dst] = dot + p.head_b[0];
+        }
+      }
+    }
+    if (et == 0) bulk_wait_read<0>();   // smem must outlive the last TMA stores
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+inline int sm_count() {
+  static int n[64] = {};
+  int dev = 0;
+  FS2_CUDA_OK(cudaGetDevice(&dev));
+  if (n[dev & 63] == 0) FS2_CUDA_OK(cudaDeviceGetAttribute(&n[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+  return n[dev & 63];
+}
+
+template <int BN, bool LN>
+inline void launch_bn(const ConvGemmArgs& a, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool configured[64] = {};
+  int dev = 0;
+  FS2_CUDA_OK(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    configured[dev & 63] = true;
+  }
+  const CUtensorMap tmA = make_map(a.A, a.rows, a.K, a.lda, BM, /*round_tf32=*/true, false);
+  const CUtensorMap tmW = make_map(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN, false, true);
+  const CUtensorMap tmC = a.C != nullptr ? make_map(a.C, a.rows, a.N, a.ldc, BM, false, false) : tmA;
+  const CUtensorMap tmR = a.residual != nullptr ? make_map(a.residual, a.rows, a.N, a.ldr, BM, false, false) : tmA;
+  const int tiles = ((a.rows + BM - 1) / BM) * ((a.N + BN - 1) / BN);
+  const int grid = std::min(tiles, sm_count());
+  conv_gemm_tc2_kernel<BN, LN><<<grid, THREADS, C::TOTAL, stream>>>(tmA, tmW, tmC, tmR, a);
+  FS2_LAUNCHED();
+}
+
+inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
+  require(math_mode == FS2_MATH_TF32, FS2_ERR_UNSUPPORTED, "tcgen05 engine: only FS2_MATH_TF32 is built");
+  require(a.K % 4 == 0 && a.lda % 4 == 0 && a.ldc % 4 == 0 && (a.residual == nullptr || a.ldr % 4 == 0), FS2_ERR_INVALID,
+          "tcgen05 conv_gemm: K and leading dimensions must be multiples of 4 (16-byte rows)");
+  require((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0,
+          FS2_ERR_INVALID, "tcgen05 conv_gemm: pointers must be 16-byte aligned");
+  if (a.rows <= 0) return;
+  const bool ln = a.ln_gamma != nullptr;
+  if (ln) {
+    require(a.N == 256 && a.ln_beta != nullptr, FS2_ERR_INVALID, "fused LayerNorm needs N == 256 and both affine vectors");
+    require(a.C != nullptr || a.head_out != nullptr, FS2_ERR_INVALID, "fused LayerNorm: nothing to write");
+    require(a.head_out == nullptr || (a.head_w != nullptr && a.head_b != nullptr), FS2_ERR_INVALID, "head needs weight and bias");
+    launch_bn<256, true>(a, stream);
+    return;
+  }
+  require(a.C != nullptr, FS2_ERR_INVALID, "conv_gemm: null output");
+  if (a.N % 256 == 0) launch_bn<256, false>(a, stream);
+  else if (a.N == 80) launch_bn<80, false>(a, stream);
+  else if (a.N % 128 == 0) launch_bn<128, false>(a, stream);
+  else if (a.N % 64 == 0) launch_bn<64, false>(a, stream);
+  else throw Error(FS2_ERR_UNSUPPORTED, "tcgen05 conv_gemm: N = " + std::to_string(a.N) + " has no compiled tile");
+}
+
+}  // namespace tc2
+}  // namespace fs2

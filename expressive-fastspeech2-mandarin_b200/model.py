@@ -83,7 +83,8 @@ class FastSpeech2B200(nn.Module):
                           n_arousal=len(emo["arousal_dict"]), n_valence=len(emo["valence_dict"]),
                           max_seq_len=int(model_config["max_seq_len"]))
         self.math_mode = {"tf32": _lib.MATH_TF32, "bf16": _lib.MATH_BF16}[math_mode]
-        self.engine = {"mma_sync": _lib.ENGINE_MMA_SYNC, "tcgen05": _lib.ENGINE_TCGEN05}[engine]
+        self.engine = {"mma_sync": _lib.ENGINE_MMA_SYNC, "tcgen05": _lib.ENGINE_TCGEN05,
+                       "tcgen05_v1": _lib.ENGINE_TCGEN05_V1}[engine]
 
         # Parameter tree built from the schema; values: deterministic tables where the reference
         # computes them (position_enc, bins), seeded random elsewhere (the reference random-inits).

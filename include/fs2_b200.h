@@ -39,7 +39,7 @@ enum {
 enum { FS2_MATH_TF32 = 0, FS2_MATH_BF16 = 1 };
 /* GEMM engines: the product path is TCGEN05; MMA_SYNC is the legacy-tensor-core cross-check
  * used by the unit tests and for bring-up. */
-enum { FS2_ENGINE_MMA_SYNC = 0, FS2_ENGINE_TCGEN05 = 1 };
+enum { FS2_ENGINE_MMA_SYNC = 0, FS2_ENGINE_TCGEN05 = 1, FS2_ENGINE_TCGEN05_V1 = 2 /* non-persistent bring-up variant */ };
 
 /* Model dimensions that are data (table sizes); the layer structure is fixed to
  * config/ESD-Chinese-Singing-MFA/model.yaml (d_model 256, 2 heads, 4+6 FFT blocks,
@@ -143,6 +143,14 @@ int fs2_op_conv_gemm(fs2_stream stream, int engine, int math_mode, const float* 
                      const float* W, const float* bias, int taps, int pad, int K, int N, int act,
                      const float* residual, int ldr, const int32_t* row_vpos, const int32_t* row_room,
                      int extra, float* C, int ldc);
+/* The same contraction with the fused post-LayerNorm epilogue of the persistent tcgen05 engine
+ * (N = 256): y = LayerNorm(act(conv + bias) + residual) * gamma + beta, masked rows -> 0
+ * (SubLayers.py:54-55,87-91; modules.py:243-247), optional head dot[r] = y[r,:].head_w + head_b
+ * (modules.py:245-246).  C may be NULL when only `head_out` ([rows]) is wanted. */
+int fs2_op_conv_gemm_ln(fs2_stream stream, int engine, const float* A, int lda, int rows, const float* W,
+                        const float* bias, int taps, int pad, int K, int act, const float* residual, int ldr,
+                        const float* gamma, const float* beta, const int32_t* row_vpos, const int32_t* row_room,
+                        int extra, float* C, int ldc, const float* head_w, const float* head_b, float* head_out);
 /* Varlen 2-head self-attention over packed rows (SubLayers.py:42-52, Modules.py:14-25):
  * qkv [rows,768] = [q | k | v], heads are 128-wide halves; utterance b owns rows
  * [starts[b], starts[b]+lens[b]); rows = rows of the qkv buffer.  out [rows,256]. */

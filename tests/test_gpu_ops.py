@@ -11,7 +11,7 @@ from oracle import fs2_oracle as O
 from gpu_util import DEV, lib, ptr, round_tf32, stream
 
 pytestmark = pytest.mark.gpu
-ENGINES = [0] + ([1] if os.environ.get("FS2_TEST_TCGEN05", "1") == "1" else [])
+ENGINES = [0] + ([1, 2] if os.environ.get("FS2_TEST_TCGEN05", "1") == "1" else [])
 
 
 def conv_ref(A, W, bias, pad, act, residual, vpos, room, extra):
@@ -47,6 +47,9 @@ CASES = [
     (333, 512, 512, 5, 2, False, True, "postnet_mid"),
     (129, 512, 80, 5, 0, True, True, "postnet_last"),
     (5, 256, 256, 1, 0, False, False, "tiny"),
+    (40000, 256, 768, 1, 0, False, False, "qkv_many_tiles"),
+    (30011, 1024, 256, 1, 0, True, True, "w2_many_tiles"),
+    (25000, 512, 80, 5, 0, True, True, "postnet_last_many_tiles"),
 ]
 
 
@@ -78,6 +81,54 @@ def test_conv_gemm(case, engine):
     err = (got - want).abs().max().item()
     # operands are TF32-exact, so only the fp32 accumulation order differs
     assert err < 2e-4, f"max abs err {err}"
+
+
+LN_CASES = [
+    # rows, K, taps, act, residual, store C, head, name
+    (300, 256, 1, 0, True, True, False, "fc_residual_ln"),
+    (1000, 1024, 1, 0, True, True, False, "w2_residual_ln"),
+    (137, 256, 3, 1, False, True, False, "predictor_conv1_relu_ln"),
+    (137, 256, 3, 1, False, False, True, "predictor_conv2_relu_ln_head"),
+    (20000, 256, 1, 0, True, True, True, "many_tiles"),
+]
+
+
+@pytest.mark.parametrize("case", LN_CASES, ids=[c[-1] for c in LN_CASES])
+def test_conv_gemm_fused_layernorm(case):
+    """Persistent tcgen05 engine: LayerNorm(act(conv + bias) + residual) fused into the GEMM epilogue."""
+    rows, K, taps, act, use_res, store, use_head, _ = case
+    g = torch.Generator().manual_seed(rows + K + taps)
+    A = round_tf32(torch.randn(rows, K, generator=g))
+    W = round_tf32(torch.randn(taps, 256, K, generator=g) / np.sqrt(K * taps))
+    bias = torch.randn(256, generator=g) * 0.3
+    res = torch.randn(rows, 256, generator=g) if use_res else None
+    gamma, beta = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.2
+    hw, hb = torch.randn(256, generator=g) / 16, torch.randn(1, generator=g)
+    vpos = torch.randint(-3, 3, (rows,), generator=g, dtype=torch.int32)
+    room = torch.randint(0, 3, (rows,), generator=g, dtype=torch.int32)
+    extra = 1
+    pre = conv_ref(A, W, bias, (taps - 1) // 2, act, res, None, None, 0)
+    y = torch.nn.functional.layer_norm(pre, (256,), gamma.double(), beta.double(), 1e-5)
+    live = vpos < torch.minimum(torch.full_like(room, extra), room)
+    dot = y @ hw.double() + hb.double()
+    y = y * live.unsqueeze(1)
+    d = lambda t: t.to(DEV) if t is not None else None
+    dA, dW, db, dres, dg, dbe, dv, dr, dhw, dhb = map(d, (A, W, bias, res, gamma, beta, vpos, room, hw, hb))
+    out = torch.full((rows, 256), float("nan"), device=DEV) if store else None
+    head = torch.zeros(rows, device=DEV) if use_head else None
+    code = lib().fs2_op_conv_gemm_ln(stream(), 1, ptr(dA), K, rows, ptr(dW), ptr(db), taps, (taps - 1) // 2, K, act,
+                                     ptr(dres), 256, ptr(dg), ptr(dbe), ptr(dv), ptr(dr), extra, ptr(out), 256,
+                                     ptr(dhw) if use_head else None, ptr(dhb) if use_head else None, ptr(head))
+    assert code == 0, lib().fs2_last_error(None)
+    torch.cuda.synchronize()
+    if store:
+        got = out.cpu().double()
+        assert torch.isfinite(got).all()
+        assert (got - y).abs().max().item() < 3e-4
+    if use_head:
+        got = head.cpu().double()
+        assert (got[live] - dot[live]).abs().max().item() < 3e-4
+        assert (got[~live] == 0).all()
 
 
 @pytest.mark.parametrize("engine", ENGINES)
