@@ -9,7 +9,9 @@
 //                             row mask, or the full post-LN of the FFT block and the predictors
 //                             (LayerNorm over the 256-wide row held in TMEM, optional 256->1 head)
 //                             -> swizzled smem staging -> TMA store (coalesced, asynchronous).
-// Residual tiles are fetched by TMA into smem (never by per-thread strided loads).
+// Residual tiles are fetched by TMA into smem (never by per-thread strided loads).  Every epilogue
+// warp owns its 32 rows end to end (own staging buffers, own TMA loads/stores, own mbarriers), so
+// the steady state has no CTA-wide barrier.
 #pragma once
 
 #include "common.cuh"
@@ -24,7 +26,8 @@ using namespace tc;
 constexpr int BM = 128;
 constexpr int BK = 32;
 constexpr int THREADS = 192;
-constexpr int CHUNK_BYTES = BM * 128;   // one [128 rows x 32 fp32] swizzled sub-tile
+constexpr int WCHUNK = 32 * 128;        // one warp's [32 rows x 32 fp32] swizzled sub-tile (4 KB)
+constexpr int MAX_N = 1024;
 
 template <int BN>
 struct Cfg {
@@ -32,10 +35,10 @@ struct Cfg {
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OFF_CST = STAGES * STAGE_BYTES;      // 2 output staging chunks
-  static constexpr int OFF_RES = OFF_CST + 2 * CHUNK_BYTES; // 2 residual chunks
-  static constexpr int OFF_PAR = OFF_RES + 2 * CHUNK_BYTES; // bias | gamma | beta | head_w (256 floats each)
-  static constexpr int OFF_BAR = OFF_PAR + 4096;
+  static constexpr int OFF_CST = STAGES * STAGE_BYTES;      // 4 warps x 2 output staging sub-tiles
+  static constexpr int OFF_RES = OFF_CST + 8 * WCHUNK;      // 4 warps x 2 residual sub-tiles
+  static constexpr int OFF_PAR = OFF_RES + 8 * WCHUNK;      // bias[1024] | gamma[256] | beta[256] | head_w[256]
+  static constexpr int OFF_BAR = OFF_PAR + 8192;
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
   static constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
@@ -59,7 +62,18 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
 
-// byte offset of (row r, 16-byte chunk cc) inside a [128 x 128 B] SWIZZLE_128B sub-tile
+// explicit shared-space 16-byte accesses (the generic pointers derived from the aligned dynamic
+// smem base would otherwise compile to generic LD/ST)
+__device__ __forceinline__ float4 lds4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// byte offset of (row r, 16-byte chunk cc) inside a [rows x 128 B] SWIZZLE_128B sub-tile
 __device__ __forceinline__ int swz_off(int r, int cc) { return r * 128 + ((cc ^ (r & 7)) << 4); }
 
 template <int BN, bool LN>
@@ -72,15 +86,15 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint8_t* cst = smem + C::OFF_CST;
   uint8_t* res = smem + C::OFF_RES;
   float* bias_s = reinterpret_cast<float*>(smem + C::OFF_PAR);
-  float* gamma_s = bias_s + 256;
-  float* beta_s = bias_s + 512;
-  float* headw_s = bias_s + 768;
+  float* gamma_s = bias_s + MAX_N;
+  float* beta_s = gamma_s + 256;
+  float* headw_s = beta_s + 256;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* empty = full + C::STAGES;
   uint64_t* acc_full = empty + C::STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
-  uint64_t* res_full = acc_empty + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+  uint64_t* res_full = acc_empty + 2;       // [4 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = (p.K + BK - 1) / BK;
@@ -105,8 +119,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int u = 0; u < 2; ++u) {
       mbar_init(&acc_full[u], 1);
       mbar_init(&acc_empty[u], 128);
-      mbar_init(&res_full[u], 1);
     }
+    for (int u = 0; u < 8; ++u) mbar_init(&res_full[u], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
@@ -161,11 +175,19 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else {
-    // ---------------- epilogue (128 threads; thread = one accumulator row)
+    // ---------------- epilogue (4 independent warps; thread = one accumulator row)
     const int et = threadIdx.x - 64;
     const int q = warp & 3;
     const int r = q * 32 + lane;                     // row inside the tile
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    uint8_t* my_cst = cst + q * 2 * WCHUNK;
+    uint8_t* my_res = res + q * 2 * WCHUNK;
+    uint64_t* my_res_full = res_full + q * 2;
+    const uint32_t bias_sa = smem_u32(bias_s), gamma_sa = smem_u32(gamma_s), beta_sa = smem_u32(beta_s),
+                   headw_sa = smem_u32(headw_s), cst_sa = smem_u32(my_cst), res_sa = smem_u32(my_res);
+    const uint32_t swz_x = (uint32_t)(lane & 7) << 4;
+    const int act = p.act;
+    for (int i = et; i < p.N; i += 128) bias_s[i] = p.bias[i];
     if (LN) {
       for (int i = et; i < 256; i += 128) {
         gamma_s[i] = p.ln_gamma[i];
@@ -173,12 +195,13 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         headw_s[i] = p.head_w != nullptr ? p.head_w[i] : 0.f;
       }
     }
-    int g_res = 0;   // residual chunks consumed so far (buffer = g & 1, parity = (g >> 1) & 1)
-    int g_st = 0;    // staging chunks produced so far
-    if (has_res && et == 0) {  // first residual chunk of the first tile
+    epi_barrier();   // the only CTA-level epilogue barrier: parameters are in smem
+    int g_res = 0;   // residual sub-tiles consumed so far (buffer = g & 1, parity = (g >> 1) & 1)
+    int g_st = 0;    // staging sub-tiles produced so far
+    if (has_res && lane == 0) {  // first residual sub-tile of the first tile
       const int t = blockIdx.x;
-      mbar_expect_tx(&res_full[0], CHUNK_BYTES);
-      tma_load_2d(res, &tmR, (t % n_tiles_n) * BN, (t / n_tiles_n) * BM, &res_full[0]);
+      mbar_expect_tx(&my_res_full[0], WCHUNK);
+      tma_load_2d(my_res, &tmR, (t % n_tiles_n) * BN, (t / n_tiles_n) * BM + q * 32, &my_res_full[0]);
     }
     int lt = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
@@ -188,61 +211,66 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const bool in_range = row < p.rows;
       bool live = in_range;
       if (in_range && p.row_vpos != nullptr) live = row_live(p.row_vpos[row], p.row_room[row], p.extra);
-      epi_barrier();   // previous tile's readers of bias_s are done
-      for (int i = et; i < BN; i += 128) bias_s[i] = (n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
-      epi_barrier();
       mbar_wait(&acc_full[u], (lt >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + lane_sel + u * C::ACC_COLS;
       const int t_next = t + gridDim.x;
 
-      // residual prefetch of the chunk after (tile t, chunk c): next chunk of this tile or chunk 0 of the next tile
+      // prefetch the residual sub-tile after (tile t, chunk c): next chunk of this tile or chunk 0 of
+      // the next tile.  Called by the whole warp AFTER a __syncwarp that follows the previous reads.
       auto prefetch_res = [&](int c) {
-        if (!has_res || et != 0) return;
+        if (!has_res || lane != 0) return;
         int tt = t, cc = c + 1;
         if (cc >= C::NCHUNK) { tt = t_next; cc = 0; }
         if (tt >= total_tiles) return;
         const int buf = (g_res + 1) & 1;
-        mbar_expect_tx(&res_full[buf], CHUNK_BYTES);
-        tma_load_2d(res + buf * CHUNK_BYTES, &tmR, (tt % n_tiles_n) * BN + cc * 32, (tt / n_tiles_n) * BM, &res_full[buf]);
+        mbar_expect_tx(&my_res_full[buf], WCHUNK);
+        tma_load_2d(my_res + buf * WCHUNK, &tmR, (tt % n_tiles_n) * BN + cc * 32, (tt / n_tiles_n) * BM + q * 32,
+                    &my_res_full[buf]);
       };
-      // v = act(acc + bias) (+ residual from the smem chunk)
+      // v = act(acc + bias) (+ residual from this warp's smem sub-tile)
       auto finish = [&](float (&v)[32], int c0, int width) {
+        const uint32_t ba = bias_sa + (uint32_t)(n0 + c0) * 4;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < width) {
-            float x = v[j] + bias_s[c0 + j];
-            if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
-            else if (p.act == ACT_TANH) x = tanhf(x);
-            v[j] = x;
+        for (int cc = 0; cc < 8; ++cc) {
+          if (cc * 4 < width) {
+            const float4 b4 = lds4(ba + cc * 16);
+            v[cc * 4 + 0] += b4.x; v[cc * 4 + 1] += b4.y; v[cc * 4 + 2] += b4.z; v[cc * 4 + 3] += b4.w;
           }
         }
+        if (act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (act == ACT_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+        }
         if (has_res) {
-          mbar_wait(&res_full[g_res & 1], (g_res >> 1) & 1);
-          const uint8_t* rb = res + (g_res & 1) * CHUNK_BYTES;
+          mbar_wait(&my_res_full[g_res & 1], (g_res >> 1) & 1);
+          const uint32_t rb = res_sa + (g_res & 1) * WCHUNK + lane * 128;
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
             if (cc * 4 < width) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rb + swz_off(r, cc));
+              const float4 r4 = lds4(rb + ((cc << 4) ^ swz_x));
               v[cc * 4 + 0] += r4.x; v[cc * 4 + 1] += r4.y; v[cc * 4 + 2] += r4.z; v[cc * 4 + 3] += r4.w;
             }
           }
         }
       };
-      // staging chunk -> TMA store
+      // this warp's [32 x 32] sub-tile -> swizzled staging -> TMA store
       auto stage_out = [&](const float (&v)[32], int c0, int width) {
-        if (et == 0) bulk_wait_read<1>();     // the store that used this staging buffer two chunks ago is done
-        epi_barrier();
-        uint8_t* sb = cst + (g_st & 1) * CHUNK_BYTES;
+        if (lane == 0) bulk_wait_read<1>();   // the store that used this staging buffer two sub-tiles ago is done
+        __syncwarp();
+        uint8_t* sb = my_cst + (g_st & 1) * WCHUNK;
+        const uint32_t sa = cst_sa + (g_st & 1) * WCHUNK + lane * 128;
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
-          if (cc * 4 < width)
-            *reinterpret_cast<float4*>(sb + swz_off(r, cc)) = make_float4(v[cc * 4], v[cc * 4 + 1], v[cc * 4 + 2], v[cc * 4 + 3]);
+          if (cc * 4 < width) sts4(sa + ((cc << 4) ^ swz_x), make_float4(v[cc * 4], v[cc * 4 + 1], v[cc * 4 + 2], v[cc * 4 + 3]));
         }
         fence_async_smem();
-        epi_barrier();
-        if (et == 0) {
-          tma_store_2d(&tmC, sb, n0 + c0, m0);
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmC, sb, n0 + c0, m0 + q * 32);
           bulk_commit();
         }
         ++g_st;
@@ -255,10 +283,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int width = (BN - c0) >= 32 ? 32 : 16;
           float v[32];
           if (width == 32) tmem_ld32(acc + c0, v); else tmem_ld16(acc + c0, v);
-          if (has_res) {
-            epi_barrier();          // everyone finished reading the other residual buffer
-            prefetch_res(c);
-          }
+          prefetch_res(c);            // all lanes passed the __syncwarp of the previous stage_out
           finish(v, c0, width);
           if (has_res) ++g_res;
           if (!live) {
@@ -279,7 +304,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           float v[32];
           tmem_ld32(acc + c * 32, v);
           if (has_res) {
-            epi_barrier();
+            __syncwarp();             // every lane finished reading the other residual buffer
             prefetch_res(c);
           }
           finish(v, c * 32, 32);
@@ -308,10 +333,22 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           float v[32];
           tmem_ld32(acc + c * 32, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float y = (v[j] - mean) * rstd * gamma_s[c * 32 + j] + beta_s[c * 32 + j];
-            dot = fmaf(y, headw_s[c * 32 + j], dot);
-            v[j] = live ? y : 0.f;
+          for (int cc = 0; cc < 8; ++cc) {
+            const float4 g4 = lds4(gamma_sa + c * 128 + cc * 16), b4 = lds4(beta_sa + c * 128 + cc * 16);
+            const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[cc * 4 + e] = fmaf((v[cc * 4 + e] - mean) * rstd, gg[e], bb[e]);
+          }
+          if (p.head_out != nullptr) {
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              const float4 w4 = lds4(headw_sa + c * 128 + cc * 16);
+              dot = fmaf(v[cc * 4], w4.x, fmaf(v[cc * 4 + 1], w4.y, fmaf(v[cc * 4 + 2], w4.z, fmaf(v[cc * 4 + 3], w4.w, dot))));
+            }
+          }
+          if (!live) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
           if (c == C::NCHUNK - 1) {
             tc_fence_before();
@@ -325,7 +362,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
     }
-    if (et == 0) bulk_wait_read<0>();   // smem must outlive the last TMA stores
+    if (lane == 0) bulk_wait_read<0>();   // smem must outlive the last TMA stores
   }
   tc_fence_before();
   __syncthreads();
@@ -355,8 +392,8 @@ inline void launch_bn(const ConvGemmArgs& a, cudaStream_t stream) {
   }
   const CUtensorMap tmA = make_map(a.A, a.rows, a.K, a.lda, BM, /*round_tf32=*/true, false);
   const CUtensorMap tmW = make_map(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN, false, true);
-  const CUtensorMap tmC = a.C != nullptr ? make_map(a.C, a.rows, a.N, a.ldc, BM, false, false) : tmA;
-  const CUtensorMap tmR = a.residual != nullptr ? make_map(a.residual, a.rows, a.N, a.ldr, BM, false, false) : tmA;
+  const CUtensorMap tmC = a.C != nullptr ? make_map(a.C, a.rows, a.N, a.ldc, 32, false, false) : tmA;
+  const CUtensorMap tmR = a.residual != nullptr ? make_map(a.residual, a.rows, a.N, a.ldr, 32, false, false) : tmA;
   const int tiles = ((a.rows + BM - 1) / BM) * ((a.N + BN - 1) / BN);
   const int grid = std::min(tiles, sm_count());
   conv_gemm_tc2_kernel<BN, LN><<<grid, THREADS, C::TOTAL, stream>>>(tmA, tmW, tmC, tmR, a);
@@ -371,6 +408,7 @@ inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
               (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0,
           FS2_ERR_INVALID, "tcgen05 conv_gemm: pointers must be 16-byte aligned");
   if (a.rows <= 0) return;
+  require(a.N <= MAX_N, FS2_ERR_UNSUPPORTED, "tcgen05 conv_gemm: N > 1024");
   const bool ln = a.ln_gamma != nullptr;
   if (ln) {
     require(a.N == 256 && a.ln_beta != nullptr, FS2_ERR_INVALID, "fused LayerNorm needs N == 256 and both affine vectors");
