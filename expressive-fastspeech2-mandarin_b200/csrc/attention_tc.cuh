@@ -71,13 +71,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* kv_s = smem + Q_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   uint64_t* q_full = bars;            // [1]
-  uint64_t* kv_full = bars + 1;       // [2]
-  uint64_t* kv_empty = bars + 3;      // [2]
-  uint64_t* s_full = bars + 5;        // [2]
-  uint64_t* p_full = bars + 7;        // [2]
-  uint64_t* o_full = bars + 9;        // [2]
-  uint64_t* o_free = bars + 11;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* k_full = bars + 1;        // [2]
+  uint64_t* k_empty = bars + 3;       // [2]  K_j is free as soon as Q K_j^T has been read
+  uint64_t* v_full = bars + 5;        // [2]
+  uint64_t* v_empty = bars + 7;       // [2]  V_j is free after P_j V_j
+  uint64_t* s_full = bars + 9;        // [2]
+  uint64_t* p_full = bars + 11;       // [2]
+  uint64_t* o_full = bars + 13;       // [2]
+  uint64_t* o_free = bars + 15;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -86,8 +88,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
     mbar_init(q_full, 1);
     for (int u = 0; u < 2; ++u) {
-      mbar_init(&kv_full[u], 1);
-      mbar_init(&kv_empty[u], 1);
+      mbar_init(&k_full[u], 1);
+      mbar_init(&k_empty[u], 1);
+      mbar_init(&v_full[u], 1);
+      mbar_init(&v_empty[u], 1);
       mbar_init(&s_full[u], 1);
       mbar_init(&p_full[u], 128);
       mbar_init(&o_full[u], 1);
@@ -116,15 +120,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int dc = 0; dc < 4; ++dc) tma_load_2d(q_s + dc * (BQ * 128), &tmQ, h * D_HEAD + dc * 32, row0 + q0, q_full);
       for (int j = 0; j < n_tiles; ++j) {
         const int u = j & 1;
-        mbar_wait(&kv_empty[u], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[u], KV_STAGE_BYTES);
+        const uint32_t par = ((j >> 1) & 1) ^ 1;
         uint8_t* k_s = kv_s + u * KV_STAGE_BYTES;
         uint8_t* v_s = k_s + K_BYTES;
+        mbar_wait(&k_empty[u], par);
+        mbar_expect_tx(&k_full[u], K_BYTES);
 #pragma unroll
-        for (int dc = 0; dc < 4; ++dc) {
-          tma_load_2d(k_s + dc * (BKV * 128), &tmKV, D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &kv_full[u]);
-          tma_load_2d(v_s + dc * (BKV * 128), &tmV, 2 * D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &kv_full[u]);
-        }
+        for (int dc = 0; dc < 4; ++dc)
+          tma_load_2d(k_s + dc * (BKV * 128), &tmKV, D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &k_full[u]);
+        mbar_wait(&v_empty[u], par);
+        mbar_expect_tx(&v_full[u], K_BYTES);
+#pragma unroll
+        for (int dc = 0; dc < 4; ++dc)
+          tma_load_2d(v_s + dc * (BKV * 128), &tmV, 2 * D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &v_full[u]);
       }
     }
   } else if (warp == 1) {
@@ -134,7 +142,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       constexpr uint32_t idesc_pv = idesc_tf32(BQ, D_HEAD, 1);
       auto issue_qk = [&](int j) {
         const int u = j & 1;
-        mbar_wait(&kv_full[u], (j >> 1) & 1);
+        mbar_wait(&k_full[u], (j >> 1) & 1);
         tc_fence_after();
         const uint8_t* k_s = kv_s + u * KV_STAGE_BYTES;
 #pragma unroll
@@ -144,6 +152,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int kk = 0; kk < 4; ++kk) umma_tf32(tmem_s + u * BKV, da + 2 * kk, db + 2 * kk, idesc_qk, (dc | kk) != 0);
         }
         umma_commit(&s_full[u]);
+        umma_commit(&k_empty[u]);
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
@@ -153,6 +162,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (j + 1 < n_tiles) issue_qk(j + 1);
         mbar_wait(&p_full[u], par);
         mbar_wait(&o_free[u], par ^ 1);
+        mbar_wait(&v_full[u], par);
         tc_fence_after();
         const uint8_t* v_s = kv_s + u * KV_STAGE_BYTES + K_BYTES;
         const uint64_t dv = umma_desc_mn(v_s, BKV * 128, 512);
@@ -170,7 +180,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           umma_tf32_ts(tmem_o + u * D_HEAD, tmem_s + u * BKV + k8 * 8, dv + (uint64_t)(k8 * (1024 >> 4)), idesc_pv, k8 != 0);
         }
         umma_commit(&o_full[u]);
-        umma_commit(&kv_empty[u]);
+        umma_commit(&v_empty[u]);
       }
     }
   } else {

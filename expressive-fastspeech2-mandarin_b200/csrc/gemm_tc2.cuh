@@ -297,8 +297,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           stage_out(v, c0, width);
         }
       } else {
-        // ---- LayerNorm over the 256-wide row held in TMEM (eps 1e-5, biased variance, two-pass)
-        float sum = 0.f;
+        // ---- LayerNorm over the 256-wide row held in TMEM (eps 1e-5, biased variance).  Statistics are
+        // exact two-pass inside each 32-column chunk (in registers) and merged across chunks with
+        // Chan's update, so the accumulator is read only twice.
+        float mean = 0.f, var = 0.f;   // var holds M2 = sum (v - mean)^2 until the merge is complete
 #pragma unroll 1
         for (int c = 0; c < C::NCHUNK; ++c) {
           float v[32];
@@ -309,23 +311,23 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
           finish(v, c * 32, 32);
           if (has_res) ++g_res;
+          float cs = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum += v[j];
+          for (int j = 0; j < 32; ++j) cs += v[j];
+          const float cm = cs * (1.f / 32.f);
+          float cm2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = v[j] - cm;
+            cm2 = fmaf(d, d, cm2);
+          }
+          const float delta = cm - mean;
+          const float n_old = 32.f * c, n_new = 32.f * (c + 1);
+          mean = fmaf(delta, 32.f / n_new, mean);
+          var += cm2 + delta * delta * (n_old * 32.f / n_new);
           tmem_st32(acc + c * 32, v);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-        const float mean = sum * (1.f / 256.f);
-        float var = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < C::NCHUNK; ++c) {
-          float v[32];
-          tmem_ld32(acc + c * 32, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = v[j] - mean;
-            var = fmaf(d, d, var);
-          }
-        }
         const float rstd = 1.f / sqrtf(var * (1.f / 256.f) + 1e-5f);
         float dot = 0.f;
 #pragma unroll 1
