@@ -46,6 +46,24 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
 
 
+def hbm_kernels(prof, runs, frames, phonemes, batch, t_max, peak_gbs):
+    """Achieved GB/s of the memory-bound kernels from their algorithmic bytes."""
+    algo = {
+        # LengthRegulator + PE add: read one 1 KB phoneme row per frame (L2-served repeats counted once:
+        # 1024*P), the PE row (L2) and write 1024*F
+        "length_regulator": 1024 * phonemes + 4 * phonemes + 1024 * frames,
+        # unpack: read 2 x 320 B per valid frame, write 2 x 320 B per padded frame + 1 B mask
+        "unpack": 2 * 320 * frames + (2 * 320 + 1) * batch * t_max,
+    }
+    out = {}
+    for k, nbytes in algo.items():
+        if k in prof and prof[k][1] > 0:
+            ms = prof[k][1] / prof[k][0]
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            out[k] = {"bytes": nbytes, "ms": ms, "achieved_gbs": gbs, "frac_of_measured_hbm": gbs / peak_gbs}
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -245,6 +263,19 @@ def main():
             a[1] += float(ms)
     lib.fs2_profile_enable(model._ctx, 0)
 
+    # p50 single-utterance latency (BASELINE config 1), device-resident inputs, host sync included
+    c1 = syn.config1_batch()
+    c1_args = [c1[k].to(dev) for k in names]
+    lat = []
+    for i in range(230):
+        t0 = time.perf_counter()
+        o1 = model(*c1_args, c1["max_src_len"])
+        torch.cuda.synchronize()
+        if i >= 30:
+            lat.append((time.perf_counter() - t0) * 1e3)
+    c1_frames = int(o1[9].sum())
+    c1_launches = model.last_launch_count
+
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms, float(sum(e2e_ms)), float(frames)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -287,6 +318,11 @@ def main():
                          "peak_source": f"{peaks['source']} bf16_tflops_sustained" +
                                         (" / 2 (TF32 runs at half the bf16 tensor rate)" if args.math == "tf32" else "")},
             "kernel_ms_per_step": kernel_ms,
+            "latency": {"workload": "config1: single utterance, 16 phonemes, controls 1.0", "p50_ms": float(np.percentile(lat, 50)),
+                        "p90_ms": float(np.percentile(lat, 90)), "frames": c1_frames, "gpu_launches": c1_launches,
+                        "calls": len(lat)},
+            "hbm_kernels": hbm_kernels(prof, PROF_RUNS, frames, int(batch["src_lens"].sum()), args.batch,
+                                       int(out[0].shape[1]), peaks["hbm_gbs"]),
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = torch.get_num_threads()

@@ -8,6 +8,8 @@
 // Q/K/V are read straight out of the packed [rows,768] QKV buffer by TMA (TFLOAT32 tensor map:
 // rounded to TF32 on load); keys beyond the utterance are masked by length, never by a mask tensor.
 // S/P and O_j are double-buffered in TMEM so that Q K_{j+1}^T overlaps the softmax of tile j.
+// Q itself is moved into TMEM once (A operand of Q K^T from tensor memory), which frees its
+// 64 KB of shared memory for a third K and V stage: loads run three tiles ahead of the MMAs.
 #pragma once
 
 #include "common.cuh"
@@ -21,10 +23,10 @@ using namespace tc;
 constexpr int BQ = 128, BKV = 64, THREADS = 192;
 constexpr int Q_BYTES = BQ * D_HEAD * 4;          // 64 KB: 4 sub-tiles [128 rows x 128 B]
 constexpr int K_BYTES = BKV * D_HEAD * 4;         // 32 KB: 4 sub-tiles [64 rows x 128 B]
-constexpr int KV_STAGE_BYTES = 2 * K_BYTES;
-constexpr int BAR_OFF = Q_BYTES + 2 * KV_STAGE_BYTES;
+constexpr int KV_STAGES = 3;
+constexpr int BAR_OFF = Q_BYTES + 4 * K_BYTES;    // [Q | K2 V2] [K0 K1] [V0 V1]
 constexpr int SMEM_TOTAL = BAR_OFF + 256 + 1024;
-constexpr int TMEM_COLS = 512;                    // S0,S1: 2 x 64 | O0,O1: 2 x 128
+constexpr int TMEM_COLS = 512;                    // S0,S1: 2 x 64 | O0,O1: 2 x 128 | Q: 128
 constexpr int LDQKV = 3 * D_MODEL;
 
 __host__ __device__ constexpr uint32_t idesc_tf32(int m, int n, int b_mn_major) {
@@ -68,30 +70,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_s = smem;
-  uint8_t* kv_s = smem + Q_BYTES;
+  // stage 2 of both rings reuses the Q region once Q lives in TMEM
+  auto k_stage = [&](int s) -> uint8_t* { return s < 2 ? smem + Q_BYTES + s * K_BYTES : smem; };
+  auto v_stage = [&](int s) -> uint8_t* { return s < 2 ? smem + Q_BYTES + 2 * K_BYTES + s * K_BYTES : smem + K_BYTES; };
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   uint64_t* q_full = bars;            // [1]
-  uint64_t* k_full = bars + 1;        // [2]
-  uint64_t* k_empty = bars + 3;       // [2]  K_j is free as soon as Q K_j^T has been read
-  uint64_t* v_full = bars + 5;        // [2]
-  uint64_t* v_empty = bars + 7;       // [2]  V_j is free after P_j V_j
-  uint64_t* s_full = bars + 9;        // [2]
-  uint64_t* p_full = bars + 11;       // [2]
-  uint64_t* o_full = bars + 13;       // [2]
-  uint64_t* o_free = bars + 15;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* q_moved = bars + 1;       // [1]  Q copied to TMEM: its smem may be overwritten
+  uint64_t* k_full = bars + 2;        // [3]
+  uint64_t* k_empty = bars + 5;       // [3]  K_j is free as soon as Q K_j^T has been read
+  uint64_t* v_full = bars + 8;        // [3]
+  uint64_t* v_empty = bars + 11;      // [3]  V_j is free after P_j V_j
+  uint64_t* s_full = bars + 14;       // [2]
+  uint64_t* p_full = bars + 16;       // [2]
+  uint64_t* o_full = bars + 18;       // [2]
+  uint64_t* o_free = bars + 20;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index(), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmKV)) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
     mbar_init(q_full, 1);
-    for (int u = 0; u < 2; ++u) {
+    mbar_init(q_moved, 128);
+    for (int u = 0; u < KV_STAGES; ++u) {
       mbar_init(&k_full[u], 1);
       mbar_init(&k_empty[u], 1);
       mbar_init(&v_full[u], 1);
       mbar_init(&v_empty[u], 1);
+    }
+    for (int u = 0; u < 2; ++u) {
       mbar_init(&s_full[u], 1);
       mbar_init(&p_full[u], 128);
       mbar_init(&o_full[u], 1);
@@ -111,77 +119,98 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;          // + u*64
   const uint32_t tmem_o = tmem_base + 128;    // + u*128
+  const uint32_t tmem_q = tmem_base + 384;    // 128 columns
+  const bool trace = dbg == 4 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const long long t_start = clock64();
+  float* tr = out + (size_t)row0 * D_MODEL;
+#define FS2_TRACE(tile, k) do { if (trace && (threadIdx.x & 31) == 0) tr[(tile) * 16 + (k)] = (float)(clock64() - t_start); } while (0)
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---- TMA producer: Q once, then (K_j, V_j) into the 2-stage ring
+    // ---- TMA producer (whole warp, one elected lane issues): Q once, then K_j / V_j into 3-stage rings
+    const bool leader = elect_one();
+    if (leader) {
       mbar_expect_tx(q_full, Q_BYTES);
 #pragma unroll
       for (int dc = 0; dc < 4; ++dc) tma_load_2d(q_s + dc * (BQ * 128), &tmQ, h * D_HEAD + dc * 32, row0 + q0, q_full);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int u = j & 1;
-        const uint32_t par = ((j >> 1) & 1) ^ 1;
-        uint8_t* k_s = kv_s + u * KV_STAGE_BYTES;
-        uint8_t* v_s = k_s + K_BYTES;
-        mbar_wait(&k_empty[u], par);
-        mbar_expect_tx(&k_full[u], K_BYTES);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int sk = j % KV_STAGES;
+      const uint32_t par = ((j / KV_STAGES) & 1) ^ 1;
+      if (j == 2) mbar_wait(q_moved, 0);      // stage 2 lives where Q was staged
+      uint8_t* k_s = k_stage(sk);
+      uint8_t* v_s = v_stage(sk);
+      mbar_wait(&k_empty[sk], par);
+      if (leader) {
+        mbar_expect_tx(&k_full[sk], K_BYTES);
 #pragma unroll
         for (int dc = 0; dc < 4; ++dc)
-          tma_load_2d(k_s + dc * (BKV * 128), &tmKV, D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &k_full[u]);
-        mbar_wait(&v_empty[u], par);
-        mbar_expect_tx(&v_full[u], K_BYTES);
-#pragma unroll
-        for (int dc = 0; dc < 4; ++dc)
-          tma_load_2d(v_s + dc * (BKV * 128), &tmV, 2 * D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &v_full[u]);
+          tma_load_2d(k_s + dc * (BKV * 128), &tmKV, D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &k_full[sk]);
       }
+      __syncwarp();
+      mbar_wait(&v_empty[sk], par);
+      if (leader) {
+        mbar_expect_tx(&v_full[sk], K_BYTES);
+#pragma unroll
+        for (int dc = 0; dc < 4; ++dc)
+          tma_load_2d(v_s + dc * (BKV * 128), &tmV, 2 * D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &v_full[sk]);
+      }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---- MMA issuer
-      constexpr uint32_t idesc_qk = idesc_tf32(BQ, BKV, 0);
-      constexpr uint32_t idesc_pv = idesc_tf32(BQ, D_HEAD, 1);
-      auto issue_qk = [&](int j) {
-        const int u = j & 1;
-        mbar_wait(&k_full[u], (j >> 1) & 1);
-        tc_fence_after();
-        const uint8_t* k_s = kv_s + u * KV_STAGE_BYTES;
+    // ---- MMA issuer (whole warp runs the loop, one elected lane issues)
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_qk = idesc_tf32(BQ, BKV, 0);
+    constexpr uint32_t idesc_pv = idesc_tf32(BQ, D_HEAD, 1);
+    auto issue_qk = [&](int j) {
+      const int u = j & 1, sk = j % KV_STAGES;
+      FS2_TRACE(j, 8);
+      mbar_wait(&k_full[sk], (j / KV_STAGES) & 1);
+      FS2_TRACE(j, 9);
+      tc_fence_after();
+      const uint8_t* k_s = k_stage(sk);
+      if (leader) {
 #pragma unroll
         for (int dc = 0; dc < 4; ++dc) {
-          const uint64_t da = umma_desc(q_s + dc * (BQ * 128)), db = umma_desc(k_s + dc * (BKV * 128));
+          const uint64_t db = umma_desc(k_s + dc * (BKV * 128));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_tf32(tmem_s + u * BKV, da + 2 * kk, db + 2 * kk, idesc_qk, (dc | kk) != 0);
+          for (int kk = 0; kk < 4; ++kk)
+            umma_tf32_ts(tmem_s + u * BKV, tmem_q + dc * 32 + kk * 8, db + 2 * kk, idesc_qk, (dc | kk) != 0);
         }
+        FS2_TRACE(j, 10);
         umma_commit(&s_full[u]);
-        umma_commit(&k_empty[u]);
-      };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int u = j & 1;
-        const uint32_t par = (j >> 1) & 1;
-        if (j + 1 < n_tiles) issue_qk(j + 1);
-        mbar_wait(&p_full[u], par);
-        mbar_wait(&o_free[u], par ^ 1);
-        mbar_wait(&v_full[u], par);
-        tc_fence_after();
-        const uint8_t* v_s = kv_s + u * KV_STAGE_BYTES + K_BYTES;
-        const uint64_t dv = umma_desc_mn(v_s, BKV * 128, 512);
-        if (dbg == 2) {        // A = Q[:, 0:64] from smem (K-major), B = V MN-major
-          for (int k8 = 0; k8 < BKV / 8; ++k8)
-            umma_tf32(tmem_o + u * D_HEAD, umma_desc(q_s + (k8 >> 2) * (BQ * 128)) + 2 * (k8 & 3),
-                      dv + (uint64_t)(k8 * (1024 >> 4)), idesc_pv, k8 != 0);
-        } else if (dbg == 3) { // A = P[:, 0:32] from TMEM, B = K sub-tile 0 (K-major, N = 64 keys, K = 32)
-          const uint8_t* k_s = kv_s + u * KV_STAGE_BYTES;
-          for (int k8 = 0; k8 < 4; ++k8)
-            umma_tf32_ts(tmem_o + u * D_HEAD, tmem_s + u * BKV + k8 * 8, umma_desc(k_s) + 2 * k8, idesc_qk, k8 != 0);
-        } else {
+        umma_commit(&k_empty[sk]);
+        FS2_TRACE(j, 11);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_moved, 0);
+    tc_fence_after();
+    issue_qk(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int u = j & 1;
+      const uint32_t par = (j >> 1) & 1;
+      if (j + 1 < n_tiles) issue_qk(j + 1);
+      const int sk = j % KV_STAGES;
+      FS2_TRACE(j, 4);
+      mbar_wait(&p_full[u], par);
+      FS2_TRACE(j, 5);
+      mbar_wait(&o_free[u], par ^ 1);
+      mbar_wait(&v_full[sk], (j / KV_STAGES) & 1);
+      FS2_TRACE(j, 6);
+      tc_fence_after();
+      const uint8_t* v_s = v_stage(sk);
+      const uint64_t dv = umma_desc_mn(v_s, BKV * 128, 512);
+      if (leader) {
 #pragma unroll
         for (int k8 = 0; k8 < BKV / 8; ++k8)
           umma_tf32_ts(tmem_o + u * D_HEAD, tmem_s + u * BKV + k8 * 8, dv + (uint64_t)(k8 * (1024 >> 4)), idesc_pv, k8 != 0);
-        }
+        FS2_TRACE(j, 12);
         umma_commit(&o_full[u]);
-        umma_commit(&v_empty[u]);
+        umma_commit(&v_empty[sk]);
+        FS2_TRACE(j, 13);
       }
+      __syncwarp();
     }
   } else {
     // ---- softmax + accumulation: thread = query row
@@ -189,6 +218,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int qrow = q0 + q * 32 + lane;                       // row inside the utterance
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const float c = 1.4426950408889634f / sqrtf((float)D_HEAD);  // log2(e) / temperature
+    {
+      // Q (TF32-rounded by TMA) from swizzled smem to TMEM: thread = query row = TMEM lane
+      mbar_wait(q_full, 0);
+      const int r = q * 32 + lane;
+      const uint32_t qa = smem_u32(q_s) + r * 128;
+      const uint32_t sx = (uint32_t)(r & 7) << 4;
+#pragma unroll 1
+      for (int dc = 0; dc < 4; ++dc) {
+        float v[32];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          float4 t4;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                       : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w)
+                       : "r"(qa + dc * (BQ * 128) + ((cc << 4) ^ sx)));
+          v[cc * 4] = t4.x; v[cc * 4 + 1] = t4.y; v[cc * 4 + 2] = t4.z; v[cc * 4 + 3] = t4.w;
+        }
+        tmem_st32(tmem_q + lane_sel + dc * 32, v);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads before the TMA overwrites
+      tc_fence_before();
+      mbar_arrive(q_moved);
+    }
     float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
     float o[D_HEAD];
 #pragma unroll
@@ -199,51 +252,80 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(&o_full[u], (j >> 1) & 1);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < D_HEAD; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_o + lane_sel + u * D_HEAD + c0, v);
+      for (int c0 = 0; c0 < D_HEAD; c0 += 64) {
+        float v0[32], v1[32];
+        tmem_ld32_issue(tmem_o + lane_sel + u * D_HEAD + c0, v0);
+        tmem_ld32_issue(tmem_o + lane_sel + u * D_HEAD + c0 + 32, v1);
+        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c0 + i] = fmaf(o[c0 + i], alpha, v[i]);
+        for (int i = 0; i < 32; ++i) {
+          o[c0 + i] = fmaf(o[c0 + i], alpha, v0[i]);
+          o[c0 + 32 + i] = fmaf(o[c0 + 32 + i], alpha, v1[i]);
+        }
       }
       tc_fence_before();
       mbar_arrive(&o_free[u]);
     };
 
+    // m is the running row maximum of the RAW scores; exp2 arguments are s*c - m*c (one FFMA each)
     for (int j = 0; j < n_tiles; ++j) {
       const int u = j & 1;
+      FS2_TRACE(j, 0);
       mbar_wait(&s_full[u], (j >> 1) & 1);
+      FS2_TRACE(j, 1);
       tc_fence_after();
       float s0[32], s1[32];
-      tmem_ld32(tmem_s + lane_sel + u * BKV, s0);
-      tmem_ld32(tmem_s + lane_sel + u * BKV + 32, s1);
+      tmem_ld32_issue(tmem_s + lane_sel + u * BKV, s0);
+      tmem_ld32_issue(tmem_s + lane_sel + u * BKV + 32, s1);
+      tmem_ld_wait();
       const int key0 = j * BKV;
-      float mx = m;
+      if (key0 + BKV > len) {   // only the last tile has keys beyond the utterance
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        s0[i] = (key0 + i < len) ? s0[i] * c : -INFINITY;
-        s1[i] = (key0 + 32 + i < len) ? s1[i] * c : -INFINITY;
-        mx = fmaxf(mx, fmaxf(s0[i], s1[i]));
+        for (int i = 0; i < 32; ++i) {
+          if (key0 + i >= len) s0[i] = -INFINITY;
+          if (key0 + 32 + i >= len) s1[i] = -INFINITY;
+        }
       }
-      const float alpha = exp2f(m - mx);   // 0 on the first tile (m = -inf, mx finite: key0 < len)
-      m = mx;
-      float sum = 0.f;
+      float mx[4] = {m, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        s0[i] = tf32_rna(exp2f(s0[i] - m));
-        s1[i] = tf32_rna(exp2f(s1[i] - m));
-        sum += s0[i] + s1[i];
+      for (int i = 0; i < 32; i += 2) {
+        mx[0] = fmaxf(mx[0], s0[i]);
+        mx[1] = fmaxf(mx[1], s0[i + 1]);
+        mx[2] = fmaxf(mx[2], s1[i]);
+        mx[3] = fmaxf(mx[3], s1[i + 1]);
       }
-      l = fmaf(l, alpha, sum);
+      const float m_new = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));   // finite: key0 < len
+      const float alpha = ex2_approx((m - m_new) * c);                        // 0 on the first tile (m = -inf)
+      m = m_new;
+      const float mc = m_new * c;
+      float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        s0[i] = tf32_rna(ex2_approx(fmaf(s0[i], c, -mc)));
+        s0[i + 1] = tf32_rna(ex2_approx(fmaf(s0[i + 1], c, -mc)));
+        s1[i] = tf32_rna(ex2_approx(fmaf(s1[i], c, -mc)));
+        s1[i + 1] = tf32_rna(ex2_approx(fmaf(s1[i + 1], c, -mc)));
+        sum[0] += s0[i];
+        sum[1] += s0[i + 1];
+        sum[2] += s1[i];
+        sum[3] += s1[i + 1];
+      }
+      l = fmaf(l, alpha, (sum[0] + sum[1]) + (sum[2] + sum[3]));
       tmem_st32(tmem_s + lane_sel + u * BKV, s0);
       tmem_st32(tmem_s + lane_sel + u * BKV + 32, s1);
       asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
       tc_fence_before();
       mbar_arrive(&p_full[u]);
+      FS2_TRACE(j, 2);
       if (j >= 1) accumulate(j - 1, alpha_prev);
+      FS2_TRACE(j, 3);
       alpha_prev = alpha;
     }
     accumulate(n_tiles - 1, alpha_prev);
 
+    if (dbg == 4) {
+      // timestamps only
+    } else
     if (dbg != 0 && qrow < len) {   // raw dumps for bring-up
       float* dst = out + (size_t)(row0 + qrow) * D_MODEL + h * D_HEAD;
       if (dbg == 1) {               // P of tile 0 read back from TMEM (64 values), then l

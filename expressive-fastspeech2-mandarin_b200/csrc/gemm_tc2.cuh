@@ -96,7 +96,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* res_full = acc_empty + 2;       // [4 warps][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index(), lane = threadIdx.x & 31;
   const int kchunks = (p.K + BK - 1) / BK;
   const int iters = p.taps * kchunks;
   const int n_tiles_n = (p.N + BN - 1) / BN;
@@ -135,44 +135,49 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer
-      int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m0 = (t / n_tiles_n) * BM, n0 = (t % n_tiles_n) * BN;
-        for (int i = 0; i < iters; ++i, ++it) {
-          const int s = it % C::STAGES;
-          mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
+    // ---------------- TMA producer (whole warp runs the loop, one elected lane issues)
+    const bool leader = elect_one();
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m0 = (t / n_tiles_n) * BM, n0 = (t % n_tiles_n) * BN;
+      for (int i = 0; i < iters; ++i, ++it) {
+        const int s = it % C::STAGES;
+        mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
+        const int tap = i / kchunks, kc = i - tap * kchunks;
+        uint8_t* a_s = smem + s * C::STAGE_BYTES;
+        if (leader) {
           mbar_expect_tx(&full[s], C::STAGE_BYTES);
-          const int tap = i / kchunks, kc = i - tap * kchunks;
-          uint8_t* a_s = smem + s * C::STAGE_BYTES;
           tma_load_2d(a_s, &tmA, kc * BK, m0 + tap - p.pad, &full[s]);
           tma_load_2d(a_s + C::A_BYTES, &tmW, kc * BK, tap * p.N + n0, &full[s]);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer
-      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
-      int it = 0, lt = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-        const int u = lt & 1;
-        mbar_wait(&acc_empty[u], ((lt >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+    // ---------------- MMA issuer (whole warp runs the loop, one elected lane issues)
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+    int it = 0, lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      const int u = lt & 1;
+      mbar_wait(&acc_empty[u], ((lt >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + u * C::ACC_COLS;
+      for (int i = 0; i < iters; ++i, ++it) {
+        const int s = it % C::STAGES;
+        mbar_wait(&full[s], (it / C::STAGES) & 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + u * C::ACC_COLS;
-        for (int i = 0; i < iters; ++i, ++it) {
-          const int s = it % C::STAGES;
-          mbar_wait(&full[s], (it / C::STAGES) & 1);
-          tc_fence_after();
-          const uint8_t* a_s = smem + s * C::STAGE_BYTES;
-          const uint64_t da = umma_desc(a_s), db = umma_desc(a_s + C::A_BYTES);
+        const uint8_t* a_s = smem + s * C::STAGE_BYTES;
+        const uint64_t da = umma_desc(a_s), db = umma_desc(a_s + C::A_BYTES);
+        if (leader) {
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) umma_tf32(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
           umma_commit(&empty[s]);
         }
-        umma_commit(&acc_full[u]);
+        __syncwarp();
       }
+      if (leader) umma_commit(&acc_full[u]);
+      __syncwarp();
     }
   } else {
     // ---------------- epilogue (4 independent warps; thread = one accumulator row)

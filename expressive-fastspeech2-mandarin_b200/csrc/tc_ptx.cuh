@@ -11,6 +11,20 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// One lane of a fully converged warp (elect.sync): issuing TMA / tcgen05 instructions under this
+// predicate from warp-uniform code keeps their operands in uniform registers (no per-lane
+// "waterfall" loop around every UTMALDG / UTCHMMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -91,6 +105,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// Asynchronous variant: issue now, call tmem_ld_wait() before the first use of v.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
+        "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
+        "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[32]) {
   uint32_t r[16];
   asm volatile(
@@ -149,23 +182,42 @@ inline EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D fp32 tensor [rows, cols] with row pitch ld (elements); box = [box_rows, 32 columns]
-inline CUtensorMap make_map(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool round_tf32,
-                            bool reused, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+// 2-D fp32 tensor [rows, cols] with row pitch ld (elements); box = [box_rows, 32 columns].
+// Encoding a descriptor costs a few microseconds of host time and the same handful of buffers
+// is described over and over, so descriptors are cached per thread by their full key.
+struct MapKey {
+  const void* base;
+  int64_t rows, cols, ld;
+  int box_rows, flags;
+  bool operator<(const MapKey& o) const {
+    if (base != o.base) return base < o.base;
+    if (rows != o.rows) return rows < o.rows;
+    if (cols != o.cols) return cols < o.cols;
+    if (ld != o.ld) return ld < o.ld;
+    if (box_rows != o.box_rows) return box_rows < o.box_rows;
+    return flags < o.flags;
+  }
+};
+
+inline const CUtensorMap& make_map(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool round_tf32,
+                                   bool reused, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  static thread_local std::map<MapKey, CUtensorMap> cache;
+  const MapKey key{base, rows, cols, ld, box_rows, (round_tf32 ? 1 : 0) | (reused ? 2 : 0) | ((int)swizzle << 2)};
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  if (cache.size() > 4096) cache.clear();
   CUtensorMap m;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};  // 32 fp32 = one 128-byte swizzle row
   cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode_fn()(&m, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                                 const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 swizzle,
+                                 const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                                  reused ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   require(r == CUDA_SUCCESS, FS2_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
-  return m;
+  return cache.emplace(key, m).first->second;
 }
-
 
 }  // namespace tc
 }  // namespace fs2
