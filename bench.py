@@ -249,8 +249,8 @@ def main():
     # per-kernel-class CUDA-event timing (same workload, same process, after the timed region)
     lib = _lib.load_library()
     lib.fs2_profile_enable(model._ctx, 1)
-    prof = {}
-    PROF_RUNS = 3
+    runs = {}
+    PROF_RUNS = 7
     for _ in range(PROF_RUNS):
         flush.zero_()
         model(*dev_args, L)
@@ -258,10 +258,11 @@ def main():
         lib.fs2_profile_read(model._ctx, buf, 8192)
         for line in buf.value.decode().splitlines():
             label, n, ms = line.split()
-            a = prof.setdefault(label, [0, 0.0])
-            a[0] += int(n)
-            a[1] += float(ms)
+            runs.setdefault(label, []).append((int(n), float(ms)))
     lib.fs2_profile_enable(model._ctx, 0)
+    # per label: launches per forward and the MEDIAN over the runs of the summed duration, scaled back to
+    # PROF_RUNS forwards so that the consumers below keep dividing by PROF_RUNS (robust to one slow run)
+    prof = {k: [v[0][0] * PROF_RUNS, float(np.median([x[1] for x in v])) * PROF_RUNS] for k, v in runs.items()}
 
     # p50 single-utterance latency (BASELINE config 1), device-resident inputs, host sync included
     c1 = syn.config1_batch()
