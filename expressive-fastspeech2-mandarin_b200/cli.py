@@ -1,0 +1,188 @@
+"""Command-line front end with the flags of the reference's synthesize_chinese_pinyin.py
+(:156-308): single-sentence or batch synthesis of mel spectrograms on the B200 engine.
+
+    python -m fs2_b200.cli --restore_step 900000 --mode single --text "今天天气真好" \\
+        --speaker_id 0001 --emotion Happy -p preprocess.yaml -m model.yaml -t train.yaml
+
+What differs from the reference script, by design: the acoustic model is `FastSpeech2B200`; the
+HiFi-GAN vocoder is outside the accelerated path (its weights are not shipped with the reference
+either), so the result is the postnet mel saved as `<result_path>/<id>.npy` (+ `<id>.json` with
+durations / pitch / energy) instead of a wav and a plot.  `--random_init` replaces the checkpoint
+by the seeded synthetic weights so that the CLI runs without trained weights.
+"""
+import argparse
+import json
+import os
+
+import numpy as np
+import torch
+import yaml
+
+# ---- symbol table of text/symbols_pinyin.py:3-26 (ids are positions; later duplicates win) ----
+_PAD, _SPECIAL, _PUNCT = "_", "-", "!'(),.:;? "
+_LETTERS = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz"
+PHONEMES = ("a ai ao b c ch d e ei er f g h i ia iao ie iu j k l m n ng o ou p q r s sh spn t u ua uai ue ui uo "
+            "w x y z zh").split()
+SYMBOLS = [_PAD] + list(_SPECIAL) + list(_PUNCT) + list(_LETTERS) + PHONEMES
+SYMBOL_TO_ID = {s: i for i, s in enumerate(SYMBOLS)}
+
+# emotion -> (arousal, valence) keys (synthesize_chinese_pinyin.py:281-287)
+EMOTION_AV = {"Angry": ("0.9", "0.1"), "Happy": ("0.8", "0.8"), "Neutral": ("0.5", "0.5"), "Sad": ("0.3", "0.2"),
+              "Surprise": ("0.8", "0.6")}
+
+# syllable -> phonemes (synthesize_chinese_pinyin.py:35-96): longest initial first, finals table,
+# unknown finals fall back to per-character lookup
+_INITIALS = ["zh", "ch", "sh", "b", "p", "m", "f", "d", "t", "n", "l", "g", "k", "h", "j", "q", "x", "r", "z", "c", "s",
+             "y", "w"]
+_FINALS = {"a": "a", "o": "o", "e": "e", "i": "i", "u": "u", "v": "y", "ai": "ai", "ei": "ei", "ui": "ui", "ao": "ao",
+           "ou": "ou", "iu": "iu", "ie": "ie", "ue": "ue", "ve": "ue", "an": "a n", "en": "e n", "in": "i n", "un": "u n",
+           "vn": "y n", "ang": "a ng", "eng": "e ng", "ing": "i ng", "ong": "o ng", "er": "er", "iao": "iao",
+           "ian": "ia n", "iang": "ia ng", "iong": "io ng", "uai": "uai", "uan": "ua n", "uang": "ua ng"}
+# enough hanzi for the repository's own demo sentences when pypinyin is not installed
+_DEMO_PINYIN = {"今": "jin", "天": "tian", "气": "qi", "真": "zhen", "好": "hao", "你": "ni", "世": "shi", "界": "jie"}
+
+
+def syllable_to_phonemes(syllable):
+    initial = next((i for i in _INITIALS if syllable.startswith(i)), "")
+    final = syllable[len(initial):]
+    out = [initial] if initial else []
+    if final in _FINALS:
+        out += _FINALS[final].split()
+    else:
+        for ch in final:
+            out += _FINALS[ch].split() if ch in _FINALS else [ch]
+    return out
+
+
+def text_to_phonemes(text):
+    """'{a b c}' is a literal phoneme list (:110-112); anything else is Chinese text (:24-104)."""
+    if text.startswith("{") and text.endswith("}"):
+        return text[1:-1].split()
+    try:
+        from pypinyin import Style, lazy_pinyin
+        syllables = lazy_pinyin(text, style=Style.NORMAL)
+    except ImportError:
+        missing = [ch for ch in text if ch not in _DEMO_PINYIN]
+        if missing:
+            raise SystemExit("pypinyin is not installed; pass phonemes as '{j i n ...}' or install pypinyin")
+        syllables = [_DEMO_PINYIN[ch] for ch in text]
+    phonemes = []
+    for s in syllables:
+        phonemes += syllable_to_phonemes(s)
+    return phonemes
+
+
+def phonemes_to_ids(phonemes):
+    """Unknown phonemes map to the padding id 0, as in the reference (:120-124)."""
+    return np.array([SYMBOL_TO_ID.get(p, SYMBOL_TO_ID[_PAD]) for p in phonemes], dtype=np.int64)
+
+
+def single_batch(args, preprocess_config):
+    """The 9-tuple of synthesize_chinese_pinyin.py:262-300."""
+    root = preprocess_config["path"]["preprocessed_path"]
+    with open(os.path.join(root, "speakers.json")) as f:
+        speaker_map = json.load(f)
+    with open(os.path.join(root, "emotions.json")) as f:
+        emo = json.load(f)
+    arousal, valence = EMOTION_AV[args.emotion]
+    ids = phonemes_to_ids(text_to_phonemes(args.text))
+    name = args.output_name or f"synthesis_{args.speaker_id}_{args.emotion}"
+    return ([name], [args.text], np.array([speaker_map[args.speaker_id]]), np.array([emo["emotion_dict"][args.emotion]]),
+            np.array([emo["arousal_dict"][arousal]]), np.array([emo["valence_dict"][valence]]), np.array([ids]),
+            np.array([len(ids)]), int(len(ids)))
+
+
+def source_batches(path, preprocess_config, batch_size=8):
+    """Batch mode: lines `basename|speaker|{p1 p2 ...}|raw_text|...|emotion|arousal|valence`
+    (dataset_chinese.py:246-262,221-232); texts zero-padded per batch (:264-276)."""
+    root = preprocess_config["path"]["preprocessed_path"]
+    with open(os.path.join(root, "speakers.json")) as f:
+        speaker_map = json.load(f)
+    with open(os.path.join(root, "emotions.json")) as f:
+        emo = json.load(f)
+    rows = []
+    with open(path, encoding="utf-8") as f:
+        for line in f:
+            parts = line.strip("\n").split("|")
+            if len(parts) < 4:
+                continue
+            emotion, arousal, valence = parts[-3], parts[-2], parts[-1]
+            rows.append((parts[0], parts[3], speaker_map[parts[1]], emo["emotion_dict"][emotion],
+                         emo["arousal_dict"][arousal], emo["valence_dict"][valence],
+                         phonemes_to_ids(text_to_phonemes(parts[2]))))
+    for i in range(0, len(rows), batch_size):
+        chunk = rows[i:i + batch_size]
+        lens = np.array([len(r[6]) for r in chunk])
+        texts = np.zeros((len(chunk), int(lens.max())), dtype=np.int64)
+        for j, r in enumerate(chunk):
+            texts[j, : len(r[6])] = r[6]
+        yield ([r[0] for r in chunk], [r[1] for r in chunk], np.array([r[2] for r in chunk]),
+               np.array([r[3] for r in chunk]), np.array([r[4] for r in chunk]), np.array([r[5] for r in chunk]), texts,
+               lens, int(lens.max()))
+
+
+def build_parser():
+    p = argparse.ArgumentParser(description="FastSpeech2 synthesis on the B200 engine (mel output)")
+    p.add_argument("--restore_step", type=int, required=True)
+    p.add_argument("--mode", type=str, choices=["batch", "single"], required=True)
+    p.add_argument("--source", type=str, default=None)
+    p.add_argument("--text", type=str, default=None)
+    p.add_argument("--speaker_id", type=str, default="0001")
+    p.add_argument("--emotion", type=str, default="Neutral", choices=list(EMOTION_AV))
+    p.add_argument("--output_name", type=str, default=None)
+    p.add_argument("-p", "--preprocess_config", type=str, required=True)
+    p.add_argument("-m", "--model_config", type=str, required=True)
+    p.add_argument("-t", "--train_config", type=str, required=True)
+    p.add_argument("--pitch_control", type=float, default=1.0)
+    p.add_argument("--energy_control", type=float, default=1.0)
+    p.add_argument("--duration_control", type=float, default=1.0)
+    p.add_argument("--random_init", action="store_true", help="seeded synthetic weights instead of a checkpoint")
+    return p
+
+
+def load_model(args, preprocess_config, model_config, train_config, device="cuda"):
+    """utils/model.py:11-34: construct, torch.load(<ckpt_path>/<step>.pth.tar)["model"], eval."""
+    from .model import FastSpeech2B200
+    model = FastSpeech2B200(preprocess_config, model_config)
+    if args.random_init:
+        from .synthetic import synthetic_state_dict
+        model.load_state_dict(synthetic_state_dict(seed=0))
+    else:
+        path = os.path.join(train_config["path"]["ckpt_path"], f"{args.restore_step}.pth.tar")
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        model.load_state_dict(ckpt["model"])
+    return model.to(device).eval()
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    if args.mode == "batch":
+        assert args.source is not None and args.text is None
+    else:
+        assert args.source is None and args.text is not None
+    with open(args.preprocess_config) as f:
+        preprocess_config = yaml.load(f, Loader=yaml.FullLoader)
+    with open(args.model_config) as f:
+        model_config = yaml.load(f, Loader=yaml.FullLoader)
+    with open(args.train_config) as f:
+        train_config = yaml.load(f, Loader=yaml.FullLoader)
+    model = load_model(args, preprocess_config, model_config, train_config)
+    batches = [single_batch(args, preprocess_config)] if args.mode == "single" else \
+        source_batches(args.source, preprocess_config)
+    out_dir = train_config["path"]["result_path"]
+    os.makedirs(out_dir, exist_ok=True)
+    for ids, raw_texts, speakers, emotions, arousals, valences, texts, text_lens, max_len in batches:
+        host = dict(speakers=speakers, emotions=emotions, arousals=arousals, valences=valences, texts=texts,
+                    src_lens=text_lens, max_src_len=max_len)
+        mel, mel_lens, _, _ = model.synthesize_host(host, p_control=args.pitch_control, e_control=args.energy_control,
+                                                    d_control=args.duration_control)
+        for i, name in enumerate(ids):
+            np.save(os.path.join(out_dir, f"{name}.npy"), mel[i, : int(mel_lens[i])].copy())
+            with open(os.path.join(out_dir, f"{name}.json"), "w", encoding="utf-8") as f:
+                json.dump({"text": raw_texts[i], "n_phonemes": int(text_lens[i]), "n_frames": int(mel_lens[i])}, f,
+                          ensure_ascii=False)
+            print(f"{name}: {int(text_lens[i])} phonemes -> {int(mel_lens[i])} mel frames -> {out_dir}/{name}.npy")
+
+
+if __name__ == "__main__":
+    main()
