@@ -53,6 +53,7 @@ SIGNATURES = {
     "fs2_debug_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "fs2_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, c_i64p, c_i64p]),
     "fs2_debug_set_flag": (C.c_int, [C.c_int, C.c_int]),
+    "fs2_debug_read_trace": (C.c_int, [c_i64p, C.c_int]),
     "fs2_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "fs2_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "fs2_op_conv_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,

@@ -32,7 +32,8 @@ def build_library(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libfs2b200.so cannot be built (and there is no CPU fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    trace = ["-DFS2_TRACE_BUILD"] if os.environ.get("FS2_TRACE_BUILD") else []   # tools/trace_*.py instrumentation
+    cmd = [nvcc] + NVCC_FLAGS + trace + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB_PATH, os.path.join(CSRC, "fs2_api.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

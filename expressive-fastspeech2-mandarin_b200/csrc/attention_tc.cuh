@@ -120,10 +120,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_s = tmem_base;          // + u*64
   const uint32_t tmem_o = tmem_base + 128;    // + u*128
   const uint32_t tmem_q = tmem_base + 384;    // 128 columns
+#ifdef FS2_TRACE_BUILD   // phase timestamps for tools/trace_attention.py (block 0 only, dbg == 4)
   const bool trace = dbg == 4 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   const long long t_start = clock64();
   float* tr = out + (size_t)row0 * D_MODEL;
 #define FS2_TRACE(tile, k) do { if (trace && (threadIdx.x & 31) == 0) tr[(tile) * 16 + (k)] = (float)(clock64() - t_start); } while (0)
+#else
+#define FS2_TRACE(tile, k) do { } while (0)
+#endif
 
   if (warp == 0) {
     // ---- TMA producer (whole warp, one elected lane issues): Q once, then K_j / V_j into 3-stage rings

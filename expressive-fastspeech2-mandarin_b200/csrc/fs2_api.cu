@@ -1,6 +1,8 @@
 // libfs2b200.so -- C ABI (include/fs2_b200.h) and the orchestration of the forward pass.
 // One context per device; all work is enqueued on the caller's stream.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 
@@ -382,6 +384,7 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   require(out->pitch && out->energy && out->log_d && out->d_rounded && out->src_mask && out->mel_lens, FS2_ERR_INVALID,
           "null output tensor");
   FS2_CUDA_OK(cudaSetDevice(c->device));
+  const auto t_begin = std::chrono::steady_clock::now();
   g_launches = 0;
   c->stage1_done = false;
   for (auto& r : c->prof) { c->event_pool.push_back(r.beg); c->event_pool.push_back(r.end); }
@@ -481,10 +484,18 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
                                                  c->fs.totals, c->status);
   FS2_LAUNCHED();
 
+  static const bool timing = std::getenv("FS2_TIMING") != nullptr;
+  const auto t_enq = std::chrono::steady_clock::now();
   // ---- the one blocking point: sizes of the frame side
   FS2_CUDA_OK(cudaMemcpyAsync(c->h_totals, c->fs.totals, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   FS2_CUDA_OK(cudaMemcpyAsync(c->h_totals + 3, c->status, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   FS2_CUDA_OK(cudaStreamSynchronize(s));
+  if (timing) {
+    const auto t_end = std::chrono::steady_clock::now();
+    fprintf(stderr, "[fs2] stage1: enqueue %.1f us (%d launches), wait %.1f us\n",
+            std::chrono::duration<double, std::micro>(t_enq - t_begin).count(), g_launches,
+            std::chrono::duration<double, std::micro>(t_end - t_enq).count());
+  }
   check_status(c, *reinterpret_cast<int32_t*>(c->h_totals + 3));
   c->frame_rows = c->h_totals[0];
   c->max_mel_len = (int)c->h_totals[1];
@@ -501,6 +512,7 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
 static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
   require(c->stage1_done, FS2_ERR_STATE, "fs2_forward_stage2 called without a completed fs2_forward_stage1");
   require(io && io->mel && io->postnet && io->mel_mask, FS2_ERR_INVALID, "null stage-2 output");
+  const auto t_begin2 = std::chrono::steady_clock::now();
   FS2_CUDA_OK(cudaSetDevice(c->device));
   g_launches = 0;
   const int B = c->batch, L = c->max_src_len, T = c->max_mel_len;
@@ -560,6 +572,11 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
     }
   }
   c->last_launches += g_launches;
+  static const bool timing2 = std::getenv("FS2_TIMING") != nullptr;
+  if (timing2) {
+    fprintf(stderr, "[fs2] stage2: enqueue %.1f us (%d launches)\n",
+            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin2).count(), g_launches);
+  }
 }
 
 static void prepare(fs2_ctx* c, cudaStream_t s) {
@@ -740,9 +757,22 @@ int fs2_debug_fetch(fs2_ctx* c, const char* name, void* host_dst, int64_t max_by
   });
 }
 
+static long long* g_trace_buf = nullptr;
+static int g_trace_on = 0;
+
 int fs2_debug_set_flag(int which, int value) {
   if (which == 0) fs2::attn_tc::debug_flag() = value;
+  if (which == 1) {
+    g_trace_on = value;
+    if (value && g_trace_buf == nullptr) cudaMalloc(reinterpret_cast<void**>(&g_trace_buf), 64 * sizeof(long long));
+  }
   return FS2_OK;
+}
+
+int fs2_debug_read_trace(int64_t* host_dst, int n) {
+  if (g_trace_buf == nullptr || n > 64) return FS2_ERR_INVALID;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(host_dst, g_trace_buf, n * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? FS2_OK : FS2_ERR_CUDA;
 }
 
 int fs2_profile_enable(fs2_ctx* c, int on) {
@@ -786,6 +816,7 @@ int fs2_op_conv_gemm(fs2_stream stream, int engine, int math_mode, const float* 
     ConvGemmArgs a{};
     a.A = A; a.lda = lda; a.rows = rows; a.W = Wt; a.bias = bias; a.taps = taps; a.pad = pad; a.K = K; a.N = N; a.act = act;
     a.residual = residual; a.ldr = ldr; a.row_vpos = row_vpos; a.row_room = row_room; a.extra = extra; a.C = C; a.ldc = ldc;
+    if (g_trace_on) a.trace = g_trace_buf;
     conv_gemm(engine, math_mode, a, static_cast<cudaStream_t>(stream));
   });
 }

@@ -36,6 +36,7 @@ struct ConvGemmArgs {
   const float* head_b;
   float* head_out;
   const int32_t* slot;
+  long long* trace;   // bring-up only: CTA 0 writes globaltimer stamps of its phases (nullptr in normal operation)
 };
 
 namespace mma {

@@ -82,6 +82,16 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, ConvGemmArgs p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
+  auto stamp = [&](int k) {
+#ifdef FS2_TRACE_BUILD   // phase timestamps for tools/trace_gemm.py
+    if (p.trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      p.trace[k] = t;
+    }
+#endif
+  };
+  if (threadIdx.x == 0) stamp(0);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* cst = smem + C::OFF_CST;
   uint8_t* res = smem + C::OFF_RES;
@@ -133,6 +143,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) stamp(1);
 
   if (warp == 0) {
     // ---------------- TMA producer (whole warp runs the loop, one elected lane issues)
@@ -166,6 +177,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int i = 0; i < iters; ++i, ++it) {
         const int s = it % C::STAGES;
         mbar_wait(&full[s], (it / C::STAGES) & 1);
+        if (it == 0) stamp(2);
         tc_fence_after();
         const uint8_t* a_s = smem + s * C::STAGE_BYTES;
         const uint64_t da = umma_desc(a_s), db = umma_desc(a_s + C::A_BYTES);
@@ -178,6 +190,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       if (leader) umma_commit(&acc_full[u]);
       __syncwarp();
+      if (lt == 0) stamp(3);
     }
   } else {
     // ---------------- epilogue (4 independent warps; thread = one accumulator row)
@@ -217,6 +230,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       bool live = in_range;
       if (in_range && p.row_vpos != nullptr) live = row_live(p.row_vpos[row], p.row_room[row], p.extra);
       mbar_wait(&acc_full[u], (lt >> 1) & 1);
+      if (lt == 0 && warp == 2) stamp(4);
       tc_fence_after();
       const uint32_t acc = tmem_base + lane_sel + u * C::ACC_COLS;
       const int t_next = t + gridDim.x;
@@ -369,13 +383,16 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
     }
+    if (warp == 2) stamp(5);
     if (lane == 0) bulk_wait_read<0>();   // smem must outlive the last TMA stores
+    if (warp == 2) stamp(6);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
+    stamp(7);
   }
 }
 

@@ -127,6 +127,8 @@ int fs2_debug_fetch(fs2_ctx* ctx, const char* name, void* host_dst, int64_t max_
 
 /* Bring-up switches (0 = attention kernel raw-dump mode); 0 in normal operation. */
 int fs2_debug_set_flag(int which, int value);
+/* which = 1: CTA 0 of the next fs2_op_conv_gemm writes globaltimer stamps; read them back here. */
+int fs2_debug_read_trace(int64_t* host_dst, int n);
 
 /* Per-kernel-class timing with CUDA events on the launching stream.  After a forward run with
  * profiling enabled, fs2_profile_read writes lines "label launches total_ms\n" (NUL-terminated). */

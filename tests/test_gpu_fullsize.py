@@ -1,0 +1,86 @@
+"""BASELINE.json's full-size configurations on the GPU, checked through size-independent
+properties (the oracle needs ~10 s per batch-64 forward on a CPU, so only a slice of each case is
+compared with it) plus the long-form case against the oracle end to end."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fs2_oracle as O
+from gpu_util import DEV, err_stats, model_for, run
+from helpers import OUT_NAMES, call, valid_rows
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config2_batch64_properties(sd32, syn):
+    model = model_for(sd32)
+    batch = syn.config2_batch(seed=0)
+    out = run(model, batch)
+    mel, post, pitch, energy, log_d, d_round, src_mask, mel_mask, src_lens, mel_lens = out
+    B, L = batch["texts"].shape
+    # shapes / dtypes of the reference tuple
+    T = int(mel_lens.max())
+    assert mel.shape == (B, T, 80) and post.shape == (B, T, 80) and mel.dtype == torch.float32
+    assert pitch.shape == (B, L) and d_round.shape == (B, L) and src_mask.dtype == torch.bool and mel_lens.dtype == torch.int64
+    assert all(torch.isfinite(t).all() for t in (mel, post, pitch, energy, log_d, d_round))
+    # integer bookkeeping: mel_lens = sum trunc(d), masks from lengths, d = clamp(round(exp(logd)-1)) on the device values
+    assert torch.equal(mel_lens, torch.clamp(torch.trunc(d_round), min=0).sum(1).long())
+    assert torch.equal(d_round, torch.clamp(torch.round(torch.exp(log_d) - 1) * 1.0, min=0) * (~src_mask))
+    assert torch.equal(mel_mask, torch.arange(T, device=DEV)[None, :] >= mel_lens[:, None])
+    assert torch.equal(src_mask, torch.arange(L, device=DEV)[None, :] >= batch["src_lens"].to(DEV)[:, None])
+    bias = sd32["mel_linear.bias"].to(DEV)
+    assert all(torch.equal(mel[b, int(t):], bias.expand(T - int(t), 80)) for b, t in enumerate(mel_lens) if int(t) < T)
+    # permutation of the utterances permutes the results bit for bit (teacher-forced: same durations / T_max)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1))
+    pb = {k: (v[perm] if torch.is_tensor(v) else v) for k, v in batch.items()}
+    forced = dict(d_targets=d_round.cpu(), p_targets=pitch.cpu(), e_targets=energy.cpu())
+    a = run(model, batch, **forced)
+    b = run(model, pb, **{k: v[perm] for k, v in forced.items()})
+    assert torch.equal(a[1][perm], b[1]) and torch.equal(a[0][perm], b[0]) and torch.equal(a[9][perm], b[9])
+    # a slice of the batch against the oracle: 4 utterances alone with the batch's L_max and T_max forced
+    idx = [0, 17, 40, 63]
+    sub = {k: (v[idx] if torch.is_tensor(v) else v) for k, v in batch.items()}
+    want = dict(zip(OUT_NAMES, call(O.forward, sub, O.cast_state_dict(sd32, torch.float64), d_targets=d_round.cpu()[idx].double(),
+                                    p_targets=pitch.cpu()[idx].double(), e_targets=energy.cpu()[idx].double(),
+                                    mel_lens=mel_lens.cpu()[idx], max_mel_len=T)))
+    lens = mel_lens.cpu()[idx].tolist()
+    for i, n in ((0, "mel"), (1, "postnet")):
+        mx, mean = err_stats(valid_rows(a[i][idx].cpu().numpy(), lens), valid_rows(want[n].numpy(), lens))
+        assert mx <= 3e-3 and mean <= 4e-4, (n, mx, mean)
+
+
+@pytest.mark.parametrize("d_control", [0.5, 2.0])
+def test_config4_longform(d_control, sd32, syn):
+    """400 phonemes, ~1.3k / ~5.4k frames: crosses max_seq_len=2000 on the decoder side (regenerated
+    sinusoid rows, transformer/Models.py:145-152), long attention, large expansion."""
+    model = model_for(sd32)
+    batch = syn.config4_batch()
+    want = dict(zip(OUT_NAMES, call(O.forward, batch, sd32, d_control=d_control)))   # fp32 oracle: ~5 s at 5.4k frames
+    free = run(model, batch, d_control=d_control)
+    n = batch["src_lens"].tolist()
+    mx, _ = err_stats(valid_rows(free[4].cpu().numpy(), n), valid_rows(want["log_d"].numpy(), n))
+    assert mx <= 5e-3
+    got = run(model, batch, d_targets=want["d_rounded"], p_targets=want["pitch"], e_targets=want["energy"],
+              mel_lens=want["mel_lens"], max_mel_len=int(want["mel_lens"].max()))
+    assert torch.equal(got[9].cpu(), want["mel_lens"])
+    T = want["mel_lens"].tolist()
+    assert (d_control == 2.0) == (T[0] > 2000)
+    for i, name in ((0, "mel"), (1, "postnet")):
+        mx, mean = err_stats(valid_rows(got[i].cpu().numpy(), T), valid_rows(want[name].numpy(), T))
+        assert mx <= 3e-3 and mean <= 4e-4, (name, mx, mean)
+
+
+def test_sharded_batch_matches_oracle_per_shard(sd32, syn):
+    """Multi-GPU semantics on one GPU: each LPT shard is its own batch (its own L_max / T_max)."""
+    from fs2_b200 import partition
+    model = model_for(sd32)
+    batch = syn.make_batch(syn.random_lengths(10, lo=10, hi=60, seed=3), seed=61)
+    sd64 = O.cast_state_dict(sd32, torch.float64)
+    for shard in partition.lpt_partition(batch["src_lens"].tolist(), 2):
+        sub = partition.take(batch, shard)
+        want = dict(zip(OUT_NAMES, call(O.forward, sub, sd64)))
+        got = run(model, sub, d_targets=want["d_rounded"].float(), p_targets=want["pitch"].float(),
+                  e_targets=want["energy"].float(), mel_lens=want["mel_lens"], max_mel_len=int(want["mel_lens"].max()))
+        T = want["mel_lens"].tolist()
+        mx, mean = err_stats(valid_rows(got[1].cpu().numpy(), T), valid_rows(want["postnet"].numpy(), T))
+        assert mx <= 3e-3 and mean <= 4e-4

@@ -1,0 +1,22 @@
+import os, sys, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np, torch
+from gpu_util import DEV, lib, ptr, stream
+L = lib()
+for rows, K, N, taps in [(128, 256, 768, 1), (128, 256, 1024, 9), (26788, 256, 768, 1)]:
+    A = torch.randn(rows, K, device=DEV); W = torch.randn(taps, N, K, device=DEV) / 16; bias = torch.randn(N, device=DEV)
+    out = torch.empty(rows, N, device=DEV)
+    call = lambda: L.fs2_op_conv_gemm(stream(), 1, 0, ptr(A), K, rows, ptr(W), ptr(bias), taps, (taps - 1) // 2, K, N, 0, None, N, None, None, 0, ptr(out), N)
+    for _ in range(3): call()
+    torch.cuda.synchronize()
+    L.fs2_debug_set_flag(1, 1)
+    # bracket with two tiny torch kernels to see launch-to-start gaps via globaltimer of our own stamps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); call(); e1.record(); torch.cuda.synchronize()
+    buf = (ctypes.c_int64 * 8)()
+    L.fs2_debug_read_trace(buf, 8)
+    L.fs2_debug_set_flag(1, 0)
+    t = np.array(list(buf), dtype=np.int64)
+    rel = (t - t[0]) / 1e3
+    print(f"rows={rows} K={K} N={N} taps={taps}: event time {e0.elapsed_time(e1)*1e3:.1f} us | stamps(us) entry 0, prologue_done {rel[1]:.2f}, first_tma_landed {rel[2]:.2f}, mma_issued_tile0 {rel[3]:.2f}, acc_ready {rel[4]:.2f}, epi_done {rel[5]:.2f}, stores_read {rel[6]:.2f}, dealloc {rel[7]:.2f}")
