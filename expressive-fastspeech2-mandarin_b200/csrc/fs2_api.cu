@@ -771,6 +771,7 @@ int fs2_debug_set_flag(int which, int value) {
 
 int fs2_debug_read_trace(int64_t* host_dst, int n) {
   if (g_trace_buf == nullptr || n > 64) return FS2_ERR_INVALID;
+  g_trace_on = g_trace_on ? 1 : 0;
   cudaDeviceSynchronize();
   return cudaMemcpy(host_dst, g_trace_buf, n * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? FS2_OK : FS2_ERR_CUDA;
 }
@@ -816,7 +817,7 @@ int fs2_op_conv_gemm(fs2_stream stream, int engine, int math_mode, const float* 
     ConvGemmArgs a{};
     a.A = A; a.lda = lda; a.rows = rows; a.W = Wt; a.bias = bias; a.taps = taps; a.pad = pad; a.K = K; a.N = N; a.act = act;
     a.residual = residual; a.ldr = ldr; a.row_vpos = row_vpos; a.row_room = row_room; a.extra = extra; a.C = C; a.ldc = ldc;
-    if (g_trace_on) a.trace = g_trace_buf;
+    if (g_trace_on) { a.trace = g_trace_buf + 8 * ((g_trace_on - 1) % 8); ++g_trace_on; }
     conv_gemm(engine, math_mode, a, static_cast<cudaStream_t>(stream));
   });
 }

@@ -20,3 +20,22 @@ for rows, K, N, taps in [(128, 256, 768, 1), (128, 256, 1024, 9), (26788, 256, 7
     t = np.array(list(buf), dtype=np.int64)
     rel = (t - t[0]) / 1e3
     print(f"rows={rows} K={K} N={N} taps={taps}: event time {e0.elapsed_time(e1)*1e3:.1f} us | stamps(us) entry 0, prologue_done {rel[1]:.2f}, first_tma_landed {rel[2]:.2f}, mma_issued_tile0 {rel[3]:.2f}, acc_ready {rel[4]:.2f}, epi_done {rel[5]:.2f}, stores_read {rel[6]:.2f}, dealloc {rel[7]:.2f}")
+
+print("==== back-to-back launches: gap between exit of kernel i and entry of kernel i+1")
+rows, K, N, taps = 128, 256, 768, 1
+A = torch.randn(rows, K, device=DEV); W = torch.randn(taps, N, K, device=DEV) / 16; bias = torch.randn(N, device=DEV)
+out = torch.empty(rows, N, device=DEV)
+call = lambda: L.fs2_op_conv_gemm(stream(), 1, 0, ptr(A), K, rows, ptr(W), ptr(bias), taps, 0, K, N, 0, None, N, None, None, 0, ptr(out), N)
+for _ in range(3): call()
+torch.cuda.synchronize()
+L.fs2_debug_set_flag(1, 1)
+for _ in range(6): call()
+torch.cuda.synchronize()
+buf = (ctypes.c_int64 * 64)()
+L.fs2_debug_read_trace(buf, 64)
+L.fs2_debug_set_flag(1, 0)
+t = np.array(list(buf), dtype=np.int64).reshape(8, 8)
+for i in range(6):
+    line = f"launch {i}: entry {0 if i == 0 else (t[i,0]-t[0,0])/1e3:8.2f} us, inside {(t[i,7]-t[i,0])/1e3:6.2f} us"
+    if i > 0: line += f", gap after previous exit {(t[i,0]-t[i-1,7])/1e3:6.2f} us"
+    print(line)
