@@ -63,10 +63,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const __grid_constant__ CUtensorMap tmV, const int32_t* __restrict__ starts, const int32_t* __restrict__ lens, float* __restrict__ out, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
-  const int len = lens[b];
-  if (q0 >= len) return;
-  const int row0 = starts[b];
-  const int n_tiles = (len + BKV - 1) / BKV;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_s = smem;
@@ -117,6 +113,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // ---- the prologue above overlaps the previous kernel's tail (programmatic dependent launch);
+  // lens / starts / qkv are produced by earlier kernels of this forward
+  pdl_trigger();
+  pdl_wait();
+  const int len = lens[b];
+  const bool active = q0 < len;              // CTAs beyond the utterance only tear down
+  const int row0 = starts[b];
+  const int n_tiles = (len + BKV - 1) / BKV;
   const uint32_t tmem_s = tmem_base;          // + u*64
   const uint32_t tmem_o = tmem_base + 128;    // + u*128
   const uint32_t tmem_q = tmem_base + 384;    // 128 columns
@@ -129,7 +133,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #define FS2_TRACE(tile, k) do { } while (0)
 #endif
 
-  if (warp == 0) {
+  if (!active) {
+    // nothing to do
+  } else if (warp == 0) {
     // ---- TMA producer (whole warp, one elected lane issues): Q once, then K_j / V_j into 3-stage rings
     const bool leader = elect_one();
     if (leader) {
@@ -377,7 +383,7 @@ inline void launch(const float* qkv, int rows, const int32_t* starts, const int3
   const CUtensorMap tmKV = make_map(qkv, rows, LDQKV, LDQKV, BKV, true, true);
   const CUtensorMap tmV = make_map(qkv, rows, LDQKV, LDQKV, BKV, true, true, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   dim3 grid((max_len + BQ - 1) / BQ, N_HEAD, batch);
-  attention_tc_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(tmQ, tmKV, tmV, starts, lens, out, debug_flag());
+  launch_pdl(attention_tc_kernel, grid, dim3(THREADS), SMEM_TOTAL, stream, tmQ, tmKV, tmV, starts, lens, out, debug_flag());
   FS2_LAUNCHED();
 }
 

@@ -110,10 +110,6 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int kchunks = (p.K + BK - 1) / BK;
   const int iters = p.taps * kchunks;
   const int n_tiles_n = (p.N + BN - 1) / BN;
-  int rows_live = p.rows;
-  if (p.live_rows != nullptr) rows_live = min(rows_live, *p.live_rows);
-  const int total_tiles = ((rows_live + BM - 1) / BM) * n_tiles_n;
-  if ((int)blockIdx.x >= total_tiles) return;
   const bool has_res = p.residual != nullptr;
   const bool has_out = p.C != nullptr;
 
@@ -144,6 +140,12 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) stamp(1);
+  // ---- everything above overlaps the previous kernel's tail; from here on its results are read
+  pdl_trigger();
+  pdl_wait();
+  int rows_live = p.rows;
+  if (p.live_rows != nullptr) rows_live = min(rows_live, *p.live_rows);
+  const int total_tiles = ((rows_live + BM - 1) / BM) * n_tiles_n;   // CTAs beyond it fall through to the teardown
 
   if (warp == 0) {
     // ---------------- TMA producer (whole warp runs the loop, one elected lane issues)
@@ -216,7 +218,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     epi_barrier();   // the only CTA-level epilogue barrier: parameters are in smem
     int g_res = 0;   // residual sub-tiles consumed so far (buffer = g & 1, parity = (g >> 1) & 1)
     int g_st = 0;    // staging sub-tiles produced so far
-    if (has_res && lane == 0) {  // first residual sub-tile of the first tile
+    if (has_res && lane == 0 && (int)blockIdx.x < total_tiles) {  // first residual sub-tile of the first tile
       const int t = blockIdx.x;
       mbar_expect_tx(&my_res_full[0], WCHUNK);
       tma_load_2d(my_res, &tmR, (t % n_tiles_n) * BN, (t / n_tiles_n) * BM + q * 32, &my_res_full[0]);
@@ -420,7 +422,7 @@ inline void launch_bn(const ConvGemmArgs& a, cudaStream_t stream) {
   const CUtensorMap tmR = a.residual != nullptr ? make_map(a.residual, a.rows, a.N, a.ldr, 32, false, false) : tmA;
   const int tiles = ((a.rows + BM - 1) / BM) * ((a.N + BN - 1) / BN);
   const int grid = std::min(tiles, sm_count());
-  conv_gemm_tc2_kernel<BN, LN><<<grid, THREADS, C::TOTAL, stream>>>(tmA, tmW, tmC, tmR, a);
+  launch_pdl(conv_gemm_tc2_kernel<BN, LN>, dim3(grid), dim3(THREADS), C::TOTAL, stream, tmA, tmW, tmC, tmR, a);
   FS2_LAUNCHED();
 }
 

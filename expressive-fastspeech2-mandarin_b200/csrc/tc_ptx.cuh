@@ -4,6 +4,8 @@
 
 #include <cuda.h>  // CUtensorMap and enums only; cuTensorMapEncodeTiled is resolved at run time
 
+#include <utility>
+
 #include "common.cuh"
 
 namespace fs2 {
@@ -24,6 +26,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ int warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
+// Programmatic dependent launch: a kernel launched with the stream-serialization attribute may
+// start while its predecessor is still running; everything up to pdl_wait() (barrier init, TMEM
+// allocation, descriptor prefetch, constant loads) overlaps with the predecessor's tail.  No global
+// memory written by an earlier kernel may be touched before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
@@ -217,6 +226,21 @@ inline const CUtensorMap& make_map(const float* base, int64_t rows, int64_t cols
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   require(r == CUDA_SUCCESS, FS2_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return cache.emplace(key, m).first->second;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FS2_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
 
 }  // namespace tc
