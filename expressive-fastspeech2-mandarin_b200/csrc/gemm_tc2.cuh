@@ -444,6 +444,13 @@ inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
     return;
   }
   require(a.C != nullptr, FS2_ERR_INVALID, "conv_gemm: null output");
+  // Small problems (single utterances): a 128 x 256 tile would leave most SMs idle while one CTA
+  // walks the whole K loop at 512 cycles per stage, so narrower tiles spread the columns over more
+  // CTAs whose stages are proportionally shorter.
+  const int m_tiles = (a.rows + BM - 1) / BM;
+  const int sms = sm_count();
+  if (a.N % 256 == 0 && m_tiles * (a.N / 256) * 4 <= sms) { launch_bn<64, false>(a, stream); return; }
+  if (a.N % 256 == 0 && m_tiles * (a.N / 256) * 2 <= sms) { launch_bn<128, false>(a, stream); return; }
   if (a.N % 256 == 0) launch_bn<256, false>(a, stream);
   else if (a.N == 80) launch_bn<80, false>(a, stream);
   else if (a.N % 128 == 0) launch_bn<128, false>(a, stream);
