@@ -322,39 +322,48 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // exact two-pass inside each 32-column chunk (in registers) and merged across chunks with
         // Chan's update, so the accumulator is read only twice.
         float mean = 0.f, var = 0.f;   // var holds M2 = sum (v - mean)^2 until the merge is complete
-#pragma unroll 1
-        for (int c = 0; c < C::NCHUNK; ++c) {
-          float v[32];
-          tmem_ld32(acc + c * 32, v);
+        float va[32], vb[32];          // double-buffered chunk registers: the TMEM load of chunk c+1 is in
+                                       // flight while chunk c is processed
+        auto pass1 = [&](float (&v)[32], int c) {
           if (has_res) {
             __syncwarp();             // every lane finished reading the other residual buffer
             prefetch_res(c);
           }
           finish(v, c * 32, 32);
           if (has_res) ++g_res;
-          float cs = 0.f;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 32; ++j) cs += v[j];
-          const float cm = cs * (1.f / 32.f);
-          float cm2 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = v[j] - cm;
-            cm2 = fmaf(d, d, cm2);
+          for (int j = 0; j < 32; j += 4) {
+            s4[0] += v[j]; s4[1] += v[j + 1]; s4[2] += v[j + 2]; s4[3] += v[j + 3];
           }
+          const float cm = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.f / 32.f);
+          float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float d0 = v[j] - cm, d1 = v[j + 1] - cm, d2 = v[j + 2] - cm, d3 = v[j + 3] - cm;
+            q4[0] = fmaf(d0, d0, q4[0]); q4[1] = fmaf(d1, d1, q4[1]); q4[2] = fmaf(d2, d2, q4[2]); q4[3] = fmaf(d3, d3, q4[3]);
+          }
+          const float cm2 = (q4[0] + q4[1]) + (q4[2] + q4[3]);
           const float delta = cm - mean;
           const float n_old = 32.f * c, n_new = 32.f * (c + 1);
           mean = fmaf(delta, 32.f / n_new, mean);
           var += cm2 + delta * delta * (n_old * 32.f / n_new);
           tmem_st32(acc + c * 32, v);
+        };
+        tmem_ld32_issue(acc, va);
+#pragma unroll 1
+        for (int c = 0; c < C::NCHUNK; c += 2) {
+          tmem_ld_wait();
+          tmem_ld32_issue(acc + (c + 1) * 32, vb);
+          pass1(va, c);
+          tmem_ld_wait();
+          if (c + 2 < C::NCHUNK) tmem_ld32_issue(acc + (c + 2) * 32, va);
+          pass1(vb, c + 1);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         const float rstd = 1.f / sqrtf(var * (1.f / 256.f) + 1e-5f);
         float dot = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < C::NCHUNK; ++c) {
-          float v[32];
-          tmem_ld32(acc + c * 32, v);
+        auto pass2 = [&](float (&v)[32], int c) {
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
             const float4 g4 = lds4(gamma_sa + c * 128 + cc * 16), b4 = lds4(beta_sa + c * 128 + cc * 16);
@@ -363,21 +372,35 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int e = 0; e < 4; ++e) v[cc * 4 + e] = fmaf((v[cc * 4 + e] - mean) * rstd, gg[e], bb[e]);
           }
           if (p.head_out != nullptr) {
+            float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {
               const float4 w4 = lds4(headw_sa + c * 128 + cc * 16);
-              dot = fmaf(v[cc * 4], w4.x, fmaf(v[cc * 4 + 1], w4.y, fmaf(v[cc * 4 + 2], w4.z, fmaf(v[cc * 4 + 3], w4.w, dot))));
+              d4[0] = fmaf(v[cc * 4], w4.x, d4[0]); d4[1] = fmaf(v[cc * 4 + 1], w4.y, d4[1]);
+              d4[2] = fmaf(v[cc * 4 + 2], w4.z, d4[2]); d4[3] = fmaf(v[cc * 4 + 3], w4.w, d4[3]);
             }
+            dot += (d4[0] + d4[1]) + (d4[2] + d4[3]);
           }
           if (!live) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
-          if (c == C::NCHUNK - 1) {
+          if (has_out) stage_out(v, c * 32, 32);
+        };
+        tmem_ld32_issue(acc, va);
+#pragma unroll 1
+        for (int c = 0; c < C::NCHUNK; c += 2) {
+          tmem_ld_wait();
+          tmem_ld32_issue(acc + (c + 1) * 32, vb);
+          pass2(va, c);
+          tmem_ld_wait();
+          if (c + 2 < C::NCHUNK) {
+            tmem_ld32_issue(acc + (c + 2) * 32, va);
+          } else {                      // the last TMEM read of this tile has landed: release the accumulator
             tc_fence_before();
             mbar_arrive(&acc_empty[u]);
           }
-          if (has_out) stage_out(v, c * 32, 32);
+          pass2(vb, c + 1);
         }
         if (p.head_out != nullptr && live) {
           const int dst = p.slot != nullptr ? p.slot[row] : row;

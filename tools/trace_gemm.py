@@ -39,3 +39,19 @@ for i in range(6):
     line = f"launch {i}: entry {0 if i == 0 else (t[i,0]-t[0,0])/1e3:8.2f} us, inside {(t[i,7]-t[i,0])/1e3:6.2f} us"
     if i > 0: line += f", gap after previous exit {(t[i,0]-t[i-1,7])/1e3:6.2f} us"
     print(line)
+
+print("==== fused-LN GEMMs, single tile and many tiles")
+for rows, K in [(128, 256), (128, 1024), (26788, 256), (26788, 1024)]:
+    A = torch.randn(rows, K, device=DEV); W = torch.randn(1, 256, K, device=DEV) / 16; bias = torch.randn(256, device=DEV)
+    res = torch.randn(rows, 256, device=DEV); gm = torch.ones(256, device=DEV); bt = torch.zeros(256, device=DEV)
+    out = torch.empty(rows, 256, device=DEV)
+    call = lambda: L.fs2_op_conv_gemm_ln(stream(), 1, ptr(A), K, rows, ptr(W), ptr(bias), 1, 0, K, 0, ptr(res), 256, ptr(gm), ptr(bt), None, None, 0, ptr(out), 256, None, None, None)
+    for _ in range(3): call()
+    torch.cuda.synchronize()
+    L.fs2_debug_set_flag(1, 1)
+    call(); torch.cuda.synchronize()
+    buf = (ctypes.c_int64 * 8)()
+    L.fs2_debug_read_trace(buf, 8)
+    L.fs2_debug_set_flag(1, 0)
+    t = np.array(list(buf), dtype=np.int64); rel = (t - t[0]) / 1e3
+    print(f"LN rows={rows} K={K}: prologue {rel[1]:.2f}, first_tma {rel[2]:.2f}, mma_tile0 {rel[3]:.2f}, acc_ready {rel[4]:.2f}, epi_done(all tiles) {rel[5]:.2f}, exit {rel[7]:.2f}")
