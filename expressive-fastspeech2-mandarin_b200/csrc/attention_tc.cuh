@@ -72,15 +72,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   uint64_t* q_full = bars;            // [1]
   uint64_t* q_moved = bars + 1;       // [1]  Q copied to TMEM: its smem may be overwritten
-  uint64_t* k_full = bars + 2;        // [3]
-  uint64_t* k_empty = bars + 5;       // [3]  K_j is free as soon as Q K_j^T has been read
-  uint64_t* v_full = bars + 8;        // [3]
-  uint64_t* v_empty = bars + 11;      // [3]  V_j is free after P_j V_j
-  uint64_t* s_full = bars + 14;       // [2]
-  uint64_t* p_full = bars + 16;       // [2]
-  uint64_t* o_full = bars + 18;       // [2]
-  uint64_t* o_free = bars + 20;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* kv_full = bars + 2;       // [3]  K_j and V_j of one tile share a stage and a barrier pair
+  uint64_t* kv_empty = bars + 5;      // [3]  free after P_j V_j (three stages: loads run two tiles ahead)
+  uint64_t* s_full = bars + 8;        // [2]
+  uint64_t* p_full = bars + 10;       // [2]  also implies that O_{j-2} has been accumulated (program order
+                                      //      of the softmax threads), so P_j V_j may overwrite that buffer
+  uint64_t* o_full = bars + 12;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = warp_index(), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -90,16 +88,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(q_full, 1);
     mbar_init(q_moved, 128);
     for (int u = 0; u < KV_STAGES; ++u) {
-      mbar_init(&k_full[u], 1);
-      mbar_init(&k_empty[u], 1);
-      mbar_init(&v_full[u], 1);
-      mbar_init(&v_empty[u], 1);
+      mbar_init(&kv_full[u], 1);
+      mbar_init(&kv_empty[u], 1);
     }
     for (int u = 0; u < 2; ++u) {
       mbar_init(&s_full[u], 1);
       mbar_init(&p_full[u], 128);
       mbar_init(&o_full[u], 1);
-      mbar_init(&o_free[u], 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -150,20 +145,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (j == 2) mbar_wait(q_moved, 0);      // stage 2 lives where Q was staged
       uint8_t* k_s = k_stage(sk);
       uint8_t* v_s = v_stage(sk);
-      mbar_wait(&k_empty[sk], par);
+      mbar_wait(&kv_empty[sk], par);
       if (leader) {
-        mbar_expect_tx(&k_full[sk], K_BYTES);
+        mbar_expect_tx(&kv_full[sk], 2 * K_BYTES);
 #pragma unroll
         for (int dc = 0; dc < 4; ++dc)
-          tma_load_2d(k_s + dc * (BKV * 128), &tmKV, D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &k_full[sk]);
-      }
-      __syncwarp();
-      mbar_wait(&v_empty[sk], par);
-      if (leader) {
-        mbar_expect_tx(&v_full[sk], K_BYTES);
+          tma_load_2d(k_s + dc * (BKV * 128), &tmKV, D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &kv_full[sk]);
 #pragma unroll
         for (int dc = 0; dc < 4; ++dc)
-          tma_load_2d(v_s + dc * (BKV * 128), &tmV, 2 * D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &v_full[sk]);
+          tma_load_2d(v_s + dc * (BKV * 128), &tmV, 2 * D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &kv_full[sk]);
       }
       __syncwarp();
     }
@@ -175,7 +165,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     auto issue_qk = [&](int j) {
       const int u = j & 1, sk = j % KV_STAGES;
       FS2_TRACE(j, 8);
-      mbar_wait(&k_full[sk], (j / KV_STAGES) & 1);
+      mbar_wait(&kv_full[sk], (j / KV_STAGES) & 1);
       FS2_TRACE(j, 9);
       tc_fence_after();
       const uint8_t* k_s = k_stage(sk);
@@ -189,7 +179,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         FS2_TRACE(j, 10);
         umma_commit(&s_full[u]);
-        umma_commit(&k_empty[sk]);
         FS2_TRACE(j, 11);
       }
       __syncwarp();
@@ -203,10 +192,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (j + 1 < n_tiles) issue_qk(j + 1);
       const int sk = j % KV_STAGES;
       FS2_TRACE(j, 4);
-      mbar_wait(&p_full[u], par);
+      mbar_wait(&p_full[u], par);      // P_j written; O buffer u drained (see p_full above); V_j landed with K_j
       FS2_TRACE(j, 5);
-      mbar_wait(&o_free[u], par ^ 1);
-      mbar_wait(&v_full[sk], (j / KV_STAGES) & 1);
       FS2_TRACE(j, 6);
       tc_fence_after();
       const uint8_t* v_s = v_stage(sk);
@@ -217,7 +204,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           umma_tf32_ts(tmem_o + u * D_HEAD, tmem_s + u * BKV + k8 * 8, dv + (uint64_t)(k8 * (1024 >> 4)), idesc_pv, k8 != 0);
         FS2_TRACE(j, 12);
         umma_commit(&o_full[u]);
-        umma_commit(&v_empty[sk]);
+        umma_commit(&kv_empty[sk]);
         FS2_TRACE(j, 13);
       }
       __syncwarp();
@@ -273,8 +260,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           o[c0 + 32 + i] = fmaf(o[c0 + 32 + i], alpha, v1[i]);
         }
       }
-      tc_fence_before();
-      mbar_arrive(&o_free[u]);
+      tc_fence_before();   // ordered before this thread's next p_full arrive, which releases the O buffer
     };
 
     // m is the running row maximum of the RAW scores; exp2 arguments are s*c - m*c (one FFMA each)
@@ -310,11 +296,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float mc = m_new * c;
       float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
+      // P is rounded to TF32 (nearest, ties away) with integer arithmetic: (bits + 0x1000) & ~0x1fff runs on
+      // the ALU pipe, whereas cvt.rna.tf32 shares the XU pipe with ex2 and would double its load.  p is in [0, 1].
+      auto p_of = [&](float s) {
+        const uint32_t bits = (__float_as_uint(ex2_approx(fmaf(s, c, -mc))) + 0x1000u) & 0xFFFFE000u;
+        return __uint_as_float(bits);
+      };
       for (int i = 0; i < 32; i += 2) {
-        s0[i] = tf32_rna(ex2_approx(fmaf(s0[i], c, -mc)));
-        s0[i + 1] = tf32_rna(ex2_approx(fmaf(s0[i + 1], c, -mc)));
-        s1[i] = tf32_rna(ex2_approx(fmaf(s1[i], c, -mc)));
-        s1[i + 1] = tf32_rna(ex2_approx(fmaf(s1[i + 1], c, -mc)));
+        s0[i] = p_of(s0[i]);
+        s0[i + 1] = p_of(s0[i + 1]);
+        s1[i] = p_of(s1[i]);
+        s1[i + 1] = p_of(s1[i + 1]);
         sum[0] += s0[i];
         sum[1] += s0[i + 1];
         sum[2] += s1[i];
