@@ -375,7 +375,7 @@ inline void launch(const float* qkv, int rows, const int32_t* starts, const int3
   const CUtensorMap tmKV = make_map(qkv, rows, LDQKV, LDQKV, BKV, true, true);
   const CUtensorMap tmV = make_map(qkv, rows, LDQKV, LDQKV, BKV, true, true, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   dim3 grid((max_len + BQ - 1) / BQ, N_HEAD, batch);
-  launch_pdl(attention_tc_kernel, grid, dim3(THREADS), SMEM_TOTAL, stream, tmQ, tmKV, tmV, starts, lens, out, debug_flag());
+  launch_pdl(attention_tc_kernel, grid, dim3(THREADS), SMEM_TOTAL, stream, 1, tmQ, tmKV, tmV, starts, lens, out, debug_flag());
   FS2_LAUNCHED();
 }
 

@@ -762,6 +762,7 @@ static int g_trace_on = 0;
 
 int fs2_debug_set_flag(int which, int value) {
   if (which == 0) fs2::attn_tc::debug_flag() = value;
+  if (which == 2) fs2::tc2::cluster_size_flag() = value == 1 ? 1 : 2;
   if (which == 1) {
     g_trace_on = value;
     if (value && g_trace_buf == nullptr) cudaMalloc(reinterpret_cast<void**>(&g_trace_buf), 64 * sizeof(long long));

@@ -9,6 +9,9 @@
 //                             row mask, or the full post-LN of the FFT block and the predictors
 //                             (LayerNorm over the 256-wide row held in TMEM, optional 256->1 head)
 //                             -> swizzled smem staging -> TMA store (coalesced, asynchronous).
+// With CL = 2 the kernel runs as thread-block clusters of two CTAs that work on vertically adjacent
+// row tiles of the SAME column tile: each CTA loads half of the weight tile and TMA-multicasts it into
+// both CTAs' shared memory, halving the L2 traffic of the B operand (two thirds of all operand bytes).
 // Residual tiles are fetched by TMA into smem (never by per-thread strided loads).  Every epilogue
 // warp owns its 32 rows end to end (own staging buffers, own TMA loads/stores, own mbarriers), so
 // the steady state has no CTA-wide barrier.
@@ -76,7 +79,7 @@ __device__ __forceinline__ void sts4(uint32_t saddr, float4 v) {
 // byte offset of (row r, 16-byte chunk cc) inside a [rows x 128 B] SWIZZLE_128B sub-tile
 __device__ __forceinline__ int swz_off(int r, int cc) { return r * 128 + ((cc ^ (r & 7)) << 4); }
 
-template <int BN, bool LN>
+template <int BN, bool LN, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, ConvGemmArgs p) {
@@ -120,7 +123,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (has_res) asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);   // a stage is refilled by both CTAs of the cluster: both consumers must release it
     }
     for (int u = 0; u < 2; ++u) {
       mbar_init(&acc_full[u], 1);
@@ -140,19 +143,27 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) stamp(1);
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  if (CL > 1) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
   // ---- everything above overlaps the previous kernel's tail; from here on its results are read
   pdl_trigger();
   pdl_wait();
   int rows_live = p.rows;
   if (p.live_rows != nullptr) rows_live = min(rows_live, *p.live_rows);
-  const int total_tiles = ((rows_live + BM - 1) / BM) * n_tiles_n;   // CTAs beyond it fall through to the teardown
+  // work item = CL vertically adjacent row tiles x one column tile; the CTAs of a cluster walk the items in
+  // lock step (a trailing odd row tile is processed as an all-zero tile whose stores TMA clips away)
+  const int m_groups = ((rows_live + BM - 1) / BM + CL - 1) / CL;
+  const int total_items = m_groups * n_tiles_n;
+  const int w_first = blockIdx.x / CL, w_step = gridDim.x / CL;
+  auto item_m0 = [&](int w) { return ((w / n_tiles_n) * CL + rank) * BM; };
+  auto item_n0 = [&](int w) { return (w % n_tiles_n) * BN; };
 
   if (warp == 0) {
     // ---------------- TMA producer (whole warp runs the loop, one elected lane issues)
     const bool leader = elect_one();
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int m0 = (t / n_tiles_n) * BM, n0 = (t % n_tiles_n) * BN;
+    for (int w = w_first; w < total_items; w += w_step) {
+      const int m0 = item_m0(w), n0 = item_n0(w);
       for (int i = 0; i < iters; ++i, ++it) {
         const int s = it % C::STAGES;
         mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
@@ -161,7 +172,12 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (leader) {
           mbar_expect_tx(&full[s], C::STAGE_BYTES);
           tma_load_2d(a_s, &tmA, kc * BK, m0 + tap - p.pad, &full[s]);
-          tma_load_2d(a_s + C::A_BYTES, &tmW, kc * BK, tap * p.N + n0, &full[s]);
+          if (CL == 1) {
+            tma_load_2d(a_s + C::A_BYTES, &tmW, kc * BK, tap * p.N + n0, &full[s]);
+          } else {   // this CTA's half of the weight tile, delivered to both CTAs of the cluster
+            tma_load_2d_mc(a_s + C::A_BYTES + rank * (C::B_BYTES / 2), &tmW, kc * BK, tap * p.N + n0 + rank * (BN / 2), &full[s],
+                           (uint16_t)0x3);
+          }
         }
         __syncwarp();
       }
@@ -171,9 +187,11 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const bool leader = elect_one();
     constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
     int it = 0, lt = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+    for (int w = w_first; w < total_items; w += w_step, ++lt) {
       const int u = lt & 1;
+      if (lt < 6) stamp(8 + lt * 4 + 0);
       mbar_wait(&acc_empty[u], ((lt >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+      if (lt < 6) stamp(8 + lt * 4 + 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + u * C::ACC_COLS;
       for (int i = 0; i < iters; ++i, ++it) {
@@ -186,7 +204,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (leader) {
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) umma_tf32(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
-          umma_commit(&empty[s]);
+          if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], (uint16_t)0x3);
         }
         __syncwarp();
       }
@@ -218,14 +236,13 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     epi_barrier();   // the only CTA-level epilogue barrier: parameters are in smem
     int g_res = 0;   // residual sub-tiles consumed so far (buffer = g & 1, parity = (g >> 1) & 1)
     int g_st = 0;    // staging sub-tiles produced so far
-    if (has_res && lane == 0 && (int)blockIdx.x < total_tiles) {  // first residual sub-tile of the first tile
-      const int t = blockIdx.x;
+    if (has_res && lane == 0 && w_first < total_items) {  // first residual sub-tile of the first tile
       mbar_expect_tx(&my_res_full[0], WCHUNK);
-      tma_load_2d(my_res, &tmR, (t % n_tiles_n) * BN, (t / n_tiles_n) * BM + q * 32, &my_res_full[0]);
+      tma_load_2d(my_res, &tmR, item_n0(w_first), item_m0(w_first) + q * 32, &my_res_full[0]);
     }
     int lt = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-      const int m0 = (t / n_tiles_n) * BM, n0 = (t % n_tiles_n) * BN;
+    for (int w = w_first; w < total_items; w += w_step, ++lt) {
+      const int m0 = item_m0(w), n0 = item_n0(w);
       const int u = lt & 1;
       const int row = m0 + r;
       const bool in_range = row < p.rows;
@@ -233,21 +250,21 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (in_range && p.row_vpos != nullptr) live = row_live(p.row_vpos[row], p.row_room[row], p.extra);
       mbar_wait(&acc_full[u], (lt >> 1) & 1);
       if (lt == 0 && warp == 2) stamp(4);
+      if (lt < 6 && warp == 2) stamp(8 + lt * 4 + 2);
       tc_fence_after();
       const uint32_t acc = tmem_base + lane_sel + u * C::ACC_COLS;
-      const int t_next = t + gridDim.x;
+      const int w_next = w + w_step;
 
       // prefetch the residual sub-tile after (tile t, chunk c): next chunk of this tile or chunk 0 of
       // the next tile.  Called by the whole warp AFTER a __syncwarp that follows the previous reads.
       auto prefetch_res = [&](int c) {
         if (!has_res || lane != 0) return;
-        int tt = t, cc = c + 1;
-        if (cc >= C::NCHUNK) { tt = t_next; cc = 0; }
-        if (tt >= total_tiles) return;
+        int ww = w, cc = c + 1;
+        if (cc >= C::NCHUNK) { ww = w_next; cc = 0; }
+        if (ww >= total_items) return;
         const int buf = (g_res + 1) & 1;
         mbar_expect_tx(&my_res_full[buf], WCHUNK);
-        tma_load_2d(my_res + buf * WCHUNK, &tmR, (tt % n_tiles_n) * BN + cc * 32, (tt / n_tiles_n) * BM + q * 32,
-                    &my_res_full[buf]);
+        tma_load_2d(my_res + buf * WCHUNK, &tmR, item_n0(ww) + cc * 32, item_m0(ww) + q * 32, &my_res_full[buf]);
       };
       // v = act(acc + bias) (+ residual from this warp's smem sub-tile)
       auto finish = [&](float (&v)[32], int c0, int width) {
@@ -407,6 +424,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (dst >= 0) p.head_out[dst] = dot + p.head_b[0];
         }
       }
+      if (lt < 6 && warp == 2) stamp(8 + lt * 4 + 3);
     }
     if (warp == 2) stamp(5);
     if (lane == 0) bulk_wait_read<0>();   // smem must outlive the last TMA stores
@@ -414,6 +432,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // the peer may still multicast commits into this CTA's barriers until it is done too
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
@@ -429,24 +448,36 @@ inline int sm_count() {
   return n[dev & 63];
 }
 
-template <int BN, bool LN>
-inline void launch_bn(const ConvGemmArgs& a, cudaStream_t stream) {
+inline int& cluster_size_flag() {   // 2 = weight tiles multicast across CTA pairs (default), 1 = independent CTAs
+  static int f = 2;
+  return f;
+}
+
+template <int BN, bool LN, int CL>
+inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool configured[64] = {};
   int dev = 0;
   FS2_CUDA_OK(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
     configured[dev & 63] = true;
   }
   const CUtensorMap tmA = make_map(a.A, a.rows, a.K, a.lda, BM, /*round_tf32=*/true, false);
-  const CUtensorMap tmW = make_map(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN, false, true);
+  const CUtensorMap tmW = make_map(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN / CL, false, true);
   const CUtensorMap tmC = a.C != nullptr ? make_map(a.C, a.rows, a.N, a.ldc, 32, false, false) : tmA;
   const CUtensorMap tmR = a.residual != nullptr ? make_map(a.residual, a.rows, a.N, a.ldr, 32, false, false) : tmA;
-  const int tiles = ((a.rows + BM - 1) / BM) * ((a.N + BN - 1) / BN);
-  const int grid = std::min(tiles, sm_count());
-  launch_pdl(conv_gemm_tc2_kernel<BN, LN>, dim3(grid), dim3(THREADS), C::TOTAL, stream, tmA, tmW, tmC, tmR, a);
+  const int items = (((a.rows + BM - 1) / BM + CL - 1) / CL) * ((a.N + BN - 1) / BN);
+  const int grid = std::min(items, sm_count() / CL) * CL;
+  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL>, dim3(grid), dim3(THREADS), C::TOTAL, stream, CL, tmA, tmW, tmC, tmR, a);
   FS2_LAUNCHED();
+}
+
+template <int BN, bool LN>
+inline void launch_bn(const ConvGemmArgs& a, cudaStream_t stream) {
+  // a single row tile has no partner to share weights with
+  if (cluster_size_flag() == 2 && a.rows > BM) launch_bn_cl<BN, LN, 2>(a, stream);
+  else launch_bn_cl<BN, LN, 1>(a, stream);
 }
 
 inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {

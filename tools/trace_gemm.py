@@ -55,3 +55,25 @@ for rows, K in [(128, 256), (128, 1024), (26788, 256), (26788, 1024)]:
     L.fs2_debug_set_flag(1, 0)
     t = np.array(list(buf), dtype=np.int64); rel = (t - t[0]) / 1e3
     print(f"LN rows={rows} K={K}: prologue {rel[1]:.2f}, first_tma {rel[2]:.2f}, mma_tile0 {rel[3]:.2f}, acc_ready {rel[4]:.2f}, epi_done(all tiles) {rel[5]:.2f}, exit {rel[7]:.2f}")
+
+print("==== per-tile timeline of CTA 0 (us from kernel entry): mma_begin, acc_free(after wait), epi_begin(acc ready), epi_end")
+for name, K, N, taps, ln in [("qkv", 256, 768, 1, False), ("fc_ln", 256, 256, 1, True), ("w2_ln", 1024, 256, 1, True), ("conv9", 256, 1024, 9, False)]:
+    rows = 26788
+    A = torch.randn(rows, K, device=DEV); W = torch.randn(taps, N, K, device=DEV) / 16; bias = torch.randn(N, device=DEV)
+    res = torch.randn(rows, N, device=DEV); gm = torch.ones(256, device=DEV); bt = torch.zeros(256, device=DEV)
+    out = torch.empty(rows, N, device=DEV)
+    if ln:
+        call = lambda: L.fs2_op_conv_gemm_ln(stream(), 1, ptr(A), K, rows, ptr(W), ptr(bias), taps, (taps-1)//2, K, 0, ptr(res), 256, ptr(gm), ptr(bt), None, None, 0, ptr(out), 256, None, None, None)
+    else:
+        call = lambda: L.fs2_op_conv_gemm(stream(), 1, 0, ptr(A), K, rows, ptr(W), ptr(bias), taps, (taps-1)//2, K, N, 0, None, N, None, None, 0, ptr(out), N)
+    for _ in range(3): call()
+    torch.cuda.synchronize()
+    L.fs2_debug_set_flag(1, 1)
+    call(); torch.cuda.synchronize()
+    buf = (ctypes.c_int64 * 40)()
+    L.fs2_debug_read_trace(buf, 40)
+    L.fs2_debug_set_flag(1, 0)
+    t = np.array(list(buf), dtype=np.int64); rel = (t - t[0]) / 1e3
+    print(name, "exit %.1f" % rel[7])
+    for j in range(6):
+        print("   tile", j, " ".join(f"{x:8.2f}" for x in rel[8 + 4 * j: 12 + 4 * j]))
