@@ -313,7 +313,11 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": dom + " (decoder FFN Conv1d k=9 implicit GEMM, 256->1024)",
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tensor_peak if tensor_peak else None, "traffic": None,
+                         "frac": achieved / tensor_peak if tensor_peak else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed
+                         # `ncu --set full` capture profiles/r01_ncu_full_tc2_conv9_raw.csv (37.10 MB + 55.88 MB)
+                         "traffic": 92.98e6 if (args.engine == "tcgen05" and args.batch == 64) else None,
+                         "algorithmic_bytes_per_launch": 4 * (frames * 256 + 9 * 1024 * 256 + frames * 1024),
                          "per_launch_ms": per_launch_ms, "launches_per_step": n_dom // PROF_RUNS,
                          "flops_per_launch": flops_per_launch,
                          "peak_source": f"{peaks['source']} bf16_tflops_sustained" +

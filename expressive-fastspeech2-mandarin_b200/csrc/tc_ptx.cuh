@@ -248,7 +248,7 @@ inline const CUtensorMap& make_map(const float* base, int64_t rows, int64_t cols
   cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode_fn()(&m, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                                  const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
-                                 reused ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   require(r == CUDA_SUCCESS, FS2_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return cache.emplace(key, m).first->second;
