@@ -12,6 +12,8 @@
 // 64 KB of shared memory for a third K and V stage: loads run three tiles ahead of the MMAs.
 #pragma once
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "gemm_tcgen05.cuh"
 
@@ -60,7 +62,8 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                    const __grid_constant__ CUtensorMap tmV, const int32_t* __restrict__ starts, const int32_t* __restrict__ lens, float* __restrict__ out, int dbg) {
+                    const __grid_constant__ CUtensorMap tmV, const int32_t* __restrict__ starts, const int32_t* __restrict__ lens, float* __restrict__ out,
+                    __nv_bfloat16* __restrict__ out_b, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
 
@@ -342,10 +345,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     } else
     if (qrow < len) {
       const float inv = 1.f / l;
-      float* dst = out + (size_t)(row0 + qrow) * D_MODEL + h * D_HEAD;
+      if (out_b != nullptr) {   // BF16 mode: the context is only ever the A operand of the fc contraction
+        __nv_bfloat16* dst = out_b + (size_t)(row0 + qrow) * D_MODEL + h * D_HEAD;
 #pragma unroll
-      for (int i = 0; i < D_HEAD; i += 4)
-        *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+        for (int i = 0; i < D_HEAD; i += 8) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(o[i + 2 * e] * inv, o[i + 2 * e + 1] * inv);
+            w[e] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
+          *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      } else {
+        float* dst = out + (size_t)(row0 + qrow) * D_MODEL + h * D_HEAD;
+#pragma unroll
+        for (int i = 0; i < D_HEAD; i += 4)
+          *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+      }
     }
   }
   tc_fence_before();
@@ -362,7 +379,7 @@ inline int& debug_flag() {
 }
 
 inline void launch(const float* qkv, int rows, const int32_t* starts, const int32_t* lens, int batch, int max_len,
-                   float* out, cudaStream_t stream) {
+                   float* out, cudaStream_t stream, void* out_bf16 = nullptr) {
   if (batch <= 0 || max_len <= 0 || rows <= 0) return;
   static bool configured[64] = {};
   int dev = 0;
@@ -375,7 +392,8 @@ inline void launch(const float* qkv, int rows, const int32_t* starts, const int3
   const CUtensorMap tmKV = make_map(qkv, rows, LDQKV, LDQKV, BKV, true, true);
   const CUtensorMap tmV = make_map(qkv, rows, LDQKV, LDQKV, BKV, true, true, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   dim3 grid((max_len + BQ - 1) / BQ, N_HEAD, batch);
-  launch_pdl(attention_tc_kernel, grid, dim3(THREADS), SMEM_TOTAL, stream, 1, tmQ, tmKV, tmV, starts, lens, out, debug_flag());
+  launch_pdl(attention_tc_kernel, grid, dim3(THREADS), SMEM_TOTAL, stream, 1, tmQ, tmKV, tmV, starts, lens, out,
+             static_cast<__nv_bfloat16*>(out_bf16), debug_flag());
   FS2_LAUNCHED();
 }
 

@@ -50,6 +50,11 @@ struct Pool {  // activation buffers of one side
   float* hid = nullptr;                                  // [rows,1024]
   float *mel = nullptr, *post = nullptr;                 // [rows,80]   (frame side only)
   float* pn[2] = {nullptr, nullptr};                     // [rows,512]  (frame side only)
+  // FS2_MATH_BF16: bf16 copies that serve as the A operands (the fp32 hid / pn buffers are not allocated)
+  __nv_bfloat16* actb[4] = {nullptr, nullptr, nullptr, nullptr};  // mirrors of act[i]
+  __nv_bfloat16* hidb = nullptr;                                   // [rows,1024]
+  __nv_bfloat16* melb = nullptr;                                   // [rows,80]
+  __nv_bfloat16* pnb[2] = {nullptr, nullptr};                      // [rows,512]
   int rows = 0;
 };
 
@@ -154,11 +159,20 @@ static float* keep(fs2_ctx* c, size_t n) {
 }
 
 // [Cout][Cin][k] -> [k][Cout][Cin], optional per-Cout scale, TF32-rounded operands
-static float* repack_conv(fs2_ctx* c, const float* w, int cout, int cin, int k, const float* scale, cudaStream_t s) {
+// In FS2_MATH_BF16 the result is a bf16 array behind the float* (ConvGemmArgs::a_bf16 tells the kernel).
+static void repack_into(fs2_ctx* c, const float* w, int cout, int cin, int k, const float* scale, float* out, cudaStream_t s) {
   const int64_t n = (int64_t)cout * cin * k;
-  float* out = keep(c, n);
-  repack_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, cout, cin, k, scale, 1, out);
+  if (c->cfg.math_mode == FS2_MATH_BF16) {
+    repack_conv_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, cout, cin, k, scale,
+                                                                        reinterpret_cast<__nv_bfloat16*>(out));
+  } else {
+    repack_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, cout, cin, k, scale, 1, out);
+  }
   FS2_LAUNCHED();
+}
+static float* repack_conv(fs2_ctx* c, const float* w, int cout, int cin, int k, const float* scale, cudaStream_t s) {
+  float* out = keep(c, (size_t)cout * cin * k);
+  repack_into(c, w, cout, cin, k, scale, out, s);
   return out;
 }
 
@@ -171,8 +185,10 @@ static void prepare_fft(fs2_ctx* c, const std::string& p, FFTLayer& L, cudaStrea
     const auto& w = W(c, p + ".slf_attn." + names[i] + ".weight", {d, d});
     const auto& b = W(c, p + ".slf_attn." + names[i] + ".bias", {d});
     // Linear weight [N][K] is already K-major: repack as a 1-tap conv to round the operands
-    repack_conv_kernel<<<(d * d + 255) / 256, 256, 0, s>>>(w.ptr, d, d, 1, nullptr, 1, L.wqkv + (size_t)i * d * d);
-    FS2_LAUNCHED();
+    const size_t off = (size_t)i * d * d;   // in elements of the operand type
+    repack_into(c, w.ptr, d, d, 1, nullptr,
+                c->cfg.math_mode == FS2_MATH_BF16 ? reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(L.wqkv) + off)
+                                                  : L.wqkv + off, s);
     FS2_CUDA_OK(cudaMemcpyAsync(L.bqkv + i * d, b.ptr, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
   L.wfc = repack_conv(c, W(c, p + ".slf_attn.fc.weight", {d, d}).ptr, d, d, 1, nullptr, s);
@@ -239,26 +255,39 @@ static void conv_gemm(int engine, int math, const ConvGemmArgs& a, cudaStream_t 
   if (engine == FS2_ENGINE_TCGEN05) {
     tc2::launch(a, math, s);
   } else if (engine == FS2_ENGINE_TCGEN05_V1) {
-    require(a.ln_gamma == nullptr, FS2_ERR_UNSUPPORTED, "the non-persistent tcgen05 engine has no fused LayerNorm");
+    require(a.ln_gamma == nullptr && !a.a_bf16 && a.C2 == nullptr, FS2_ERR_UNSUPPORTED,
+            "the non-persistent tcgen05 engine has no fused LayerNorm and no bf16 mode");
     tc::launch(a, math, s);
   } else {
-    require(a.ln_gamma == nullptr, FS2_ERR_UNSUPPORTED, "the mma.sync engine has no fused LayerNorm");
+    require(a.ln_gamma == nullptr && !a.a_bf16 && a.C2 == nullptr, FS2_ERR_UNSUPPORTED,
+            "the mma.sync engine has no fused LayerNorm and no bf16 mode");
     require(math == FS2_MATH_TF32, FS2_ERR_UNSUPPORTED, "the mma.sync engine implements TF32 only");
     mma::launch(a, s);
   }
 }
 
 static void attention(int engine, const float* qkv, int rows, const int32_t* starts, const int32_t* lens, int batch,
-                      int max_len, float* out, cudaStream_t s) {
-  if (engine != FS2_ENGINE_MMA_SYNC) attn_tc::launch(qkv, rows, starts, lens, batch, max_len, out, s);
+                      int max_len, float* out, cudaStream_t s, void* out_bf16 = nullptr) {
+  if (engine != FS2_ENGINE_MMA_SYNC) attn_tc::launch(qkv, rows, starts, lens, batch, max_len, out, s, out_bf16);
   else attn::launch(qkv, starts, lens, batch, max_len, out, s);
 }
+
+// bf16-operand variant: A and W are bf16 behind the float* fields
+static ConvGemmArgs gemm_args_b(const void* A, int lda, int rows, const float* Wt, const float* bias, int taps, int K, int N,
+                                int act, float* C, int ldc, void* C2, int ldc2);
 
 static ConvGemmArgs gemm_args(const float* A, int lda, int rows, const float* Wt, const float* bias, int taps, int K,
                               int N, int act, float* C, int ldc) {
   ConvGemmArgs a{};
   a.A = A; a.lda = lda; a.rows = rows; a.W = Wt; a.bias = bias; a.taps = taps; a.pad = (taps - 1) / 2;
   a.K = K; a.N = N; a.act = act; a.C = C; a.ldc = ldc;
+  return a;
+}
+
+static ConvGemmArgs gemm_args_b(const void* A, int lda, int rows, const float* Wt, const float* bias, int taps, int K, int N,
+                                int act, float* C, int ldc, void* C2, int ldc2) {
+  ConvGemmArgs a = gemm_args(static_cast<const float*>(A), lda, rows, Wt, bias, taps, K, N, act, C, ldc);
+  a.a_bf16 = 1; a.C2 = C2; a.ldc2 = ldc2;
   return a;
 }
 
@@ -274,6 +303,30 @@ static void layernorm(cudaStream_t s, const float* x, int rows, const float* g, 
 static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSide& side, Pool& pool, int rows, int batch,
                       int max_len, float* x, float* t1, float* t2, bool frame) {
   const int eng = c->cfg.engine, math = c->cfg.math_mode;
+  if (math == FS2_MATH_BF16) {
+    // Same five launches; every A operand is the bf16 mirror written by the producing epilogue, the residual
+    // stream (x, t2) and the attention inputs (qkv) stay fp32.
+    __nv_bfloat16 *xb = pool.actb[0], *t1b = pool.actb[1], *t2b = pool.actb[2];
+    const int32_t* live = reinterpret_cast<const int32_t*>(side.totals);
+    ConvGemmArgs a = gemm_args_b(xb, D_MODEL, rows, L.wqkv, L.bqkv, 1, D_MODEL, 3 * D_MODEL, ACT_NONE, pool.qkv, 3 * D_MODEL,
+                                 nullptr, 0);
+    a.live_rows = live;
+    { ProfScope ps(c, s, frame ? "dec.gemm_qkv" : "enc.gemm_qkv"); conv_gemm(eng, math, a, s); }
+    { ProfScope ps(c, s, frame ? "dec.attention" : "enc.attention");
+      attention(eng, pool.qkv, rows, side.starts, side.lens, batch, max_len, t1, s, t1b); }
+    a = gemm_args_b(t1b, D_MODEL, rows, L.wfc, L.bfc, 1, D_MODEL, D_MODEL, ACT_NONE, t2, D_MODEL, t2b, D_MODEL);
+    a.residual = x; a.ldr = D_MODEL; a.live_rows = live;
+    a.ln_gamma = L.ln1_g; a.ln_beta = L.ln1_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
+    { ProfScope ps(c, s, frame ? "dec.gemm_fc_ln" : "enc.gemm_fc_ln"); conv_gemm(eng, math, a, s); }
+    a = gemm_args_b(t2b, D_MODEL, rows, L.w1, L.b1, FFN_TAPS, D_MODEL, D_INNER, ACT_RELU, nullptr, 0, pool.hidb, D_INNER);
+    a.live_rows = live;
+    { ProfScope ps(c, s, frame ? "dec.gemm_conv9" : "enc.gemm_conv9"); conv_gemm(eng, math, a, s); }
+    a = gemm_args_b(pool.hidb, D_INNER, rows, L.w2, L.b2, 1, D_INNER, D_MODEL, ACT_NONE, x, D_MODEL, xb, D_MODEL);
+    a.residual = t2; a.ldr = D_MODEL; a.live_rows = live;
+    a.ln_gamma = L.ln2_g; a.ln_beta = L.ln2_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
+    { ProfScope ps(c, s, frame ? "dec.gemm_w2_ln" : "enc.gemm_w2_ln"); conv_gemm(eng, math, a, s); }
+    return;
+  }
   ConvGemmArgs a = gemm_args(x, D_MODEL, rows, L.wqkv, L.bqkv, 1, D_MODEL, 3 * D_MODEL, ACT_NONE, pool.qkv, 3 * D_MODEL);
   a.live_rows = reinterpret_cast<const int32_t*>(side.totals);  // low word of totals[0] (little endian)
   { ProfScope ps(c, s, frame ? "dec.gemm_qkv" : "enc.gemm_qkv"); conv_gemm(eng, math, a, s); }
@@ -309,9 +362,21 @@ static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSi
 
 // VariancePredictor (model/modules.py:242-250) over the packed rows; head_out is [B, Lmax], pre-zeroed.
 static void predictor(fs2_ctx* c, cudaStream_t s, const Predictor& P, const RowSide& side, int rows, const float* x,
-                      float* t1, float* t2, float* head_out) {
+                      float* t1, float* t2, float* head_out, const __nv_bfloat16* xb = nullptr, __nv_bfloat16* t1b = nullptr) {
   ProfScope ps(c, s, "predictor");
   const int eng = c->cfg.engine, math = c->cfg.math_mode;
+  if (math == FS2_MATH_BF16) {
+    ConvGemmArgs f = gemm_args_b(xb, D_MODEL, rows, P.w1, P.b1, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, nullptr, 0, t1b, D_MODEL);
+    f.live_rows = reinterpret_cast<const int32_t*>(side.totals);
+    f.ln_gamma = P.ln1_g; f.ln_beta = P.ln1_b; f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 1;
+    conv_gemm(eng, math, f, s);
+    f = gemm_args_b(t1b, D_MODEL, rows, P.w2, P.b2, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, nullptr, 0, nullptr, 0);
+    f.live_rows = reinterpret_cast<const int32_t*>(side.totals);
+    f.ln_gamma = P.ln2_g; f.ln_beta = P.ln2_b; f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 0;
+    f.head_w = P.head_w; f.head_b = P.head_b; f.head_out = head_out; f.slot = side.slot;
+    conv_gemm(eng, math, f, s);
+    return;
+  }
   if (eng == FS2_ENGINE_TCGEN05) {
     ConvGemmArgs f = gemm_args(x, D_MODEL, rows, P.w1, P.b1, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, t1, D_MODEL);
     f.live_rows = reinterpret_cast<const int32_t*>(side.totals);
@@ -350,16 +415,27 @@ static void ensure_side(RowSide& sd, int batch, int rows) {
   if (!sd.totals) regrow(sd.totals, 3);
 }
 
-static void ensure_pool(Pool& p, int rows, bool frame_side) {
+static void ensure_pool(Pool& p, int rows, bool frame_side, bool bf16) {
   if (rows <= p.rows) return;
   for (auto& a : p.act) regrow(a, (size_t)rows * D_MODEL);
   regrow(p.qkv, (size_t)rows * 3 * D_MODEL);
-  regrow(p.hid, (size_t)rows * D_INNER);
+  if (bf16) {
+    for (auto& a : p.actb) regrow(a, (size_t)rows * D_MODEL);
+    regrow(p.hidb, (size_t)rows * D_INNER);
+  } else {
+    regrow(p.hid, (size_t)rows * D_INNER);
+  }
   if (frame_side) {
     regrow(p.mel, (size_t)rows * N_MEL);
     regrow(p.post, (size_t)rows * N_MEL);
-    regrow(p.pn[0], (size_t)rows * PN_DIM);
-    regrow(p.pn[1], (size_t)rows * PN_DIM);
+    if (bf16) {
+      regrow(p.melb, (size_t)rows * N_MEL);
+      regrow(p.pnb[0], (size_t)rows * PN_DIM);
+      regrow(p.pnb[1], (size_t)rows * PN_DIM);
+    } else {
+      regrow(p.pn[0], (size_t)rows * PN_DIM);
+      regrow(p.pn[1], (size_t)rows * PN_DIM);
+    }
   }
   p.rows = rows;
 }
@@ -399,7 +475,8 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   const int rows = round_up((int)bound, 128);
   ensure_side(c->ps, B, rows);
   ensure_side(c->fs, B, 0);
-  ensure_pool(c->pp, rows, false);
+  const bool bf = c->cfg.math_mode == FS2_MATH_BF16;
+  ensure_pool(c->pp, rows, false, bf);
   const int64_t BL = (int64_t)B * L;
   if (BL > c->scratch_bl) {
     regrow(c->cum, BL);
@@ -436,7 +513,7 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   float *x = pp.act[0], *t1 = pp.act[1], *t2 = pp.act[2], *t3 = pp.act[3];
   const float* pe = position_rows(c, "encoder.position_enc", L, s);
   embed_pe_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in->texts, L, c->raw.at("encoder.src_word_emb.weight").ptr,
-                                                 c->cfg.n_src_vocab, pe, ps.meta(), ps.lens, rows, x, c->status);
+                                                 c->cfg.n_src_vocab, pe, ps.meta(), ps.lens, rows, x, c->status, pp.actb[0]);
   FS2_LAUNCHED();
   tap(c, s, "p_start", ps.starts, 1, B + 1);
   tap(c, s, "enc_in", x, rows, D_MODEL);
@@ -453,20 +530,20 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
                                 c->raw.at("emotion_linear.0.bias").ptr, c->cond_spk, c->cond_emo, c->status);
   FS2_LAUNCHED();
   float* xc = t3;
-  add_cond_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, ps.meta(), c->cond_spk, c->cond_emo, 2, rows, xc);
+  add_cond_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, ps.meta(), c->cond_spk, c->cond_emo, 2, rows, xc, pp.actb[3]);
   FS2_LAUNCHED();
   tap(c, s, "cond_x", xc, rows, D_MODEL);
 
   // ---- VarianceAdaptor (model/modules.py:102-135)
-  predictor(c, s, c->pred[0], ps, rows, xc, t1, t2, out->log_d);
-  predictor(c, s, c->pred[1], ps, rows, xc, t1, t2, c->raw_pitch);
+  predictor(c, s, c->pred[0], ps, rows, xc, t1, t2, out->log_d, pp.actb[3], pp.actb[1]);
+  predictor(c, s, c->pred[1], ps, rows, xc, t1, t2, c->raw_pitch, pp.actb[3], pp.actb[1]);
   float* xe = x;  // encoder output is no longer needed
   bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
       xc, ps.meta(), ps.slot, 2, rows, c->raw_pitch, in->p_targets, in->p_control,
       c->raw.at("variance_adaptor.pitch_bins").ptr, N_BINS - 1, c->raw.at("variance_adaptor.pitch_embedding.weight").ptr,
-      out->pitch, nullptr, xe);
+      out->pitch, nullptr, xe, pp.actb[0]);
   FS2_LAUNCHED();
-  predictor(c, s, c->pred[2], ps, rows, xe, t1, t2, c->raw_energy);
+  predictor(c, s, c->pred[2], ps, rows, xe, t1, t2, c->raw_energy, pp.actb[0], pp.actb[1]);
   float* xf = t3;
   bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
       xe, ps.meta(), ps.slot, 0, rows, c->raw_energy, in->e_targets, in->p_control /* sic: modules.py:123-125 */,
@@ -519,7 +596,8 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
   const int rows = round_up((int)c->frame_rows, 128);
   const int eng = c->cfg.engine, math = c->cfg.math_mode;
   ensure_side(c->fs, B, rows);
-  ensure_pool(c->fp, rows, true);
+  const bool bf = math == FS2_MATH_BF16;
+  ensure_pool(c->fp, rows, true, bf);
   RowSide& fsd = c->fs;
   Pool& fp = c->fp;
 
@@ -533,7 +611,7 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
     {
       ProfScope ps(c, s, "length_regulator");
       length_regulate_kernel<<<(rows + 7) / 8, 256, 0, s>>>(c->lr_input, c->ps.starts, c->cum, L, fsd.meta(), fsd.lens, pe,
-                                                            rows, x);
+                                                            rows, x, fp.actb[0]);
       FS2_LAUNCHED();
     }
     tap(c, s, "f_start", fsd.starts, 1, B + 1);
@@ -543,18 +621,28 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
       if (c->debug) tap(c, s, ("dec_" + std::to_string(i)).c_str(), x, rows, D_MODEL);
     }
     // ---- mel_linear (fastspeech2.py:134); the first min(10, T_max - T_b) reserved rows get the bias
-    ConvGemmArgs a = gemm_args(x, D_MODEL, rows, c->mel_w, c->mel_b, 1, D_MODEL, N_MEL, ACT_NONE, fp.mel, N_MEL);
+    ConvGemmArgs a = bf ? gemm_args_b(fp.actb[0], D_MODEL, rows, c->mel_w, c->mel_b, 1, D_MODEL, N_MEL, ACT_NONE, fp.mel, N_MEL,
+                                      fp.melb, N_MEL)
+                        : gemm_args(x, D_MODEL, rows, c->mel_w, c->mel_b, 1, D_MODEL, N_MEL, ACT_NONE, fp.mel, N_MEL);
     a.row_vpos = fsd.vpos; a.row_room = fsd.room; a.extra = PN_VIRTUAL;
     { ProfScope ps(c, s, "mel_linear"); conv_gemm(eng, math, a, s); }
     tap(c, s, "mel_p", fp.mel, rows, N_MEL);
     // ---- PostNet (Layers.py:129-137) + residual (fastspeech2.py:136), BatchNorm folded
     const float* src = fp.mel;
+    const __nv_bfloat16* srcb = fp.melb;
     int ld = N_MEL;
     for (int j = 0; j < PN_LAYERS; ++j) {
       const PostConv& pc = c->post[j];
       const bool last = j == PN_LAYERS - 1;
       float* dst = last ? fp.post : fp.pn[j & 1];
-      a = gemm_args(src, ld, rows, pc.w, pc.b, PN_TAPS, pc.cin, pc.cout, last ? ACT_NONE : ACT_TANH, dst, pc.cout);
+      if (bf) {   // intermediate layers exist only as bf16 operands; the last one writes the fp32 result
+        __nv_bfloat16* dstb = last ? nullptr : fp.pnb[j & 1];
+        a = gemm_args_b(srcb, ld, rows, pc.w, pc.b, PN_TAPS, pc.cin, pc.cout, last ? ACT_NONE : ACT_TANH,
+                        last ? fp.post : nullptr, pc.cout, dstb, pc.cout);
+        srcb = dstb;
+      } else {
+        a = gemm_args(src, ld, rows, pc.w, pc.b, PN_TAPS, pc.cin, pc.cout, last ? ACT_NONE : ACT_TANH, dst, pc.cout);
+      }
       a.row_vpos = fsd.vpos; a.row_room = fsd.room; a.extra = PN_VIRTUAL - 2 * (j + 1);
       if (last) { a.residual = fp.mel; a.ldr = N_MEL; }
       { ProfScope ps(c, s, j == 0 ? "postnet.conv_80_512" : (last ? "postnet.conv_512_80" : "postnet.conv_512_512"));
@@ -649,6 +737,8 @@ int fs2_create(const fs2_config* cfg, int device, fs2_ctx** out) {
     require(cfg->math_mode == FS2_MATH_TF32 || cfg->math_mode == FS2_MATH_BF16, FS2_ERR_UNSUPPORTED, "unknown math_mode");
     require(cfg->engine == FS2_ENGINE_MMA_SYNC || cfg->engine == FS2_ENGINE_TCGEN05 ||
                 cfg->engine == FS2_ENGINE_TCGEN05_V1, FS2_ERR_UNSUPPORTED, "unknown engine");
+    require(cfg->math_mode == FS2_MATH_TF32 || cfg->engine == FS2_ENGINE_TCGEN05, FS2_ERR_UNSUPPORTED,
+            "FS2_MATH_BF16 is implemented by the persistent tcgen05 engine only");
     require(cfg->n_src_vocab > 0 && cfg->n_speaker > 0 && cfg->n_emotion > 0 && cfg->n_arousal > 0 && cfg->n_valence > 0 &&
                 cfg->max_seq_len > 0, FS2_ERR_INVALID, "table sizes must be positive");
     int n_dev = 0;
@@ -684,6 +774,8 @@ void fs2_destroy(fs2_ctx* c) {
   for (Pool* p : {&c->pp, &c->fp}) {
     for (float* a : p->act) cudaFree(a);
     cudaFree(p->qkv); cudaFree(p->hid); cudaFree(p->mel); cudaFree(p->post); cudaFree(p->pn[0]); cudaFree(p->pn[1]);
+    for (auto* a : p->actb) cudaFree(a);
+    cudaFree(p->hidb); cudaFree(p->melb); cudaFree(p->pnb[0]); cudaFree(p->pnb[1]);
   }
   cudaFree(c->status); cudaFree(c->cum); cudaFree(c->mel_lens32); cudaFree(c->raw_pitch); cudaFree(c->raw_energy);
   cudaFree(c->cond_spk); cudaFree(c->cond_emo); cudaFree(c->pe_long);
@@ -835,6 +927,22 @@ int fs2_op_conv_gemm_ln(fs2_stream stream, int engine, const float* A, int lda, 
     a.ln_gamma = gamma; a.ln_beta = beta; a.head_w = head_w; a.head_b = head_b; a.head_out = head_out;
     if (g_trace_on) { a.trace = g_trace_buf + 8 * ((g_trace_on - 1) % 8); ++g_trace_on; }
     conv_gemm(engine, FS2_MATH_TF32, a, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int fs2_op_conv_gemm_bf16(fs2_stream stream, const void* A, int lda, int rows, const void* Wt, const float* bias, int taps,
+                          int pad, int K, int N, int act, const float* residual, int ldr, const float* gamma,
+                          const float* beta, const int32_t* row_vpos, const int32_t* row_room, int extra, float* C, int ldc,
+                          void* C2, int ldc2) {
+  return guarded(nullptr, [&] {
+    require(A && Wt && bias && (C || C2) && rows >= 0 && taps >= 1 && K > 0 && N > 0, FS2_ERR_INVALID,
+            "bad conv_gemm_bf16 argument");
+    ConvGemmArgs a{};
+    a.A = static_cast<const float*>(A); a.lda = lda; a.rows = rows; a.W = static_cast<const float*>(Wt); a.bias = bias;
+    a.taps = taps; a.pad = pad; a.K = K; a.N = N; a.act = act; a.residual = residual; a.ldr = ldr;
+    a.row_vpos = row_vpos; a.row_room = row_room; a.extra = extra; a.C = C; a.ldc = ldc; a.C2 = C2; a.ldc2 = ldc2;
+    a.ln_gamma = gamma; a.ln_beta = beta; a.a_bf16 = 1;
+    conv_gemm(FS2_ENGINE_TCGEN05, FS2_MATH_BF16, a, static_cast<cudaStream_t>(stream));
   });
 }
 

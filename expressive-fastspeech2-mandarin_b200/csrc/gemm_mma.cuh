@@ -36,6 +36,12 @@ struct ConvGemmArgs {
   const float* head_b;
   float* head_out;
   const int32_t* slot;
+  // BF16 operand mode (persistent tcgen05 engine only): A is bf16 [rows, lda] and W is bf16 [taps][N][K]
+  // (both pointers reinterpret the float* fields); bias, residual and C stay fp32.  C2, when set, receives
+  // a bf16 copy of the output [rows, ldc2] (the A operand of the next contraction); C may then be nullptr.
+  int a_bf16;
+  void* C2;
+  int ldc2;
   long long* trace;   // bring-up only: CTA 0 writes globaltimer stamps of its phases (nullptr in normal operation)
 };
 

@@ -17,6 +17,8 @@
 // the steady state has no CTA-wide barrier.
 #pragma once
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "gemm_mma.cuh"
 #include "tc_ptx.cuh"
@@ -79,11 +81,25 @@ __device__ __forceinline__ void sts4(uint32_t saddr, float4 v) {
 // byte offset of (row r, 16-byte chunk cc) inside a [rows x 128 B] SWIZZLE_128B sub-tile
 __device__ __forceinline__ int swz_off(int r, int cc) { return r * 128 + ((cc ^ (r & 7)) << 4); }
 
-template <int BN, bool LN, int CL>
+// 16-byte shared store of eight values rounded to bf16 (round to nearest even)
+__device__ __forceinline__ void sts8_bf16(uint32_t saddr, const float* v) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+
+// BF = bf16 operands (kind::f16, 64 elements per 128-byte K chunk) instead of TF32 (32 elements).
+template <int BN, bool LN, int CL, bool BF>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, ConvGemmArgs p) {
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                     const __grid_constant__ CUtensorMap tmC2, ConvGemmArgs p) {
   using C = Cfg<BN>;
+  constexpr int BKE = BF ? 64 : 32;   // operand elements per 128-byte swizzle row
   extern __shared__ uint8_t smem_raw[];
   auto stamp = [&](int k) {
 #ifdef FS2_TRACE_BUILD   // phase timestamps for tools/trace_gemm.py
@@ -110,16 +126,18 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 8);
 
   const int warp = warp_index(), lane = threadIdx.x & 31;
-  const int kchunks = (p.K + BK - 1) / BK;
+  const int kchunks = (p.K + BKE - 1) / BKE;
   const int iters = p.taps * kchunks;
   const int n_tiles_n = (p.N + BN - 1) / BN;
   const bool has_res = p.residual != nullptr;
   const bool has_out = p.C != nullptr;
+  const bool has_out2 = p.C2 != nullptr;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
     if (has_out) asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+    if (has_out2) asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmC2)) : "memory");
     if (has_res) asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full[s], 1);
@@ -171,11 +189,11 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint8_t* a_s = smem + s * C::STAGE_BYTES;
         if (leader) {
           mbar_expect_tx(&full[s], C::STAGE_BYTES);
-          tma_load_2d(a_s, &tmA, kc * BK, m0 + tap - p.pad, &full[s]);
+          tma_load_2d(a_s, &tmA, kc * BKE, m0 + tap - p.pad, &full[s]);
           if (CL == 1) {
-            tma_load_2d(a_s + C::A_BYTES, &tmW, kc * BK, tap * p.N + n0, &full[s]);
+            tma_load_2d(a_s + C::A_BYTES, &tmW, kc * BKE, tap * p.N + n0, &full[s]);
           } else {   // this CTA's half of the weight tile, delivered to both CTAs of the cluster
-            tma_load_2d_mc(a_s + C::A_BYTES + rank * (C::B_BYTES / 2), &tmW, kc * BK, tap * p.N + n0 + rank * (BN / 2), &full[s],
+            tma_load_2d_mc(a_s + C::A_BYTES + rank * (C::B_BYTES / 2), &tmW, kc * BKE, tap * p.N + n0 + rank * (BN / 2), &full[s],
                            (uint16_t)0x3);
           }
         }
@@ -185,7 +203,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (warp == 1) {
     // ---------------- MMA issuer (whole warp runs the loop, one elected lane issues)
     const bool leader = elect_one();
-    constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+    constexpr uint32_t idesc = BF ? umma_idesc_bf16(BM, BN) : umma_idesc_tf32(BM, BN);
     int it = 0, lt = 0;
     for (int w = w_first; w < total_items; w += w_step, ++lt) {
       const int u = lt & 1;
@@ -203,7 +221,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint64_t da = umma_desc(a_s), db = umma_desc(a_s + C::A_BYTES);
         if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 8; ++kk) umma_tf32(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) {   // four 32-byte K slices per stage: K = 8 (tf32) or 16 (bf16) each
+            if (BF) umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
+            else umma_tf32(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
+          }
           if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], (uint16_t)0x3);
         }
         __syncwarp();
@@ -313,6 +334,25 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         ++g_st;
       };
+      // the same sub-tile rounded to bf16: [32 rows x 64 B], SWIZZLE_64B (16-byte chunk ^= (row >> 1) & 3)
+      auto stage_out_b = [&](const float (&v)[32], int c0, int width) {
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        uint8_t* sb = my_cst + (g_st & 1) * WCHUNK;
+        const uint32_t sa = cst_sa + (g_st & 1) * WCHUNK + lane * 64;
+        const uint32_t sx = (uint32_t)((lane >> 1) & 3) << 4;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          if (cc * 8 < width) sts8_bf16(sa + ((cc << 4) ^ sx), &v[cc * 8]);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmC2, sb, n0 + c0, m0 + q * 32);
+          bulk_commit();
+        }
+        ++g_st;
+      };
 
       if (!LN) {
 #pragma unroll 1
@@ -332,7 +372,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             tc_fence_before();
             mbar_arrive(&acc_empty[u]);
           }
-          stage_out(v, c0, width);
+          if (has_out) stage_out(v, c0, width);
+          if (has_out2) stage_out_b(v, c0, width);
         }
       } else {
         // ---- LayerNorm over the 256-wide row held in TMEM (eps 1e-5, biased variance).  Statistics are
@@ -403,6 +444,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
           if (has_out) stage_out(v, c * 32, 32);
+          if (has_out2) stage_out_b(v, c * 32, 32);
         };
         tmem_ld32_issue(acc, va);
 #pragma unroll 1
@@ -453,51 +495,63 @@ inline int& cluster_size_flag() {   // 2 = weight tiles multicast across CTA pai
   return f;
 }
 
-template <int BN, bool LN, int CL>
+template <int BN, bool LN, int CL, bool BF>
 inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool configured[64] = {};
   int dev = 0;
   FS2_CUDA_OK(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN, CL, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
     configured[dev & 63] = true;
   }
-  const CUtensorMap tmA = make_map(a.A, a.rows, a.K, a.lda, BM, /*round_tf32=*/true, false);
-  const CUtensorMap tmW = make_map(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN / CL, false, true);
+  constexpr CUtensorMapSwizzle SW128 = CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUtensorMap tmA = BF ? make_map_any(a.A, a.rows, a.K, a.lda, BM, 64, MAP_BF16, SW128)
+                             : make_map(a.A, a.rows, a.K, a.lda, BM, /*round_tf32=*/true, false);
+  const CUtensorMap tmW = BF ? make_map_any(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN / CL, 64, MAP_BF16, SW128)
+                             : make_map(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN / CL, false, true);
   const CUtensorMap tmC = a.C != nullptr ? make_map(a.C, a.rows, a.N, a.ldc, 32, false, false) : tmA;
   const CUtensorMap tmR = a.residual != nullptr ? make_map(a.residual, a.rows, a.N, a.ldr, 32, false, false) : tmA;
+  const CUtensorMap tmC2 =
+      a.C2 != nullptr ? make_map_any(a.C2, a.rows, a.N, a.ldc2, 32, 32, MAP_BF16, CU_TENSOR_MAP_SWIZZLE_64B) : tmA;
   const int items = (((a.rows + BM - 1) / BM + CL - 1) / CL) * ((a.N + BN - 1) / BN);
   const int grid = std::min(items, sm_count() / CL) * CL;
-  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL>, dim3(grid), dim3(THREADS), C::TOTAL, stream, CL, tmA, tmW, tmC, tmR, a);
+  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL, BF>, dim3(grid), dim3(THREADS), C::TOTAL, stream, CL, tmA, tmW, tmC, tmR, tmC2, a);
   FS2_LAUNCHED();
 }
 
 template <int BN, bool LN>
 inline void launch_bn(const ConvGemmArgs& a, cudaStream_t stream) {
   // a single row tile has no partner to share weights with
-  if (cluster_size_flag() == 2 && a.rows > BM) launch_bn_cl<BN, LN, 2>(a, stream);
-  else launch_bn_cl<BN, LN, 1>(a, stream);
+  const bool pair = cluster_size_flag() == 2 && a.rows > BM;
+  if (a.a_bf16) {
+    if (pair) launch_bn_cl<BN, LN, 2, true>(a, stream); else launch_bn_cl<BN, LN, 1, true>(a, stream);
+  } else {
+    if (pair) launch_bn_cl<BN, LN, 2, false>(a, stream); else launch_bn_cl<BN, LN, 1, false>(a, stream);
+  }
 }
 
 inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
-  require(math_mode == FS2_MATH_TF32, FS2_ERR_UNSUPPORTED, "tcgen05 engine: only FS2_MATH_TF32 is built");
-  require(a.K % 4 == 0 && a.lda % 4 == 0 && a.ldc % 4 == 0 && (a.residual == nullptr || a.ldr % 4 == 0), FS2_ERR_INVALID,
-          "tcgen05 conv_gemm: K and leading dimensions must be multiples of 4 (16-byte rows)");
+  (void)math_mode;   // the operand type travels with the arguments (a_bf16)
+  const int am = a.a_bf16 ? 8 : 4;   // elements per 16 bytes of the A / W rows
+  require(a.K % am == 0 && a.lda % am == 0 && (a.C == nullptr || a.ldc % 4 == 0) && (a.residual == nullptr || a.ldr % 4 == 0) &&
+              (a.C2 == nullptr || a.ldc2 % 8 == 0), FS2_ERR_INVALID,
+          "tcgen05 conv_gemm: K and leading dimensions must describe 16-byte-aligned rows");
   require((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0 &&
-              (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0,
+              (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(a.C2) & 15) == 0,
           FS2_ERR_INVALID, "tcgen05 conv_gemm: pointers must be 16-byte aligned");
   if (a.rows <= 0) return;
   require(a.N <= MAX_N, FS2_ERR_UNSUPPORTED, "tcgen05 conv_gemm: N > 1024");
   const bool ln = a.ln_gamma != nullptr;
   if (ln) {
     require(a.N == 256 && a.ln_beta != nullptr, FS2_ERR_INVALID, "fused LayerNorm needs N == 256 and both affine vectors");
-    require(a.C != nullptr || a.head_out != nullptr, FS2_ERR_INVALID, "fused LayerNorm: nothing to write");
+    require(a.C != nullptr || a.C2 != nullptr || a.head_out != nullptr, FS2_ERR_INVALID, "fused LayerNorm: nothing to write");
     require(a.head_out == nullptr || (a.head_w != nullptr && a.head_b != nullptr), FS2_ERR_INVALID, "head needs weight and bias");
     launch_bn<256, true>(a, stream);
     return;
   }
-  require(a.C != nullptr, FS2_ERR_INVALID, "conv_gemm: null output");
+  require(a.C != nullptr || a.C2 != nullptr, FS2_ERR_INVALID, "conv_gemm: null output");
   // Small problems (single utterances): a 128 x 256 tile would leave most SMs idle while one CTA
   // walks the whole K loop at 512 cycles per stage, so narrower tiles spread the columns over more
   // CTAs whose stages are proportionally shorter.

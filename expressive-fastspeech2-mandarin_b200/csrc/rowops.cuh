@@ -4,6 +4,8 @@
 // one row and moves it with 16-byte accesses.
 #pragma once
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace fs2 {
@@ -13,6 +15,12 @@ enum { ERR_BAD_LEN = 1, ERR_BAD_ID = 2, ERR_MAXLEN_SMALL = 4, ERR_BAD_INDEX = 8 
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// optional bf16 copy of a row (BF16 mode: the copy is the A operand of the next contraction); no-op when p == nullptr
+__device__ __forceinline__ void st4b(__nv_bfloat16* p, float4 v) {
+  if (p == nullptr) return;
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -125,15 +133,19 @@ __global__ void row_meta_kernel(const int32_t* __restrict__ starts, const int32_
 // Encoder input: src_word_emb[texts] + position_enc[:L]  (transformer/Models.py:82-91).
 __global__ void embed_pe_kernel(const int64_t* __restrict__ texts, int max_src_len, const float* __restrict__ emb,
                                 int n_vocab, const float* __restrict__ pe, RowMeta meta, const int32_t* __restrict__ lens,
-                                int rows, float* __restrict__ x, int32_t* __restrict__ status) {
+                                int rows, float* __restrict__ x, int32_t* __restrict__ status,
+                                __nv_bfloat16* __restrict__ xb = nullptr) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int u = meta.utt[row], vp = meta.vpos[row];
   float* dst = x + (size_t)row * D_MODEL;
+  __nv_bfloat16* dstb = xb != nullptr ? xb + (size_t)row * D_MODEL : nullptr;
   if (u < 0 || vp >= 0) {
     st4(dst + lane * 4, make_float4(0, 0, 0, 0));
     st4(dst + 128 + lane * 4, make_float4(0, 0, 0, 0));
+    st4b(dstb ? dstb + lane * 4 : nullptr, make_float4(0, 0, 0, 0));
+    st4b(dstb ? dstb + 128 + lane * 4 : nullptr, make_float4(0, 0, 0, 0));
     return;
   }
   const int pos = vp + lens[u];
@@ -144,8 +156,13 @@ __global__ void embed_pe_kernel(const int64_t* __restrict__ texts, int max_src_l
   }
   const float* e = emb + (size_t)id * D_MODEL;
   const float* p = pe + (size_t)pos * D_MODEL;
-  st4(dst + lane * 4, add4(ld4(e + lane * 4), ld4(p + lane * 4)));
-  st4(dst + 128 + lane * 4, add4(ld4(e + 128 + lane * 4), ld4(p + 128 + lane * 4)));
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = h * 128 + lane * 4;
+    const float4 v = add4(ld4(e + c), ld4(p + c));
+    st4(dst + c, v);
+    st4b(dstb ? dstb + c : nullptr, v);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -187,15 +204,19 @@ __global__ void cond_kernel(const int64_t* __restrict__ speakers, const int64_t*
 // rows (the reference adds the vectors on padding rows too and the predictors read them --
 // SURVEY.md B.4); every other row is zero.
 __global__ void add_cond_kernel(const float* __restrict__ x, RowMeta meta, const float* __restrict__ spk,
-                                const float* __restrict__ emo, int extra, int rows, float* __restrict__ y) {
+                                const float* __restrict__ emo, int extra, int rows, float* __restrict__ y,
+                                __nv_bfloat16* __restrict__ yb = nullptr) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int u = meta.utt[row];
   float* dst = y + (size_t)row * D_MODEL;
+  __nv_bfloat16* dstb = yb != nullptr ? yb + (size_t)row * D_MODEL : nullptr;
   if (u < 0 || !row_live(meta.vpos[row], meta.room[row], extra)) {
     st4(dst + lane * 4, make_float4(0, 0, 0, 0));
     st4(dst + 128 + lane * 4, make_float4(0, 0, 0, 0));
+    st4b(dstb ? dstb + lane * 4 : nullptr, make_float4(0, 0, 0, 0));
+    st4b(dstb ? dstb + 128 + lane * 4 : nullptr, make_float4(0, 0, 0, 0));
     return;
   }
   const float* src = x + (size_t)row * D_MODEL;
@@ -204,7 +225,9 @@ __global__ void add_cond_kernel(const float* __restrict__ x, RowMeta meta, const
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int c = h * 128 + lane * 4;
-    st4(dst + c, add4(add4(ld4(src + c), ld4(s + c)), ld4(e + c)));
+    const float4 v = add4(add4(ld4(src + c), ld4(s + c)), ld4(e + c));
+    st4(dst + c, v);
+    st4b(dstb ? dstb + c : nullptr, v);
   }
 }
 
@@ -284,15 +307,18 @@ __global__ void bucket_embed_add_kernel(const float* __restrict__ x, RowMeta met
                                         const float* __restrict__ target, float control,
                                         const float* __restrict__ bins, int n_bins, const float* __restrict__ table,
                                         float* __restrict__ pred_out, int32_t* __restrict__ idx_out,
-                                        float* __restrict__ y) {
+                                        float* __restrict__ y, __nv_bfloat16* __restrict__ yb = nullptr) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   float* dst = y + (size_t)row * D_MODEL;
+  __nv_bfloat16* dstb = yb != nullptr ? yb + (size_t)row * D_MODEL : nullptr;
   const int sl = slot[row];
   if (meta.utt[row] < 0 || sl < 0 || !row_live(meta.vpos[row], meta.room[row], extra)) {
     st4(dst + lane * 4, make_float4(0, 0, 0, 0));
     st4(dst + 128 + lane * 4, make_float4(0, 0, 0, 0));
+    st4b(dstb ? dstb + lane * 4 : nullptr, make_float4(0, 0, 0, 0));
+    st4b(dstb ? dstb + 128 + lane * 4 : nullptr, make_float4(0, 0, 0, 0));
     return;
   }
   const bool real = meta.vpos[row] < 0;
@@ -306,8 +332,13 @@ __global__ void bucket_embed_add_kernel(const float* __restrict__ x, RowMeta met
   }
   const float* src = x + (size_t)row * D_MODEL;
   const float* e = table + (size_t)idx * D_MODEL;
-  st4(dst + lane * 4, add4(ld4(src + lane * 4), ld4(e + lane * 4)));
-  st4(dst + 128 + lane * 4, add4(ld4(src + 128 + lane * 4), ld4(e + 128 + lane * 4)));
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = h * 128 + lane * 4;
+    const float4 v = add4(ld4(src + c), ld4(e + c));
+    st4(dst + c, v);
+    st4b(dstb ? dstb + c : nullptr, v);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -380,23 +411,31 @@ __global__ void frame_map_kernel(const int32_t* __restrict__ cum, int batch, int
 __global__ void length_regulate_kernel(const float* __restrict__ x, const int32_t* __restrict__ p_starts,
                                        const int32_t* __restrict__ cum, int max_src_len, RowMeta fmeta,
                                        const int32_t* __restrict__ f_lens, const float* __restrict__ pe, int rows,
-                                       float* __restrict__ y) {
+                                       float* __restrict__ y, __nv_bfloat16* __restrict__ yb = nullptr) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int u = fmeta.utt[row], vp = fmeta.vpos[row];
   float* dst = y + (size_t)row * D_MODEL;
+  __nv_bfloat16* dstb = yb != nullptr ? yb + (size_t)row * D_MODEL : nullptr;
   if (u < 0 || vp >= 0) {
     st4(dst + lane * 4, make_float4(0, 0, 0, 0));
     st4(dst + 128 + lane * 4, make_float4(0, 0, 0, 0));
+    st4b(dstb ? dstb + lane * 4 : nullptr, make_float4(0, 0, 0, 0));
+    st4b(dstb ? dstb + 128 + lane * 4 : nullptr, make_float4(0, 0, 0, 0));
     return;
   }
   const int t = vp + f_lens[u];
   const int j = phoneme_of_frame(cum + (size_t)u * max_src_len, max_src_len, t);
   const float* src = x + (size_t)(p_starts[u] + j) * D_MODEL;
   const float* p = pe + (size_t)t * D_MODEL;
-  st4(dst + lane * 4, add4(ld4(src + lane * 4), ld4(p + lane * 4)));
-  st4(dst + 128 + lane * 4, add4(ld4(src + 128 + lane * 4), ld4(p + 128 + lane * 4)));
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = h * 128 + lane * 4;
+    const float4 v = add4(ld4(src + c), ld4(p + c));
+    st4(dst + c, v);
+    st4b(dstb ? dstb + c : nullptr, v);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -454,6 +493,19 @@ __global__ void repack_conv_kernel(const float* __restrict__ w, int cout, int ci
   float v = w[((size_t)co * cin + ci) * k + t];
   if (scale != nullptr) v *= scale[co];
   out[i] = round_operand ? round_tf32(v) : v;
+}
+
+// The same repack with the operands rounded to bf16 (round to nearest even) -- FS2_MATH_BF16.
+__global__ void repack_conv_bf16_kernel(const float* __restrict__ w, int cout, int cin, int k,
+                                        const float* __restrict__ scale, __nv_bfloat16* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)cout * cin * k) return;
+  const int ci = (int)(i % cin);
+  const int co = (int)((i / cin) % cout);
+  const int t = (int)(i / ((int64_t)cin * cout));
+  float v = w[((size_t)co * cin + ci) * k + t];
+  if (scale != nullptr) v *= scale[co];
+  out[i] = __float2bfloat16_rn(v);
 }
 
 // s = gamma / sqrt(var + eps);  b' = (b - mean) * s + beta

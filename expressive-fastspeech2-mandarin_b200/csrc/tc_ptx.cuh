@@ -112,6 +112,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// cute::UMMA::InstrDescriptor for kind::f16 with bf16 operands (a_format = b_format = 1), fp32 accumulate, K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -217,7 +229,7 @@ inline EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D fp32 tensor [rows, cols] with row pitch ld (elements); box = [box_rows, 32 columns].
+// 2-D tensor [rows, cols] with row pitch ld (elements); box = [box_rows, box_cols columns].
 // Encoding a descriptor costs a few microseconds of host time and the same handful of buffers
 // is described over and over, so descriptors are cached per thread by their full key.
 struct MapKey {
@@ -234,24 +246,33 @@ struct MapKey {
   }
 };
 
-inline const CUtensorMap& make_map(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool round_tf32,
-                                   bool reused, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+enum MapType { MAP_F32 = 0, MAP_TF32 = 1 /* fp32 in memory, rounded to TF32 by the TMA unit */, MAP_BF16 = 2 };
+
+inline const CUtensorMap& make_map_any(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
+                                       MapType type, CUtensorMapSwizzle swizzle) {
   static thread_local std::map<MapKey, CUtensorMap> cache;
-  const MapKey key{base, rows, cols, ld, box_rows, (round_tf32 ? 1 : 0) | (reused ? 2 : 0) | ((int)swizzle << 2)};
+  const MapKey key{base, rows, cols, ld, box_rows, (int)type | ((int)swizzle << 2) | (box_cols << 8)};
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   if (cache.size() > 4096) cache.clear();
   CUtensorMap m;
+  const int elt = type == MAP_BF16 ? 2 : 4;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};  // 32 fp32 = one 128-byte swizzle row
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * elt};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  const CUresult r = encode_fn()(&m, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                                 const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = type == MAP_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : type == MAP_TF32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUresult r = encode_fn()(&m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   require(r == CUDA_SUCCESS, FS2_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return cache.emplace(key, m).first->second;
+}
+
+// fp32 tensor, box = [box_rows, 32 columns] (32 fp32 = one 128-byte swizzle row)
+inline const CUtensorMap& make_map(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool round_tf32,
+                                   bool /*reused*/, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  return make_map_any(base, rows, cols, ld, box_rows, 32, round_tf32 ? MAP_TF32 : MAP_F32, swizzle);
 }
 
 template <typename... KArgs, typename... Args>

@@ -35,7 +35,10 @@ enum {
   FS2_ERR_UNSUPPORTED = -4  /* hyper-parameters the kernels are not compiled for */
 };
 
-/* Arithmetic of the tensor-core contractions (accumulation, LayerNorm and softmax are fp32 in both). */
+/* Arithmetic of the tensor-core contractions (accumulation, LayerNorm and softmax are fp32 in both).
+ * TF32: fp32 activations, operands rounded to TF32.  BF16: every Conv1d/Linear takes bf16 operands (weights
+ * rounded once, activations written as bf16 by the producing epilogue); the residual stream, the attention
+ * (TF32), LayerNorm, softmax and all outputs stay fp32.  BF16 needs FS2_ENGINE_TCGEN05. */
 enum { FS2_MATH_TF32 = 0, FS2_MATH_BF16 = 1 };
 /* GEMM engines: the product path is TCGEN05; MMA_SYNC is the legacy-tensor-core cross-check
  * used by the unit tests and for bring-up. */
@@ -153,6 +156,14 @@ int fs2_op_conv_gemm_ln(fs2_stream stream, int engine, const float* A, int lda, 
                         const float* bias, int taps, int pad, int K, int act, const float* residual, int ldr,
                         const float* gamma, const float* beta, const int32_t* row_vpos, const int32_t* row_room,
                         int extra, float* C, int ldc, const float* head_w, const float* head_b, float* head_out);
+/* FS2_MATH_BF16 form of the two contractions above: A [rows,lda] and W [taps][N][K] are bf16 (kind::f16 MMAs,
+ * fp32 accumulation); bias / residual / gamma / beta are fp32.  gamma != NULL selects the fused LayerNorm
+ * epilogue (N = 256).  The result is written as fp32 to C and/or as bf16 to C2 (either may be NULL): C2 is the
+ * A operand of the next contraction of the forward. */
+int fs2_op_conv_gemm_bf16(fs2_stream stream, const void* A, int lda, int rows, const void* W, const float* bias,
+                          int taps, int pad, int K, int N, int act, const float* residual, int ldr,
+                          const float* gamma, const float* beta, const int32_t* row_vpos, const int32_t* row_room,
+                          int extra, float* C, int ldc, void* C2, int ldc2);
 /* Varlen 2-head self-attention over packed rows (SubLayers.py:42-52, Modules.py:14-25):
  * qkv [rows,768] = [q | k | v], heads are 128-wide halves; utterance b owns rows
  * [starts[b], starts[b]+lens[b]); rows = rows of the qkv buffer.  out [rows,256]. */
