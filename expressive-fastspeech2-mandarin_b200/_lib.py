@@ -17,7 +17,8 @@ c_u8p = C.POINTER(C.c_uint8)
 class Config(C.Structure):
     _fields_ = [("n_src_vocab", C.c_int32), ("n_speaker", C.c_int32), ("n_emotion", C.c_int32),
                 ("n_arousal", C.c_int32), ("n_valence", C.c_int32), ("max_seq_len", C.c_int32),
-                ("math_mode", C.c_int32), ("engine", C.c_int32)]
+                ("math_mode", C.c_int32), ("engine", C.c_int32),
+                ("pitch_frame_level", C.c_int32), ("energy_frame_level", C.c_int32)]
 
 
 class Inputs(C.Structure):
@@ -36,7 +37,8 @@ class Stage1Out(C.Structure):
 
 
 class Stage2IO(C.Structure):
-    _fields_ = [("mel", C.c_void_p), ("postnet", C.c_void_p), ("mel_mask", C.c_void_p)]
+    _fields_ = [("mel", C.c_void_p), ("postnet", C.c_void_p), ("mel_mask", C.c_void_p),
+                ("pitch_frames", C.c_void_p), ("energy_frames", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/fs2_b200.h declares

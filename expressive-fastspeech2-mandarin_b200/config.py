@@ -89,5 +89,5 @@ def check_supported(preprocess_config, model_config):
     if int(pp["mel"]["n_mel_channels"]) != 80:
         raise ValueError("fs2_b200 kernels are specialised for 80 mel channels")
     for f in ("pitch", "energy"):
-        if pp[f]["feature"] != "phoneme_level":
-            raise ValueError(f"{f}.feature='frame_level' is outside the accelerated path (SURVEY §8f rank 3)")
+        if pp[f]["feature"] not in ("phoneme_level", "frame_level"):        # model/modules.py:34-35
+            raise ValueError(f"{f}.feature must be 'phoneme_level' or 'frame_level'")

@@ -93,6 +93,10 @@ struct fs2_ctx {
   int batch = 0, max_src_len = 0, max_mel_len = 0;
   int64_t frame_rows = 0;
   const float* lr_input = nullptr;
+  const float *p_targets = nullptr, *e_targets = nullptr;  // frame_level teacher forcing: consumed in stage 2
+  float p_control = 1.f;
+  int64_t scratch_bt = 0;                                   // frame_level: raw predictions [B, T_max]
+  float *raw_pitch_f = nullptr, *raw_energy_f = nullptr;
   int last_launches = 0;
 
   std::map<std::string, std::pair<void*, std::vector<int64_t>>> taps;  // name -> (device copy, {rows, cols, elt})
@@ -536,20 +540,35 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
 
   // ---- VarianceAdaptor (model/modules.py:102-135)
   predictor(c, s, c->pred[0], ps, rows, xc, t1, t2, out->log_d, pp.actb[3], pp.actb[1]);
-  predictor(c, s, c->pred[1], ps, rows, xc, t1, t2, c->raw_pitch, pp.actb[3], pp.actb[1]);
-  float* xe = x;  // encoder output is no longer needed
-  bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
-      xc, ps.meta(), ps.slot, 2, rows, c->raw_pitch, in->p_targets, in->p_control,
-      c->raw.at("variance_adaptor.pitch_bins").ptr, N_BINS - 1, c->raw.at("variance_adaptor.pitch_embedding.weight").ptr,
-      out->pitch, nullptr, xe, pp.actb[0]);
-  FS2_LAUNCHED();
-  predictor(c, s, c->pred[2], ps, rows, xe, t1, t2, c->raw_energy, pp.actb[0], pp.actb[1]);
-  float* xf = t3;
-  bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
-      xe, ps.meta(), ps.slot, 0, rows, c->raw_energy, in->e_targets, in->p_control /* sic: modules.py:123-125 */,
-      c->raw.at("variance_adaptor.energy_bins").ptr, N_BINS - 1,
-      c->raw.at("variance_adaptor.energy_embedding.weight").ptr, out->energy, nullptr, xf);
-  FS2_LAUNCHED();
+  // phoneme_level features run here (modules.py:114-125); frame_level ones after the LengthRegulator in stage 2
+  const bool pitch_here = !c->cfg.pitch_frame_level, energy_here = !c->cfg.energy_frame_level;
+  float* cur = xc;                       // lives in act[3]
+  __nv_bfloat16* curb = pp.actb[3];
+  if (pitch_here) {
+    predictor(c, s, c->pred[1], ps, rows, cur, t1, t2, c->raw_pitch, curb, pp.actb[1]);
+    float* xe = x;  // encoder output is no longer needed
+    bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
+        cur, ps.meta(), ps.slot, 2, rows, c->raw_pitch, in->p_targets, in->p_control,
+        c->raw.at("variance_adaptor.pitch_bins").ptr, N_BINS - 1, c->raw.at("variance_adaptor.pitch_embedding.weight").ptr,
+        out->pitch, nullptr, xe, pp.actb[0]);
+    FS2_LAUNCHED();
+    cur = xe;
+    curb = pp.actb[0];
+  }
+  if (energy_here) {
+    predictor(c, s, c->pred[2], ps, rows, cur, t1, t2, c->raw_energy, curb, pp.actb[1]);
+    float* xf = cur == t3 ? x : t3;
+    bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
+        cur, ps.meta(), ps.slot, 0, rows, c->raw_energy, in->e_targets, in->p_control /* sic: modules.py:123-125 */,
+        c->raw.at("variance_adaptor.energy_bins").ptr, N_BINS - 1,
+        c->raw.at("variance_adaptor.energy_embedding.weight").ptr, out->energy, nullptr, xf);
+    FS2_LAUNCHED();
+    cur = xf;
+  }
+  float* xf = cur;
+  c->p_targets = in->p_targets;
+  c->e_targets = in->e_targets;
+  c->p_control = in->p_control;
   tap(c, s, "va_x", xf, rows, D_MODEL);
 
   const bool forced = in->d_targets != nullptr;
@@ -608,10 +627,54 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
     // ---- LengthRegulator + decoder positional encoding (modules.py:167-194, Models.py:145-162)
     float *x = fp.act[0], *t1 = fp.act[1], *t2 = fp.act[2];
     const float* pe = position_rows(c, "decoder.position_enc", T, s);
+    const bool pitch_f = c->cfg.pitch_frame_level != 0, energy_f = c->cfg.energy_frame_level != 0;
     {
       ProfScope ps(c, s, "length_regulator");
-      length_regulate_kernel<<<(rows + 7) / 8, 256, 0, s>>>(c->lr_input, c->ps.starts, c->cum, L, fsd.meta(), fsd.lens, pe,
-                                                            rows, x, fp.actb[0]);
+      length_regulate_kernel<<<(rows + 7) / 8, 256, 0, s>>>(c->lr_input, c->ps.starts, c->cum, L, fsd.meta(), fsd.lens,
+                                                            (pitch_f || energy_f) ? nullptr : pe, rows, x, fp.actb[0]);
+      FS2_LAUNCHED();
+    }
+    if (pitch_f || energy_f) {
+      // frame_level predictors (modules.py:139-148) on the expanded rows: padding rows of the LengthRegulator output
+      // are zero (utils/tools.py:360-378), the masked prediction there is 0 and its bucket embedding is still added,
+      // so the first two reserved rows are carried exactly as on the phoneme side.  The positional encoding is added
+      // afterwards and every reserved row returns to zero for the decoder.
+      const int64_t BT = (int64_t)B * T;
+      if (BT > c->scratch_bt) {
+        regrow(c->raw_pitch_f, BT);
+        regrow(c->raw_energy_f, BT);
+        c->scratch_bt = BT;
+      }
+      float* cur = x;                    // act[0]
+      __nv_bfloat16* curb = fp.actb[0];
+      if (pitch_f) {
+        require(io->pitch_frames != nullptr, FS2_ERR_INVALID, "pitch is frame_level: stage-2 io needs pitch_frames");
+        FS2_CUDA_OK(cudaMemsetAsync(io->pitch_frames, 0, BT * sizeof(float), s));
+        FS2_CUDA_OK(cudaMemsetAsync(c->raw_pitch_f, 0, BT * sizeof(float), s));
+        predictor(c, s, c->pred[1], fsd, rows, cur, t1, t2, c->raw_pitch_f, curb, fp.actb[1]);
+        bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
+            cur, fsd.meta(), fsd.slot, energy_f ? 2 : 0, rows, c->raw_pitch_f, c->p_targets, c->p_control,
+            c->raw.at("variance_adaptor.pitch_bins").ptr, N_BINS - 1,
+            c->raw.at("variance_adaptor.pitch_embedding.weight").ptr, io->pitch_frames, nullptr, fp.act[3], fp.actb[3]);
+        FS2_LAUNCHED();
+        cur = fp.act[3];
+        curb = fp.actb[3];
+      }
+      if (energy_f) {
+        require(io->energy_frames != nullptr, FS2_ERR_INVALID, "energy is frame_level: stage-2 io needs energy_frames");
+        FS2_CUDA_OK(cudaMemsetAsync(io->energy_frames, 0, BT * sizeof(float), s));
+        FS2_CUDA_OK(cudaMemsetAsync(c->raw_energy_f, 0, BT * sizeof(float), s));
+        predictor(c, s, c->pred[2], fsd, rows, cur, t1, t2, c->raw_energy_f, curb, fp.actb[1]);
+        float* dst = cur == x ? fp.act[3] : x;
+        bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
+            cur, fsd.meta(), fsd.slot, 0, rows, c->raw_energy_f, c->e_targets, c->p_control /* sic */,
+            c->raw.at("variance_adaptor.energy_bins").ptr, N_BINS - 1,
+            c->raw.at("variance_adaptor.energy_embedding.weight").ptr, io->energy_frames, nullptr, dst);
+        FS2_LAUNCHED();
+        cur = dst;
+      }
+      tap(c, s, "va_frames", cur, rows, D_MODEL);
+      add_pe_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, fsd.meta(), fsd.lens, pe, rows, x, fp.actb[0]);
       FS2_LAUNCHED();
     }
     tap(c, s, "f_start", fsd.starts, 1, B + 1);
@@ -778,7 +841,7 @@ void fs2_destroy(fs2_ctx* c) {
     cudaFree(p->hidb); cudaFree(p->melb); cudaFree(p->pnb[0]); cudaFree(p->pnb[1]);
   }
   cudaFree(c->status); cudaFree(c->cum); cudaFree(c->mel_lens32); cudaFree(c->raw_pitch); cudaFree(c->raw_energy);
-  cudaFree(c->cond_spk); cudaFree(c->cond_emo); cudaFree(c->pe_long);
+  cudaFree(c->cond_spk); cudaFree(c->cond_emo); cudaFree(c->pe_long); cudaFree(c->raw_pitch_f); cudaFree(c->raw_energy_f);
   cudaFreeHost(c->h_totals);
   delete c;
 }

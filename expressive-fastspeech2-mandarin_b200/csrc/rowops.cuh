@@ -428,11 +428,35 @@ __global__ void length_regulate_kernel(const float* __restrict__ x, const int32_
   const int t = vp + f_lens[u];
   const int j = phoneme_of_frame(cum + (size_t)u * max_src_len, max_src_len, t);
   const float* src = x + (size_t)(p_starts[u] + j) * D_MODEL;
-  const float* p = pe + (size_t)t * D_MODEL;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int c = h * 128 + lane * 4;
-    const float4 v = add4(ld4(src + c), ld4(p + c));
+    float4 v = ld4(src + c);
+    if (pe != nullptr) v = add4(v, ld4(pe + (size_t)t * D_MODEL + c));   // nullptr: a frame_level predictor runs first
+    st4(dst + c, v);
+    st4b(dstb ? dstb + c : nullptr, v);
+  }
+}
+
+// Decoder input when a frame_level predictor sits between the LengthRegulator and the decoder
+// (model/modules.py:139-148, transformer/Models.py:154-162): real rows get x + position_enc[t], every
+// reserved row returns to zero (the FFT stacks need zero gaps).  In place is fine (row-wise).
+__global__ void add_pe_kernel(const float* __restrict__ x, RowMeta fmeta, const int32_t* __restrict__ f_lens,
+                              const float* __restrict__ pe, int rows, float* __restrict__ y,
+                              __nv_bfloat16* __restrict__ yb = nullptr) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int u = fmeta.utt[row], vp = fmeta.vpos[row];
+  float* dst = y + (size_t)row * D_MODEL;
+  __nv_bfloat16* dstb = yb != nullptr ? yb + (size_t)row * D_MODEL : nullptr;
+  const bool real = u >= 0 && vp < 0;
+  const float* src = x + (size_t)row * D_MODEL;
+  const float* p = pe + (size_t)(real ? vp + f_lens[u] : 0) * D_MODEL;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = h * 128 + lane * 4;
+    const float4 v = real ? add4(ld4(src + c), ld4(p + c)) : make_float4(0, 0, 0, 0);
     st4(dst + c, v);
     st4b(dstb ? dstb + c : nullptr, v);
   }

@@ -82,6 +82,9 @@ class FastSpeech2B200(nn.Module):
         self._dims = dict(n_src_vocab=N_SRC_VOCAB, n_speaker=n_speaker, n_emotion=len(emo["emotion_dict"]),
                           n_arousal=len(emo["arousal_dict"]), n_valence=len(emo["valence_dict"]),
                           max_seq_len=int(model_config["max_seq_len"]))
+        pp = preprocess_config["preprocessing"]                    # model/modules.py:28-35
+        self.pitch_frame_level = pp["pitch"]["feature"] == "frame_level"
+        self.energy_frame_level = pp["energy"]["feature"] == "frame_level"
         self.math_mode = {"tf32": _lib.MATH_TF32, "bf16": _lib.MATH_BF16}[math_mode]
         self.engine = {"mma_sync": _lib.ENGINE_MMA_SYNC, "tcgen05": _lib.ENGINE_TCGEN05,
                        "tcgen05_v1": _lib.ENGINE_TCGEN05_V1}[engine]
@@ -162,7 +165,8 @@ class FastSpeech2B200(nn.Module):
             lib.fs2_destroy(self._ctx)
             self._ctx = None
         if self._ctx is None:
-            cfg = _lib.Config(math_mode=self.math_mode, engine=self.engine, **self._dims)
+            cfg = _lib.Config(math_mode=self.math_mode, engine=self.engine, pitch_frame_level=int(self.pitch_frame_level),
+                              energy_frame_level=int(self.energy_frame_level), **self._dims)
             ctx = C.c_void_p()
             code = lib.fs2_create(C.byref(cfg), dev.index if dev.index is not None else torch.cuda.current_device(),
                                   C.byref(ctx))
@@ -218,7 +222,7 @@ class FastSpeech2B200(nn.Module):
             return None
         if not torch.is_tensor(t) or t.device != self._device():
             raise RuntimeError(f"{name} must be a tensor on {self._device()}")
-        if tuple(t.shape) != tuple(shape):
+        if shape is not None and tuple(t.shape) != tuple(shape):
             raise RuntimeError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
         return t.to(torch.float32).contiguous()
 
@@ -241,8 +245,9 @@ class FastSpeech2B200(nn.Module):
         val = self._idx(valences, "valences", (B,))
         txt = self._idx(texts, "texts", (B, L))
         lens = self._idx(src_lens, "src_lens", (B,))
-        p_t = self._target(p_targets, "p_targets", (B, L))
-        e_t = self._target(e_targets, "e_targets", (B, L))
+        # frame_level targets live on the frame axis ([B, max_mel_len]); their shape is checked once T is known
+        p_t = self._target(p_targets, "p_targets", None if self.pitch_frame_level else (B, L))
+        e_t = self._target(e_targets, "e_targets", None if self.energy_frame_level else (B, L))
         d_t = self._target(d_targets, "d_targets", (B, L))
 
         f32 = dict(dtype=torch.float32, device=dev)
@@ -269,7 +274,16 @@ class FastSpeech2B200(nn.Module):
         mel = torch.empty(B, T, 80, **f32)
         post = torch.empty(B, T, 80, **f32)
         mel_mask = torch.empty(B, T, dtype=torch.bool, device=dev)
-        io = _lib.Stage2IO(mel=ptr(mel), postnet=ptr(post), mel_mask=ptr(mel_mask))
+        for flag, t, name in ((self.pitch_frame_level, p_t, "p_targets"), (self.energy_frame_level, e_t, "e_targets")):
+            if flag and t is not None and tuple(t.shape) != (B, T):
+                raise RuntimeError(f"{name} has shape {tuple(t.shape)}, expected {(B, T)} (frame_level feature)")
+        if self.pitch_frame_level:                                  # model/modules.py:139-143: prediction is [B, T]
+            pitch = torch.empty(B, T, **f32)
+        if self.energy_frame_level:                                 # model/modules.py:144-148
+            energy = torch.empty(B, T, **f32)
+        io = _lib.Stage2IO(mel=ptr(mel), postnet=ptr(post), mel_mask=ptr(mel_mask),
+                           pitch_frames=ptr(pitch) if self.pitch_frame_level else None,
+                           energy_frames=ptr(energy) if self.energy_frame_level else None)
         _lib.check(lib, self._ctx, lib.fs2_forward_stage2(self._ctx, stream, C.byref(io)))
         self.last_total_frames = int(s1.total_frames)
         return (mel, post, pitch, energy, log_d, d_targets if d_targets is not None else d_round, src_mask, mel_mask,

@@ -56,6 +56,10 @@ typedef struct {
   int32_t max_seq_len;  /* model.yaml:27; position_enc has max_seq_len+1 rows */
   int32_t math_mode;    /* FS2_MATH_*  */
   int32_t engine;       /* FS2_ENGINE_* */
+  /* preprocess.yaml preprocessing.{pitch,energy}.feature (model/modules.py:28-35): 0 = phoneme_level (the
+   * predictor runs before the LengthRegulator, modules.py:114-125), 1 = frame_level (after it, :139-148). */
+  int32_t pitch_frame_level;
+  int32_t energy_frame_level;
 } fs2_config;
 
 /* Arguments of FastSpeech2.forward (model/fastspeech2.py:73-91). */
@@ -68,8 +72,9 @@ typedef struct {
   const int64_t* valences; /* device [B] */
   const int64_t* texts;    /* device [B, max_src_len] */
   const int64_t* src_lens; /* device [B] */
-  const float* p_targets;  /* device [B, max_src_len] or NULL (model/modules.py:82-83) */
-  const float* e_targets;  /* device [B, max_src_len] or NULL (model/modules.py:93-94) */
+  const float* p_targets;  /* device [B, max_src_len] or NULL (model/modules.py:82-83); [B, max_mel_len] when the
+                              feature is frame_level (must stay valid until fs2_forward_stage2 has been enqueued) */
+  const float* e_targets;  /* device [B, max_src_len] or NULL (model/modules.py:93-94); frame_level: as above */
   const float* d_targets;  /* device [B, max_src_len] or NULL (model/modules.py:128-130) */
   float p_control;         /* scales pitch AND energy (model/modules.py:118-125) */
   float e_control;         /* accepted and ignored, as in the reference */
@@ -94,6 +99,10 @@ typedef struct {
   float* mel;         /* device [B, max_mel_len, 80]  output[0]; padding rows = mel_linear.bias */
   float* postnet;     /* device [B, max_mel_len, 80]  output[1]; padding rows = mel_linear.bias (outside the contract) */
   uint8_t* mel_mask;  /* device [B, max_mel_len]      output[7], 1 = padding */
+  /* frame_level features only (NULL otherwise): the predictions live on the frame axis and are written here
+   * instead of fs2_stage1_out.pitch / .energy (which are then left zero-filled) */
+  float* pitch_frames;   /* device [B, max_mel_len]  output[2] when pitch_frame_level  */
+  float* energy_frames;  /* device [B, max_mel_len]  output[3] when energy_frame_level */
 } fs2_stage2_io;
 
 /* --- lifetime ------------------------------------------------------------------------ */

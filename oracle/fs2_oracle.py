@@ -188,25 +188,30 @@ def length_regulate(x, durations, max_len=None, loop=False):
 
 
 def variance_adaptor(sd, x, src_pad, mel_pad, max_len, p_target, e_target, d_target,
-                     p_control, e_control, d_control, taps=None, loop_lr=False):
-    """model/modules.py:102-158, phoneme-level branches.  Note energy is scaled by
-    p_control (modules.py:123-125): e_control is accepted and ignored, as in the reference."""
+                     p_control, e_control, d_control, taps=None, loop_lr=False,
+                     pitch_level="phoneme_level", energy_level="phoneme_level"):
+    """model/modules.py:102-158.  Note energy is scaled by p_control (modules.py:123-125 and
+    :146-148): e_control is accepted and ignored, as in the reference.  `*_level` is
+    preprocess.yaml's preprocessing.{pitch,energy}.feature (modules.py:28-35): phoneme_level
+    features are predicted before the LengthRegulator (:114-125), frame_level ones after (:139-148)."""
     va = "variance_adaptor"
+    pitch = energy = None
+
+    def feature(name, x, target, pad):
+        pred = variance_predictor(sd, f"{va}.{name}_predictor", x, pad)
+        if target is not None:
+            idx = bucket_index(target, sd[f"{va}.{name}_bins"])
+        else:
+            pred = pred * p_control
+            idx = bucket_index(pred, sd[f"{va}.{name}_bins"])
+        return pred, idx, x + F.embedding(idx, sd[f"{va}.{name}_embedding.weight"])
+
     log_d = variance_predictor(sd, f"{va}.duration_predictor", x, src_pad)
-    pitch = variance_predictor(sd, f"{va}.pitch_predictor", x, src_pad)
-    if p_target is not None:
-        p_idx = bucket_index(p_target, sd[f"{va}.pitch_bins"])
-    else:
-        pitch = pitch * p_control
-        p_idx = bucket_index(pitch, sd[f"{va}.pitch_bins"])
-    x = x + F.embedding(p_idx, sd[f"{va}.pitch_embedding.weight"])
-    energy = variance_predictor(sd, f"{va}.energy_predictor", x, src_pad)
-    if e_target is not None:
-        e_idx = bucket_index(e_target, sd[f"{va}.energy_bins"])
-    else:
-        energy = energy * p_control
-        e_idx = bucket_index(energy, sd[f"{va}.energy_bins"])
-    x = x + F.embedding(e_idx, sd[f"{va}.energy_embedding.weight"])
+    p_idx = e_idx = None
+    if pitch_level == "phoneme_level":
+        pitch, p_idx, x = feature("pitch", x, p_target, src_pad)
+    if energy_level == "phoneme_level":
+        energy, e_idx, x = feature("energy", x, e_target, src_pad)
     if taps is not None:
         taps["va_x"], taps["p_idx"], taps["e_idx"] = x, p_idx, e_idx
     if d_target is not None:
@@ -216,6 +221,12 @@ def variance_adaptor(sd, x, src_pad, mel_pad, max_len, p_target, e_target, d_tar
         d_round = duration_rounded(log_d, d_control)
         x, mel_len = length_regulate(x, d_round, max_len, loop=loop_lr)
         mel_pad = pad_mask(mel_len)
+    if pitch_level == "frame_level":
+        pitch, p_idx, x = feature("pitch", x, p_target, mel_pad)
+    if energy_level == "frame_level":
+        energy, e_idx, x = feature("energy", x, e_target, mel_pad)
+    if taps is not None and "frame_level" in (pitch_level, energy_level):
+        taps["va_frames"], taps["p_idx_f"], taps["e_idx_f"] = x, p_idx, e_idx
     return x, pitch, energy, log_d, d_round, mel_len, mel_pad
 
 
@@ -238,7 +249,8 @@ def postnet(sd, mel):
 @torch.no_grad()
 def forward(sd, speakers, emotions, arousals, valences, texts, src_lens, max_src_len,
             mels=None, mel_lens=None, max_mel_len=None, p_targets=None, e_targets=None,
-            d_targets=None, p_control=1.0, e_control=1.0, d_control=1.0, taps=None, loop_lr=False):
+            d_targets=None, p_control=1.0, e_control=1.0, d_control=1.0, taps=None, loop_lr=False,
+            pitch_level="phoneme_level", energy_level="phoneme_level"):
     """model/fastspeech2.py:73-149.  Returns the reference's 10-tuple."""
     src_pad = pad_mask(src_lens, max_src_len)
     mel_pad = pad_mask(mel_lens, max_mel_len) if mel_lens is not None else None
@@ -250,7 +262,7 @@ def forward(sd, speakers, emotions, arousals, valences, texts, src_lens, max_src
         taps["cond_x"] = x
     x, pitch, energy, log_d, d_round, mel_lens, mel_pad = variance_adaptor(
         sd, x, src_pad, mel_pad, max_mel_len, p_targets, e_targets, d_targets,
-        p_control, e_control, d_control, taps, loop_lr)
+        p_control, e_control, d_control, taps, loop_lr, pitch_level, energy_level)
     if taps is not None:
         taps["lr_out"] = x
     x = decoder(sd, x, mel_pad, taps)

@@ -40,12 +40,16 @@ def import_reference():
     return FastSpeech2
 
 
-def build_reference_model(sd, dtype=torch.float64):
+def build_reference_model(sd, dtype=torch.float64, pitch_level=None, energy_level=None):
     import fs2_b200
     FastSpeech2 = import_reference()
     cfg_dir = os.path.join(REF, "config", "ESD-Chinese-Singing-MFA")
     preprocess = yaml.load(open(os.path.join(cfg_dir, "preprocess.yaml")), Loader=yaml.FullLoader)
     model_cfg = yaml.load(open(os.path.join(cfg_dir, "model.yaml")), Loader=yaml.FullLoader)
+    if pitch_level:      # preprocess.yaml preprocessing.pitch.feature (model/modules.py:28-35)
+        preprocess["preprocessing"]["pitch"]["feature"] = pitch_level
+    if energy_level:
+        preprocess["preprocessing"]["energy"]["feature"] = energy_level
     tmp = tempfile.mkdtemp(prefix="fs2_fixture_")
     fs2_b200.synthetic.write_fixture_jsons(tmp)
     preprocess["path"]["preprocessed_path"] = tmp
@@ -81,7 +85,52 @@ def golden_cases():
     return cases
 
 
+def frame_level_fixtures(out_dir, sd):
+    """frame_level pitch / energy: the same state dict under the two other feature
+    configurations, free-running and teacher-forced (targets on the frame axis)."""
+    import fs2_b200
+    syn = fs2_b200.synthetic
+    for tag, pl, el in (("frame_both", "frame_level", "frame_level"), ("frame_energy", "phoneme_level", "frame_level"),
+                        ("frame_pitch", "frame_level", "phoneme_level")):
+        model = build_reference_model(sd, pitch_level=pl, energy_level=el)
+        batch = syn.make_batch([14, 9, 14, 3], seed=21)
+        kw = {"p_control": 1.2, "d_control": 1.0} if tag == "frame_both" else {}
+        out = run_reference(model, batch, **kw)
+        rec = {f"in_{k}": (v.numpy() if torch.is_tensor(v) else np.array(v)) for k, v in batch.items()}
+        for k, v in kw.items():
+            rec[f"kw_{k}"] = np.array(v)
+        for n, v in zip(NAMES, out):
+            rec[f"out_{n}"] = v.numpy()
+        rec["cfg_pitch_level"], rec["cfg_energy_level"] = np.array(pl), np.array(el)
+        np.savez_compressed(os.path.join(out_dir, f"{tag}.npz"), **rec)
+        print(tag, "mel_lens", out[9].tolist(), "pitch", tuple(out[2].shape), "energy", tuple(out[3].shape))
+        if tag != "frame_both":
+            continue
+        # teacher-forced: targets of frame_level features are [B, max_mel_len]; max_mel_len > max(mel_lens)
+        g = torch.Generator().manual_seed(123)
+        d_t = torch.randint(0, 7, out[5].shape, generator=g) * (~out[6])
+        mel_lens = d_t.sum(1)
+        T = int(mel_lens.max()) + 5
+        fmask = torch.arange(T).unsqueeze(0) >= mel_lens.unsqueeze(1)
+        p_t = (torch.randn(d_t.shape[0], T, generator=g, dtype=torch.float64) * 1.5) * (~fmask)
+        e_t = (torch.randn(d_t.shape[0], T, generator=g, dtype=torch.float64) * 1.5) * (~fmask)
+        kw = dict(mel_lens=mel_lens, max_mel_len=T, p_targets=p_t, e_targets=e_t, d_targets=d_t)
+        out = run_reference(model, batch, **kw)
+        rec = {f"in_{k}": (v.numpy() if torch.is_tensor(v) else np.array(v)) for k, v in batch.items()}
+        for k, v in kw.items():
+            rec[f"kw_{k}"] = v.numpy() if torch.is_tensor(v) else np.array(v)
+        for n, v in zip(NAMES, out):
+            rec[f"out_{n}"] = v.numpy()
+        rec["cfg_pitch_level"], rec["cfg_energy_level"] = np.array(pl), np.array(el)
+        np.savez_compressed(os.path.join(out_dir, "frame_both_forced.npz"), **rec)
+        print("frame_both_forced mel_lens", out[9].tolist())
+
+
 def main():
+    if "--frame-level-only" in sys.argv:    # adds the frame_level fixtures without rewriting the others
+        import fs2_b200
+        frame_level_fixtures(os.path.dirname(os.path.abspath(__file__)), fs2_b200.synthetic.synthetic_state_dict(seed=0))
+        return
     import fs2_b200
     syn = fs2_b200.synthetic
     out_dir = os.path.dirname(os.path.abspath(__file__))
@@ -135,6 +184,7 @@ def main():
     rec["mel_row_stride"] = np.array(13)
     np.savez_compressed(os.path.join(out_dir, "longform.npz"), **rec)
     print("longform mel_lens", out[9].tolist())
+    frame_level_fixtures(out_dir, sd)
 
 
 if __name__ == "__main__":

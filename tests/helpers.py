@@ -9,9 +9,22 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 OUT_NAMES = ["mel", "postnet", "pitch", "energy", "log_d", "d_rounded", "src_mask", "mel_mask", "src_lens", "mel_lens"]
 
 
-def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0]
-                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not p.endswith("meta.npz"))
+def golden_names(frame_level=None):
+    """All fixtures; frame_level=False -> only the default (phoneme_level) configuration, True -> only the
+    fixtures recorded with a frame_level pitch and/or energy feature."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0]
+                   for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not p.endswith("meta.npz"))
+    if frame_level is None:
+        return names
+    return [n for n in names if n.startswith("frame_") == frame_level]
+
+
+def golden_levels(name):
+    """preprocessing.{pitch,energy}.feature the fixture was recorded with (model/modules.py:28-35)."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    if "cfg_pitch_level" not in z.files:
+        return {"pitch_level": "phoneme_level", "energy_level": "phoneme_level"}
+    return {"pitch_level": str(z["cfg_pitch_level"]), "energy_level": str(z["cfg_energy_level"])}
 
 
 def load_golden(name):

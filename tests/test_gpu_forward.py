@@ -76,7 +76,7 @@ def check_frame_side(tag, got, want, mel_lens, stride=1):
         assert mx <= TOL_MEL_MAX and mean <= TOL_MEL_MEAN, (tag, n, mx, mean)
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", golden_names(frame_level=False))
 def test_golden_fixture(name, sd32):
     """The reference's own outputs (tests/golden/*.npz, float64 run of the unmodified module)."""
     model = model_for(sd32)
