@@ -8,7 +8,7 @@ when the library is not built.
 """
 from . import config, synthetic  # noqa: F401
 
-__all__ = ["config", "synthetic", "FastSpeech2B200", "load_library"]
+__all__ = ["config", "synthetic", "FastSpeech2B200", "HiFiGANGeneratorB200", "get_vocoder", "vocoder_infer", "load_library"]
 
 
 def __getattr__(name):
@@ -17,6 +17,9 @@ def __getattr__(name):
     if name in ("FastSpeech2B200", "get_model"):
         from . import model
         return getattr(model, name)
+    if name in ("HiFiGANGeneratorB200", "get_vocoder", "vocoder_infer"):
+        from . import vocoder
+        return getattr(vocoder, name)
     if name == "load_library":
         from ._lib import load_library
         return load_library

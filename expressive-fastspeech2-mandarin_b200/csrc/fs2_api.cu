@@ -13,6 +13,7 @@
 #include "gemm_tcgen05.cuh"
 #include "gemm_tc2.cuh"
 #include "rowops.cuh"
+#include "vocoder.cuh"
 
 namespace fs2 {
 
@@ -1057,5 +1058,261 @@ int fs2_op_frame_map(fs2_stream stream, const int32_t* cum, int batch, int max_s
     FS2_LAUNCHED();
   });
 }
+
+
+}  // extern "C"
+
+// ============================================================================ HiFi-GAN generator
+struct fs2_voc {
+  int device = 0;
+  std::string err;
+  bool prepared = false;
+  std::map<std::string, fs2::DevTensor> raw;
+  std::vector<void*> owned;
+  fs2::voc::ConvW pre, res1[fs2::voc::N_UPS][fs2::voc::N_RES][3], res2[fs2::voc::N_UPS][fs2::voc::N_RES][3];
+  fs2::voc::UpW ups[fs2::voc::N_UPS];
+  const float *post_w = nullptr, *post_b = nullptr;
+  fs2::RowSide side;
+  int64_t* lens64 = nullptr;
+  float* melp = nullptr;        // packed mel [rows, 80]
+  float* a0 = nullptr;          // conv_pre output [rows, 512]
+  float* buf[7] = {};           // U, T1, P0, P1, R0, R1, R2: rows * 8192 floats each
+  int rows_alloc = 0;
+  int32_t* status = nullptr;
+  int last_launches = 0;
+};
+
+namespace fs2 {
+namespace voc {
+
+static const DevTensor& VW(fs2_voc* c, const std::string& key, std::initializer_list<int64_t> shape) {
+  auto it = c->raw.find(key);
+  require(it != c->raw.end(), FS2_ERR_INVALID, "missing vocoder weight: " + key);
+  require(it->second.shape == std::vector<int64_t>(shape), FS2_ERR_INVALID, "unexpected shape for vocoder weight: " + key);
+  return it->second;
+}
+static float* vkeep(fs2_voc* c, size_t n) {
+  float* p = dalloc<float>(n);
+  c->owned.push_back(p);
+  return p;
+}
+static ConvW conv_w(fs2_voc* c, const std::string& p, int cout, int cin, int k, cudaStream_t s) {
+  ConvW w;
+  w.cin = cin; w.cout = cout; w.k = k;
+  const int64_t n = (int64_t)cout * cin * k;
+  w.w = vkeep(c, n);
+  repack_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(VW(c, p + ".weight", {cout, cin, k}).ptr, cout, cin, k, nullptr, 1, w.w);
+  FS2_LAUNCHED();
+  w.b = VW(c, p + ".bias", {cout}).ptr;
+  return w;
+}
+
+static void prepare(fs2_voc* c, cudaStream_t s) {
+  FS2_CUDA_OK(cudaSetDevice(c->device));
+  for (void* p : c->owned) cudaFree(p);
+  c->owned.clear();
+  c->prepared = false;
+  c->pre = conv_w(c, "conv_pre", UP_INITIAL, N_MEL, 7, s);          // models.py:117-119
+  int ch = UP_INITIAL;
+  for (int i = 0; i < N_UPS; ++i) {                                   // models.py:122-135
+    UpW& u = c->ups[i];
+    u.cin = ch; u.cout = ch / 2; u.s = UP_RATE[i];
+    const std::string p = "ups." + std::to_string(i);
+    const int64_t n = 3LL * u.s * u.cout * u.cin;
+    u.w = vkeep(c, n);
+    repack_convT_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(VW(c, p + ".weight", {u.cin, u.cout, UP_KERNEL[i]}).ptr, u.cin,
+                                                                    u.cout, UP_KERNEL[i], u.s, u.w);
+    FS2_LAUNCHED();
+    u.b = vkeep(c, (size_t)u.s * u.cout);
+    tile_bias_kernel<<<(u.s * u.cout + 255) / 256, 256, 0, s>>>(VW(c, p + ".bias", {u.cout}).ptr, u.cout, u.s, u.b);
+    FS2_LAUNCHED();
+    ch /= 2;
+    for (int j = 0; j < N_RES; ++j) {                                 // models.py:137-143
+      const std::string rp = "resblocks." + std::to_string(i * N_RES + j);
+      for (int m = 0; m < 3; ++m) {
+        c->res1[i][j][m] = conv_w(c, rp + ".convs1." + std::to_string(m), ch, ch, RES_KERNEL[j], s);
+        c->res2[i][j][m] = conv_w(c, rp + ".convs2." + std::to_string(m), ch, ch, RES_KERNEL[j], s);
+      }
+    }
+  }
+  c->post_w = VW(c, "conv_post.weight", {1, ch, POST_K}).ptr;          // models.py:145
+  c->post_b = VW(c, "conv_post.bias", {1}).ptr;
+  FS2_CUDA_OK(cudaStreamSynchronize(s));
+  c->prepared = true;
+}
+
+static void forward(fs2_voc* c, cudaStream_t s, const float* mel, int64_t sb, int64_t sc, int64_t st, int B, int T,
+                    const int64_t* mel_lens, float* wav) {
+  require(c->prepared, FS2_ERR_STATE, "fs2_voc_forward called before fs2_voc_prepare");
+  require(mel && wav && B > 0 && B <= 65535 && T > 0, FS2_ERR_INVALID, "bad vocoder argument");
+  FS2_CUDA_OK(cudaSetDevice(c->device));
+  g_launches = 0;
+  const int64_t bound = (int64_t)VOC_GAP + (int64_t)B * (T + VOC_GAP);
+  require(bound * HOP < (1LL << 31), FS2_ERR_INVALID, "vocoder batch too large (2^31 audio rows)");
+  const int rows = round_up((int)bound, 128);
+  RowSide& sd = c->side;
+  ensure_side(sd, B, rows);
+  if (rows > c->rows_alloc) {
+    regrow(c->melp, (size_t)rows * N_MEL);
+    regrow(c->a0, (size_t)rows * UP_INITIAL);
+    for (auto& b : c->buf) regrow(b, (size_t)rows * 8192);
+    regrow(c->lens64, 65536);
+    c->rows_alloc = rows;
+  }
+  FS2_CUDA_OK(cudaMemsetAsync(c->status, 0, sizeof(int32_t), s));
+  FS2_CUDA_OK(cudaMemsetAsync(wav, 0, (size_t)B * T * HOP * sizeof(float), s));
+  if (mel_lens == nullptr) {   // every frame of the padded batch is data, exactly as vocoder(mels) treats it
+    fill_i64_kernel<<<(B + 255) / 256, 256, 0, s>>>(c->lens64, B, T);
+    FS2_LAUNCHED();
+    mel_lens = c->lens64;
+  }
+  layout_scan_kernel<int64_t><<<1, 1024, 0, s>>>(mel_lens, B, VOC_GAP, T, T, sd.starts, sd.lens, sd.totals, c->status);
+  FS2_LAUNCHED();
+  row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(sd.starts, sd.lens, B, VOC_GAP, T, nullptr, rows, sd.utt, sd.vpos, sd.room,
+                                                     sd.slot);
+  FS2_LAUNCHED();
+  pack_mel_kernel<<<(rows + 7) / 8, 256, 0, s>>>(mel, sb, sc, st, sd.meta(), sd.lens, rows, c->melp);
+  FS2_LAUNCHED();
+  const int32_t* live = reinterpret_cast<const int32_t*>(sd.totals);
+
+  auto conv = [&](const float* A, int rows_now, int shift, const float* W, const float* bias, int taps, int dil, int K, int N,
+                  int act, const float* residual, int act2, float* C, int ldc) {
+    ConvGemmArgs a{};
+    a.A = A; a.lda = K; a.rows = rows_now; a.W = W; a.bias = bias; a.taps = taps; a.dil = dil; a.pad = dil * (taps - 1) / 2;
+    a.K = K; a.N = N; a.act = act; a.slope = SLOPE; a.residual = residual; a.ldr = N; a.res_inv_lrelu = residual != nullptr;
+    a.act2 = act2; a.C = C; a.ldc = ldc; a.row_vpos = sd.vpos; a.row_room = sd.room; a.extra = 0; a.mask_shift = shift;
+    a.live_rows = live;
+    tc2::launch(a, FS2_MATH_TF32, s);
+  };
+
+  // conv_pre (models.py:149) with the leaky ReLU of the first upsampling stage (:151) applied on the way out
+  conv(c->melp, rows, 0, c->pre.w, c->pre.b, 7, 1, N_MEL, UP_INITIAL, ACT_LRELU, nullptr, ACT_NONE, c->a0, UP_INITIAL);
+  float *U = c->buf[0], *T1 = c->buf[1], *P[2] = {c->buf[2], c->buf[3]}, *R[3] = {c->buf[4], c->buf[5], c->buf[6]};
+  const float* a_in = c->a0;
+  int rows_now = rows, shift = 0;
+  for (int i = 0; i < N_UPS; ++i) {
+    const UpW& u = c->ups[i];
+    // ConvTranspose1d (models.py:152) as a 3-tap GEMM over the input-rate rows; output = lrelu(x) for the ResBlocks
+    const int n_total = u.s * u.cout;
+    for (int n0 = 0; n0 < n_total; n0 += tc2::MAX_N) {
+      // columns [n0, n0 + n) of every tap: the weight of tap t starts at row t * n_total, so a column slice needs its
+      // own launch only when the whole N does not fit the kernel's bias/parameter stage (never with MAX_N = 2048)
+      require(n_total <= tc2::MAX_N, FS2_ERR_UNSUPPORTED, "upsampling GEMM wider than the compiled parameter stage");
+      conv(a_in, rows_now, shift, u.w, u.b, 3, 1, u.cin, n_total, ACT_LRELU, nullptr, ACT_NONE, U, n_total);
+    }
+    rows_now *= u.s;
+    shift += u.s == 8 ? 3 : 1;
+    const int ch = u.cout;
+    for (int j = 0; j < N_RES; ++j) {            // three ResBlocks from the same input (models.py:156-161)
+      const float* cur = U;
+      for (int m = 0; m < 3; ++m) {              // models.py:97-103
+        const ConvW &w1 = c->res1[i][j][m], &w2 = c->res2[i][j][m];
+        conv(cur, rows_now, shift, w1.w, w1.b, w1.k, RES_DIL[m], ch, ch, ACT_LRELU, nullptr, ACT_NONE, T1, ch);
+        float* out = m == 2 ? R[j] : P[m & 1];
+        conv(T1, rows_now, shift, w2.w, w2.b, w2.k, 1, ch, ch, ACT_NONE, cur, m == 2 ? ACT_NONE : ACT_LRELU, out, ch);
+        cur = out;
+      }
+    }
+    if (i + 1 < N_UPS) {
+      const int64_t n4 = (int64_t)rows_now * ch / 4;
+      sum3_lrelu_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<const float4*>(R[0]), reinterpret_cast<const float4*>(R[1]),
+                                                reinterpret_cast<const float4*>(R[2]), n4, reinterpret_cast<float4*>(T1));
+      FS2_LAUNCHED();
+      a_in = T1;
+      std::swap(T1, P[0]);   // T1 now feeds the next upsampling: the next stage uses another scratch buffer
+    }
+  }
+  post_kernel<<<rows, 256, 0, s>>>(R[0], R[1], R[2], (int64_t)rows_now, c->post_w, c->post_b, sd.meta(), sd.starts, T, wav);
+  FS2_LAUNCHED();
+  c->last_launches = g_launches;
+}
+
+template <typename F>
+static int vguarded(fs2_voc* c, F&& f) {
+  try {
+    f();
+    return FS2_OK;
+  } catch (const Error& e) {
+    if (c) c->err = e.msg; else g_create_error = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    if (c) c->err = e.what(); else g_create_error = e.what();
+    return FS2_ERR_INVALID;
+  }
+}
+
+}  // namespace voc
+}  // namespace fs2
+
+extern "C" {
+
+int fs2_voc_create(int device, fs2_voc** out) {
+  return fs2::voc::vguarded(nullptr, [&] {
+    require(out != nullptr, FS2_ERR_INVALID, "null argument");
+    int n_dev = 0;
+    FS2_CUDA_OK(cudaGetDeviceCount(&n_dev));
+    require(device >= 0 && device < n_dev, FS2_ERR_INVALID, "no such CUDA device");
+    FS2_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    FS2_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    require(prop.major == 10, FS2_ERR_UNSUPPORTED, std::string("libfs2b200 is built for sm_100a (B200) only; device is ") + prop.name);
+    auto* c = new fs2_voc();
+    c->device = device;
+    c->status = dalloc<int32_t>(1);
+    *out = c;
+  });
+}
+
+void fs2_voc_destroy(fs2_voc* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : c->raw) cudaFree(kv.second.ptr);
+  for (void* p : c->owned) cudaFree(p);
+  RowSide* sd = &c->side;
+  cudaFree(sd->starts); cudaFree(sd->lens); cudaFree(sd->utt); cudaFree(sd->vpos); cudaFree(sd->room); cudaFree(sd->slot);
+  cudaFree(sd->totals);
+  cudaFree(c->lens64); cudaFree(c->melp); cudaFree(c->a0); cudaFree(c->status);
+  for (float* b : c->buf) cudaFree(b);
+  delete c;
+}
+
+const char* fs2_voc_last_error(const fs2_voc* c) { return c ? c->err.c_str() : fs2_last_error(nullptr); }
+
+int fs2_voc_set_weight(fs2_voc* c, const char* key, const void* dev_ptr, const int64_t* shape, int ndim) {
+  if (!c) return FS2_ERR_INVALID;
+  return fs2::voc::vguarded(c, [&] {
+    require(key && dev_ptr && shape && ndim >= 1 && ndim <= 3, FS2_ERR_INVALID, "bad fs2_voc_set_weight argument");
+    FS2_CUDA_OK(cudaSetDevice(c->device));
+    DevTensor t;
+    t.numel = 1;
+    for (int i = 0; i < ndim; ++i) {
+      require(shape[i] > 0, FS2_ERR_INVALID, std::string("non-positive dimension in ") + key);
+      t.shape.push_back(shape[i]);
+      t.numel *= shape[i];
+    }
+    t.ptr = dalloc<float>(t.numel);
+    FS2_CUDA_OK(cudaMemcpy(t.ptr, dev_ptr, t.numel * sizeof(float), cudaMemcpyDeviceToDevice));
+    auto it = c->raw.find(key);
+    if (it != c->raw.end()) cudaFree(it->second.ptr);
+    c->raw[key] = t;
+    c->prepared = false;
+  });
+}
+
+int fs2_voc_prepare(fs2_voc* c, fs2_stream stream) {
+  if (!c) return FS2_ERR_INVALID;
+  return fs2::voc::vguarded(c, [&] { fs2::voc::prepare(c, static_cast<cudaStream_t>(stream)); });
+}
+
+int fs2_voc_forward(fs2_voc* c, fs2_stream stream, const float* mel, int64_t stride_b, int64_t stride_c, int64_t stride_t,
+                    int batch, int n_frames, const int64_t* mel_lens, float* wav) {
+  if (!c) return FS2_ERR_INVALID;
+  return fs2::voc::vguarded(c, [&] {
+    fs2::voc::forward(c, static_cast<cudaStream_t>(stream), mel, stride_b, stride_c, stride_t, batch, n_frames, mel_lens, wav);
+  });
+}
+
+int fs2_voc_last_launch_count(const fs2_voc* c) { return c ? c->last_launches : 0; }
 
 }  // extern "C"

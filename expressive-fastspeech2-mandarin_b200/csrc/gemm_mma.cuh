@@ -7,7 +7,7 @@
 
 namespace fs2 {
 
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_LRELU = 3 /* leaky ReLU, slope = ConvGemmArgs::slope */ };
 
 struct ConvGemmArgs {
   const float* A;        // [rows, lda] activations, token-major
@@ -42,6 +42,13 @@ struct ConvGemmArgs {
   int a_bf16;
   void* C2;
   int ldc2;
+  // Vocoder extensions (persistent tcgen05 engine only; zero-initialised = off):
+  int dil;            // dilation: tap t reads row r + t*dil - pad (0 is treated as 1; pad is in rows)
+  int mask_shift;     // the row mask is looked up at row >> mask_shift (rows upsampled 2^shift times share a frame);
+                      // live_rows, when set, counts rows at that coarser rate too
+  float slope;        // ACT_LRELU slope
+  int act2;           // activation applied AFTER the residual add (ACT_NONE / ACT_LRELU)
+  int res_inv_lrelu;  // the residual buffer holds lrelu(x): recover x = y >= 0 ? y : y / slope before adding
   long long* trace;   // bring-up only: CTA 0 writes globaltimer stamps of its phases (nullptr in normal operation)
 };
 

@@ -32,7 +32,7 @@ constexpr int BM = 128;
 constexpr int BK = 32;
 constexpr int THREADS = 192;
 constexpr int WCHUNK = 32 * 128;        // one warp's [32 rows x 32 fp32] swizzled sub-tile (4 KB)
-constexpr int MAX_N = 1024;
+constexpr int MAX_N = 2048;
 
 template <int BN>
 struct Cfg {
@@ -42,8 +42,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OFF_CST = STAGES * STAGE_BYTES;      // 4 warps x 2 output staging sub-tiles
   static constexpr int OFF_RES = OFF_CST + 8 * WCHUNK;      // 4 warps x 2 residual sub-tiles
-  static constexpr int OFF_PAR = OFF_RES + 8 * WCHUNK;      // bias[1024] | gamma[256] | beta[256] | head_w[256]
-  static constexpr int OFF_BAR = OFF_PAR + 8192;
+  static constexpr int OFF_PAR = OFF_RES + 8 * WCHUNK;      // bias[2048] | gamma[256] | beta[256] | head_w[256]
+  static constexpr int OFF_BAR = OFF_PAR + 12288;
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
   static constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
@@ -132,6 +132,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const bool has_res = p.residual != nullptr;
   const bool has_out = p.C != nullptr;
   const bool has_out2 = p.C2 != nullptr;
+  const int dil = p.dil > 0 ? p.dil : 1;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -167,7 +168,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   pdl_trigger();
   pdl_wait();
   int rows_live = p.rows;
-  if (p.live_rows != nullptr) rows_live = min(rows_live, *p.live_rows);
+  if (p.live_rows != nullptr) rows_live = min(rows_live, *p.live_rows << p.mask_shift);
   // work item = CL vertically adjacent row tiles x one column tile; the CTAs of a cluster walk the items in
   // lock step (a trailing odd row tile is processed as an all-zero tile whose stores TMA clips away)
   const int m_groups = ((rows_live + BM - 1) / BM + CL - 1) / CL;
@@ -189,7 +190,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint8_t* a_s = smem + s * C::STAGE_BYTES;
         if (leader) {
           mbar_expect_tx(&full[s], C::STAGE_BYTES);
-          tma_load_2d(a_s, &tmA, kc * BKE, m0 + tap - p.pad, &full[s]);
+          tma_load_2d(a_s, &tmA, kc * BKE, m0 + tap * dil - p.pad, &full[s]);
           if (CL == 1) {
             tma_load_2d(a_s + C::A_BYTES, &tmW, kc * BKE, tap * p.N + n0, &full[s]);
           } else {   // this CTA's half of the weight tile, delivered to both CTAs of the cluster
@@ -268,7 +269,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int row = m0 + r;
       const bool in_range = row < p.rows;
       bool live = in_range;
-      if (in_range && p.row_vpos != nullptr) live = row_live(p.row_vpos[row], p.row_room[row], p.extra);
+      if (in_range && p.row_vpos != nullptr) {
+        const int mr = row >> p.mask_shift;
+        live = row_live(p.row_vpos[mr], p.row_room[mr], p.extra);
+      }
       mbar_wait(&acc_full[u], (lt >> 1) & 1);
       if (lt == 0 && warp == 2) stamp(4);
       if (lt < 6 && warp == 2) stamp(8 + lt * 4 + 2);
@@ -303,17 +307,26 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         } else if (act == ACT_TANH) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+        } else if (act == ACT_LRELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * p.slope;
         }
         if (has_res) {
           mbar_wait(&my_res_full[g_res & 1], (g_res >> 1) & 1);
           const uint32_t rb = res_sa + (g_res & 1) * WCHUNK + lane * 128;
+          const float inv = p.res_inv_lrelu ? 1.f / p.slope : 1.f;   // residual stored as lrelu(x): undo it
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
             if (cc * 4 < width) {
               const float4 r4 = lds4(rb + ((cc << 4) ^ swz_x));
-              v[cc * 4 + 0] += r4.x; v[cc * 4 + 1] += r4.y; v[cc * 4 + 2] += r4.z; v[cc * 4 + 3] += r4.w;
+              v[cc * 4 + 0] += r4.x >= 0.f ? r4.x : r4.x * inv; v[cc * 4 + 1] += r4.y >= 0.f ? r4.y : r4.y * inv;
+              v[cc * 4 + 2] += r4.z >= 0.f ? r4.z : r4.z * inv; v[cc * 4 + 3] += r4.w >= 0.f ? r4.w : r4.w * inv;
             }
           }
+        }
+        if (p.act2 == ACT_LRELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * p.slope;
         }
       };
       // this warp's [32 x 32] sub-tile -> swizzled staging -> TMA store
@@ -542,7 +555,7 @@ inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
               (reinterpret_cast<uintptr_t>(a.C2) & 15) == 0,
           FS2_ERR_INVALID, "tcgen05 conv_gemm: pointers must be 16-byte aligned");
   if (a.rows <= 0) return;
-  require(a.N <= MAX_N, FS2_ERR_UNSUPPORTED, "tcgen05 conv_gemm: N > 1024");
+  require(a.N <= MAX_N, FS2_ERR_UNSUPPORTED, "tcgen05 conv_gemm: N > 2048");
   const bool ln = a.ln_gamma != nullptr;
   if (ln) {
     require(a.N == 256 && a.ln_beta != nullptr, FS2_ERR_INVALID, "fused LayerNorm needs N == 256 and both affine vectors");
@@ -563,6 +576,7 @@ inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
   else if (a.N == 80) launch_bn<80, false>(a, stream);
   else if (a.N % 128 == 0) launch_bn<128, false>(a, stream);
   else if (a.N % 64 == 0) launch_bn<64, false>(a, stream);
+  else if (a.N == 32) launch_bn<32, false>(a, stream);
   else throw Error(FS2_ERR_UNSUPPORTED, "tcgen05 conv_gemm: N = " + std::to_string(a.N) + " has no compiled tile");
 }
 

@@ -215,3 +215,50 @@ def algorithmic_flops(src_lens, mel_lens):
         L, T = int(L), int(T)
         total += L * 25_429_504 + 4096 * L * L + 131_072 + T * 43_327_488 + 6144 * T * T
     return total
+
+
+# ---------------------------------------------------------------------------------------------------
+# HiFi-GAN generator (hifigan/models.py:112-146, hifigan/config.json): the reference ships no vocoder
+# weights either (.MISSING_LARGE_BLOBS), so parity runs on seeded weights of the V1 architecture.
+VOC_UP_RATES, VOC_UP_KERNELS, VOC_UP_INITIAL = (8, 8, 2, 2), (16, 16, 4, 4), 512
+VOC_RES_KERNELS, VOC_RES_DILATIONS = (3, 7, 11), (1, 3, 5)
+
+
+def vocoder_schema():
+    """(key, shape) of Generator.state_dict() after remove_weight_norm(), in its order."""
+    out = [("conv_pre.weight", (VOC_UP_INITIAL, 80, 7)), ("conv_pre.bias", (VOC_UP_INITIAL,))]
+    ch = VOC_UP_INITIAL
+    for i, k in enumerate(VOC_UP_KERNELS):
+        out += [(f"ups.{i}.weight", (ch, ch // 2, k)), (f"ups.{i}.bias", (ch // 2,))]   # ConvTranspose1d: [in, out, k]
+        ch //= 2
+    ch = VOC_UP_INITIAL
+    for i in range(len(VOC_UP_RATES)):
+        ch //= 2
+        for j, k in enumerate(VOC_RES_KERNELS):
+            n = i * len(VOC_RES_KERNELS) + j
+            for grp in ("convs1", "convs2"):
+                for m in range(3):
+                    out += [(f"resblocks.{n}.{grp}.{m}.weight", (ch, ch, k)), (f"resblocks.{n}.{grp}.{m}.bias", (ch,))]
+    out += [("conv_post.weight", (1, ch, 7)), ("conv_post.bias", (1,))]
+    return out
+
+
+def synthetic_vocoder_state_dict(seed=0):
+    """Variance-preserving seeded weights (the reference's N(0, 0.01) init, models.py:10-13, would make every
+    activation ~1e-6 and the parity test vacuous): std = gain / sqrt(fan_in taps that actually contribute)."""
+    sd = {}
+    for key, shape in vocoder_schema():
+        g = _gen("voc." + key, seed)
+        if key.endswith("bias"):
+            sd[key] = 0.05 * torch.randn(shape, generator=g)
+        elif key.startswith("ups."):
+            cin, _, k = shape
+            stride = VOC_UP_RATES[int(key.split(".")[1])]
+            sd[key] = torch.randn(shape, generator=g) * (1.3 / math.sqrt(cin * k / stride))
+        else:
+            _, cin, k = shape
+            gain = 0.6 if ".convs2." in key else 1.3      # the residual branch adds to x: keep the sum bounded
+            if key.startswith("conv_pre") or key.startswith("conv_post"):
+                gain = 0.45                               # activations ~1, pre-tanh output ~0.4 (tanh not saturated)
+            sd[key] = torch.randn(shape, generator=g) * (gain / math.sqrt(cin * k))
+    return sd

@@ -199,6 +199,30 @@ int fs2_op_bucketize(fs2_stream stream, const float* values, int64_t n, const fl
 int fs2_op_frame_map(fs2_stream stream, const int32_t* cum, int batch, int max_src_len,
                      int max_mel_len, int32_t* map);
 
+/* ======================================================================================
+ * HiFi-GAN generator: the vocoder step that follows FastSpeech2.forward in the reference's
+ * synthesis scripts (utils/model.py:37-71 `get_vocoder`, :74-92 `vocoder_infer`;
+ * hifigan/models.py:112-174 `Generator`; architecture hifigan/config.json, V1).
+ * Same conventions as above; one context per device, not thread-safe. */
+typedef struct fs2_voc fs2_voc;
+int fs2_voc_create(int device, fs2_voc** out);
+void fs2_voc_destroy(fs2_voc* voc);
+const char* fs2_voc_last_error(const fs2_voc* voc);
+/* `key` is a key of Generator.state_dict() after remove_weight_norm() (utils/model.py:66): conv_pre.*, ups.{0..3}.*,
+ * resblocks.{0..11}.convs{1,2}.{0..2}.*, conv_post.* (weight, bias); fp32 on the context's device; copied. */
+int fs2_voc_set_weight(fs2_voc* voc, const char* key, const void* dev_ptr, const int64_t* shape, int ndim);
+/* Repack: Conv1d [Cout,Cin,k] -> [k][Cout][Cin]; ConvTranspose1d [Cin,Cout,2s] -> 3-tap GEMM form [3][s*Cout][Cin]. */
+int fs2_voc_prepare(fs2_voc* voc, fs2_stream stream);
+/* Generator.forward (hifigan/models.py:148-167): mel [batch, 80, n_frames] (element strides given, so the
+ * [B, T, 80] postnet output of fs2_forward_stage2 can be passed transposed without a copy) ->
+ * wav [batch, n_frames * 256] fp32 in [-1, 1].  mel_lens == NULL: every frame of the padded batch is data, exactly
+ * as `vocoder(mels)` treats it.  mel_lens != NULL (device int64 [batch]): frames beyond mel_lens[b] are skipped,
+ * utterance b is synthesised as if it were alone (zero padding at both ends) and wav[b, 256*mel_lens[b]:] = 0 --
+ * what `vocoder_infer(..., lengths=)` keeps after trimming, up to the receptive field at the tail. */
+int fs2_voc_forward(fs2_voc* voc, fs2_stream stream, const float* mel, int64_t stride_b, int64_t stride_c,
+                    int64_t stride_t, int batch, int n_frames, const int64_t* mel_lens, float* wav);
+int fs2_voc_last_launch_count(const fs2_voc* voc);
+
 #ifdef __cplusplus
 }
 #endif

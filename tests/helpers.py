@@ -13,7 +13,8 @@ def golden_names(frame_level=None):
     """All fixtures; frame_level=False -> only the default (phoneme_level) configuration, True -> only the
     fixtures recorded with a frame_level pitch and/or energy feature."""
     names = sorted(os.path.splitext(os.path.basename(p))[0]
-                   for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not p.endswith("meta.npz"))
+                   for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                   if os.path.basename(p) not in ("meta.npz", "vocoder.npz"))
     if frame_level is None:
         return names
     return [n for n in names if n.startswith("frame_") == frame_level]
