@@ -4,11 +4,13 @@
     python -m fs2_b200.cli --restore_step 900000 --mode single --text "今天天气真好" \\
         --speaker_id 0001 --emotion Happy -p preprocess.yaml -m model.yaml -t train.yaml
 
-What differs from the reference script, by design: the acoustic model is `FastSpeech2B200`; the
-HiFi-GAN vocoder is outside the accelerated path (its weights are not shipped with the reference
-either), so the result is the postnet mel saved as `<result_path>/<id>.npy` (+ `<id>.json` with
-durations / pitch / energy) instead of a wav and a plot.  `--random_init` replaces the checkpoint
-by the seeded synthetic weights so that the CLI runs without trained weights.
+What differs from the reference script, by design: the acoustic model is `FastSpeech2B200` and the vocoder is
+`HiFiGANGeneratorB200` (both on libfs2b200.so).  Per utterance the CLI writes `<result_path>/<id>.wav` (int16,
+`synth_samples`, utils/tools.py:258-271) when vocoder weights are available (`hifigan/generator_<speaker>.pth.tar` as in
+utils/model.py:60-63, or `--vocoder_ckpt`), and always the postnet mel `<id>.npy` plus `<id>.json` (text, phoneme and
+frame counts).  The spectrogram PNG of the reference needs matplotlib and is not produced.  `--random_init` replaces
+both checkpoints by the seeded synthetic weights so that the CLI runs end to end without trained weights;
+`--no_vocoder` stops after the mel.
 """
 import argparse
 import json
@@ -136,7 +138,9 @@ def build_parser():
     p.add_argument("--pitch_control", type=float, default=1.0)
     p.add_argument("--energy_control", type=float, default=1.0)
     p.add_argument("--duration_control", type=float, default=1.0)
-    p.add_argument("--random_init", action="store_true", help="seeded synthetic weights instead of a checkpoint")
+    p.add_argument("--random_init", action="store_true", help="seeded synthetic weights instead of the checkpoints")
+    p.add_argument("--vocoder_ckpt", type=str, default=None, help="generator checkpoint (default hifigan/generator_<speaker>.pth.tar)")
+    p.add_argument("--no_vocoder", action="store_true", help="write the mel only")
     return p
 
 
@@ -154,6 +158,27 @@ def load_model(args, preprocess_config, model_config, train_config, device="cuda
     return model.to(device).eval()
 
 
+def load_vocoder(args, model_config, device="cuda"):
+    """utils/model.py:37-71.  Returns None when no generator weights can be found (the reference ships none)."""
+    if args.no_vocoder:
+        return None
+    from .vocoder import get_vocoder
+    if args.random_init:
+        return get_vocoder(model_config, device, random_init=True)
+    path = args.vocoder_ckpt or os.path.join("hifigan", f"generator_{model_config['vocoder']['speaker']}.pth.tar")
+    if not os.path.exists(path):
+        print(f"[fs2_b200] no vocoder weights at {path}: writing mel spectrograms only")
+        return None
+    return get_vocoder(model_config, device, ckpt_path=path)
+
+
+def write_wavs(out_dir, ids, wavs, sampling_rate):
+    """utils/tools.py:268-271: one int16 wav per utterance."""
+    from scipy.io import wavfile
+    for name, wav in zip(ids, wavs):
+        wavfile.write(os.path.join(out_dir, f"{name}.wav"), sampling_rate, wav)
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
     if args.mode == "batch":
@@ -167,6 +192,9 @@ def main(argv=None):
     with open(args.train_config) as f:
         train_config = yaml.load(f, Loader=yaml.FullLoader)
     model = load_model(args, preprocess_config, model_config, train_config)
+    vocoder = load_vocoder(args, model_config)
+    hop = preprocess_config["preprocessing"]["stft"]["hop_length"]
+    sampling_rate = preprocess_config["preprocessing"]["audio"]["sampling_rate"]
     batches = [single_batch(args, preprocess_config)] if args.mode == "single" else \
         source_batches(args.source, preprocess_config)
     out_dir = train_config["path"]["result_path"]
@@ -176,12 +204,18 @@ def main(argv=None):
                     src_lens=text_lens, max_src_len=max_len)
         mel, mel_lens, _, _ = model.synthesize_host(host, p_control=args.pitch_control, e_control=args.energy_control,
                                                     d_control=args.duration_control)
+        if vocoder is not None:        # utils/tools.py:258-271
+            from .vocoder import vocoder_infer
+            mels_dev = model.last_postnet.transpose(1, 2)
+            wavs = vocoder_infer(mels_dev, vocoder, model_config, preprocess_config, lengths=[int(n) * hop for n in mel_lens])
+            write_wavs(out_dir, ids, wavs, sampling_rate)
         for i, name in enumerate(ids):
             np.save(os.path.join(out_dir, f"{name}.npy"), mel[i, : int(mel_lens[i])].copy())
             with open(os.path.join(out_dir, f"{name}.json"), "w", encoding="utf-8") as f:
                 json.dump({"text": raw_texts[i], "n_phonemes": int(text_lens[i]), "n_frames": int(mel_lens[i])}, f,
                           ensure_ascii=False)
-            print(f"{name}: {int(text_lens[i])} phonemes -> {int(mel_lens[i])} mel frames -> {out_dir}/{name}.npy")
+            print(f"{name}: {int(text_lens[i])} phonemes -> {int(mel_lens[i])} mel frames -> {out_dir}/{name}.npy" +
+                  (f", {out_dir}/{name}.wav" if vocoder is not None else ""))
 
 
 if __name__ == "__main__":

@@ -311,6 +311,7 @@ class FastSpeech2B200(nn.Module):
                            dev_t["src_lens"], int(batch["max_src_len"]), p_control=p_control, e_control=e_control,
                            d_control=d_control)
         post, lens = out[1], out[9]
+        self.last_postnet = post      # device tensor [B, T, 80]: what the vocoder consumes next (utils/tools.py:258-262)
         key = ("post", tuple(post.shape))
         if key not in self._pinned:
             self._pinned[key] = torch.empty(post.shape, dtype=torch.float32).pin_memory()

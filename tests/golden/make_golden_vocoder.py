@@ -18,6 +18,8 @@ sys.path.insert(0, REPO)
 def build_reference_generator(sd, dtype=torch.float64):
     if REF not in sys.path:
         sys.path.insert(1, REF)
+    if "hifigan" in sys.modules and not hasattr(sys.modules["hifigan"], "AttrDict"):
+        del sys.modules["hifigan"]            # a stub left by another test
     import hifigan
     with open(os.path.join(REF, "hifigan", "config.json")) as f:
         cfg = hifigan.AttrDict(json.load(f))

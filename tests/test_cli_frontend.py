@@ -42,7 +42,7 @@ def test_syllable_split_matches_reference_rules(syllable):
         stub.lazy_pinyin = lambda text, style=None: [stub.current]
     sys.modules["pypinyin"] = stub
     stub.current = syllable
-    for name in ("hifigan", "dataset_chinese", "dataset"):
+    for name in ("dataset_chinese", "dataset"):      # hifigan itself imports fine (torch only)
         sys.modules.setdefault(name, types.ModuleType(name))
     sys.modules["dataset_chinese"].TextDataset = object
     import importlib

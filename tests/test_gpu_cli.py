@@ -29,3 +29,33 @@ def test_cli_single_sentence(sd32):
     meta = json.load(open(os.path.join(d, "result", "synthesis_0001_Happy.json")))
     assert mel.ndim == 2 and mel.shape[1] == 80 and mel.shape[0] == meta["n_frames"] > 16
     assert meta["n_phonemes"] == 16 and np.isfinite(mel).all()
+    # the vocoder step of the reference script (utils/tools.py:258-271): an int16 wav of n_frames * hop samples
+    from scipy.io import wavfile
+    rate, wav = wavfile.read(os.path.join(d, "result", "synthesis_0001_Happy.wav"))
+    assert rate == 22050 and wav.dtype == np.int16 and wav.shape == (meta["n_frames"] * 256,)
+    assert np.abs(wav.astype(np.int32)).max() > 100
+
+
+def test_cli_batch_mode_writes_one_wav_per_line(sd32):
+    """--mode batch --source file (dataset_chinese.py:193-276 line format) -> mel + wav per utterance."""
+    d = tempfile.mkdtemp(prefix="fs2_cli_")
+    fs2_b200.synthetic.write_fixture_jsons(d)
+    cfgs = {"p": fs2_b200.config.default_preprocess_config(d), "m": fs2_b200.config.default_model_config(),
+            "t": {"path": {"ckpt_path": d, "result_path": os.path.join(d, "result")}}}
+    paths = {}
+    for k, v in cfgs.items():
+        paths[k] = os.path.join(d, k + ".yaml")
+        with open(paths[k], "w") as f:
+            yaml.safe_dump(v, f)
+    src = os.path.join(d, "val.txt")
+    with open(src, "w", encoding="utf-8") as f:
+        f.write("u1|0001|{j i n t ia n}|今天|Happy|0.8|0.8\n")
+        f.write("u2|0003|{n i h ao sh i j ie}|你好世界|Sad|0.3|0.2\n")
+        f.write("u3|0002|{h ao}|好|Neutral|0.5|0.5\n")
+    cli.main(["--restore_step", "1", "--mode", "batch", "--source", src, "-p", paths["p"], "-m", paths["m"], "-t", paths["t"],
+              "--random_init"])
+    from scipy.io import wavfile
+    for name in ("u1", "u2", "u3"):
+        mel = np.load(os.path.join(d, "result", f"{name}.npy"))
+        rate, wav = wavfile.read(os.path.join(d, "result", f"{name}.wav"))
+        assert wav.shape == (mel.shape[0] * 256,) and wav.dtype == np.int16
