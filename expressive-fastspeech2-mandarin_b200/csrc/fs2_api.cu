@@ -919,6 +919,7 @@ static int g_trace_on = 0;
 int fs2_debug_set_flag(int which, int value) {
   if (which == 0) fs2::attn_tc::debug_flag() = value;
   if (which == 2) fs2::tc2::cluster_size_flag() = value == 1 ? 1 : 2;
+  if (which == 3) fs2::tc2::a_resident_flag() = value ? 1 : 0;
   if (which == 1) {
     g_trace_on = value;
     if (value && g_trace_buf == nullptr) cudaMalloc(reinterpret_cast<void**>(&g_trace_buf), 64 * sizeof(long long));
@@ -991,6 +992,21 @@ int fs2_op_conv_gemm_ln(fs2_stream stream, int engine, const float* A, int lda, 
     a.ln_gamma = gamma; a.ln_beta = beta; a.head_w = head_w; a.head_b = head_b; a.head_out = head_out;
     if (g_trace_on) { a.trace = g_trace_buf + 8 * ((g_trace_on - 1) % 8); ++g_trace_on; }
     conv_gemm(engine, FS2_MATH_TF32, a, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int fs2_op_conv_gemm_ex(fs2_stream stream, const float* A, int lda, int rows, const float* Wt, const float* bias, int taps,
+                        int dil, int K, int N, int act, float slope, const float* residual, int ldr, int res_inv_lrelu,
+                        int act2, const int32_t* row_vpos, const int32_t* row_room, int extra, int mask_shift, float* C,
+                        int ldc) {
+  return guarded(nullptr, [&] {
+    require(A && Wt && bias && C && rows >= 0 && taps >= 1 && dil >= 1 && K > 0 && N > 0 && mask_shift >= 0, FS2_ERR_INVALID,
+            "bad conv_gemm_ex argument");
+    ConvGemmArgs a{};
+    a.A = A; a.lda = lda; a.rows = rows; a.W = Wt; a.bias = bias; a.taps = taps; a.dil = dil; a.pad = dil * (taps - 1) / 2;
+    a.K = K; a.N = N; a.act = act; a.slope = slope; a.residual = residual; a.ldr = ldr; a.res_inv_lrelu = res_inv_lrelu;
+    a.act2 = act2; a.row_vpos = row_vpos; a.row_room = row_room; a.extra = extra; a.mask_shift = mask_shift; a.C = C; a.ldc = ldc;
+    conv_gemm(FS2_ENGINE_TCGEN05, FS2_MATH_TF32, a, static_cast<cudaStream_t>(stream));
   });
 }
 

@@ -34,13 +34,23 @@ constexpr int THREADS = 192;
 constexpr int WCHUNK = 32 * 128;        // one warp's [32 rows x 32 fp32] swizzled sub-tile (4 KB)
 constexpr int MAX_N = 2048;
 
-template <int BN>
+// A-resident mode (AR, small K with many taps -- the vocoder's 32/64-channel dilated convs): the activation tile is
+// loaded ONCE per output tile with its halo rows ([m0 - pad, m0 - pad + AR_ROWS) for every K chunk) and each tap is an
+// MMA whose A descriptor starts tap*dil rows further down the same shared-memory tile; only the weights stream through
+// the ring.  Without it every tap re-fetches the whole 128-row tile from L2 (11x the traffic for k = 11).
+constexpr int AR_ROWS = 192;      // 128 + (taps - 1) * dil <= 192  (k = 11, dilation 5: 178)
+constexpr int AR_CHUNKS = 2;      // K <= 64 fp32
+
+template <int BN, bool AR = false>
 struct Cfg {
   static constexpr int STAGES = BN > 128 ? 3 : 4;
-  static constexpr int A_BYTES = BM * 128;
+  static constexpr int A_BYTES = AR ? 0 : BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OFF_CST = STAGES * STAGE_BYTES;      // 4 warps x 2 output staging sub-tiles
+  static constexpr int AR_CHUNK_BYTES = AR_ROWS * 128;
+  static constexpr int AR_BUF_BYTES = AR ? AR_CHUNKS * AR_CHUNK_BYTES : 0;   // one tile's activations; two buffers
+  static constexpr int OFF_RING = 2 * AR_BUF_BYTES;
+  static constexpr int OFF_CST = OFF_RING + STAGES * STAGE_BYTES;      // 4 warps x 2 output staging sub-tiles
   static constexpr int OFF_RES = OFF_CST + 8 * WCHUNK;      // 4 warps x 2 residual sub-tiles
   static constexpr int OFF_PAR = OFF_RES + 8 * WCHUNK;      // bias[2048] | gamma[256] | beta[256] | head_w[256]
   static constexpr int OFF_BAR = OFF_PAR + 12288;
@@ -93,12 +103,27 @@ __device__ __forceinline__ void sts8_bf16(uint32_t saddr, const float* v) {
 }
 
 // BF = bf16 operands (kind::f16, 64 elements per 128-byte K chunk) instead of TF32 (32 elements).
-template <int BN, bool LN, int CL, bool BF>
+// K-major SWIZZLE_128B descriptor that starts `rows` rows inside a larger tile whose swizzle pattern begins on a
+// 1024-byte boundary (where TMA put it).  Measured on B200 (tools/ar_probe.py): the tensor core applies the XOR to the
+// absolute shared-memory address bits [7,10), so a row-shifted start address needs nothing else; the base-offset field
+// (bits [49,52)) describes a PATTERN that starts off-boundary and must stay 0 here (setting it to the row phase
+// permutes the 16-byte chunks of every row whose phase carries into bit 2).
+__device__ __forceinline__ uint64_t umma_desc_rowshift(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN, bool LN, int CL, bool BF, bool AR = false>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                      const __grid_constant__ CUtensorMap tmC2, ConvGemmArgs p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, AR>;
+  static_assert(!(AR && (BF || LN)), "A-resident mode: fp32 activations, plain epilogue");
   constexpr int BKE = BF ? 64 : 32;   // operand elements per 128-byte swizzle row
   extern __shared__ uint8_t smem_raw[];
   auto stamp = [&](int k) {
@@ -123,7 +148,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* acc_full = empty + C::STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
   uint64_t* res_full = acc_empty + 2;       // [4 warps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 8);
+  uint64_t* a_full = res_full + 8;          // [2]  AR: the resident activation tile of buffer u has landed
+  uint64_t* a_empty = a_full + 2;           // [2]  AR: every MMA that reads buffer u has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 2);
+  uint8_t* ring = smem + C::OFF_RING;
 
   const int warp = warp_index(), lane = threadIdx.x & 31;
   const int kchunks = (p.K + BKE - 1) / BKE;
@@ -149,6 +177,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&acc_empty[u], 128);
     }
     for (int u = 0; u < 8; ++u) mbar_init(&res_full[u], 1);
+    for (int u = 0; u < 2; ++u) {
+      mbar_init(&a_full[u], 1);
+      mbar_init(&a_empty[u], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
@@ -180,17 +212,27 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0) {
     // ---------------- TMA producer (whole warp runs the loop, one elected lane issues)
     const bool leader = elect_one();
-    int it = 0;
-    for (int w = w_first; w < total_items; w += w_step) {
+    int it = 0, lt = 0;
+    for (int w = w_first; w < total_items; w += w_step, ++lt) {
       const int m0 = item_m0(w), n0 = item_n0(w);
+      if (AR) {   // the whole activation tile with its halo, once
+        const int u = lt & 1;
+        mbar_wait(&a_empty[u], ((lt >> 1) & 1) ^ 1);
+        if (leader) {
+          mbar_expect_tx(&a_full[u], (uint32_t)kchunks * C::AR_CHUNK_BYTES);
+          for (int kc = 0; kc < kchunks; ++kc)
+            tma_load_2d(smem + u * C::AR_BUF_BYTES + kc * C::AR_CHUNK_BYTES, &tmA, kc * BKE, m0 - p.pad, &a_full[u]);
+        }
+        __syncwarp();
+      }
       for (int i = 0; i < iters; ++i, ++it) {
         const int s = it % C::STAGES;
         mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
         const int tap = i / kchunks, kc = i - tap * kchunks;
-        uint8_t* a_s = smem + s * C::STAGE_BYTES;
+        uint8_t* a_s = ring + s * C::STAGE_BYTES;
         if (leader) {
           mbar_expect_tx(&full[s], C::STAGE_BYTES);
-          tma_load_2d(a_s, &tmA, kc * BKE, m0 + tap * dil - p.pad, &full[s]);
+          if (!AR) tma_load_2d(a_s, &tmA, kc * BKE, m0 + tap * dil - p.pad, &full[s]);
           if (CL == 1) {
             tma_load_2d(a_s + C::A_BYTES, &tmW, kc * BKE, tap * p.N + n0, &full[s]);
           } else {   // this CTA's half of the weight tile, delivered to both CTAs of the cluster
@@ -213,13 +255,21 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (lt < 6) stamp(8 + lt * 4 + 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + u * C::ACC_COLS;
+      if (AR) mbar_wait(&a_full[u], (lt >> 1) & 1);
       for (int i = 0; i < iters; ++i, ++it) {
         const int s = it % C::STAGES;
         mbar_wait(&full[s], (it / C::STAGES) & 1);
         if (it == 0) stamp(2);
         tc_fence_after();
-        const uint8_t* a_s = smem + s * C::STAGE_BYTES;
-        const uint64_t da = umma_desc(a_s), db = umma_desc(a_s + C::A_BYTES);
+        const uint8_t* a_s = ring + s * C::STAGE_BYTES;
+        uint64_t da;
+        if (AR) {   // tap t of K chunk kc = the resident tile, t*dil rows down
+          const int tap = i / kchunks, kc = i - tap * kchunks;
+          da = umma_desc_rowshift(smem_u32(smem + u * C::AR_BUF_BYTES + kc * C::AR_CHUNK_BYTES) + (uint32_t)(tap * dil) * 128u);
+        } else {
+          da = umma_desc(a_s);
+        }
+        const uint64_t db = umma_desc(a_s + C::A_BYTES);
         if (leader) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {   // four 32-byte K slices per stage: K = 8 (tf32) or 16 (bf16) each
@@ -230,7 +280,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         __syncwarp();
       }
-      if (leader) umma_commit(&acc_full[u]);
+      if (leader) {
+        umma_commit(&acc_full[u]);
+        if (AR) umma_commit(&a_empty[u]);   // the resident tile may be overwritten once these MMAs have read it
+      }
       __syncwarp();
       if (lt == 0) stamp(3);
     }
@@ -508,19 +561,19 @@ inline int& cluster_size_flag() {   // 2 = weight tiles multicast across CTA pai
   return f;
 }
 
-template <int BN, bool LN, int CL, bool BF>
+template <int BN, bool LN, int CL, bool BF, bool AR = false>
 inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, AR>;
   static bool configured[64] = {};
   int dev = 0;
   FS2_CUDA_OK(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN, CL, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
     configured[dev & 63] = true;
   }
   constexpr CUtensorMapSwizzle SW128 = CU_TENSOR_MAP_SWIZZLE_128B;
   const CUtensorMap tmA = BF ? make_map_any(a.A, a.rows, a.K, a.lda, BM, 64, MAP_BF16, SW128)
-                             : make_map(a.A, a.rows, a.K, a.lda, BM, /*round_tf32=*/true, false);
+                             : make_map(a.A, a.rows, a.K, a.lda, AR ? AR_ROWS : BM, /*round_tf32=*/true, false);
   const CUtensorMap tmW = BF ? make_map_any(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN / CL, 64, MAP_BF16, SW128)
                              : make_map(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN / CL, false, true);
   const CUtensorMap tmC = a.C != nullptr ? make_map(a.C, a.rows, a.N, a.ldc, 32, false, false) : tmA;
@@ -529,8 +582,19 @@ inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
       a.C2 != nullptr ? make_map_any(a.C2, a.rows, a.N, a.ldc2, 32, 32, MAP_BF16, CU_TENSOR_MAP_SWIZZLE_64B) : tmA;
   const int items = (((a.rows + BM - 1) / BM + CL - 1) / CL) * ((a.N + BN - 1) / BN);
   const int grid = std::min(items, sm_count() / CL) * CL;
-  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL, BF>, dim3(grid), dim3(THREADS), C::TOTAL, stream, CL, tmA, tmW, tmC, tmR, tmC2, a);
+  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR>, dim3(grid), dim3(THREADS), C::TOTAL, stream, CL, tmA, tmW, tmC, tmR, tmC2, a);
   FS2_LAUNCHED();
+}
+
+inline int& a_resident_flag() {   // 1 = use the A-resident variant where it applies (default), 0 = always stream A
+  static int f = 1;
+  return f;
+}
+
+template <int BN>
+inline void launch_ar(const ConvGemmArgs& a, cudaStream_t stream) {
+  if (cluster_size_flag() == 2 && a.rows > BM) launch_bn_cl<BN, false, 2, false, true>(a, stream);
+  else launch_bn_cl<BN, false, 1, false, true>(a, stream);
 }
 
 template <int BN, bool LN>
@@ -565,6 +629,13 @@ inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
     return;
   }
   require(a.C != nullptr || a.C2 != nullptr, FS2_ERR_INVALID, "conv_gemm: null output");
+  {   // small K, several taps: keep the activation tile resident and shift the descriptor per tap
+    const int d = a.dil > 0 ? a.dil : 1;
+    if (a_resident_flag() && !a.a_bf16 && a.taps > 1 && a.K <= 32 * AR_CHUNKS && BM + (a.taps - 1) * d <= AR_ROWS) {
+      if (a.N == 32) { launch_ar<32>(a, stream); return; }
+      if (a.N == 64) { launch_ar<64>(a, stream); return; }
+    }
+  }
   // Small problems (single utterances): a 128 x 256 tile would leave most SMs idle while one CTA
   // walks the whole K loop at 512 cycles per stage, so narrower tiles spread the columns over more
   // CTAs whose stages are proportionally shorter.

@@ -137,7 +137,7 @@ int fs2_debug_enable(fs2_ctx* ctx, int on);
 int fs2_debug_fetch(fs2_ctx* ctx, const char* name, void* host_dst, int64_t max_bytes,
                     int64_t* rows, int64_t* cols);
 
-/* Bring-up switches (0 = attention kernel raw-dump mode); 0 in normal operation. */
+/* Bring-up switches (0 = attention kernel raw-dump mode, 2 = GEMM cluster size, 3 = A-resident GEMM variant on/off). */
 int fs2_debug_set_flag(int which, int value);
 /* which = 1: CTA 0 of the next fs2_op_conv_gemm writes globaltimer stamps; read them back here. */
 int fs2_debug_read_trace(int64_t* host_dst, int n);
@@ -165,6 +165,16 @@ int fs2_op_conv_gemm_ln(fs2_stream stream, int engine, const float* A, int lda, 
                         const float* bias, int taps, int pad, int K, int act, const float* residual, int ldr,
                         const float* gamma, const float* beta, const int32_t* row_vpos, const int32_t* row_room,
                         int extra, float* C, int ldc, const float* head_w, const float* head_b, float* head_out);
+/* The vocoder's form of the contraction (persistent tcgen05 engine, TF32): dilated taps (tap t reads row
+ * r + (t - (taps-1)/2) * dil; hifigan/models.py:27-55), leaky ReLU (act = 3, `slope`) before and/or after (`act2`) the
+ * residual add, a residual buffer that holds lrelu(x) and is inverted on the fly (`res_inv_lrelu`), and a row mask
+ * looked up at row >> mask_shift (rows of an upsampled stage share the mask of their mel frame).  Small-K multi-tap
+ * shapes run in the A-resident variant (activation tile + halo loaded once, one shifted descriptor per tap);
+ * fs2_debug_set_flag(3, 0) forces the streaming variant for cross-checks. */
+int fs2_op_conv_gemm_ex(fs2_stream stream, const float* A, int lda, int rows, const float* W, const float* bias, int taps,
+                        int dil, int K, int N, int act, float slope, const float* residual, int ldr, int res_inv_lrelu,
+                        int act2, const int32_t* row_vpos, const int32_t* row_room, int extra, int mask_shift, float* C,
+                        int ldc);
 /* FS2_MATH_BF16 form of the two contractions above: A [rows,lda] and W [taps][N][K] are bf16 (kind::f16 MMAs,
  * fp32 accumulation); bias / residual / gamma / beta are fp32.  gamma != NULL selects the fused LayerNorm
  * epilogue (N = 256).  The result is written as fp32 to C and/or as bf16 to C2 (either may be NULL): C2 is the

@@ -82,3 +82,72 @@ def test_vocoder_infer_matches_reference_api(voc, vsd):
 def test_cpu_tensor_is_rejected(voc):
     with pytest.raises(RuntimeError):
         voc(torch.zeros(1, 80, 4))
+
+
+# ------------------------------------------------------------------ the vocoder's GEMM form, operator level
+def _conv_ex_ref(A, W, bias, dil, act, slope, res, inv, act2, live):
+    rows, K = A.shape
+    taps, N, _ = W.shape
+    pad = dil * (taps - 1) // 2
+    A64 = torch.zeros(rows + 2 * pad + 1, K, dtype=torch.float64)
+    A64[pad: pad + rows] = A.double()
+    out = bias.double().unsqueeze(0).repeat(rows, 1)
+    for t in range(taps):
+        out += A64[t * dil: t * dil + rows] @ W[t].double().T
+    lrelu = lambda x: torch.where(x >= 0, x, x * slope)
+    if act == 3:
+        out = lrelu(out)
+    if res is not None:
+        r = res.double()
+        out = out + (torch.where(r >= 0, r, r / slope) if inv else r)
+    if act2 == 3:
+        out = lrelu(out)
+    return out * live.unsqueeze(1)
+
+
+EX_CASES = [
+    # rows, K, N, taps, dil, residual, mask_shift, name             (K <= 64 with several taps -> A-resident variant)
+    (1000, 32, 32, 3, 1, False, 0, "c32_k3"),
+    (5000, 32, 32, 11, 5, True, 3, "c32_k11_d5_res"),
+    (3001, 64, 64, 7, 3, True, 1, "c64_k7_d3_res"),
+    (2500, 64, 64, 11, 5, False, 0, "c64_k11_d5"),
+    (777, 64, 64, 3, 1, True, 0, "up_64_to_2x32"),
+    (900, 128, 128, 11, 5, True, 2, "c128_k11_d5_streaming"),
+    (300, 256, 256, 7, 3, True, 0, "c256_k7_d3_streaming"),
+    (40000, 32, 32, 7, 5, True, 8, "c32_many_tiles"),
+]
+
+
+@pytest.mark.parametrize("resident", [1, 0])
+@pytest.mark.parametrize("case", EX_CASES, ids=[c[-1] for c in EX_CASES])
+def test_conv_gemm_ex(case, resident):
+    from gpu_util import lib, ptr, round_tf32, stream
+    rows, K, N, taps, dil, use_res, shift, _ = case
+    g = torch.Generator().manual_seed(rows + K + taps * 13 + dil)
+    A = round_tf32(torch.randn(rows, K, generator=g))
+    W = round_tf32(torch.randn(taps, N, K, generator=g) / np.sqrt(K * taps))
+    bias = torch.randn(N, generator=g) * 0.2
+    res = torch.randn(rows, N, generator=g) if use_res else None
+    n_mask = (rows >> shift) + 1
+    vpos = torch.randint(-6, 2, (n_mask,), generator=g, dtype=torch.int32)
+    room = torch.zeros(n_mask, dtype=torch.int32)
+    live = (vpos < 0)[torch.arange(rows) >> shift]
+    slope = 0.1
+    want = _conv_ex_ref(A, W, bias, dil, 3 if not use_res else 0, slope, res, True, 3 if use_res else 0, live)
+    d = lambda t: t.to(DEV) if t is not None else None
+    dA, dW, db, dres, dv, dr = map(d, (A, W, bias, res, vpos, room))
+    out = torch.full((rows, N), float("nan"), device=DEV)
+    L = lib()
+    L.fs2_debug_set_flag(3, resident)
+    try:
+        code = L.fs2_op_conv_gemm_ex(stream(), ptr(dA), K, rows, ptr(dW), ptr(db), taps, dil, K, N, 0 if use_res else 3, slope,
+                                     ptr(dres), N, 1 if use_res else 0, 3 if use_res else 0, ptr(dv), ptr(dr), 0, shift,
+                                     ptr(out), N)
+        assert code == 0, L.fs2_last_error(None)
+        torch.cuda.synchronize()
+    finally:
+        L.fs2_debug_set_flag(3, 1)
+    got = out.cpu().double()
+    assert torch.isfinite(got).all()
+    err = (got - want).abs().max().item()
+    assert err < 3e-4, f"max abs err {err}"
