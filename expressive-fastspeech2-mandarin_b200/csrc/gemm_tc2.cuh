@@ -38,17 +38,21 @@ constexpr int MAX_N = 2048;
 // loaded ONCE per output tile with its halo rows ([m0 - pad, m0 - pad + AR_ROWS) for every K chunk) and each tap is an
 // MMA whose A descriptor starts tap*dil rows further down the same shared-memory tile; only the weights stream through
 // the ring.  Without it every tap re-fetches the whole 128-row tile from L2 (11x the traffic for k = 11).
+// The weight ring then moves 16 KB stages that hold several (tap, K chunk) units each: with 4 KB weight tiles a
+// one-unit stage is pure mbarrier latency (measured: 530 cycles per tap for 64 cycles of MMA).
 constexpr int AR_ROWS = 192;      // 128 + (taps - 1) * dil <= 192  (k = 11, dilation 5: 178)
-constexpr int AR_CHUNKS = 2;      // K <= 64 fp32
+constexpr int AR_STAGE_BYTES = 16384;
 
-template <int BN, bool AR = false>
+// AR = 0: activations stream with the weights; AR = 1 / 2: resident activation tile of 1 / 2 K chunks (K <= 32 / 64)
+template <int BN, int AR = 0>
 struct Cfg {
-  static constexpr int STAGES = BN > 128 ? 3 : 4;
+  static constexpr int STAGES = AR == 2 ? 3 : (BN > 128 ? 3 : 4);
   static constexpr int A_BYTES = AR ? 0 : BM * 128;
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = AR ? AR_STAGE_BYTES : A_BYTES + B_BYTES;
+  static constexpr int UNITS = AR ? AR_STAGE_BYTES / B_BYTES : 1;          // (tap, K chunk) weight tiles per ring stage
   static constexpr int AR_CHUNK_BYTES = AR_ROWS * 128;
-  static constexpr int AR_BUF_BYTES = AR ? AR_CHUNKS * AR_CHUNK_BYTES : 0;   // one tile's activations; two buffers
+  static constexpr int AR_BUF_BYTES = AR * AR_CHUNK_BYTES;                  // one tile's activations; two buffers
   static constexpr int OFF_RING = 2 * AR_BUF_BYTES;
   static constexpr int OFF_CST = OFF_RING + STAGES * STAGE_BYTES;      // 4 warps x 2 output staging sub-tiles
   static constexpr int OFF_RES = OFF_CST + 8 * WCHUNK;      // 4 warps x 2 residual sub-tiles
@@ -117,7 +121,7 @@ __device__ __forceinline__ uint64_t umma_desc_rowshift(uint32_t saddr) {
   return d;
 }
 
-template <int BN, bool LN, int CL, bool BF, bool AR = false>
+template <int BN, bool LN, int CL, bool BF, int AR = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -225,6 +229,24 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         __syncwarp();
       }
+      if (AR) {   // weights: several (tap, K chunk) units per 16 KB stage
+        for (int i0 = 0; i0 < iters; i0 += C::UNITS, ++it) {
+          const int s = it % C::STAGES;
+          mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
+          const int n_units = min(C::UNITS, iters - i0);
+          if (leader) {
+            mbar_expect_tx(&full[s], (uint32_t)n_units * C::B_BYTES);
+            for (int j = 0; j < n_units; ++j) {
+              const int tap = (i0 + j) / kchunks, kc = (i0 + j) - tap * kchunks;
+              uint8_t* b_s = ring + s * C::STAGE_BYTES + j * C::B_BYTES;
+              if (CL == 1) tma_load_2d(b_s, &tmW, kc * BKE, tap * p.N + n0, &full[s]);
+              else tma_load_2d_mc(b_s + rank * (C::B_BYTES / 2), &tmW, kc * BKE, tap * p.N + n0 + rank * (BN / 2), &full[s], (uint16_t)0x3);
+            }
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       for (int i = 0; i < iters; ++i, ++it) {
         const int s = it % C::STAGES;
         mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
@@ -232,7 +254,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint8_t* a_s = ring + s * C::STAGE_BYTES;
         if (leader) {
           mbar_expect_tx(&full[s], C::STAGE_BYTES);
-          if (!AR) tma_load_2d(a_s, &tmA, kc * BKE, m0 + tap * dil - p.pad, &full[s]);
+          tma_load_2d(a_s, &tmA, kc * BKE, m0 + tap * dil - p.pad, &full[s]);
           if (CL == 1) {
             tma_load_2d(a_s + C::A_BYTES, &tmW, kc * BKE, tap * p.N + n0, &full[s]);
           } else {   // this CTA's half of the weight tile, delivered to both CTAs of the cluster
@@ -255,20 +277,40 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (lt < 6) stamp(8 + lt * 4 + 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + u * C::ACC_COLS;
-      if (AR) mbar_wait(&a_full[u], (lt >> 1) & 1);
+      if (AR) {
+        mbar_wait(&a_full[u], (lt >> 1) & 1);
+        const uint32_t a_base = smem_u32(smem + u * C::AR_BUF_BYTES);
+        for (int i0 = 0; i0 < iters; i0 += C::UNITS, ++it) {
+          const int s = it % C::STAGES;
+          mbar_wait(&full[s], (it / C::STAGES) & 1);
+          tc_fence_after();
+          const int n_units = min(C::UNITS, iters - i0);
+          if (leader) {
+            for (int j = 0; j < n_units; ++j) {   // tap t of K chunk kc = the resident tile, t*dil rows further down
+              const int tap = (i0 + j) / kchunks, kc = (i0 + j) - tap * kchunks;
+              const uint64_t da = umma_desc_rowshift(a_base + kc * C::AR_CHUNK_BYTES + (uint32_t)(tap * dil) * 128u);
+              const uint64_t db = umma_desc(ring + s * C::STAGE_BYTES + j * C::B_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) umma_tf32(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i0 | j | kk) != 0 ? 1u : 0u);
+            }
+            if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], (uint16_t)0x3);
+          }
+          __syncwarp();
+        }
+        if (leader) {
+          umma_commit(&acc_full[u]);
+          umma_commit(&a_empty[u]);   // the resident tile may be overwritten once these MMAs have read it
+        }
+        __syncwarp();
+        continue;
+      }
       for (int i = 0; i < iters; ++i, ++it) {
         const int s = it % C::STAGES;
         mbar_wait(&full[s], (it / C::STAGES) & 1);
         if (it == 0) stamp(2);
         tc_fence_after();
         const uint8_t* a_s = ring + s * C::STAGE_BYTES;
-        uint64_t da;
-        if (AR) {   // tap t of K chunk kc = the resident tile, t*dil rows down
-          const int tap = i / kchunks, kc = i - tap * kchunks;
-          da = umma_desc_rowshift(smem_u32(smem + u * C::AR_BUF_BYTES + kc * C::AR_CHUNK_BYTES) + (uint32_t)(tap * dil) * 128u);
-        } else {
-          da = umma_desc(a_s);
-        }
+        const uint64_t da = umma_desc(a_s);
         const uint64_t db = umma_desc(a_s + C::A_BYTES);
         if (leader) {
 #pragma unroll
@@ -280,10 +322,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         __syncwarp();
       }
-      if (leader) {
-        umma_commit(&acc_full[u]);
-        if (AR) umma_commit(&a_empty[u]);   // the resident tile may be overwritten once these MMAs have read it
-      }
+      if (leader) umma_commit(&acc_full[u]);
       __syncwarp();
       if (lt == 0) stamp(3);
     }
@@ -561,7 +600,7 @@ inline int& cluster_size_flag() {   // 2 = weight tiles multicast across CTA pai
   return f;
 }
 
-template <int BN, bool LN, int CL, bool BF, bool AR = false>
+template <int BN, bool LN, int CL, bool BF, int AR = 0>
 inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
   using C = Cfg<BN, AR>;
   static bool configured[64] = {};
@@ -593,8 +632,12 @@ inline int& a_resident_flag() {   // 1 = use the A-resident variant where it app
 
 template <int BN>
 inline void launch_ar(const ConvGemmArgs& a, cudaStream_t stream) {
-  if (cluster_size_flag() == 2 && a.rows > BM) launch_bn_cl<BN, false, 2, false, true>(a, stream);
-  else launch_bn_cl<BN, false, 1, false, true>(a, stream);
+  const bool pair = cluster_size_flag() == 2 && a.rows > BM;
+  if (a.K <= 32) {
+    if (pair) launch_bn_cl<BN, false, 2, false, 1>(a, stream); else launch_bn_cl<BN, false, 1, false, 1>(a, stream);
+  } else {
+    if (pair) launch_bn_cl<BN, false, 2, false, 2>(a, stream); else launch_bn_cl<BN, false, 1, false, 2>(a, stream);
+  }
 }
 
 template <int BN, bool LN>
@@ -631,7 +674,7 @@ inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
   require(a.C != nullptr || a.C2 != nullptr, FS2_ERR_INVALID, "conv_gemm: null output");
   {   // small K, several taps: keep the activation tile resident and shift the descriptor per tap
     const int d = a.dil > 0 ? a.dil : 1;
-    if (a_resident_flag() && !a.a_bf16 && a.taps > 1 && a.K <= 32 * AR_CHUNKS && BM + (a.taps - 1) * d <= AR_ROWS) {
+    if (a_resident_flag() && !a.a_bf16 && a.taps > 1 && a.K <= 64 && BM + (a.taps - 1) * d <= AR_ROWS) {
       if (a.N == 32) { launch_ar<32>(a, stream); return; }
       if (a.N == 64) { launch_ar<64>(a, stream); return; }
     }
