@@ -270,6 +270,28 @@ def main():
         other = (f16, float(sum(ms16)), float(sum(e16)))
         del m16
 
+    # the step after the path: HiFi-GAN generator on the mel this batch produced, reported beside
+    # the headline (device-resident mel, L2 flushed); never part of `value`
+    voc_line = None
+    if args.engine == "tcgen05" and world == 1:
+        try:
+            voc = fs2_b200.HiFiGANGeneratorB200()
+            voc.load_state_dict(syn.synthetic_vocoder_state_dict(0))
+            voc = voc.to(dev)
+            mel_t, lens_t = out[1].transpose(1, 2), out[9]
+            for _ in range(2):
+                voc(mel_t, mel_lens=lens_t)
+            v_ms = timed_loop(lambda: voc(mel_t, mel_lens=lens_t), min(args.steps, 5))
+            v = float(np.median(v_ms))
+            voc_line = {"workload": "HiFi-GAN V1 generator (hifigan/config.json) on the postnet mel of the same batch, "
+                                    "random-init weights, TF32", "ms_per_step": v, "mel_frames_per_s": frames / v * 1e3,
+                        "audio_samples_per_s": frames * 256 / v * 1e3, "x_realtime_22050hz": frames * 256 / 22050 / (v * 1e-3),
+                        "gpu_launches": voc.last_launch_count}
+            del voc
+            torch.cuda.empty_cache()
+        except Exception as e:   # the vocoder is an extra: never let it take the headline line down
+            voc_line = {"error": str(e)[:200]}
+
     # per-kernel-class CUDA-event timing (same workload, same process, after the timed region)
     lib = _lib.load_library()
     lib.fs2_profile_enable(model._ctx, 1)
@@ -360,6 +382,8 @@ def main():
                                  "unit": UNIT, "ms_per_step": o[1] / args.steps,
                                  "note": "same workload with math_mode='bf16' (bf16 operands, fp32 accumulate/residual/outputs); "
                                          "tolerance stated in tests/test_gpu_bf16.py; not the headline"}
+        if voc_line is not None:
+            line["vocoder"] = voc_line
         if world == 1 and not args.no_cpu_baseline:
             cores = torch.get_num_threads()
             f_cpu, times = oracle_cpu_run(sd, syn.config2_batch(seed=0), CPU_SAMPLE_UTTS, CPU_SAMPLE_STEPS, 1)
