@@ -60,6 +60,7 @@ __device__ __forceinline__ bool row_live(int vpos, int room, int extra) {
   do {                                                                                 \
     cudaError_t e__ = (call);                                                          \
     if (e__ != cudaSuccess) {                                                          \
+      (void)cudaGetLastError(); /* clear the sticky state: the error travels as an exception */ \
       char buf__[512];                                                                 \
       snprintf(buf__, sizeof(buf__), "%s:%d: %s -> %s", __FILE__, __LINE__, #call,     \
                cudaGetErrorString(e__));                                               \

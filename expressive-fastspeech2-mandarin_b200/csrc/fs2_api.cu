@@ -91,7 +91,7 @@ struct fs2_ctx {
 
   // state carried from stage 1 to stage 2
   bool stage1_done = false;
-  int batch = 0, max_src_len = 0, max_mel_len = 0;
+  int batch = 0, max_src_len = 0, max_mel_len = 0, phon_rows = 0;
   int64_t frame_rows = 0;
   const float* lr_input = nullptr;
   const float *p_targets = nullptr, *e_targets = nullptr;  // frame_level teacher forcing: consumed in stage 2
@@ -600,6 +600,7 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   out->max_mel_len = c->max_mel_len;
   require(c->frame_rows < (1LL << 30), FS2_ERR_INVALID, "expanded batch too large");
   c->batch = B;
+  c->phon_rows = rows;
   c->max_src_len = L;
   c->lr_input = xf;
   c->stage1_done = true;
@@ -631,8 +632,14 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
     const bool pitch_f = c->cfg.pitch_frame_level != 0, energy_f = c->cfg.energy_frame_level != 0;
     {
       ProfScope ps(c, s, "length_regulator");
-      length_regulate_kernel<<<(rows + 7) / 8, 256, 0, s>>>(c->lr_input, c->ps.starts, c->cum, L, fsd.meta(), fsd.lens,
-                                                            (pitch_f || energy_f) ? nullptr : pe, rows, x, fp.actb[0]);
+      // source-driven expansion: one warp per phoneme row + one per reserved frame row (the frame->phoneme search of
+      // length_regulate_kernel / fs2_op_frame_map stays as the cross-check used by the tests)
+      const int rows_p = c->phon_rows;                                 // phoneme rows laid out by stage 1
+      const int reserved = (B + 1) * GAP_FRAME + 128;                  // gaps + the round-up tail
+      const int warps = rows_p + reserved;
+      length_regulate_scatter_kernel<<<(warps + 7) / 8, 256, 0, s>>>(
+          c->lr_input, c->ps.meta(), c->ps.lens, rows_p, c->cum, L, fsd.starts, fsd.lens, B, GAP_FRAME, fsd.totals,
+          (pitch_f || energy_f) ? nullptr : pe, rows, x, fp.actb[0]);
       FS2_LAUNCHED();
     }
     if (pitch_f || energy_f) {
@@ -718,7 +725,7 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
     const int64_t out_rows = (int64_t)B * T;
     {
       ProfScope ps(c, s, "unpack");
-      unpack_mel_kernel<<<(unsigned)((out_rows + 7) / 8), 256, 0, s>>>(fp.mel, fp.post, fsd.starts, fsd.lens, B, T,
+      unpack_mel_kernel<<<(unsigned)((out_rows * (N_MEL / 4) + 255) / 256), 256, 0, s>>>(fp.mel, fp.post, fsd.starts, fsd.lens, B, T,
                                                                        c->mel_b, io->mel, io->postnet, io->mel_mask);
       FS2_LAUNCHED();
     }
@@ -1095,6 +1102,7 @@ struct fs2_voc {
   float* buf[7] = {};           // U, T1, P0, P1, R0, R1, R2: rows * 8192 floats each
   int rows_alloc = 0;
   int32_t* status = nullptr;
+  int64_t* h_totals = nullptr;   // pinned
   int last_launches = 0;
 };
 
@@ -1164,26 +1172,39 @@ static void forward(fs2_voc* c, cudaStream_t s, const float* mel, int64_t sb, in
   FS2_CUDA_OK(cudaSetDevice(c->device));
   g_launches = 0;
   const int64_t bound = (int64_t)VOC_GAP + (int64_t)B * (T + VOC_GAP);
-  require(bound * HOP < (1LL << 31), FS2_ERR_INVALID, "vocoder batch too large (2^31 audio rows)");
-  const int rows = round_up((int)bound, 128);
   RowSide& sd = c->side;
+  ensure_side(sd, B, 0);
+  if (c->lens64 == nullptr) regrow(c->lens64, 65536);
+  if (c->h_totals == nullptr) FS2_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&c->h_totals), 4 * sizeof(int64_t)));
+  FS2_CUDA_OK(cudaMemsetAsync(c->status, 0, sizeof(int32_t), s));
+  FS2_CUDA_OK(cudaMemsetAsync(wav, 0, (size_t)B * T * HOP * sizeof(float), s));
+  int64_t used = bound;
+  if (mel_lens == nullptr) {   // every frame of the padded batch is data, exactly as vocoder(mels) treats it
+    fill_i64_kernel<<<(B + 255) / 256, 256, 0, s>>>(c->lens64, B, T);
+    FS2_LAUNCHED();
+    mel_lens = c->lens64;
+    layout_scan_kernel<int64_t><<<1, 1024, 0, s>>>(mel_lens, B, VOC_GAP, T, T, sd.starts, sd.lens, sd.totals, c->status);
+    FS2_LAUNCHED();
+  } else {
+    // ragged batch: the workspace (32 KB per mel row at the audio-rate stages) is sized from the rows actually in use,
+    // which costs one small read-back, instead of from batch * n_frames
+    layout_scan_kernel<int64_t><<<1, 1024, 0, s>>>(mel_lens, B, VOC_GAP, T, T, sd.starts, sd.lens, sd.totals, c->status);
+    FS2_LAUNCHED();
+    FS2_CUDA_OK(cudaMemcpyAsync(c->h_totals, sd.totals, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    FS2_CUDA_OK(cudaMemcpyAsync(c->h_totals + 1, c->status, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    FS2_CUDA_OK(cudaStreamSynchronize(s));
+    require(*reinterpret_cast<int32_t*>(c->h_totals + 1) == 0, FS2_ERR_INVALID, "mel_lens outside [0, n_frames]");
+    used = c->h_totals[0];
+  }
+  require(used * HOP < (1LL << 31), FS2_ERR_INVALID, "vocoder batch too large (2^31 audio rows)");
+  const int rows = round_up((int)used, 128);
   ensure_side(sd, B, rows);
   if (rows > c->rows_alloc) {
     regrow(c->melp, (size_t)rows * N_MEL);
     regrow(c->a0, (size_t)rows * UP_INITIAL);
     for (auto& b : c->buf) regrow(b, (size_t)rows * 8192);
-    regrow(c->lens64, 65536);
     c->rows_alloc = rows;
   }
-  FS2_CUDA_OK(cudaMemsetAsync(c->status, 0, sizeof(int32_t), s));
-  FS2_CUDA_OK(cudaMemsetAsync(wav, 0, (size_t)B * T * HOP * sizeof(float), s));
-  if (mel_lens == nullptr) {   // every frame of the padded batch is data, exactly as vocoder(mels) treats it
-    fill_i64_kernel<<<(B + 255) / 256, 256, 0, s>>>(c->lens64, B, T);
-    FS2_LAUNCHED();
-    mel_lens = c->lens64;
-  }
-  layout_scan_kernel<int64_t><<<1, 1024, 0, s>>>(mel_lens, B, VOC_GAP, T, T, sd.starts, sd.lens, sd.totals, c->status);
-  FS2_LAUNCHED();
   row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(sd.starts, sd.lens, B, VOC_GAP, T, nullptr, rows, sd.utt, sd.vpos, sd.room,
                                                      sd.slot);
   FS2_LAUNCHED();
@@ -1289,6 +1310,7 @@ void fs2_voc_destroy(fs2_voc* c) {
   cudaFree(sd->starts); cudaFree(sd->lens); cudaFree(sd->utt); cudaFree(sd->vpos); cudaFree(sd->room); cudaFree(sd->slot);
   cudaFree(sd->totals);
   cudaFree(c->lens64); cudaFree(c->melp); cudaFree(c->a0); cudaFree(c->status);
+  if (c->h_totals) cudaFreeHost(c->h_totals);
   for (float* b : c->buf) cudaFree(b);
   delete c;
 }

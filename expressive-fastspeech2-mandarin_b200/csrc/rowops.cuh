@@ -438,6 +438,78 @@ __global__ void length_regulate_kernel(const float* __restrict__ x, const int32_
   }
 }
 
+// The same expansion driven from the SOURCE side (the product path): a warp owns one phoneme row, keeps its 1 KB in
+// registers and streams it to the frames [cum[j-1], cum[j]) it expands to, adding the positional row of each frame.  No
+// per-frame binary search and one dependent load chain per phoneme instead of per frame, so the kernel is bound by the
+// coalesced 1 KB stores.  Warps beyond the phoneme rows zero the reserved frame rows (leading gap, the GAP rows after
+// every utterance, the tail up to `rows_f`).
+__global__ void length_regulate_scatter_kernel(const float* __restrict__ x, RowMeta pmeta, const int32_t* __restrict__ p_lens,
+                                               int rows_p, const int32_t* __restrict__ cum, int max_src_len,
+                                               const int32_t* __restrict__ f_starts, const int32_t* __restrict__ f_lens,
+                                               int batch, int gap, const int64_t* __restrict__ f_totals,
+                                               const float* __restrict__ pe, int rows_f, float* __restrict__ y,
+                                               __nv_bfloat16* __restrict__ yb) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const float4 zero = make_float4(0, 0, 0, 0);
+  auto put = [&](int row, int c, float4 v) {
+    st4(y + (size_t)row * D_MODEL + c, v);
+    if (yb != nullptr) st4b(yb + (size_t)row * D_MODEL + c, v);
+  };
+  if (w < rows_p) {
+    const int u = pmeta.utt[w], vp = pmeta.vpos[w];
+    if (u < 0 || vp >= 0) return;                      // reserved phoneme row: expands to nothing
+    const int j = vp + p_lens[u];
+    const int32_t* c = cum + (size_t)u * max_src_len;
+    const int t0 = j > 0 ? c[j - 1] : 0, t1 = c[j];
+    if (t1 <= t0) return;
+    const float* src = x + (size_t)w * D_MODEL;
+    const float4 a = ld4(src + lane * 4), b = ld4(src + 128 + lane * 4);
+    const int base = f_starts[u];
+    if (pe == nullptr) {                               // a frame_level predictor runs first: plain copies
+      for (int t = t0; t < t1; ++t) {
+        put(base + t, lane * 4, a);
+        put(base + t, 128 + lane * 4, b);
+      }
+      return;
+    }
+    int t = t0;
+    for (; t + 4 <= t1; t += 4) {                      // four positional rows in flight per lane
+      float4 pa[4], pb[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        pa[k] = ld4(pe + (size_t)(t + k) * D_MODEL + lane * 4);
+        pb[k] = ld4(pe + (size_t)(t + k) * D_MODEL + 128 + lane * 4);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        put(base + t + k, lane * 4, add4(a, pa[k]));
+        put(base + t + k, 128 + lane * 4, add4(b, pb[k]));
+      }
+    }
+    for (; t < t1; ++t) {
+      put(base + t, lane * 4, add4(a, ld4(pe + (size_t)t * D_MODEL + lane * 4)));
+      put(base + t, 128 + lane * 4, add4(b, ld4(pe + (size_t)t * D_MODEL + 128 + lane * 4)));
+    }
+    return;
+  }
+  // reserved frame rows: g = 0 .. (batch + 1) * gap - 1  ->  leading gap, then the gap after each utterance; then the tail
+  const int g = w - rows_p;
+  int row;
+  if (g < gap) {
+    row = g;
+  } else if (g < (batch + 1) * gap) {
+    const int b = g / gap - 1;
+    row = f_starts[b] + f_lens[b] + g % gap;
+  } else {
+    row = (int)f_totals[0] + (g - (batch + 1) * gap);
+  }
+  if (row < rows_f) {
+    put(row, lane * 4, zero);
+    put(row, 128 + lane * 4, zero);
+  }
+}
+
 // Decoder input when a frame_level predictor sits between the LengthRegulator and the decoder
 // (model/modules.py:139-148, transformer/Models.py:154-162): real rows get x + position_enc[t], every
 // reserved row returns to zero (the FFT stacks need zero gaps).  In place is fine (row-wise).
@@ -466,28 +538,29 @@ __global__ void add_pe_kernel(const float* __restrict__ x, RowMeta fmeta, const 
 // Packed -> padded outputs (model/fastspeech2.py:138-149): mel / postnet [B,T_max,80] and the
 // mel mask.  Padding rows of both tensors receive mel_linear.bias (what the reference's mel has
 // there; its postnet padding rows are outside the contract).  Warp per output row.
+// Thread per 16 bytes of the padded output (20 per row): consecutive threads write consecutive memory, every lane works.
 __global__ void unpack_mel_kernel(const float* __restrict__ mel_p, const float* __restrict__ post_p,
                                   const int32_t* __restrict__ f_starts, const int32_t* __restrict__ f_lens, int batch,
                                   int max_mel_len, const float* __restrict__ bias, float* __restrict__ mel,
                                   float* __restrict__ post, uint8_t* __restrict__ mask) {
-  const int64_t o = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (o >= (int64_t)batch * max_mel_len) return;
-  const int b = (int)(o / max_mel_len), t = (int)(o % max_mel_len);
+  constexpr int Q = N_MEL / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)batch * max_mel_len * Q) return;
+  const int64_t o = i / Q;
+  const int q = (int)(i - o * Q);
+  const int b = (int)(o / max_mel_len), t = (int)(o - (int64_t)b * max_mel_len);
   const bool real = t < f_lens[b];
-  if (lane == 0 && mask != nullptr) mask[o] = real ? 0 : 1;
-  if (lane < N_MEL / 4) {
-    float4 m, p;
-    if (real) {
-      const size_t src = (size_t)(f_starts[b] + t) * N_MEL + lane * 4;
-      m = ld4(mel_p + src);
-      p = ld4(post_p + src);
-    } else {
-      m = p = ld4(bias + lane * 4);
-    }
-    st4(mel + o * N_MEL + lane * 4, m);
-    st4(post + o * N_MEL + lane * 4, p);
+  if (q == 0 && mask != nullptr) mask[o] = real ? 0 : 1;
+  float4 m, p;
+  if (real) {
+    const size_t src = (size_t)(f_starts[b] + t) * N_MEL + q * 4;
+    m = ld4(mel_p + src);
+    p = ld4(post_p + src);
+  } else {
+    m = p = ld4(bias + q * 4);
   }
+  st4(mel + i * 4, m);
+  st4(post + i * 4, p);
 }
 
 __global__ void src_mask_kernel(const int64_t* __restrict__ src_lens, int batch, int max_src_len,
