@@ -1,0 +1,408 @@
+// Fused position-wise FFN of an FFT block (transformer/SubLayers.py:85-93) in ONE persistent tcgen05 kernel:
+//     y = LayerNorm( w_2( ReLU( w_1 * x ) ) + x ),  w_1 = Conv1d(256 -> 1024, k = 9, pad 4),  w_2 = Conv1d(1024 -> 256, k = 1)
+// The 1024-wide hidden row never leaves the SM.  Per 128-row tile and per 256-column chunk c of the hidden layer:
+//     acc1[128 x 256]  = sum_{tap, k} x[r + tap - 4, k] . W1[tap][c*256 + n][k]        72 ring steps, operands by TMA
+//     acc1            <- tf32( ReLU(acc1 + b1) )          in place in TENSOR MEMORY, by the epilogue warps
+//     out [128 x 256] += acc1 . W2[:, c*256 : (c+1)*256]^T                               8 ring steps, A operand FROM TMEM
+// and after the fourth chunk the post-LN epilogue of gemm_tc2.cuh runs on `out` (bias, residual by TMA, two-pass
+// statistics, affine, row mask, TMA store).  TMEM: acc1 = columns [0,256), out = [256,512).
+// Versus the two-kernel form this removes the 110 MB hidden tensor (written once, read once) and the second kernel's
+// operand-delivery-bound main loop: the second contraction's A operand is already on chip.
+// The tensor pipe executes MMAs in issue order, so conv(c+1) overwriting acc1 needs no barrier against GEMM2(c)'s reads;
+// the two hand-offs with the epilogue warps (hidden ready / out drained) are mbarriers.
+#pragma once
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "gemm_tc2.cuh"
+
+namespace fs2 {
+namespace ffn {
+
+using namespace tc2;   // (which itself brings in the PTX helpers of namespace tc)
+
+constexpr int BM = tc2::BM;              // local names win over the same-named constants of the older engines
+constexpr int THREADS = tc2::THREADS;
+constexpr int HC = 256;                       // hidden columns per chunk = N of the first MMA = K of the second
+constexpr int N_CHUNKS = D_INNER / HC;        // 4
+constexpr int KC1 = D_MODEL / 32;             // 8 K chunks of the conv
+constexpr int STEPS1 = FFN_TAPS * KC1;        // 72
+constexpr int STEPS2 = HC / 32;               // 8
+constexpr int STAGES = 3;
+constexpr int A_BYTES = BM * 128, B_BYTES = 256 * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int OFF_CST = STAGES * STAGE_BYTES;
+constexpr int OFF_RES = OFF_CST + 8 * WCHUNK;
+constexpr int OFF_PAR = OFF_RES + 8 * WCHUNK;          // b1[1024] | b2[256] | gamma[256] | beta[256]
+constexpr int OFF_BAR = OFF_PAR + 8192;
+constexpr int SMEM_TOTAL = OFF_BAR + 256 + 1024;
+static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
+
+struct Args {
+  const float* x;        // [rows, 256]: conv input AND residual
+  int rows;
+  const float* w1;       // [9][1024][256] tf32
+  const float* b1;       // [1024]
+  const float* w2;       // [256][1024] tf32
+  const float* b2;       // [256]
+  const float* gamma;    // [256]
+  const float* beta;     // [256]
+  const int32_t* row_vpos;
+  const int32_t* row_room;
+  int extra;
+  const int32_t* live_rows;
+  float* y;              // [rows, 256]
+};
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int CL>
+__global__ void __launch_bounds__(THREADS, 1)
+ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
+                 const __grid_constant__ CUtensorMap tmR, Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* cst = smem + OFF_CST;
+  uint8_t* res = smem + OFF_RES;
+  float* b1_s = reinterpret_cast<float*>(smem + OFF_PAR);
+  float* b2_s = b1_s + D_INNER;
+  float* gamma_s = b2_s + 256;
+  float* beta_s = gamma_s + 256;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* empty = full + STAGES;
+  uint64_t* hid_full = empty + STAGES;    // [1] conv MMAs of a chunk have completed
+  uint64_t* hid_ready = hid_full + 1;     // [1] 128 epilogue threads wrote ReLU(hidden) back to TMEM
+  uint64_t* out_full = hid_ready + 1;     // [1] the fourth GEMM2 of a tile has completed
+  uint64_t* out_empty = out_full + 1;     // [1] 128 epilogue threads have read the out accumulator
+  uint64_t* res_full = out_empty + 1;     // [4 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 8);
+
+  const int warp = warp_index(), lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmW1)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmW2)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], CL);
+    }
+    mbar_init(hid_full, 1);
+    mbar_init(hid_ready, 128);
+    mbar_init(out_full, 1);
+    mbar_init(out_empty, 128);
+    for (int u = 0; u < 8; ++u) mbar_init(&res_full[u], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_hid = tmem_base, tmem_out = tmem_base + 256;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  if (CL > 1) cluster_sync_all();
+  pdl_trigger();
+  pdl_wait();
+  int rows_live = p.rows;
+  if (p.live_rows != nullptr) rows_live = min(rows_live, *p.live_rows);
+  const int m_groups = ((rows_live + BM - 1) / BM + CL - 1) / CL;
+  const int w_first = blockIdx.x / CL, w_step = gridDim.x / CL;
+  auto item_m0 = [&](int w) { return (w * CL + rank) * BM; };
+
+  if (warp == 0) {
+    // ---------------- TMA producer
+    const bool leader = elect_one();
+    int it = 0;
+    for (int w = w_first; w < m_groups; w += w_step) {
+      const int m0 = item_m0(w);
+      for (int c = 0; c < N_CHUNKS; ++c) {
+        for (int i = 0; i < STEPS1 + STEPS2; ++i, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          uint8_t* a_s = smem + s * STAGE_BYTES;
+          uint8_t* b_s = a_s + A_BYTES;
+          if (leader) {
+            if (i < STEPS1) {     // conv step: activations (tap = row offset) + the chunk's W1 tile
+              const int tap = i / KC1, kc = i - tap * KC1;
+              mbar_expect_tx(&full[s], STAGE_BYTES);
+              tma_load_2d(a_s, &tmX, kc * 32, m0 + tap - FFN_TAPS / 2, &full[s]);
+              if (CL == 1) tma_load_2d(b_s, &tmW1, kc * 32, tap * D_INNER + c * HC, &full[s]);
+              else tma_load_2d_mc(b_s + rank * (B_BYTES / 2), &tmW1, kc * 32, tap * D_INNER + c * HC + rank * 128, &full[s], (uint16_t)0x3);
+            } else {              // second contraction: only the W2 tile [256 outputs x 32 hidden columns]
+              const int kc = i - STEPS1;
+              mbar_expect_tx(&full[s], B_BYTES);
+              if (CL == 1) tma_load_2d(b_s, &tmW2, c * HC + kc * 32, 0, &full[s]);
+              else tma_load_2d_mc(b_s + rank * (B_BYTES / 2), &tmW2, c * HC + kc * 32, rank * 128, &full[s], (uint16_t)0x3);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_tf32(BM, 256);
+    int it = 0, n_h = 0, lt = 0;
+    for (int w = w_first; w < m_groups; w += w_step, ++lt) {
+      for (int c = 0; c < N_CHUNKS; ++c, ++n_h) {
+        // conv chunk c -> acc1 (the previous chunk's GEMM2 reads of acc1 precede these writes in the tensor pipe)
+        for (int i = 0; i < STEPS1; ++i, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint8_t* a_s = smem + s * STAGE_BYTES;
+          const uint64_t da = umma_desc(a_s), db = umma_desc(a_s + A_BYTES);
+          if (leader) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_tf32(tmem_hid, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
+            if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], (uint16_t)0x3);
+          }
+          __syncwarp();
+        }
+        if (leader) umma_commit(hid_full);
+        __syncwarp();
+        // GEMM2 chunk c: out += ReLU(hidden chunk) (TMEM) x W2 tile (smem)
+        mbar_wait(hid_ready, n_h & 1);
+        if (c == 0) mbar_wait(out_empty, (lt & 1) ^ 1);      // the previous tile's LayerNorm has drained `out`
+        tc_fence_after();
+        for (int i = 0; i < STEPS2; ++i, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint64_t db = umma_desc(smem + s * STAGE_BYTES + A_BYTES);
+          if (leader) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_tf32_ts(tmem_out, tmem_hid + i * 32 + kk * 8, db + 2 * kk, idesc, (c | i | kk) != 0 ? 1u : 0u);
+            if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], (uint16_t)0x3);
+          }
+          __syncwarp();
+        }
+      }
+      if (leader) umma_commit(out_full);
+      __syncwarp();
+    }
+  } else {
+    // ---------------- epilogue warps: thread = accumulator row
+    const int et = threadIdx.x - 64;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    uint8_t* my_cst = cst + q * 2 * WCHUNK;
+    uint8_t* my_res = res + q * 2 * WCHUNK;
+    uint64_t* my_res_full = res_full + q * 2;
+    const uint32_t b1_sa = smem_u32(b1_s), b2_sa = smem_u32(b2_s), gamma_sa = smem_u32(gamma_s), beta_sa = smem_u32(beta_s),
+                   cst_sa = smem_u32(my_cst), res_sa = smem_u32(my_res);
+    const uint32_t swz_x = (uint32_t)(lane & 7) << 4;
+    for (int i = et; i < D_INNER; i += 128) b1_s[i] = p.b1[i];
+    for (int i = et; i < 256; i += 128) {
+      b2_s[i] = p.b2[i];
+      gamma_s[i] = p.gamma[i];
+      beta_s[i] = p.beta[i];
+    }
+    epi_barrier();
+    int g_res = 0, g_st = 0, n_h = 0, lt = 0;
+    if (lane == 0 && w_first < m_groups) {
+      mbar_expect_tx(&my_res_full[0], WCHUNK);
+      tma_load_2d(my_res, &tmR, 0, item_m0(w_first) + q * 32, &my_res_full[0]);
+    }
+    for (int w = w_first; w < m_groups; w += w_step, ++lt) {
+      const int m0 = item_m0(w);
+      const int row = m0 + r;
+      bool live = row < p.rows;
+      if (live && p.row_vpos != nullptr) live = row_live(p.row_vpos[row], p.row_room[row], p.extra);
+      const int w_next = w + w_step;
+      // ---- hidden chunks: acc1 <- tf32(ReLU(acc1 + b1)) in place
+      for (int c = 0; c < N_CHUNKS; ++c, ++n_h) {
+        mbar_wait(hid_full, n_h & 1);
+        tc_fence_after();
+        float va[32], vb[32];
+        tmem_ld32_issue(tmem_hid + lane_sel, va);
+#pragma unroll 1
+        for (int j = 0; j < 8; j += 2) {
+          tmem_ld_wait();
+          tmem_ld32_issue(tmem_hid + lane_sel + (j + 1) * 32, vb);
+          auto relu_round = [&](float (&v)[32], int jj) {
+            const uint32_t ba = b1_sa + (uint32_t)(c * HC + jj * 32) * 4;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              const float4 b4 = lds4(ba + cc * 16);
+              const float t[4] = {v[cc * 4] + b4.x, v[cc * 4 + 1] + b4.y, v[cc * 4 + 2] + b4.z, v[cc * 4 + 3] + b4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)   // ReLU, then round to TF32 (nearest, ties away) with integer arithmetic
+                v[cc * 4 + e] = __uint_as_float((__float_as_uint(fmaxf(t[e], 0.f)) + 0x1000u) & 0xFFFFE000u);
+            }
+            tmem_st32(tmem_hid + lane_sel + jj * 32, v);
+          };
+          relu_round(va, j);
+          tmem_ld_wait();
+          if (j + 2 < 8) tmem_ld32_issue(tmem_hid + lane_sel + (j + 2) * 32, va);
+          relu_round(vb, j + 1);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(hid_ready);
+      }
+      // ---- LayerNorm(out + b2 + x) -> y   (same two-pass scheme as gemm_tc2.cuh's LN epilogue)
+      mbar_wait(out_full, lt & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_out + lane_sel;
+      auto prefetch_res = [&](int c) {
+        if (lane != 0) return;
+        int ww = w, cc = c + 1;
+        if (cc >= 8) { ww = w_next; cc = 0; }
+        if (ww >= m_groups) return;
+        const int buf = (g_res + 1) & 1;
+        mbar_expect_tx(&my_res_full[buf], WCHUNK);
+        tma_load_2d(my_res + buf * WCHUNK, &tmR, cc * 32, item_m0(ww) + q * 32, &my_res_full[buf]);
+      };
+      float mean = 0.f, m2 = 0.f;
+      float va[32], vb[32];
+      auto pass1 = [&](float (&v)[32], int c) {
+        __syncwarp();
+        prefetch_res(c);
+        const uint32_t ba = b2_sa + (uint32_t)(c * 32) * 4;
+        mbar_wait(&my_res_full[g_res & 1], (g_res >> 1) & 1);
+        const uint32_t rb = res_sa + (g_res & 1) * WCHUNK + lane * 128;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          const float4 b4 = lds4(ba + cc * 16);
+          const float4 r4 = lds4(rb + ((cc << 4) ^ swz_x));
+          v[cc * 4 + 0] += b4.x + r4.x; v[cc * 4 + 1] += b4.y + r4.y; v[cc * 4 + 2] += b4.z + r4.z; v[cc * 4 + 3] += b4.w + r4.w;
+        }
+        ++g_res;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) { s4[0] += v[j]; s4[1] += v[j + 1]; s4[2] += v[j + 2]; s4[3] += v[j + 3]; }
+        const float cm = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.f / 32.f);
+        float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float d0 = v[j] - cm, d1 = v[j + 1] - cm, d2 = v[j + 2] - cm, d3 = v[j + 3] - cm;
+          q4[0] = fmaf(d0, d0, q4[0]); q4[1] = fmaf(d1, d1, q4[1]); q4[2] = fmaf(d2, d2, q4[2]); q4[3] = fmaf(d3, d3, q4[3]);
+        }
+        const float cm2 = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+        const float delta = cm - mean;
+        const float n_old = 32.f * c, n_new = 32.f * (c + 1);
+        mean = fmaf(delta, 32.f / n_new, mean);
+        m2 += cm2 + delta * delta * (n_old * 32.f / n_new);
+        tmem_st32(acc + c * 32, v);
+      };
+      tmem_ld32_issue(acc, va);
+#pragma unroll 1
+      for (int c = 0; c < 8; c += 2) {
+        tmem_ld_wait();
+        tmem_ld32_issue(acc + (c + 1) * 32, vb);
+        pass1(va, c);
+        tmem_ld_wait();
+        if (c + 2 < 8) tmem_ld32_issue(acc + (c + 2) * 32, va);
+        pass1(vb, c + 1);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+      const float rstd = 1.f / sqrtf(m2 * (1.f / 256.f) + 1e-5f);
+      auto pass2 = [&](float (&v)[32], int c) {
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          const float4 g4 = lds4(gamma_sa + c * 128 + cc * 16), b4 = lds4(beta_sa + c * 128 + cc * 16);
+          const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[cc * 4 + e] = live ? fmaf((v[cc * 4 + e] - mean) * rstd, gg[e], bb[e]) : 0.f;
+        }
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        uint8_t* sb = my_cst + (g_st & 1) * WCHUNK;
+        const uint32_t sa = cst_sa + (g_st & 1) * WCHUNK + lane * 128;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) sts4(sa + ((cc << 4) ^ swz_x), make_float4(v[cc * 4], v[cc * 4 + 1], v[cc * 4 + 2], v[cc * 4 + 3]));
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmY, sb, c * 32, m0 + q * 32);
+          bulk_commit();
+        }
+        ++g_st;
+      };
+      tmem_ld32_issue(acc, va);
+#pragma unroll 1
+      for (int c = 0; c < 8; c += 2) {
+        tmem_ld_wait();
+        tmem_ld32_issue(acc + (c + 1) * 32, vb);
+        pass2(va, c);
+        tmem_ld_wait();
+        if (c + 2 < 8) {
+          tmem_ld32_issue(acc + (c + 2) * 32, va);
+        } else {
+          tc_fence_before();
+          mbar_arrive(out_empty);
+        }
+        pass2(vb, c + 1);
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// 0 = conv9 + w2/LN as two launches, 1 = always the fused kernel, 2 = automatic (default; FS2_FFN_FUSED overrides).
+// A fused tile costs ~4.65 conv-tile times on ONE SM, the two-launch form 4 + ~1.1 spread over four column tiles: the
+// fused kernel only wins once the row tiles alone fill the machine several times over (measured: batch 64 has 210 row
+// tiles = 1.42 waves of 148 SMs and loses 11 % to the quantisation; batch 512 has 10.6 waves and gains 6 %).
+inline int& enabled_flag() {
+  static int f = [] {
+    const char* e = std::getenv("FS2_FFN_FUSED");
+    return e != nullptr ? std::atoi(e) : 2;
+  }();
+  return f;
+}
+inline bool use_fused(int rows) {
+  const int mode = enabled_flag();
+  if (mode != 2) return mode == 1;
+  return (rows + BM - 1) / BM >= 4 * sm_count();
+}
+
+template <int CL>
+inline void launch_cl(const Args& a, cudaStream_t stream) {
+  static bool configured[64] = {};
+  int dev = 0;
+  FS2_CUDA_OK(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    FS2_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    configured[dev & 63] = true;
+  }
+  const CUtensorMap tmX = make_map(a.x, a.rows, D_MODEL, D_MODEL, BM, /*round_tf32=*/true, false);
+  const CUtensorMap tmW1 = make_map(a.w1, (int64_t)FFN_TAPS * D_INNER, D_MODEL, D_MODEL, 256 / CL, false, true);
+  const CUtensorMap tmW2 = make_map(a.w2, D_MODEL, D_INNER, D_INNER, 256 / CL, false, true);
+  const CUtensorMap tmY = make_map(a.y, a.rows, D_MODEL, D_MODEL, 32, false, false);
+  const CUtensorMap tmR = make_map(a.x, a.rows, D_MODEL, D_MODEL, 32, false, false);
+  const int items = ((a.rows + BM - 1) / BM + CL - 1) / CL;
+  const int grid = std::min(items, sm_count() / CL) * CL;
+  launch_pdl(ffn_fused_kernel<CL>, dim3(grid), dim3(THREADS), SMEM_TOTAL, stream, CL, tmX, tmW1, tmW2, tmY, tmR, a);
+  FS2_LAUNCHED();
+}
+
+inline void launch(const Args& a, cudaStream_t stream) {
+  if (a.rows <= 0) return;
+  require(a.x != a.y, FS2_ERR_INVALID, "fused FFN: output must not alias the input (conv halo rows are re-read)");
+  if (cluster_size_flag() == 2 && a.rows > BM) launch_cl<2>(a, stream);
+  else launch_cl<1>(a, stream);
+}
+
+}  // namespace ffn
+}  // namespace fs2

@@ -12,6 +12,7 @@
 #include "gemm_mma.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tc2.cuh"
+#include "ffn_fused.cuh"
 #include "rowops.cuh"
 #include "vocoder.cuh"
 
@@ -343,6 +344,16 @@ static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSi
     a.residual = x; a.ldr = D_MODEL; a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
     a.ln_gamma = L.ln1_g; a.ln_beta = L.ln1_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
     { ProfScope ps(c, s, frame ? "dec.gemm_fc_ln" : "enc.gemm_fc_ln"); conv_gemm(eng, math, a, s); }
+    if (ffn::use_fused(rows)) {
+      // conv9 -> ReLU -> w2 -> +residual -> LayerNorm -> mask in one kernel; the hidden tensor stays in tensor memory
+      ffn::Args f{};
+      f.x = t2; f.rows = rows; f.w1 = L.w1; f.b1 = L.b1; f.w2 = L.w2; f.b2 = L.b2; f.gamma = L.ln2_g; f.beta = L.ln2_b;
+      f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 0;
+      f.live_rows = reinterpret_cast<const int32_t*>(side.totals); f.y = x;
+      ProfScope ps(c, s, frame ? "dec.ffn_fused" : "enc.ffn_fused");
+      ffn::launch(f, s);
+      return;
+    }
     a = gemm_args(t2, D_MODEL, rows, L.w1, L.b1, FFN_TAPS, D_MODEL, D_INNER, ACT_RELU, pool.hid, D_INNER);
     a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
     { ProfScope ps(c, s, frame ? "dec.gemm_conv9" : "enc.gemm_conv9"); conv_gemm(eng, math, a, s); }
@@ -927,6 +938,7 @@ int fs2_debug_set_flag(int which, int value) {
   if (which == 0) fs2::attn_tc::debug_flag() = value;
   if (which == 2) fs2::tc2::cluster_size_flag() = value == 1 ? 1 : 2;
   if (which == 3) fs2::tc2::a_resident_flag() = value ? 1 : 0;
+  if (which == 4) fs2::ffn::enabled_flag() = value;   // 0 off, 1 on, 2 automatic
   if (which == 1) {
     g_trace_on = value;
     if (value && g_trace_buf == nullptr) cudaMalloc(reinterpret_cast<void**>(&g_trace_buf), 64 * sizeof(long long));
@@ -999,6 +1011,18 @@ int fs2_op_conv_gemm_ln(fs2_stream stream, int engine, const float* A, int lda, 
     a.ln_gamma = gamma; a.ln_beta = beta; a.head_w = head_w; a.head_b = head_b; a.head_out = head_out;
     if (g_trace_on) { a.trace = g_trace_buf + 8 * ((g_trace_on - 1) % 8); ++g_trace_on; }
     conv_gemm(engine, FS2_MATH_TF32, a, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int fs2_op_ffn_fused(fs2_stream stream, const float* x, int rows, const float* w1, const float* b1, const float* w2,
+                     const float* b2, const float* gamma, const float* beta, const int32_t* row_vpos, const int32_t* row_room,
+                     int extra, float* y) {
+  return guarded(nullptr, [&] {
+    require(x && w1 && b1 && w2 && b2 && gamma && beta && y && rows >= 0, FS2_ERR_INVALID, "bad ffn_fused argument");
+    ffn::Args f{};
+    f.x = x; f.rows = rows; f.w1 = w1; f.b1 = b1; f.w2 = w2; f.b2 = b2; f.gamma = gamma; f.beta = beta;
+    f.row_vpos = row_vpos; f.row_room = row_room; f.extra = extra; f.y = y;
+    ffn::launch(f, static_cast<cudaStream_t>(stream));
   });
 }
 

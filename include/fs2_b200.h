@@ -137,7 +137,8 @@ int fs2_debug_enable(fs2_ctx* ctx, int on);
 int fs2_debug_fetch(fs2_ctx* ctx, const char* name, void* host_dst, int64_t max_bytes,
                     int64_t* rows, int64_t* cols);
 
-/* Bring-up switches (0 = attention kernel raw-dump mode, 2 = GEMM cluster size, 3 = A-resident GEMM variant on/off). */
+/* Bring-up switches (0 = attention kernel raw-dump mode, 2 = GEMM cluster size, 3 = A-resident GEMM variant on/off,
+ * 4 = fused FFN kernel: 0 off, 1 on, 2 automatic (default: on when the row tiles fill the SMs at least four times)). */
 int fs2_debug_set_flag(int which, int value);
 /* which = 1: CTA 0 of the next fs2_op_conv_gemm writes globaltimer stamps; read them back here. */
 int fs2_debug_read_trace(int64_t* host_dst, int n);
@@ -165,6 +166,14 @@ int fs2_op_conv_gemm_ln(fs2_stream stream, int engine, const float* A, int lda, 
                         const float* bias, int taps, int pad, int K, int act, const float* residual, int ldr,
                         const float* gamma, const float* beta, const int32_t* row_vpos, const int32_t* row_room,
                         int extra, float* C, int ldc, const float* head_w, const float* head_b, float* head_out);
+/* The whole position-wise FFN of an FFT block (transformer/SubLayers.py:85-93) in one kernel:
+ * y = LayerNorm(w2 . ReLU(conv9(x) + b1) + b2 + x) * gamma + beta, masked rows -> 0.  x, y [rows,256] (y must not
+ * alias x); w1 [9][1024][256] and w2 [256][1024] K-major, TF32 operands.  The 1024-wide hidden rows stay in tensor
+ * memory (the second contraction takes its A operand from TMEM).  The forward uses it for large batches and the
+ * two-launch form (conv9, then w2 + LayerNorm) otherwise; fs2_debug_set_flag(4, ...) / FS2_FFN_FUSED force either. */
+int fs2_op_ffn_fused(fs2_stream stream, const float* x, int rows, const float* w1, const float* b1, const float* w2,
+                     const float* b2, const float* gamma, const float* beta, const int32_t* row_vpos,
+                     const int32_t* row_room, int extra, float* y);
 /* The vocoder's form of the contraction (persistent tcgen05 engine, TF32): dilated taps (tap t reads row
  * r + (t - (taps-1)/2) * dil; hifigan/models.py:27-55), leaky ReLU (act = 3, `slope`) before and/or after (`act2`) the
  * residual add, a residual buffer that holds lrelu(x) and is inverted on the fly (`res_inv_lrelu`), and a row mask

@@ -220,3 +220,23 @@ def test_long_position_table_matches_formula():
     # exercised through the longform golden fixture; here only the table itself
     want = fs2_b200.synthetic.sinusoid_table(3000, 256).numpy()
     assert want.shape == (3000, 256)
+
+
+@pytest.mark.parametrize("name", ["pads", "controls", "longform"])
+def test_fused_ffn_forward_against_reference_fixture(name, sd32):
+    """The forward with the single-kernel FFN forced on (FS2_FFN_FUSED=1 / debug flag 4; automatic only for large batches):
+    hidden rows stay in tensor memory.  Same stated TF32 tolerances against the reference's fixtures."""
+    from gpu_util import lib
+    model = model_for(sd32)
+    batch, kw, want, stride = load_golden(name)
+    src_lens = batch["src_lens"].tolist()
+    L = lib()
+    try:
+        L.fs2_debug_set_flag(4, 1)
+        free = run(model, batch, **kw)
+        check_phoneme_side(name + "[fused ffn]", free, want, src_lens)
+        got = run(model, batch, **teacher_kwargs(want, src_lens))
+    finally:
+        L.fs2_debug_set_flag(4, 2)
+    assert np.array_equal(got[9].cpu().numpy(), want["mel_lens"])
+    check_frame_side(name + "[fused ffn]", got, want, want["mel_lens"].tolist(), stride)

@@ -270,3 +270,37 @@ def test_frame_map_bit_exact():
     assert code == 0
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), want)
+
+
+@pytest.mark.parametrize("rows", [5, 128, 300, 4097, 26788])
+def test_ffn_fused(rows):
+    """conv9 -> ReLU -> w2 -> +x -> LayerNorm -> mask in one kernel (hidden rows stay in tensor memory) against float64
+    with the hidden activations rounded to TF32 exactly as the kernel rounds them (nearest, ties away)."""
+    g = torch.Generator().manual_seed(rows)
+    x = round_tf32(torch.randn(rows, 256, generator=g))
+    w1 = round_tf32(torch.randn(9, 1024, 256, generator=g) / np.sqrt(256 * 9))
+    b1 = torch.randn(1024, generator=g) * 0.3
+    w2 = round_tf32(torch.randn(1, 256, 1024, generator=g) / np.sqrt(1024))
+    b2 = torch.randn(256, generator=g) * 0.3
+    gamma, beta = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.2
+    vpos = torch.randint(-4, 2, (rows,), generator=g, dtype=torch.int32)
+    room = torch.randint(0, 3, (rows,), generator=g, dtype=torch.int32)
+    hid = conv_ref(x, w1, b1, 4, 1, None, None, None, 0)
+    hid = round_tf32(hid.float()).double()          # the kernel sees fp32 accumulations: round those
+    pre = hid @ w2[0].double().T + b2.double() + x.double()
+    want = torch.nn.functional.layer_norm(pre, (256,), gamma.double(), beta.double(), 1e-5)
+    live = vpos < torch.minimum(torch.zeros_like(room), room)
+    want = want * live.unsqueeze(1)
+    d = lambda t: t.to(DEV)
+    dx, dw1, db1, dw2, db2, dg, dbe, dv, dr = map(d, (x, w1, b1, w2, b2, gamma, beta, vpos, room))
+    out = torch.full((rows, 256), float("nan"), device=DEV)
+    code = lib().fs2_op_ffn_fused(stream(), ptr(dx), rows, ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dg), ptr(dbe), ptr(dv),
+                                  ptr(dr), 0, ptr(out))
+    assert code == 0, lib().fs2_last_error(None)
+    torch.cuda.synchronize()
+    got = out.cpu().double()
+    assert torch.isfinite(got).all()
+    err = (got - want).abs().max().item()
+    # hidden values that sit on a TF32 rounding boundary may round the other way after a different summation order:
+    # one such flip moves an output by ~2^-11 * |w2| ~ 1e-5
+    assert err < 1e-3, f"max abs err {err}"
