@@ -140,9 +140,21 @@ def oracle_cpu_run(sd, batch, n_utts, steps, warmup):
     return frames, times
 
 
+def host_threads():
+    """All the host cores this process may use.  torchrun exports OMP_NUM_THREADS=1, which would silently turn the CPU
+    arm into a single-thread run: set the torch thread count explicitly."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(n, 1))
+    return torch.get_num_threads()
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
+    host_threads()
     import fs2_b200
     syn = fs2_b200.synthetic
     sd = syn.synthetic_state_dict(seed=0)
@@ -366,8 +378,10 @@ def main():
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                          "frac": achieved / tensor_peak if tensor_peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed
-                         # `ncu --set full` capture profiles/r01_ncu_full_tc2_conv9_raw.csv (37.10 MB + 55.88 MB)
-                         "traffic": 92.98e6 if (args.engine == "tcgen05" and args.batch == 64) else None,
+                         # `ncu --set full` captures profiles/r01_ncu_full_dec_layer_{tf32,bf16}_raw.csv
+                         # (TF32: 37.06 MB + 56.37 MB; BF16: 18.52 MB + 6.74 MB -- the bf16 hidden tensor mostly stays in L2)
+                         "traffic": ({"tf32": 93.43e6, "bf16": 25.26e6}[args.math]
+                                     if (args.engine == "tcgen05" and args.batch == 64) else None),
                          "algorithmic_bytes_per_launch": 4 * (frames * 256 + 9 * 1024 * 256 + frames * 1024),
                          "per_launch_ms": per_launch_ms, "launches_per_step": n_dom // PROF_RUNS,
                          "flops_per_launch": flops_per_launch,
@@ -388,7 +402,7 @@ def main():
         if voc_line is not None:
             line["vocoder"] = voc_line
         if world == 1 and not args.no_cpu_baseline:
-            cores = torch.get_num_threads()
+            cores = host_threads()
             f_cpu, times = oracle_cpu_run(sd, syn.config2_batch(seed=0), CPU_SAMPLE_UTTS, CPU_SAMPLE_STEPS, 1)
             line["cpu_baseline"] = {"value": f_cpu * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{len(times)} forwards over the whole config-2 batch ({CPU_SAMPLE_UTTS} utterances, "
