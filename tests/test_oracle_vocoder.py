@@ -63,3 +63,29 @@ def test_vocoder_infer_int16_and_trim(vsd):
     mel = torch.randn(2, 80, 5, generator=torch.Generator().manual_seed(2))
     wavs = H.vocoder_infer(vsd, mel, lengths=[5 * 256, 3 * 256])
     assert wavs[0].dtype == np.int16 and wavs[0].shape == (1280,) and wavs[1].shape == (768,)
+
+
+def test_facade_state_dict_is_the_generators_and_folds_weight_norm(syn, vsd):
+    """HiFiGANGeneratorB200 holds the reference generator's 156 tensors (remove_weight_norm() form), loads a weight_norm
+    checkpoint (utils/model.py:60-66) and has no CPU path."""
+    import fs2_b200
+    voc = fs2_b200.HiFiGANGeneratorB200()
+    assert [(k, tuple(v.shape)) for k, v in voc.state_dict().items()] == [(k, tuple(s)) for k, s in syn.vocoder_schema()]
+    wn = {}
+    for k, v in vsd.items():
+        if k.endswith(".weight") and not k.startswith("conv_post"):
+            base = k[: -len(".weight")]
+            wn[base + ".weight_g"] = v.reshape(v.shape[0], -1).norm(dim=1).reshape(-1, *([1] * (v.dim() - 1)))
+            wn[base + ".weight_v"] = v * 0.5
+        else:
+            wn[k] = v
+    res = voc.load_state_dict(wn, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in vsd.items():
+        assert torch.allclose(voc.state_dict()[k], v, rtol=1e-5, atol=1e-7), k
+    with pytest.raises(RuntimeError, match="CUDA"):
+        voc(torch.zeros(1, 80, 4))
+    with pytest.raises(RuntimeError, match="inference"):
+        voc.train()
+    with pytest.raises(ValueError):
+        fs2_b200.HiFiGANGeneratorB200({"upsample_rates": [8, 8, 4]})
