@@ -10,7 +10,7 @@ A step is one forward pass over one synthetic batch of BASELINE config 2 (64 utt
 are independent: no collective on the data path, weak scaling) and rank 0 prints ONE JSON line.
 `value` is timed with inputs resident in HBM; `e2e` goes through the host-buffer entry
 (`FastSpeech2B200.synthesize_host`: pinned H2D of the int64 inputs, forward, D2H of the postnet
-mel and mel_lens) with the copies inside the timed region.  `--impl reference` times the CPU
+mel rows -- packed, as `synth_samples` slices them -- and mel_lens) with the copies inside the timed region.  `--impl reference` times the CPU
 oracle port of the reference forward (oracle/fs2_oracle.py; the reference itself is Python and
 /root/reference does not exist on the GPU box) on the host cores.
 """

@@ -210,7 +210,7 @@ def main(argv=None):
             wavs = vocoder_infer(mels_dev, vocoder, model_config, preprocess_config, lengths=[int(n) * hop for n in mel_lens])
             write_wavs(out_dir, ids, wavs, sampling_rate)
         for i, name in enumerate(ids):
-            np.save(os.path.join(out_dir, f"{name}.npy"), mel[i, : int(mel_lens[i])].copy())
+            np.save(os.path.join(out_dir, f"{name}.npy"), np.array(mel[i]))   # packed per-utterance view -> own array
             with open(os.path.join(out_dir, f"{name}.json"), "w", encoding="utf-8") as f:
                 json.dump({"text": raw_texts[i], "n_phonemes": int(text_lens[i]), "n_frames": int(mel_lens[i])}, f,
                           ensure_ascii=False)

@@ -907,6 +907,23 @@ int fs2_forward_stage2(fs2_ctx* c, fs2_stream stream, const fs2_stage2_io* io) {
 
 int fs2_last_launch_count(const fs2_ctx* c) { return c ? c->last_launches : 0; }
 
+int fs2_read_packed_postnet(fs2_ctx* c, fs2_stream stream, float* host_rows, int64_t max_rows, int32_t* host_starts,
+                            int64_t* rows_out) {
+  if (!c) return FS2_ERR_INVALID;
+  return guarded(c, [&] {
+    require(c->stage1_done, FS2_ERR_STATE, "fs2_read_packed_postnet needs a completed forward");
+    require(host_rows && host_starts && rows_out, FS2_ERR_INVALID, "null argument");
+    require(max_rows >= c->frame_rows, FS2_ERR_INVALID, "fs2_read_packed_postnet: destination too small");
+    FS2_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    *rows_out = c->frame_rows;
+    if (c->frame_rows > 0 && c->max_mel_len > 0) {
+      FS2_CUDA_OK(cudaMemcpyAsync(host_rows, c->fp.post, (size_t)c->frame_rows * N_MEL * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    FS2_CUDA_OK(cudaMemcpyAsync(host_starts, c->fs.starts, (size_t)(c->batch + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  });
+}
+
 int fs2_debug_enable(fs2_ctx* c, int on) {
   if (!c) return FS2_ERR_INVALID;
   c->debug = on != 0;

@@ -290,11 +290,13 @@ class FastSpeech2B200(nn.Module):
                 src_lens, out_lens)
 
     # ------------------------------------------------------------------ host-buffer entry (what the CLI does)
-    def synthesize_host(self, batch, p_control=1.0, e_control=1.0, d_control=1.0):
+    def synthesize_host(self, batch, p_control=1.0, e_control=1.0, d_control=1.0, padded=False):
         """`to_device(batch)` (utils/tools.py:117-127) + forward + the device->host reads that
         `synth_samples` performs (utils/tools.py:228-266), on pinned staging buffers.
         `batch` holds host numpy arrays: speakers, emotions, arousals, valences, texts, src_lens,
-        max_src_len.  Returns (postnet_mel [B,T,80] numpy, mel_lens numpy, h2d_bytes, d2h_bytes)."""
+        max_src_len.  Returns (mels, mel_lens numpy, h2d_bytes, d2h_bytes) where `mels` is a list of per-utterance
+        [mel_len, 80] numpy views into one pinned buffer of PACKED rows (what `synth_samples` slices out of the padded
+        tensor; a third of its bytes at batch 64), or with padded=True the padded [B, T, 80] array itself."""
         dev = self._device()
         names = ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")
         h2d = 0
@@ -311,16 +313,39 @@ class FastSpeech2B200(nn.Module):
                            dev_t["src_lens"], int(batch["max_src_len"]), p_control=p_control, e_control=e_control,
                            d_control=d_control)
         post, lens = out[1], out[9]
+        B = int(post.shape[0])
         self.last_postnet = post      # device tensor [B, T, 80]: what the vocoder consumes next (utils/tools.py:258-262)
-        key = ("post", tuple(post.shape))
-        if key not in self._pinned:
-            self._pinned[key] = torch.empty(post.shape, dtype=torch.float32).pin_memory()
-            self._pinned[("lens", post.shape[0])] = torch.empty(post.shape[0], dtype=torch.int64).pin_memory()
-        hp, hl = self._pinned[key], self._pinned[("lens", post.shape[0])]
-        hp.copy_(post, non_blocking=True)
+        if ("lens", B) not in self._pinned:
+            self._pinned[("lens", B)] = torch.empty(B, dtype=torch.int64).pin_memory()
+        hl = self._pinned[("lens", B)]
+        stream = torch.cuda.current_stream(dev)
+        if padded:
+            key = ("post", tuple(post.shape))
+            if key not in self._pinned:
+                self._pinned[key] = torch.empty(post.shape, dtype=torch.float32).pin_memory()
+            hp = self._pinned[key]
+            hp.copy_(post, non_blocking=True)
+            hl.copy_(lens, non_blocking=True)
+            stream.synchronize()
+            return hp.numpy(), hl.numpy(), h2d, post.numel() * 4 + lens.numel() * 8
+        # packed rows straight out of the library's frame-side buffer: rows = sum(mel_lens) + 12 reserved per utterance
+        rows_cap = int(self.last_total_frames) + 12 * (B + 1)
+        cap = self._pinned.get("packed_cap", 0)
+        if rows_cap > cap or ("starts", B) not in self._pinned:
+            cap = max(rows_cap, int(cap * 1.5))
+            self._pinned["packed"] = torch.empty(cap, 80, dtype=torch.float32).pin_memory()
+            self._pinned["packed_cap"] = cap
+            self._pinned[("starts", B)] = torch.empty(B + 1, dtype=torch.int32).pin_memory()
+        hp, hs = self._pinned["packed"], self._pinned[("starts", B)]
+        rows = C.c_int64()
+        lib = _lib.load_library()
+        _lib.check(lib, self._ctx, lib.fs2_read_packed_postnet(self._ctx, stream.cuda_stream, hp.data_ptr(), cap, hs.data_ptr(),
+                                                                C.byref(rows)))
         hl.copy_(lens, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        return hp.numpy(), hl.numpy(), h2d, post.numel() * 4 + lens.numel() * 8
+        stream.synchronize()
+        packed, starts, lens_h = hp.numpy(), hs.numpy(), hl.numpy()
+        mels = [packed[int(starts[b]): int(starts[b]) + int(lens_h[b])] for b in range(B)]
+        return mels, lens_h, h2d, int(rows.value) * 80 * 4 + (B + 1) * 4 + B * 8
 
 
 def get_model(preprocess_config, model_config, state_dict=None, device="cuda", **kw):

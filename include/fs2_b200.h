@@ -126,6 +126,13 @@ int fs2_forward_stage1(fs2_ctx* ctx, fs2_stream stream, const fs2_inputs* in, fs
 /* stage 2 = LengthRegulator + Decoder + mel_linear + PostNet (modules.py:136-137,167-194;
  * fastspeech2.py:133-136); asynchronous on `stream`. */
 int fs2_forward_stage2(fs2_ctx* ctx, fs2_stream stream, const fs2_stage2_io* io);
+/* Device->host read of the result the callers actually consume (`synth_samples` slices predictions[1][i, :mel_len],
+ * utils/tools.py:228-233): the PACKED postnet mel rows, utterance b at rows [starts[b], starts[b] + mel_lens[b]) of
+ * `host_rows` ([rows, 80] fp32), separated by 12 reserved rows -- one third of the bytes of the padded [B, T_max, 80]
+ * tensor at batch 64.  Enqueued on `stream` after fs2_forward_stage2; `host_rows` / `host_starts` ([batch + 1] int32)
+ * should be pinned; `*rows_out` (written before the call returns) = rows to expect; max_rows = capacity of host_rows. */
+int fs2_read_packed_postnet(fs2_ctx* ctx, fs2_stream stream, float* host_rows, int64_t max_rows, int32_t* host_starts,
+                            int64_t* rows_out);
 /* Number of kernels the last stage1+stage2 pair launched. */
 int fs2_last_launch_count(const fs2_ctx* ctx);
 

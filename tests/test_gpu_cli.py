@@ -59,3 +59,20 @@ def test_cli_batch_mode_writes_one_wav_per_line(sd32):
         mel = np.load(os.path.join(d, "result", f"{name}.npy"))
         rate, wav = wavfile.read(os.path.join(d, "result", f"{name}.wav"))
         assert wav.shape == (mel.shape[0] * 256,) and wav.dtype == np.int16
+
+
+def test_host_entry_packed_equals_padded(sd32):
+    """synthesize_host: the packed per-utterance views (one D2H of the library's frame-side rows) equal the slices of the
+    padded tensor that `synth_samples` takes (utils/tools.py:228-233)."""
+    from gpu_util import model_for
+    syn = fs2_b200.synthetic
+    model = model_for(sd32)
+    b = syn.make_batch([30, 7, 19, 30], seed=12)
+    host = {k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in b.items()}
+    mels, lens, h2d, d2h_packed = model.synthesize_host(host)
+    mels = [np.array(m) for m in mels]
+    padded, lens2, _, d2h_padded = model.synthesize_host(host, padded=True)
+    assert np.array_equal(lens, lens2) and d2h_packed <= d2h_padded
+    for i, n in enumerate(lens):
+        assert mels[i].shape == (int(n), 80)
+        assert np.array_equal(mels[i], padded[i, : int(n)])
