@@ -44,7 +44,7 @@ constexpr int AR_ROWS = 192;      // 128 + (taps - 1) * dil <= 192  (k = 11, dil
 constexpr int AR_STAGE_BYTES = 16384;
 
 // AR = 0: activations stream with the weights; AR = 1 / 2: resident activation tile of 1 / 2 K chunks (K <= 32 / 64)
-template <int BN, int AR = 0>
+template <int BN, int AR = 0, int NS = 1>
 struct Cfg {
   static constexpr int STAGES = AR == 2 ? 3 : (BN > 128 ? 3 : 4);
   static constexpr int A_BYTES = AR ? 0 : BM * 128;
@@ -58,7 +58,8 @@ struct Cfg {
   static constexpr int OFF_RES = OFF_CST + 8 * WCHUNK;      // 4 warps x 2 residual sub-tiles
   static constexpr int OFF_PAR = OFF_RES + 8 * WCHUNK;      // bias[2048] | gamma[256] | beta[256] | head_w[256]
   static constexpr int OFF_BAR = OFF_PAR + 12288;
-  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static constexpr int OFF_STAT = OFF_BAR + 256;            // N-split: float2 [2 parities][4 source ranks][128 rows]
+  static constexpr int TOTAL = OFF_STAT + (NS > 1 ? 8192 : 0) + 1024;
   static constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static constexpr int NCHUNK = (BN + 31) / 32;
@@ -121,13 +122,49 @@ __device__ __forceinline__ uint64_t umma_desc_rowshift(uint32_t saddr) {
   return d;
 }
 
-template <int BN, bool LN, int CL, bool BF, int AR = 0>
+// ---- distributed shared memory helpers (N-split LayerNorm statistics)
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local, int cta_rank) {   // same offset in a peer CTA's smem
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_u32(local)), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void dsmem_st2(uint32_t raddr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};\n" ::"r"(raddr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t rbar) {   // release at cluster scope: the stores above are visible
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+// NS > 1 (fused-LayerNorm only): N-split.  A cluster of NS CTAs shares ONE row tile, CTA r owns the 256/NS columns
+// [r*BN, (r+1)*BN): each loads 1/NS of the activation tile and multicasts it to the others, streams only its own
+// weight columns, and the LayerNorm statistics of the row are combined across the cluster through distributed shared
+// memory (two floats per row and CTA).  For a handful of row tiles (single utterances) this puts NS SMs on a K loop
+// that one CTA would walk alone: the fused-LN GEMMs were 40 % of the single-utterance latency.
+template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                      const __grid_constant__ CUtensorMap tmC2, ConvGemmArgs p) {
-  using C = Cfg<BN, AR>;
+  using C = Cfg<BN, AR, NS>;
   static_assert(!(AR && (BF || LN)), "A-resident mode: fp32 activations, plain epilogue");
+  static_assert(NS == 1 || (LN && CL == 1 && !AR && BN * NS == 256), "N-split: fused LayerNorm over 256 columns, cluster along N");
+  constexpr int CSIZE = CL > 1 ? CL : NS;          // CTAs per cluster
+  constexpr uint16_t CMASK = (uint16_t)((1u << CSIZE) - 1);
   constexpr int BKE = BF ? 64 : 32;   // operand elements per 128-byte swizzle row
   extern __shared__ uint8_t smem_raw[];
   auto stamp = [&](int k) {
@@ -154,7 +191,9 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* res_full = acc_empty + 2;       // [4 warps][2]
   uint64_t* a_full = res_full + 8;          // [2]  AR: the resident activation tile of buffer u has landed
   uint64_t* a_empty = a_full + 2;           // [2]  AR: every MMA that reads buffer u has completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 2);
+  uint64_t* stat_full = a_empty + 2;        // [2]  NS: the peers' LayerNorm statistics of this tile parity have arrived
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_full + 2);
+  float2* stat_s = reinterpret_cast<float2*>(smem + C::OFF_STAT);        // NS: [2 parities][4 source ranks][128 rows]
   uint8_t* ring = smem + C::OFF_RING;
 
   const int warp = warp_index(), lane = threadIdx.x & 31;
@@ -174,7 +213,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (has_res) asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CL);   // a stage is refilled by both CTAs of the cluster: both consumers must release it
+      mbar_init(&empty[s], CSIZE);   // a stage is refilled by every CTA of the cluster: all consumers must release it
     }
     for (int u = 0; u < 2; ++u) {
       mbar_init(&acc_full[u], 1);
@@ -184,6 +223,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int u = 0; u < 2; ++u) {
       mbar_init(&a_full[u], 1);
       mbar_init(&a_empty[u], 1);
+      mbar_init(&stat_full[u], 128 * (NS > 1 ? NS - 1 : 1));
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -198,8 +238,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) stamp(1);
-  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
-  if (CL > 1) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
+  const int rank = CSIZE > 1 ? (int)cluster_ctarank() : 0;
+  if (CSIZE > 1) cluster_sync_all();   // the peers' barriers are initialised before anything is multicast to them
   // ---- everything above overlaps the previous kernel's tail; from here on its results are read
   pdl_trigger();
   pdl_wait();
@@ -208,10 +248,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   // work item = CL vertically adjacent row tiles x one column tile; the CTAs of a cluster walk the items in
   // lock step (a trailing odd row tile is processed as an all-zero tile whose stores TMA clips away)
   const int m_groups = ((rows_live + BM - 1) / BM + CL - 1) / CL;
-  const int total_items = m_groups * n_tiles_n;
-  const int w_first = blockIdx.x / CL, w_step = gridDim.x / CL;
-  auto item_m0 = [&](int w) { return ((w / n_tiles_n) * CL + rank) * BM; };
-  auto item_n0 = [&](int w) { return (w % n_tiles_n) * BN; };
+  const int total_items = NS > 1 ? m_groups : m_groups * n_tiles_n;       // N-split: one item = one row tile
+  const int w_first = blockIdx.x / CSIZE, w_step = gridDim.x / CSIZE;
+  auto item_m0 = [&](int w) { return NS > 1 ? w * BM : ((w / n_tiles_n) * CL + rank) * BM; };
+  auto item_n0 = [&](int w) { return NS > 1 ? rank * BN : (w % n_tiles_n) * BN; };
 
   if (warp == 0) {
     // ---------------- TMA producer (whole warp runs the loop, one elected lane issues)
@@ -254,7 +294,11 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint8_t* a_s = ring + s * C::STAGE_BYTES;
         if (leader) {
           mbar_expect_tx(&full[s], C::STAGE_BYTES);
-          tma_load_2d(a_s, &tmA, kc * BKE, m0 + tap * dil - p.pad, &full[s]);
+          if (NS > 1) {   // this CTA's 128/NS rows of the shared activation tile, delivered to every CTA of the cluster
+            tma_load_2d_mc(a_s + rank * (C::A_BYTES / NS), &tmA, kc * BKE, m0 + tap * dil - p.pad + rank * (BM / NS), &full[s], CMASK);
+          } else {
+            tma_load_2d(a_s, &tmA, kc * BKE, m0 + tap * dil - p.pad, &full[s]);
+          }
           if (CL == 1) {
             tma_load_2d(a_s + C::A_BYTES, &tmW, kc * BKE, tap * p.N + n0, &full[s]);
           } else {   // this CTA's half of the weight tile, delivered to both CTAs of the cluster
@@ -318,7 +362,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (BF) umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
             else umma_tf32(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
           }
-          if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], (uint16_t)0x3);
+          if (CSIZE == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], CMASK);
         }
         __syncwarp();
       }
@@ -524,12 +568,36 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           pass1(vb, c + 1);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        if (NS > 1) {
+          // (mean, M2) over this CTA's BN columns -> every peer; then merge the NS groups in rank order (Chan), so all
+          // CTAs of the cluster normalise with bit-identical statistics
+          const int par = lt & 1;
+#pragma unroll
+          for (int pr = 0; pr < NS; ++pr) {
+            if (pr == rank) continue;
+            dsmem_st2(dsmem_addr(&stat_s[(par * 4 + rank) * BM + r], pr), mean, var);
+            mbar_arrive_remote(dsmem_addr(&stat_full[par], pr));
+          }
+          mbar_wait_cluster(&stat_full[par], (lt >> 1) & 1);
+          float gm = 0.f, gm2 = 0.f;
+#pragma unroll
+          for (int src = 0; src < NS; ++src) {
+            float2 st = make_float2(mean, var);
+            if (src != rank) st = stat_s[(par * 4 + src) * BM + r];
+            const float delta = st.x - gm;
+            const float n_old = (float)(BN * src), n_new = (float)(BN * (src + 1));
+            gm = fmaf(delta, (float)BN / n_new, gm);
+            gm2 += st.y + delta * delta * (n_old * (float)BN / n_new);
+          }
+          mean = gm;
+          var = gm2;
+        }
         const float rstd = 1.f / sqrtf(var * (1.f / 256.f) + 1e-5f);
         float dot = 0.f;
         auto pass2 = [&](float (&v)[32], int c) {
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
-            const float4 g4 = lds4(gamma_sa + c * 128 + cc * 16), b4 = lds4(beta_sa + c * 128 + cc * 16);
+            const float4 g4 = lds4(gamma_sa + (n0 + c * 32) * 4 + cc * 16), b4 = lds4(beta_sa + (n0 + c * 32) * 4 + cc * 16);
             const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[cc * 4 + e] = fmaf((v[cc * 4 + e] - mean) * rstd, gg[e], bb[e]);
@@ -538,7 +606,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {
-              const float4 w4 = lds4(headw_sa + c * 128 + cc * 16);
+              const float4 w4 = lds4(headw_sa + (n0 + c * 32) * 4 + cc * 16);
               d4[0] = fmaf(v[cc * 4], w4.x, d4[0]); d4[1] = fmaf(v[cc * 4 + 1], w4.y, d4[1]);
               d4[2] = fmaf(v[cc * 4 + 2], w4.z, d4[2]); d4[3] = fmaf(v[cc * 4 + 3], w4.w, d4[3]);
             }
@@ -579,7 +647,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // the peer may still multicast commits into this CTA's barriers until it is done too
+  if (CSIZE > 1) cluster_sync_all();   // the peers may still multicast commits into this CTA's barriers until they are done too
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
@@ -600,29 +668,35 @@ inline int& cluster_size_flag() {   // 2 = weight tiles multicast across CTA pai
   return f;
 }
 
-template <int BN, bool LN, int CL, bool BF, int AR = 0>
+template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1>
 inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
-  using C = Cfg<BN, AR>;
+  using C = Cfg<BN, AR, NS>;
   static bool configured[64] = {};
   int dev = 0;
   FS2_CUDA_OK(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
     configured[dev & 63] = true;
   }
   constexpr CUtensorMapSwizzle SW128 = CU_TENSOR_MAP_SWIZZLE_128B;
-  const CUtensorMap tmA = BF ? make_map_any(a.A, a.rows, a.K, a.lda, BM, 64, MAP_BF16, SW128)
-                             : make_map(a.A, a.rows, a.K, a.lda, AR ? AR_ROWS : BM, /*round_tf32=*/true, false);
+  const CUtensorMap tmA = BF ? make_map_any(a.A, a.rows, a.K, a.lda, BM / NS, 64, MAP_BF16, SW128)
+                             : make_map(a.A, a.rows, a.K, a.lda, AR ? AR_ROWS : BM / NS, /*round_tf32=*/true, false);
   const CUtensorMap tmW = BF ? make_map_any(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN / CL, 64, MAP_BF16, SW128)
                              : make_map(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN / CL, false, true);
   const CUtensorMap tmC = a.C != nullptr ? make_map(a.C, a.rows, a.N, a.ldc, 32, false, false) : tmA;
   const CUtensorMap tmR = a.residual != nullptr ? make_map(a.residual, a.rows, a.N, a.ldr, 32, false, false) : tmA;
   const CUtensorMap tmC2 =
       a.C2 != nullptr ? make_map_any(a.C2, a.rows, a.N, a.ldc2, 32, 32, MAP_BF16, CU_TENSOR_MAP_SWIZZLE_64B) : tmA;
-  const int items = (((a.rows + BM - 1) / BM + CL - 1) / CL) * ((a.N + BN - 1) / BN);
-  const int grid = std::min(items, sm_count() / CL) * CL;
-  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR>, dim3(grid), dim3(THREADS), C::TOTAL, stream, CL, tmA, tmW, tmC, tmR, tmC2, a);
+  constexpr int CSIZE = CL > 1 ? CL : NS;
+  const int items = NS > 1 ? (a.rows + BM - 1) / BM : (((a.rows + BM - 1) / BM + CL - 1) / CL) * ((a.N + BN - 1) / BN);
+  const int grid = std::min(items, sm_count() / CSIZE) * CSIZE;
+  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS>, dim3(grid), dim3(THREADS), C::TOTAL, stream, CSIZE, tmA, tmW, tmC, tmR, tmC2, a);
   FS2_LAUNCHED();
+}
+
+inline int& n_split_flag() {   // 1 = N-split fused-LN GEMMs for small row counts (default), 0 = always one CTA per row tile
+  static int f = 1;
+  return f;
 }
 
 inline int& a_resident_flag() {   // 1 = use the A-resident variant where it applies (default), 0 = always stream A
@@ -668,7 +742,16 @@ inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
     require(a.N == 256 && a.ln_beta != nullptr, FS2_ERR_INVALID, "fused LayerNorm needs N == 256 and both affine vectors");
     require(a.C != nullptr || a.C2 != nullptr || a.head_out != nullptr, FS2_ERR_INVALID, "fused LayerNorm: nothing to write");
     require(a.head_out == nullptr || (a.head_w != nullptr && a.head_b != nullptr), FS2_ERR_INVALID, "head needs weight and bias");
-    launch_bn<256, true>(a, stream);
+    // few row tiles (single utterances, the encoder of a small batch): split the 256 columns over a cluster of 4 or 2 CTAs
+    const int m_tiles_ln = (a.rows + BM - 1) / BM;
+    const int ns = (n_split_flag() == 0 || a.head_out != nullptr) ? 1 : (m_tiles_ln * 4 <= sm_count() ? 4 : (m_tiles_ln * 2 <= sm_count() ? 2 : 1));
+    if (ns == 4) {
+      if (a.a_bf16) launch_bn_cl<64, true, 1, true, 0, 4>(a, stream); else launch_bn_cl<64, true, 1, false, 0, 4>(a, stream);
+    } else if (ns == 2) {
+      if (a.a_bf16) launch_bn_cl<128, true, 1, true, 0, 2>(a, stream); else launch_bn_cl<128, true, 1, false, 0, 2>(a, stream);
+    } else {
+      launch_bn<256, true>(a, stream);
+    }
     return;
   }
   require(a.C != nullptr || a.C2 != nullptr, FS2_ERR_INVALID, "conv_gemm: null output");
