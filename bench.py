@@ -292,20 +292,21 @@ def main():
     voc_line = None
     if args.engine == "tcgen05" and world == 1:
         try:
-            voc = fs2_b200.HiFiGANGeneratorB200()
-            voc.load_state_dict(syn.synthetic_vocoder_state_dict(0))
-            voc = voc.to(dev)
             mel_t, lens_t = out[1].transpose(1, 2), out[9]
-            for _ in range(2):
-                voc(mel_t, mel_lens=lens_t)
-            v_ms = timed_loop(lambda: voc(mel_t, mel_lens=lens_t), min(args.steps, 5))
-            v = float(np.median(v_ms))
             voc_line = {"workload": "HiFi-GAN V1 generator (hifigan/config.json) on the postnet mel of the same batch, "
-                                    "random-init weights, TF32", "ms_per_step": v, "mel_frames_per_s": frames / v * 1e3,
-                        "audio_samples_per_s": frames * 256 / v * 1e3, "x_realtime_22050hz": frames * 256 / 22050 / (v * 1e-3),
-                        "gpu_launches": voc.last_launch_count}
-            del voc
-            torch.cuda.empty_cache()
+                                    "random-init weights"}
+            for mode in ("tf32", "bf16"):
+                voc = fs2_b200.HiFiGANGeneratorB200(math_mode=mode)
+                voc.load_state_dict(syn.synthetic_vocoder_state_dict(0))
+                voc = voc.to(dev)
+                for _ in range(2):
+                    voc(mel_t, mel_lens=lens_t)
+                v = float(np.median(timed_loop(lambda: voc(mel_t, mel_lens=lens_t), min(args.steps, 5))))
+                voc_line[mode] = {"ms_per_step": v, "mel_frames_per_s": frames / v * 1e3,
+                                  "audio_samples_per_s": frames * 256 / v * 1e3,
+                                  "x_realtime_22050hz": frames * 256 / 22050 / (v * 1e-3), "gpu_launches": voc.last_launch_count}
+                del voc
+                torch.cuda.empty_cache()
         except Exception as e:   # the vocoder is an extra: never let it take the headline line down
             voc_line = {"error": str(e)[:200]}
 

@@ -81,7 +81,7 @@ SIGNATURES = {
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "fs2_op_bucketize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     "fs2_op_frame_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "fs2_voc_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "fs2_voc_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "fs2_voc_destroy": (None, [C.c_void_p]),
     "fs2_voc_last_error": (C.c_char_p, [C.c_void_p]),
     "fs2_voc_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, c_i64p, C.c_int]),

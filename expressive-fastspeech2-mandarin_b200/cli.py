@@ -141,13 +141,15 @@ def build_parser():
     p.add_argument("--random_init", action="store_true", help="seeded synthetic weights instead of the checkpoints")
     p.add_argument("--vocoder_ckpt", type=str, default=None, help="generator checkpoint (default hifigan/generator_<speaker>.pth.tar)")
     p.add_argument("--no_vocoder", action="store_true", help="write the mel only")
+    p.add_argument("--math_mode", type=str, default="tf32", choices=["tf32", "bf16"],
+                   help="arithmetic of the contractions of both networks (bf16: faster, tolerance in tests/test_gpu_bf16.py)")
     return p
 
 
 def load_model(args, preprocess_config, model_config, train_config, device="cuda"):
     """utils/model.py:11-34: construct, torch.load(<ckpt_path>/<step>.pth.tar)["model"], eval."""
     from .model import FastSpeech2B200
-    model = FastSpeech2B200(preprocess_config, model_config)
+    model = FastSpeech2B200(preprocess_config, model_config, math_mode=args.math_mode)
     if args.random_init:
         from .synthetic import synthetic_state_dict
         model.load_state_dict(synthetic_state_dict(seed=0))
@@ -164,12 +166,12 @@ def load_vocoder(args, model_config, device="cuda"):
         return None
     from .vocoder import get_vocoder
     if args.random_init:
-        return get_vocoder(model_config, device, random_init=True)
+        return get_vocoder(model_config, device, random_init=True, math_mode=args.math_mode)
     path = args.vocoder_ckpt or os.path.join("hifigan", f"generator_{model_config['vocoder']['speaker']}.pth.tar")
     if not os.path.exists(path):
         print(f"[fs2_b200] no vocoder weights at {path}: writing mel spectrograms only")
         return None
-    return get_vocoder(model_config, device, ckpt_path=path)
+    return get_vocoder(model_config, device, ckpt_path=path, math_mode=args.math_mode)
 
 
 def write_wavs(out_dir, ids, wavs, sampling_rate):

@@ -1130,6 +1130,7 @@ int fs2_op_frame_map(fs2_stream stream, const int32_t* cum, int batch, int max_s
 // ============================================================================ HiFi-GAN generator
 struct fs2_voc {
   int device = 0;
+  int math_mode = FS2_MATH_TF32;   // FS2_MATH_BF16: bf16 weights AND activations (fp32 accumulation, bias, output wav)
   std::string err;
   bool prepared = false;
   std::map<std::string, fs2::DevTensor> raw;
@@ -1167,7 +1168,11 @@ static ConvW conv_w(fs2_voc* c, const std::string& p, int cout, int cin, int k, 
   w.cin = cin; w.cout = cout; w.k = k;
   const int64_t n = (int64_t)cout * cin * k;
   w.w = vkeep(c, n);
-  repack_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(VW(c, p + ".weight", {cout, cin, k}).ptr, cout, cin, k, nullptr, 1, w.w);
+  if (c->math_mode == FS2_MATH_BF16)
+    repack_conv_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(VW(c, p + ".weight", {cout, cin, k}).ptr, cout, cin, k, nullptr,
+                                                                        reinterpret_cast<__nv_bfloat16*>(w.w));
+  else
+    repack_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(VW(c, p + ".weight", {cout, cin, k}).ptr, cout, cin, k, nullptr, 1, w.w);
   FS2_LAUNCHED();
   w.b = VW(c, p + ".bias", {cout}).ptr;
   return w;
@@ -1186,8 +1191,9 @@ static void prepare(fs2_voc* c, cudaStream_t s) {
     const std::string p = "ups." + std::to_string(i);
     const int64_t n = 3LL * u.s * u.cout * u.cin;
     u.w = vkeep(c, n);
-    repack_convT_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(VW(c, p + ".weight", {u.cin, u.cout, UP_KERNEL[i]}).ptr, u.cin,
-                                                                    u.cout, UP_KERNEL[i], u.s, u.w);
+    repack_convT_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+        VW(c, p + ".weight", {u.cin, u.cout, UP_KERNEL[i]}).ptr, u.cin, u.cout, UP_KERNEL[i], u.s, u.w,
+        c->math_mode == FS2_MATH_BF16 ? reinterpret_cast<__nv_bfloat16*>(u.w) : nullptr);
     FS2_LAUNCHED();
     u.b = vkeep(c, (size_t)u.s * u.cout);
     tile_bias_kernel<<<(u.s * u.cout + 255) / 256, 256, 0, s>>>(VW(c, p + ".bias", {u.cout}).ptr, u.cout, u.s, u.b);
@@ -1250,7 +1256,9 @@ static void forward(fs2_voc* c, cudaStream_t s, const float* mel, int64_t sb, in
   row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(sd.starts, sd.lens, B, VOC_GAP, T, nullptr, rows, sd.utt, sd.vpos, sd.room,
                                                      sd.slot);
   FS2_LAUNCHED();
-  pack_mel_kernel<<<(rows + 7) / 8, 256, 0, s>>>(mel, sb, sc, st, sd.meta(), sd.lens, rows, c->melp);
+  const bool bf = c->math_mode == FS2_MATH_BF16;   // every activation buffer then holds bf16 behind its float*
+  pack_mel_kernel<<<(rows + 7) / 8, 256, 0, s>>>(mel, sb, sc, st, sd.meta(), sd.lens, rows, c->melp,
+                                                 bf ? reinterpret_cast<__nv_bfloat16*>(c->melp) : nullptr);
   FS2_LAUNCHED();
   const int32_t* live = reinterpret_cast<const int32_t*>(sd.totals);
 
@@ -1259,9 +1267,10 @@ static void forward(fs2_voc* c, cudaStream_t s, const float* mel, int64_t sb, in
     ConvGemmArgs a{};
     a.A = A; a.lda = K; a.rows = rows_now; a.W = W; a.bias = bias; a.taps = taps; a.dil = dil; a.pad = dil * (taps - 1) / 2;
     a.K = K; a.N = N; a.act = act; a.slope = SLOPE; a.residual = residual; a.ldr = N; a.res_inv_lrelu = residual != nullptr;
-    a.act2 = act2; a.C = C; a.ldc = ldc; a.row_vpos = sd.vpos; a.row_room = sd.room; a.extra = 0; a.mask_shift = shift;
+    a.act2 = act2; a.row_vpos = sd.vpos; a.row_room = sd.room; a.extra = 0; a.mask_shift = shift;
     a.live_rows = live;
-    tc2::launch(a, FS2_MATH_TF32, s);
+    if (bf) { a.a_bf16 = 1; a.res_bf16 = 1; a.C2 = C; a.ldc2 = ldc; } else { a.C = C; a.ldc = ldc; }
+    tc2::launch(a, c->math_mode, s);
   };
 
   // conv_pre (models.py:149) with the leaky ReLU of the first upsampling stage (:151) applied on the way out
@@ -1294,14 +1303,19 @@ static void forward(fs2_voc* c, cudaStream_t s, const float* mel, int64_t sb, in
     }
     if (i + 1 < N_UPS) {
       const int64_t n4 = (int64_t)rows_now * ch / 4;
-      sum3_lrelu_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<const float4*>(R[0]), reinterpret_cast<const float4*>(R[1]),
-                                                reinterpret_cast<const float4*>(R[2]), n4, reinterpret_cast<float4*>(T1));
+      if (bf)
+        sum3_lrelu_bf16_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<const uint4*>(R[0]), reinterpret_cast<const uint4*>(R[1]),
+                                                       reinterpret_cast<const uint4*>(R[2]), n4 / 2, reinterpret_cast<uint4*>(T1));
+      else
+        sum3_lrelu_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<const float4*>(R[0]), reinterpret_cast<const float4*>(R[1]),
+                                                  reinterpret_cast<const float4*>(R[2]), n4, reinterpret_cast<float4*>(T1));
       FS2_LAUNCHED();
       a_in = T1;
       std::swap(T1, P[0]);   // T1 now feeds the next upsampling: the next stage uses another scratch buffer
     }
   }
-  post_kernel<<<rows, 256, 0, s>>>(R[0], R[1], R[2], (int64_t)rows_now, c->post_w, c->post_b, sd.meta(), sd.starts, T, wav);
+  if (bf) post_kernel<true><<<rows, 256, 0, s>>>(R[0], R[1], R[2], (int64_t)rows_now, c->post_w, c->post_b, sd.meta(), sd.starts, T, wav);
+  else post_kernel<false><<<rows, 256, 0, s>>>(R[0], R[1], R[2], (int64_t)rows_now, c->post_w, c->post_b, sd.meta(), sd.starts, T, wav);
   FS2_LAUNCHED();
   c->last_launches = g_launches;
 }
@@ -1325,9 +1339,10 @@ static int vguarded(fs2_voc* c, F&& f) {
 
 extern "C" {
 
-int fs2_voc_create(int device, fs2_voc** out) {
+int fs2_voc_create(int device, int math_mode, fs2_voc** out) {
   return fs2::voc::vguarded(nullptr, [&] {
     require(out != nullptr, FS2_ERR_INVALID, "null argument");
+    require(math_mode == FS2_MATH_TF32 || math_mode == FS2_MATH_BF16, FS2_ERR_UNSUPPORTED, "unknown math_mode");
     int n_dev = 0;
     FS2_CUDA_OK(cudaGetDeviceCount(&n_dev));
     require(device >= 0 && device < n_dev, FS2_ERR_INVALID, "no such CUDA device");
@@ -1337,6 +1352,7 @@ int fs2_voc_create(int device, fs2_voc** out) {
     require(prop.major == 10, FS2_ERR_UNSUPPORTED, std::string("libfs2b200 is built for sm_100a (B200) only; device is ") + prop.name);
     auto* c = new fs2_voc();
     c->device = device;
+    c->math_mode = math_mode;
     c->status = dalloc<int32_t>(1);
     *out = c;
   });

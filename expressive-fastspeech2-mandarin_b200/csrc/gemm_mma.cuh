@@ -49,6 +49,7 @@ struct ConvGemmArgs {
   float slope;        // ACT_LRELU slope
   int act2;           // activation applied AFTER the residual add (ACT_NONE / ACT_LRELU)
   int res_inv_lrelu;  // the residual buffer holds lrelu(x): recover x = y >= 0 ? y : y / slope before adding
+  int res_bf16;       // the residual buffer is bf16 [rows, ldr] (vocoder bf16 mode), not fp32
   long long* trace;   // bring-up only: CTA 0 writes globaltimer stamps of its phases (nullptr in normal operation)
 };
 

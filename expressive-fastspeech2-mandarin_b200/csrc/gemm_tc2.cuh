@@ -161,7 +161,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                      const __grid_constant__ CUtensorMap tmC2, ConvGemmArgs p) {
   using C = Cfg<BN, AR, NS>;
-  static_assert(!(AR && (BF || LN)), "A-resident mode: fp32 activations, plain epilogue");
+  static_assert(!(AR && LN), "A-resident mode: plain epilogue");
+  static_assert(!(AR == 2 && BF), "bf16 A-resident tiles hold 64 channels in one K chunk: AR = 1");
   static_assert(NS == 1 || (LN && CL == 1 && !AR && BN * NS == 256), "N-split: fused LayerNorm over 256 columns, cluster along N");
   constexpr int CSIZE = CL > 1 ? CL : NS;          // CTAs per cluster
   constexpr uint16_t CMASK = (uint16_t)((1u << CSIZE) - 1);
@@ -335,7 +336,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               const uint64_t da = umma_desc_rowshift(a_base + kc * C::AR_CHUNK_BYTES + (uint32_t)(tap * dil) * 128u);
               const uint64_t db = umma_desc(ring + s * C::STAGE_BYTES + j * C::B_BYTES);
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) umma_tf32(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i0 | j | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < 4; ++kk) {
+                if (BF) umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i0 | j | kk) != 0 ? 1u : 0u);
+                else umma_tf32(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i0 | j | kk) != 0 ? 1u : 0u);
+              }
             }
             if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], (uint16_t)0x3);
           }
@@ -394,8 +398,9 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     epi_barrier();   // the only CTA-level epilogue barrier: parameters are in smem
     int g_res = 0;   // residual sub-tiles consumed so far (buffer = g & 1, parity = (g >> 1) & 1)
     int g_st = 0;    // staging sub-tiles produced so far
+    const uint32_t res_bytes = p.res_bf16 ? WCHUNK / 2 : WCHUNK;   // [32 rows x 32 columns] fp32 or bf16
     if (has_res && lane == 0 && w_first < total_items) {  // first residual sub-tile of the first tile
-      mbar_expect_tx(&my_res_full[0], WCHUNK);
+      mbar_expect_tx(&my_res_full[0], res_bytes);
       tma_load_2d(my_res, &tmR, item_n0(w_first), item_m0(w_first) + q * 32, &my_res_full[0]);
     }
     int lt = 0;
@@ -424,7 +429,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (cc >= C::NCHUNK) { ww = w_next; cc = 0; }
         if (ww >= total_items) return;
         const int buf = (g_res + 1) & 1;
-        mbar_expect_tx(&my_res_full[buf], WCHUNK);
+        mbar_expect_tx(&my_res_full[buf], res_bytes);
         tma_load_2d(my_res + buf * WCHUNK, &tmR, item_n0(ww) + cc * 32, item_m0(ww) + q * 32, &my_res_full[buf]);
       };
       // v = act(acc + bias) (+ residual from this warp's smem sub-tile)
@@ -449,14 +454,32 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         if (has_res) {
           mbar_wait(&my_res_full[g_res & 1], (g_res >> 1) & 1);
-          const uint32_t rb = res_sa + (g_res & 1) * WCHUNK + lane * 128;
           const float inv = p.res_inv_lrelu ? 1.f / p.slope : 1.f;   // residual stored as lrelu(x): undo it
+          if (p.res_bf16) {   // [32 rows x 64 B], SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3; bf16 -> fp32 is a 16-bit shift
+            const uint32_t rb = res_sa + (g_res & 1) * WCHUNK + lane * 64;
+            const uint32_t sx64 = (uint32_t)((lane >> 1) & 3) << 4;
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            if (cc * 4 < width) {
-              const float4 r4 = lds4(rb + ((cc << 4) ^ swz_x));
-              v[cc * 4 + 0] += r4.x >= 0.f ? r4.x : r4.x * inv; v[cc * 4 + 1] += r4.y >= 0.f ? r4.y : r4.y * inv;
-              v[cc * 4 + 2] += r4.z >= 0.f ? r4.z : r4.z * inv; v[cc * 4 + 3] += r4.w >= 0.f ? r4.w : r4.w * inv;
+            for (int cc = 0; cc < 4; ++cc) {
+              if (cc * 8 < width) {
+                const float4 r4 = lds4(rb + ((cc << 4) ^ sx64));
+                const uint32_t w[4] = {__float_as_uint(r4.x), __float_as_uint(r4.y), __float_as_uint(r4.z), __float_as_uint(r4.w)};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xFFFF0000u);
+                  v[cc * 8 + 2 * e] += lo >= 0.f ? lo : lo * inv;
+                  v[cc * 8 + 2 * e + 1] += hi >= 0.f ? hi : hi * inv;
+                }
+              }
+            }
+          } else {
+            const uint32_t rb = res_sa + (g_res & 1) * WCHUNK + lane * 128;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              if (cc * 4 < width) {
+                const float4 r4 = lds4(rb + ((cc << 4) ^ swz_x));
+                v[cc * 4 + 0] += r4.x >= 0.f ? r4.x : r4.x * inv; v[cc * 4 + 1] += r4.y >= 0.f ? r4.y : r4.y * inv;
+                v[cc * 4 + 2] += r4.z >= 0.f ? r4.z : r4.z * inv; v[cc * 4 + 3] += r4.w >= 0.f ? r4.w : r4.w * inv;
+              }
             }
           }
         }
@@ -679,12 +702,14 @@ inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
     configured[dev & 63] = true;
   }
   constexpr CUtensorMapSwizzle SW128 = CU_TENSOR_MAP_SWIZZLE_128B;
-  const CUtensorMap tmA = BF ? make_map_any(a.A, a.rows, a.K, a.lda, BM / NS, 64, MAP_BF16, SW128)
+  const CUtensorMap tmA = BF ? make_map_any(a.A, a.rows, a.K, a.lda, AR ? AR_ROWS : BM / NS, 64, MAP_BF16, SW128)
                              : make_map(a.A, a.rows, a.K, a.lda, AR ? AR_ROWS : BM / NS, /*round_tf32=*/true, false);
   const CUtensorMap tmW = BF ? make_map_any(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN / CL, 64, MAP_BF16, SW128)
                              : make_map(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN / CL, false, true);
   const CUtensorMap tmC = a.C != nullptr ? make_map(a.C, a.rows, a.N, a.ldc, 32, false, false) : tmA;
-  const CUtensorMap tmR = a.residual != nullptr ? make_map(a.residual, a.rows, a.N, a.ldr, 32, false, false) : tmA;
+  const CUtensorMap tmR = a.residual == nullptr ? tmA
+                          : a.res_bf16 ? make_map_any(a.residual, a.rows, a.N, a.ldr, 32, 32, MAP_BF16, CU_TENSOR_MAP_SWIZZLE_64B)
+                                       : make_map(a.residual, a.rows, a.N, a.ldr, 32, false, false);
   const CUtensorMap tmC2 =
       a.C2 != nullptr ? make_map_any(a.C2, a.rows, a.N, a.ldc2, 32, 32, MAP_BF16, CU_TENSOR_MAP_SWIZZLE_64B) : tmA;
   constexpr int CSIZE = CL > 1 ? CL : NS;
@@ -707,7 +732,9 @@ inline int& a_resident_flag() {   // 1 = use the A-resident variant where it app
 template <int BN>
 inline void launch_ar(const ConvGemmArgs& a, cudaStream_t stream) {
   const bool pair = cluster_size_flag() == 2 && a.rows > BM;
-  if (a.K <= 32) {
+  if (a.a_bf16) {   // 64 bf16 channels fit one 128-byte K chunk
+    if (pair) launch_bn_cl<BN, false, 2, true, 1>(a, stream); else launch_bn_cl<BN, false, 1, true, 1>(a, stream);
+  } else if (a.K <= 32) {
     if (pair) launch_bn_cl<BN, false, 2, false, 1>(a, stream); else launch_bn_cl<BN, false, 1, false, 1>(a, stream);
   } else {
     if (pair) launch_bn_cl<BN, false, 2, false, 2>(a, stream); else launch_bn_cl<BN, false, 1, false, 2>(a, stream);
@@ -728,7 +755,7 @@ inline void launch_bn(const ConvGemmArgs& a, cudaStream_t stream) {
 inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
   (void)math_mode;   // the operand type travels with the arguments (a_bf16)
   const int am = a.a_bf16 ? 8 : 4;   // elements per 16 bytes of the A / W rows
-  require(a.K % am == 0 && a.lda % am == 0 && (a.C == nullptr || a.ldc % 4 == 0) && (a.residual == nullptr || a.ldr % 4 == 0) &&
+  require(a.K % am == 0 && a.lda % am == 0 && (a.C == nullptr || a.ldc % 4 == 0) && (a.residual == nullptr || a.ldr % (a.res_bf16 ? 8 : 4) == 0) &&
               (a.C2 == nullptr || a.ldc2 % 8 == 0), FS2_ERR_INVALID,
           "tcgen05 conv_gemm: K and leading dimensions must describe 16-byte-aligned rows");
   require((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0 &&
@@ -757,7 +784,7 @@ inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
   require(a.C != nullptr || a.C2 != nullptr, FS2_ERR_INVALID, "conv_gemm: null output");
   {   // small K, several taps: keep the activation tile resident and shift the descriptor per tap
     const int d = a.dil > 0 ? a.dil : 1;
-    if (a_resident_flag() && !a.a_bf16 && a.taps > 1 && a.K <= 64 && BM + (a.taps - 1) * d <= AR_ROWS) {
+    if (a_resident_flag() && a.taps > 1 && a.K <= 64 && BM + (a.taps - 1) * d <= AR_ROWS) {
       if (a.N == 32) { launch_ar<32>(a, stream); return; }
       if (a.N == 64) { launch_ar<64>(a, stream); return; }
     }

@@ -37,7 +37,9 @@ struct UpW { float* w = nullptr; float* b = nullptr; int cin = 0, cout = 0, s = 
 
 // ConvTranspose1d weight [Cin][Cout][K] (torch layout) -> GEMM form [3 taps][s*Cout][Cin]; tap t reads x[q + t - 1],
 // i.e. d = 1 - t, kernel index k = s*d + r + (K - s)/2 (zero when outside [0, K)); operands rounded to TF32.
-__global__ void repack_convT_kernel(const float* __restrict__ w, int cin, int cout, int K, int s, float* __restrict__ out) {
+// out_b != nullptr: the same repack rounded to bf16 (FS2_MATH_BF16 vocoder)
+__global__ void repack_convT_kernel(const float* __restrict__ w, int cin, int cout, int K, int s, float* __restrict__ out,
+                                    __nv_bfloat16* __restrict__ out_b = nullptr) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t per_tap = (int64_t)s * cout * cin;
   if (i >= 3 * per_tap) return;
@@ -47,7 +49,8 @@ __global__ void repack_convT_kernel(const float* __restrict__ w, int cin, int co
   const int r = n / cout, co = n % cout;
   const int k = s * (1 - tap) + r + (K - s) / 2;
   const float v = (k >= 0 && k < K) ? w[((size_t)ci * cout + co) * K + k] : 0.f;
-  out[i] = round_tf32(v);
+  if (out_b != nullptr) out_b[i] = __float2bfloat16_rn(v);
+  else out[i] = round_tf32(v);
 }
 __global__ void tile_bias_kernel(const float* __restrict__ b, int cout, int s, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,15 +63,19 @@ __global__ void fill_i64_kernel(int64_t* p, int n, int64_t v) {
 
 // mel [B, 80, T] (any strides, in elements) -> packed token-major [rows, 80]; reserved rows are zero.
 __global__ void pack_mel_kernel(const float* __restrict__ mel, int64_t sb, int64_t sc, int64_t st, RowMeta meta,
-                                const int32_t* __restrict__ lens, int rows, float* __restrict__ out) {
+                                const int32_t* __restrict__ lens, int rows, float* __restrict__ out,
+                                __nv_bfloat16* __restrict__ out_b = nullptr) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int u = meta.utt[row], vp = meta.vpos[row];
   const bool real = u >= 0 && vp < 0;
   const int t = real ? vp + lens[u] : 0;
-  for (int c = lane; c < N_MEL; c += 32)
-    out[(size_t)row * N_MEL + c] = real ? mel[(int64_t)u * sb + (int64_t)c * sc + (int64_t)t * st] : 0.f;
+  for (int c = lane; c < N_MEL; c += 32) {
+    const float v = real ? mel[(int64_t)u * sb + (int64_t)c * sc + (int64_t)t * st] : 0.f;
+    if (out_b != nullptr) out_b[(size_t)row * N_MEL + c] = __float2bfloat16_rn(v);
+    else out[(size_t)row * N_MEL + c] = v;
+  }
 }
 
 // x = (r0 + r1) + r2) / 3 (models.py:156-162) -> lrelu(x, 0.1) (models.py:153): the A operand of the next upsampling.
@@ -85,10 +92,39 @@ __global__ void sum3_lrelu_kernel(const float4* __restrict__ r0, const float4* _
   }
 }
 
+// bf16 activations: eight values per 16-byte access
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    f[2 * e] = __uint_as_float(w[e] << 16);
+    f[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+  }
+}
+__global__ void sum3_lrelu_bf16_kernel(const uint4* __restrict__ r0, const uint4* __restrict__ r1, const uint4* __restrict__ r2,
+                                       int64_t n8, uint4* __restrict__ y) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float a[8], b[8], c[8];
+    unpack8(r0[i], a); unpack8(r1[i], b); unpack8(r2[i], c);
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v0 = ((a[2 * e] + b[2 * e]) + c[2 * e]) / 3.f, v1 = ((a[2 * e + 1] + b[2 * e + 1]) + c[2 * e + 1]) / 3.f;
+      v0 = v0 >= 0.f ? v0 : v0 * SLOPE;
+      v1 = v1 >= 0.f ? v1 : v1 * SLOPE;
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+      w[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    y[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // Last stage fused: x = ((r0 + r1) + r2) / 3 -> leaky_relu(x) with the DEFAULT slope 0.01 (models.py:163, sic) ->
 // conv_post (32 -> 1, k = 7, pad 3; models.py:146,164) -> tanh (:165) -> scattered into wav[b, pos] (padded output).
 // One block = 256 consecutive audio rows = one mel frame row; thread = one sample.
 constexpr int POST_C = 32, POST_K = 7;
+template <bool BF>
 __global__ void __launch_bounds__(256)
 post_kernel(const float* __restrict__ r0, const float* __restrict__ r1, const float* __restrict__ r2, int64_t rows_audio,
             const float* __restrict__ w /*[1][32][7]*/, const float* __restrict__ bias, RowMeta meta,
@@ -109,7 +145,17 @@ post_kernel(const float* __restrict__ r0, const float* __restrict__ r1, const fl
     float4 v = make_float4(0, 0, 0, 0);
     if (r >= 0 && r < rows_audio) {
       const size_t o = (size_t)r * POST_C + c4 * 4;
-      const float4 a = ld4(r0 + o), b = ld4(r1 + o), c = ld4(r2 + o);
+      float4 a, b, c;
+      if (BF) {   // the three buffers hold bf16: four values = 8 bytes
+        auto ldb = [&](const float* base) {
+          const uint2 q = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + o);
+          return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xFFFF0000u), __uint_as_float(q.y << 16),
+                             __uint_as_float(q.y & 0xFFFF0000u));
+        };
+        a = ldb(r0); b = ldb(r1); c = ldb(r2);
+      } else {
+        a = ld4(r0 + o); b = ld4(r1 + o); c = ld4(r2 + o);
+      }
       v = make_float4(((a.x + b.x) + c.x) / 3.f, ((a.y + b.y) + c.y) / 3.f, ((a.z + b.z) + c.z) / 3.f, ((a.w + b.w) + c.w) / 3.f);
       v.x = v.x >= 0.f ? v.x : v.x * 0.01f; v.y = v.y >= 0.f ? v.y : v.y * 0.01f;
       v.z = v.z >= 0.f ? v.z : v.z * 0.01f; v.w = v.w >= 0.f ? v.w : v.w * 0.01f;

@@ -35,8 +35,9 @@ def fold_weight_norm(state_dict):
 class HiFiGANGeneratorB200(nn.Module):
     """Drop-in for `hifigan.Generator(h)` in eval mode (V1 architecture of hifigan/config.json) on one B200."""
 
-    def __init__(self, h=None, init_seed=0):
+    def __init__(self, h=None, init_seed=0, math_mode="tf32"):
         super().__init__()
+        self.math_mode = {"tf32": _lib.MATH_TF32, "bf16": _lib.MATH_BF16}[math_mode]
         if h is not None:
             want = dict(upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4], upsample_initial_channel=512,
                         resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5]] * 3, resblock="1")
@@ -91,7 +92,8 @@ class HiFiGANGeneratorB200(nn.Module):
             self._ctx = None
         if self._ctx is None:
             ctx = C.c_void_p()
-            code = lib.fs2_voc_create(dev.index if dev.index is not None else torch.cuda.current_device(), C.byref(ctx))
+            code = lib.fs2_voc_create(dev.index if dev.index is not None else torch.cuda.current_device(), self.math_mode,
+                                      C.byref(ctx))
             if code != 0:
                 raise RuntimeError(f"libfs2b200 error {code}: {lib.fs2_voc_last_error(None).decode()}")
             self._ctx, self._ctx_device, self._dirty = ctx, dev, True
@@ -143,12 +145,12 @@ class HiFiGANGeneratorB200(nn.Module):
         return wav
 
 
-def get_vocoder(config, device, ckpt_path=None, random_init=False):
+def get_vocoder(config, device, ckpt_path=None, random_init=False, math_mode="tf32"):
     """utils/model.py:37-71 (HiFi-GAN branch): build the generator, load `generator_<speaker>.pth.tar`["generator"]."""
     name = config["vocoder"]["model"]
     if name != "HiFi-GAN":
         raise ValueError("only the HiFi-GAN vocoder is implemented on the B200 engine")
-    voc = HiFiGANGeneratorB200()
+    voc = HiFiGANGeneratorB200(math_mode=math_mode)
     if not random_init:
         speaker = config["vocoder"]["speaker"]
         path = ckpt_path or os.path.join("hifigan", f"generator_{speaker}.pth.tar")

@@ -232,7 +232,9 @@ int fs2_op_frame_map(fs2_stream stream, const int32_t* cum, int batch, int max_s
  * hifigan/models.py:112-174 `Generator`; architecture hifigan/config.json, V1).
  * Same conventions as above; one context per device, not thread-safe. */
 typedef struct fs2_voc fs2_voc;
-int fs2_voc_create(int device, fs2_voc** out);
+/* math_mode: FS2_MATH_TF32 (fp32 activations, TF32 operands) or FS2_MATH_BF16 (bf16 weights and activations -- half the
+ * HBM traffic of the audio-rate stages; fp32 accumulation, biases and output waveform). */
+int fs2_voc_create(int device, int math_mode, fs2_voc** out);
 void fs2_voc_destroy(fs2_voc* voc);
 const char* fs2_voc_last_error(const fs2_voc* voc);
 /* `key` is a key of Generator.state_dict() after remove_weight_norm() (utils/model.py:66): conv_pre.*, ups.{0..3}.*,

@@ -151,3 +151,29 @@ def test_conv_gemm_ex(case, resident):
     assert torch.isfinite(got).all()
     err = (got - want).abs().max().item()
     assert err < 3e-4, f"max abs err {err}"
+
+
+# ------------------------------------------------------------------ bf16 mode of the vocoder
+def test_bf16_vocoder_against_reference_fixture_and_oracle(vsd):
+    """FS2_MATH_BF16 vocoder: bf16 weights and activations (fp32 accumulation, biases, output).  Stated tolerance on the
+    waveform in [-1, 1], ~50 convolutions deep with the ResBlock residual chains held in bf16: max-abs <= 3e-2,
+    mean-abs <= 4e-3 (measured on B200: 1.1e-2 / 1.9e-3)."""
+    import fs2_b200
+    voc16 = fs2_b200.HiFiGANGeneratorB200(math_mode="bf16")
+    voc16.load_state_dict(vsd)
+    voc16 = voc16.to(DEV)
+    z = np.load(os.path.join(GOLDEN_DIR, "vocoder.npz"))
+    got = voc16(torch.from_numpy(z["mel"]).float().to(DEV)).cpu().numpy()
+    d = np.abs(got.astype(np.float64) - z["wav"])
+    print(f"bf16 vocoder reference fixture: max {d.max():.3e} mean {d.mean():.3e}")
+    assert np.isfinite(got).all() and d.max() <= 3e-2 and d.mean() <= 4e-3
+    lens = [40, 17, 33]
+    mel_bt = torch.randn(3, 40, 80, generator=torch.Generator().manual_seed(9)) * 1.5 - 2.0
+    got = voc16(mel_bt.to(DEV).transpose(1, 2), mel_lens=torch.tensor(lens)).cpu().numpy()
+    sd64 = {k: v.double() for k, v in vsd.items()}
+    for b, n in enumerate(lens):
+        want = H.generator(sd64, mel_bt[b: b + 1, :n].transpose(1, 2).double()).numpy()[0, 0]
+        d = np.abs(got[b, 0, : n * 256] - want)
+        print(f"bf16 vocoder utt {b}: max {d.max():.3e} mean {d.mean():.3e}")
+        assert d.max() <= 3e-2 and d.mean() <= 4e-3
+        assert (got[b, 0, n * 256:] == 0).all()

@@ -10,10 +10,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--frames", type=int, default=0, help="fixed frames per utterance (0 = the config-2 mel_lens)")
+ap.add_argument("--math", default="tf32", choices=["tf32", "bf16"])
 args = ap.parse_args()
 dev = "cuda:0"
 syn = fs2_b200.synthetic
-voc = fs2_b200.HiFiGANGeneratorB200()
+voc = fs2_b200.HiFiGANGeneratorB200(math_mode=args.math)
 voc.load_state_dict(syn.synthetic_vocoder_state_dict(0))
 voc = voc.to(dev)
 if args.frames:
@@ -45,7 +46,7 @@ for _ in range(args.steps):
     ts.append(e0.elapsed_time(e1))
 ms = float(np.median(ts))
 frames = int(lens.sum())
-print(json.dumps({"workload": f"HiFi-GAN V1 generator, batch {args.batch}, {frames} mel frames ({frames * 256 / 22050:.1f} s of audio)",
+print(json.dumps({"math": args.math, "workload": f"HiFi-GAN V1 generator, batch {args.batch}, {frames} mel frames ({frames * 256 / 22050:.1f} s of audio)",
                   "ms_per_step": ms, "mel_frames_per_s": frames / ms * 1e3, "samples_per_s": frames * 256 / ms * 1e3,
                   "x_realtime": frames * 256 / 22050 / (ms * 1e-3), "launches": voc.last_launch_count,
                   "algorithmic_tflop": frames * 0.6e9 / 1e12, "finite": bool(torch.isfinite(wav).all())}))
