@@ -240,3 +240,21 @@ def test_fused_ffn_forward_against_reference_fixture(name, sd32):
         L.fs2_debug_set_flag(4, 2)
     assert np.array_equal(got[9].cpu().numpy(), want["mel_lens"])
     check_frame_side(name + "[fused ffn]", got, want, want["mel_lens"].tolist(), stride)
+
+
+def test_degenerate_batches(sd32, syn):
+    """Single phonemes, a zero-length utterance inside a batch, and a batch whose durations are all zero (empty mel)."""
+    model = model_for(sd32)
+    for lens in ([1], [1, 1, 1], [2, 120, 1], [5, 0, 7]):
+        b = syn.make_batch([max(n, 1) for n in lens], seed=3)
+        b["src_lens"] = torch.tensor(lens)
+        out = run(model, b)
+        assert torch.isfinite(out[0]).all() and torch.isfinite(out[1]).all()
+        if 0 in lens:
+            assert out[9].tolist()[lens.index(0)] == 0       # a zero-length utterance expands to zero frames
+        assert tuple(out[0].shape) == (len(lens), int(out[9].max()), 80)
+    b = syn.make_batch([6, 9], seed=4)
+    out = run(model, b, d_control=0.01)          # round(exp(logd) - 1) * 0.01 truncates to 0 frames everywhere
+    assert out[9].tolist() == [0, 0] and tuple(out[0].shape) == (2, 0, 80) and tuple(out[7].shape) == (2, 0)
+    out = run(model, b)                          # the context is still usable afterwards
+    assert int(out[9].sum()) > 0 and torch.isfinite(out[1]).all()
