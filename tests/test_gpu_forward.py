@@ -258,3 +258,23 @@ def test_degenerate_batches(sd32, syn):
     assert out[9].tolist() == [0, 0] and tuple(out[0].shape) == (2, 0, 80) and tuple(out[7].shape) == (2, 0)
     out = run(model, b)                          # the context is still usable afterwards
     assert int(out[9].sum()) > 0 and torch.isfinite(out[1]).all()
+
+
+@pytest.mark.parametrize("math_mode", ["tf32", "bf16"])
+def test_workspace_reuse_is_stateless(math_mode, sd32, syn):
+    """The library's workspace only grows: a small batch after a large one must not see the large one's rows.
+    Bit-equal to the same small batch on a context that has never run anything else."""
+    import fs2_b200, tempfile
+    used = model_for(sd32, math_mode=math_mode)
+    big = syn.make_batch(syn.random_lengths(24, seed=8), seed=81)
+    small = syn.make_batch([17, 5, 11], seed=82)
+    run(used, big)
+    a = run(used, small)
+    d = syn.write_fixture_jsons(tempfile.mkdtemp(prefix="fs2_json_"))
+    fresh = fs2_b200.FastSpeech2B200(fs2_b200.config.default_preprocess_config(d), fs2_b200.config.default_model_config(),
+                                     math_mode=math_mode)
+    fresh.load_state_dict(sd32)
+    fresh = fresh.to(DEV)
+    b = run(fresh, small)
+    for x, y in zip(a, b):
+        assert torch.equal(x.cpu(), y.cpu())
