@@ -7,7 +7,7 @@
 // and after the fourth chunk the post-LN epilogue of gemm_tc2.cuh runs on `out` (bias, residual by TMA, two-pass
 // statistics, affine, row mask, TMA store).  TMEM: acc1 = columns [0,256), out = [256,512).
 // Versus the two-kernel form this removes the 110 MB hidden tensor (written once, read once) and the second kernel's
-// operand-delivery-bound main loop (DESIGN.md 3.4): the second contraction's A operand is already on chip.
+// operand-delivery-bound main loop (DESIGN.md 3.5): the second contraction's A operand is already on chip.
 // The tensor pipe executes MMAs in issue order, so conv(c+1) overwriting acc1 needs no barrier against GEMM2(c)'s reads;
 // the two hand-offs with the epilogue warps (hidden ready / out drained) are mbarriers.
 #pragma once
