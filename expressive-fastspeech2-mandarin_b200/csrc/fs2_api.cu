@@ -1056,6 +1056,7 @@ int fs2_op_conv_gemm_ex(fs2_stream stream, const float* A, int lda, int rows, co
     a.A = A; a.lda = lda; a.rows = rows; a.W = Wt; a.bias = bias; a.taps = taps; a.dil = dil; a.pad = dil * (taps - 1) / 2;
     a.K = K; a.N = N; a.act = act; a.slope = slope; a.residual = residual; a.ldr = ldr; a.res_inv_lrelu = res_inv_lrelu;
     a.act2 = act2; a.row_vpos = row_vpos; a.row_room = row_room; a.extra = extra; a.mask_shift = mask_shift; a.C = C; a.ldc = ldc;
+    if (g_trace_on) { a.trace = g_trace_buf + 8 * ((g_trace_on - 1) % 8); ++g_trace_on; }
     conv_gemm(FS2_ENGINE_TCGEN05, FS2_MATH_TF32, a, static_cast<cudaStream_t>(stream));
   });
 }

@@ -13,6 +13,9 @@ ap.add_argument("--frames", type=int, default=0, help="fixed frames per utteranc
 ap.add_argument("--math", default="tf32", choices=["tf32", "bf16"])
 args = ap.parse_args()
 dev = "cuda:0"
+if os.environ.get("FS2_CL"):   # experiment: GEMM cluster size (2 = weight multicast across CTA pairs, 1 = independent CTAs)
+    from fs2_b200 import _lib
+    _lib.load_library().fs2_debug_set_flag(2, int(os.environ["FS2_CL"]))
 syn = fs2_b200.synthetic
 voc = fs2_b200.HiFiGANGeneratorB200(math_mode=args.math)
 voc.load_state_dict(syn.synthetic_vocoder_state_dict(0))
