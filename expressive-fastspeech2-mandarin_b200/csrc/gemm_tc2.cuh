@@ -270,19 +270,23 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         __syncwarp();
       }
-      if (AR) {   // weights: several (tap, K chunk) units per 16 KB stage
+      if (AR) {   // weights: several (tap, K chunk) units per 16 KB stage (coordinates advance without divisions)
+        int wrow = n0 + (CL > 1 ? rank * (BN / 2) : 0), kcol = 0, sidx = lt == 0 ? 0 : it % C::STAGES;
         for (int i0 = 0; i0 < iters; i0 += C::UNITS, ++it) {
-          const int s = it % C::STAGES;
+          const int s = sidx;
+          sidx = sidx + 1 == C::STAGES ? 0 : sidx + 1;
           mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
           const int n_units = min(C::UNITS, iters - i0);
-          if (leader) {
-            mbar_expect_tx(&full[s], (uint32_t)n_units * C::B_BYTES);
-            for (int j = 0; j < n_units; ++j) {
-              const int tap = (i0 + j) / kchunks, kc = (i0 + j) - tap * kchunks;
-              uint8_t* b_s = ring + s * C::STAGE_BYTES + j * C::B_BYTES;
-              if (CL == 1) tma_load_2d(b_s, &tmW, kc * BKE, tap * p.N + n0, &full[s]);
-              else tma_load_2d_mc(b_s + rank * (C::B_BYTES / 2), &tmW, kc * BKE, tap * p.N + n0 + rank * (BN / 2), &full[s], (uint16_t)0x3);
+          if (leader) mbar_expect_tx(&full[s], (uint32_t)n_units * C::B_BYTES);
+          uint8_t* b_s = ring + s * C::STAGE_BYTES + (CL > 1 ? rank * (C::B_BYTES / 2) : 0);
+          for (int j = 0; j < n_units; ++j) {
+            if (leader) {
+              if (CL == 1) tma_load_2d(b_s, &tmW, kcol, wrow, &full[s]);
+              else tma_load_2d_mc(b_s, &tmW, kcol, wrow, &full[s], (uint16_t)0x3);
             }
+            b_s += C::B_BYTES;
+            kcol += BKE;
+            if (kcol >= kchunks * BKE) { kcol = 0; wrow += p.N; }
           }
           __syncwarp();
         }
@@ -324,23 +328,39 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t d_tmem = tmem_base + u * C::ACC_COLS;
       if (AR) {
         mbar_wait(&a_full[u], (lt >> 1) & 1);
-        const uint32_t a_base = smem_u32(smem + u * C::AR_BUF_BYTES);
+        // The MMAs of these shapes are 16-32 cycles of tensor work each, so the ISSUE loop is the critical path (measured:
+        // +0.14 us per tap with one integer division and two descriptor builds per unit).  Descriptors advance by additions
+        // only: +8 per activation row (128 B >> 4), a constant per K chunk and per weight unit.
+        const uint64_t da_tile = umma_desc_rowshift(smem_u32(smem + u * C::AR_BUF_BYTES));
+        const uint64_t da_tap = (uint64_t)(dil * 8);
+        int tap = 0, kc = 0;
+        uint32_t started = 0;
         for (int i0 = 0; i0 < iters; i0 += C::UNITS, ++it) {
           const int s = it % C::STAGES;
           mbar_wait(&full[s], (it / C::STAGES) & 1);
           tc_fence_after();
           const int n_units = min(C::UNITS, iters - i0);
-          if (leader) {
-            for (int j = 0; j < n_units; ++j) {   // tap t of K chunk kc = the resident tile, t*dil rows further down
-              const int tap = (i0 + j) / kchunks, kc = (i0 + j) - tap * kchunks;
-              const uint64_t da = umma_desc_rowshift(a_base + kc * C::AR_CHUNK_BYTES + (uint32_t)(tap * dil) * 128u);
-              const uint64_t db = umma_desc(ring + s * C::STAGE_BYTES + j * C::B_BYTES);
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                if (BF) umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i0 | j | kk) != 0 ? 1u : 0u);
-                else umma_tf32(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i0 | j | kk) != 0 ? 1u : 0u);
+          uint64_t db = umma_desc(ring + s * C::STAGE_BYTES);
+          for (int j = 0; j < n_units; ++j) {   // tap t of K chunk kc = the resident tile, t*dil rows further down
+            const uint64_t da = da_tile + (uint64_t)tap * da_tap + (uint64_t)(kc * (C::AR_CHUNK_BYTES >> 4));
+            if (leader) {
+              if (BF) {
+                umma_bf16(d_tmem, da, db, idesc, started);
+                umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+                umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
+                umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+              } else {
+                umma_tf32(d_tmem, da, db, idesc, started);
+                umma_tf32(d_tmem, da + 2, db + 2, idesc, 1u);
+                umma_tf32(d_tmem, da + 4, db + 4, idesc, 1u);
+                umma_tf32(d_tmem, da + 6, db + 6, idesc, 1u);
               }
             }
+            started = 1u;
+            db += (uint64_t)(C::B_BYTES >> 4);
+            if (++kc == kchunks) { kc = 0; ++tap; }
+          }
+          if (leader) {
             if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], (uint16_t)0x3);
           }
           __syncwarp();
