@@ -258,6 +258,23 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ---------------- TMA producer (whole warp runs the loop, one elected lane issues)
     const bool leader = elect_one();
     int it = 0, lt = 0;
+    // AR with a weight tensor that fits the ring region (all 11 taps of a 32-channel conv are 44 KB): loaded ONCE per CTA
+    const bool wres = AR && iters * C::B_BYTES <= C::STAGES * C::STAGE_BYTES;
+    if (wres && w_first < total_items) {
+      int wrow = item_n0(w_first) + (CL > 1 ? rank * (BN / 2) : 0), kcol = 0;
+      uint8_t* b_s = ring + (CL > 1 ? rank * (C::B_BYTES / 2) : 0);
+      if (leader) mbar_expect_tx(&full[0], (uint32_t)iters * C::B_BYTES);
+      for (int i = 0; i < iters; ++i) {
+        if (leader) {
+          if (CL == 1) tma_load_2d(b_s, &tmW, kcol, wrow, &full[0]);
+          else tma_load_2d_mc(b_s, &tmW, kcol, wrow, &full[0], (uint16_t)0x3);
+        }
+        b_s += C::B_BYTES;
+        kcol += BKE;
+        if (kcol >= kchunks * BKE) { kcol = 0; wrow += p.N; }
+      }
+      __syncwarp();
+    }
     for (int w = w_first; w < total_items; w += w_step, ++lt) {
       const int m0 = item_m0(w), n0 = item_n0(w);
       if (AR) {   // the whole activation tile with its halo, once
@@ -270,6 +287,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         __syncwarp();
       }
+      if (AR && wres) continue;
       if (AR) {   // weights: several (tap, K chunk) units per 16 KB stage (coordinates advance without divisions)
         int wrow = n0 + (CL > 1 ? rank * (BN / 2) : 0), kcol = 0, sidx = lt == 0 ? 0 : it % C::STAGES;
         for (int i0 = 0; i0 < iters; i0 += C::UNITS, ++it) {
@@ -326,6 +344,41 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (lt < 6) stamp(8 + lt * 4 + 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + u * C::ACC_COLS;
+      if (AR && iters * C::B_BYTES <= C::STAGES * C::STAGE_BYTES) {   // resident weights (see the producer): no stages at all
+        if (lt == 0) mbar_wait(&full[0], 0);
+        mbar_wait(&a_full[u], (lt >> 1) & 1);
+        tc_fence_after();
+        const uint64_t da_tile = umma_desc_rowshift(smem_u32(smem + u * C::AR_BUF_BYTES));
+        const uint64_t da_tap = (uint64_t)(dil * 8);
+        uint64_t db = umma_desc(ring);
+        int tap = 0, kc = 0;
+        uint32_t started = 0;
+        for (int i = 0; i < iters; ++i) {
+          const uint64_t da = da_tile + (uint64_t)tap * da_tap + (uint64_t)(kc * (C::AR_CHUNK_BYTES >> 4));
+          if (leader) {
+            if (BF) {
+              umma_bf16(d_tmem, da, db, idesc, started);
+              umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+              umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
+              umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, da, db, idesc, started);
+              umma_tf32(d_tmem, da + 2, db + 2, idesc, 1u);
+              umma_tf32(d_tmem, da + 4, db + 4, idesc, 1u);
+              umma_tf32(d_tmem, da + 6, db + 6, idesc, 1u);
+            }
+          }
+          started = 1u;
+          db += (uint64_t)(C::B_BYTES >> 4);
+          if (++kc == kchunks) { kc = 0; ++tap; }
+        }
+        if (leader) {
+          umma_commit(&acc_full[u]);
+          umma_commit(&a_empty[u]);
+        }
+        __syncwarp();
+        continue;
+      }
       if (AR) {
         mbar_wait(&a_full[u], (lt >> 1) & 1);
         // The MMAs of these shapes are 16-32 cycles of tensor work each, so the ISSUE loop is the critical path (measured:
