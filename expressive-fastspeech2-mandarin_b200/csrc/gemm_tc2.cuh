@@ -199,6 +199,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   const int warp = warp_index(), lane = threadIdx.x & 31;
   const int kchunks = (p.K + BKE - 1) / BKE;
+  const bool half_chunk = BF && p.K <= 32;   // A-resident bf16 convs with 32 channels: only two of the four K slices hold data
   const int iters = p.taps * kchunks;
   const int n_tiles_n = (p.N + BN - 1) / BN;
   const bool has_res = p.residual != nullptr;
@@ -359,8 +360,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (BF) {
               umma_bf16(d_tmem, da, db, idesc, started);
               umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
-              umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
-              umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+              if (!half_chunk) {   // 32 bf16 channels fill half of the 64-element chunk: the rest is TMA zero fill
+                umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
+                umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+              }
             } else {
               umma_tf32(d_tmem, da, db, idesc, started);
               umma_tf32(d_tmem, da + 2, db + 2, idesc, 1u);
@@ -400,8 +403,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               if (BF) {
                 umma_bf16(d_tmem, da, db, idesc, started);
                 umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
-                umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
-                umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+                if (!half_chunk) {
+                  umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
+                  umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+                }
               } else {
                 umma_tf32(d_tmem, da, db, idesc, started);
                 umma_tf32(d_tmem, da + 2, db + 2, idesc, 1u);
