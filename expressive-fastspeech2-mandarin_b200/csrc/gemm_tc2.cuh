@@ -52,8 +52,12 @@ struct Cfg {
   static constexpr int STAGE_BYTES = AR ? AR_STAGE_BYTES : A_BYTES + B_BYTES;
   static constexpr int UNITS = AR ? AR_STAGE_BYTES / B_BYTES : 1;          // (tap, K chunk) weight tiles per ring stage
   static constexpr int AR_CHUNK_BYTES = AR_ROWS * 128;
-  static constexpr int AR_BUF_BYTES = AR * AR_CHUNK_BYTES;                  // one tile's activations; two buffers
-  static constexpr int OFF_RING = 2 * AR_BUF_BYTES;
+  static constexpr int AR_BUF_BYTES = AR * AR_CHUNK_BYTES;                  // one tile's activations
+  // Activation tiles in flight.  Once the issue loop is lean, the k = 3 convs alternate 0.77 / 1.28 us per tile: with two
+  // buffers the tile two ahead is only requested when the current one retires, i.e. one HBM latency (~2 us) per two tiles.
+  // Three 24 KB buffers (requested two tiles ahead) fit; three 48 KB buffers do not.
+  static constexpr int AR_BUFS = AR == 1 ? 3 : 2;
+  static constexpr int OFF_RING = AR_BUFS * AR_BUF_BYTES;
   static constexpr int OFF_CST = OFF_RING + STAGES * STAGE_BYTES;      // 4 warps x 2 output staging sub-tiles
   static constexpr int OFF_RES = OFF_CST + 8 * WCHUNK;      // 4 warps x 2 residual sub-tiles
   static constexpr int OFF_PAR = OFF_RES + 8 * WCHUNK;      // bias[2048] | gamma[256] | beta[256] | head_w[256]
@@ -190,9 +194,9 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* acc_full = empty + C::STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
   uint64_t* res_full = acc_empty + 2;       // [4 warps][2]
-  uint64_t* a_full = res_full + 8;          // [2]  AR: the resident activation tile of buffer u has landed
-  uint64_t* a_empty = a_full + 2;           // [2]  AR: every MMA that reads buffer u has completed
-  uint64_t* stat_full = a_empty + 2;        // [2]  NS: the peers' LayerNorm statistics of this tile parity have arrived
+  uint64_t* a_full = res_full + 8;          // [3]  AR: the resident activation tile of buffer lt % AR_BUFS has landed
+  uint64_t* a_empty = a_full + 3;           // [3]  AR: every MMA that reads that buffer has completed
+  uint64_t* stat_full = a_empty + 3;        // [2]  NS: the peers' LayerNorm statistics of this tile parity have arrived
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_full + 2);
   float2* stat_s = reinterpret_cast<float2*>(smem + C::OFF_STAT);        // NS: [2 parities][4 source ranks][128 rows]
   uint8_t* ring = smem + C::OFF_RING;
@@ -222,11 +226,11 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&acc_empty[u], 128);
     }
     for (int u = 0; u < 8; ++u) mbar_init(&res_full[u], 1);
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < 3; ++u) {
       mbar_init(&a_full[u], 1);
       mbar_init(&a_empty[u], 1);
-      mbar_init(&stat_full[u], 128 * (NS > 1 ? NS - 1 : 1));
     }
+    for (int u = 0; u < 2; ++u) mbar_init(&stat_full[u], 128 * (NS > 1 ? NS - 1 : 1));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
@@ -276,18 +280,25 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       __syncwarp();
     }
+    // AR: the la-th activation tile of this CTA (with its halo), requested AR_BUFS - 1 tiles ahead of the one being issued
+    auto request_a = [&](int la) {
+      const int wa = w_first + la * w_step;
+      if (wa >= total_items) return;
+      const int ua = la % C::AR_BUFS;
+      mbar_wait(&a_empty[ua], ((la / C::AR_BUFS) & 1) ^ 1);
+      if (leader) {
+        mbar_expect_tx(&a_full[ua], (uint32_t)kchunks * C::AR_CHUNK_BYTES);
+        for (int kc = 0; kc < kchunks; ++kc)
+          tma_load_2d(smem + ua * C::AR_BUF_BYTES + kc * C::AR_CHUNK_BYTES, &tmA, kc * BKE, item_m0(wa) - p.pad, &a_full[ua]);
+      }
+      __syncwarp();
+    };
+    if (AR) {
+      for (int la = 0; la < C::AR_BUFS - 1; ++la) request_a(la);
+    }
     for (int w = w_first; w < total_items; w += w_step, ++lt) {
       const int m0 = item_m0(w), n0 = item_n0(w);
-      if (AR) {   // the whole activation tile with its halo, once
-        const int u = lt & 1;
-        mbar_wait(&a_empty[u], ((lt >> 1) & 1) ^ 1);
-        if (leader) {
-          mbar_expect_tx(&a_full[u], (uint32_t)kchunks * C::AR_CHUNK_BYTES);
-          for (int kc = 0; kc < kchunks; ++kc)
-            tma_load_2d(smem + u * C::AR_BUF_BYTES + kc * C::AR_CHUNK_BYTES, &tmA, kc * BKE, m0 - p.pad, &a_full[u]);
-        }
-        __syncwarp();
-      }
+      if (AR) request_a(lt + C::AR_BUFS - 1);
       if (AR && wres) continue;
       if (AR) {   // weights: several (tap, K chunk) units per 16 KB stage (coordinates advance without divisions)
         int wrow = n0 + (CL > 1 ? rank * (BN / 2) : 0), kcol = 0, sidx = lt == 0 ? 0 : it % C::STAGES;
@@ -347,9 +358,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t d_tmem = tmem_base + u * C::ACC_COLS;
       if (AR && iters * C::B_BYTES <= C::STAGES * C::STAGE_BYTES) {   // resident weights (see the producer): no stages at all
         if (lt == 0) mbar_wait(&full[0], 0);
-        mbar_wait(&a_full[u], (lt >> 1) & 1);
+        const int ua = lt % C::AR_BUFS;
+        mbar_wait(&a_full[ua], (lt / C::AR_BUFS) & 1);
         tc_fence_after();
-        const uint64_t da_tile = umma_desc_rowshift(smem_u32(smem + u * C::AR_BUF_BYTES));
+        const uint64_t da_tile = umma_desc_rowshift(smem_u32(smem + ua * C::AR_BUF_BYTES));
         const uint64_t da_tap = (uint64_t)(dil * 8);
         uint64_t db = umma_desc(ring);
         int tap = 0, kc = 0;
@@ -377,17 +389,18 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         if (leader) {
           umma_commit(&acc_full[u]);
-          umma_commit(&a_empty[u]);
+          umma_commit(&a_empty[ua]);
         }
         __syncwarp();
         continue;
       }
       if (AR) {
-        mbar_wait(&a_full[u], (lt >> 1) & 1);
+        const int ua = lt % C::AR_BUFS;
+        mbar_wait(&a_full[ua], (lt / C::AR_BUFS) & 1);
         // The MMAs of these shapes are 16-32 cycles of tensor work each, so the ISSUE loop is the critical path (measured:
         // +0.14 us per tap with one integer division and two descriptor builds per unit).  Descriptors advance by additions
         // only: +8 per activation row (128 B >> 4), a constant per K chunk and per weight unit.
-        const uint64_t da_tile = umma_desc_rowshift(smem_u32(smem + u * C::AR_BUF_BYTES));
+        const uint64_t da_tile = umma_desc_rowshift(smem_u32(smem + ua * C::AR_BUF_BYTES));
         const uint64_t da_tap = (uint64_t)(dil * 8);
         int tap = 0, kc = 0;
         uint32_t started = 0;
@@ -425,7 +438,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         if (leader) {
           umma_commit(&acc_full[u]);
-          umma_commit(&a_empty[u]);   // the resident tile may be overwritten once these MMAs have read it
+          umma_commit(&a_empty[ua]);   // the resident tile may be overwritten once these MMAs have read it
         }
         __syncwarp();
         continue;
