@@ -299,16 +299,23 @@ class FastSpeech2B200(nn.Module):
         tensor; a third of its bytes at batch 64), or with padded=True the padded [B, T, 80] array itself."""
         dev = self._device()
         names = ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")
-        h2d = 0
-        dev_t = {}
-        for n in names:
-            a = np.ascontiguousarray(batch[n], dtype=np.int64)
-            key = (n, a.shape)
-            if key not in self._pinned:
-                self._pinned[key] = torch.empty(a.shape, dtype=torch.int64).pin_memory()
-            self._pinned[key].numpy()[...] = a
-            dev_t[n] = self._pinned[key].to(dev, non_blocking=True)
-            h2d += a.nbytes
+        # one pinned staging buffer and ONE host->device copy for the six int64 inputs; the device tensors are views of it
+        arrays = [np.ascontiguousarray(batch[n], dtype=np.int64) for n in names]
+        total = sum(a.size for a in arrays)
+        key = ("inputs", total)
+        if key not in self._pinned:
+            self._pinned[key] = torch.empty(total, dtype=torch.int64).pin_memory()
+        stage = self._pinned[key]
+        stage_np, off = stage.numpy(), 0
+        for a in arrays:
+            stage_np[off: off + a.size] = a.reshape(-1)
+            off += a.size
+        on_dev = stage.to(dev, non_blocking=True)
+        h2d = total * 8
+        dev_t, off = {}, 0
+        for n, a in zip(names, arrays):
+            dev_t[n] = on_dev[off: off + a.size].view(a.shape)
+            off += a.size
         out = self.forward(dev_t["speakers"], dev_t["emotions"], dev_t["arousals"], dev_t["valences"], dev_t["texts"],
                            dev_t["src_lens"], int(batch["max_src_len"]), p_control=p_control, e_control=e_control,
                            d_control=d_control)
