@@ -380,6 +380,8 @@ def main():
             "roofline": {"bound": "tensor", "kernel": dom + " (decoder FFN Conv1d k=9 implicit GEMM, 256->1024)",
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                          "frac": achieved / tensor_peak if tensor_peak else None,
+                         # the same against the BURST cuBLAS rate (a kernel timed alone): never above 1
+                         "frac_of_burst_peak": achieved / (peaks["bf16_burst"] * (0.5 if args.math == "tf32" else 1.0)),
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed
                          # `ncu --set full` captures profiles/r01_ncu_full_dec_layer_{tf32,bf16}_raw.csv
                          # (TF32: 37.06 MB + 56.37 MB; BF16: 18.52 MB + 6.74 MB -- the bf16 hidden tensor mostly stays in L2)
