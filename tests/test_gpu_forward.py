@@ -278,3 +278,37 @@ def test_workspace_reuse_is_stateless(math_mode, sd32, syn):
     b = run(fresh, small)
     for x, y in zip(a, b):
         assert torch.equal(x.cpu(), y.cpu())
+
+
+def test_postnet_tail_semantics_all_pad_widths(sd32, sd64, syn):
+    """the PostNet and mel_linear are NOT masked in the reference, so an utterance's last frames
+    depend on how many padding frames follow it (T_max - T_i, up to the 10-frame receptive field).  Thirteen utterances
+    with T_max - T_i = 0 .. 12, durations / pitch / energy forced, against the fp64 oracle."""
+    n = 13
+    batch = syn.make_batch([9] * n, seed=91)
+    g = torch.Generator().manual_seed(7)
+    d_t = torch.zeros(n, 9)
+    for i in range(n):
+        d_t[i] = torch.tensor([5, 4, 5, 4, 5, 4, 5, 4, 4]).float()       # 40 frames ...
+        k = i
+        for j in range(9):                                                 # ... minus i
+            take = min(k, int(d_t[i, j]) - 1)
+            d_t[i, j] -= take
+            k -= take
+    mel_lens = d_t.sum(1).long()
+    assert mel_lens.tolist() == [40 - i for i in range(n)]
+    p_t = torch.randn(n, 9, generator=g) * 1.5
+    e_t = torch.randn(n, 9, generator=g) * 1.5
+    kw = dict(d_targets=d_t, p_targets=p_t, e_targets=e_t, mel_lens=mel_lens, max_mel_len=40)
+    want = call(O.forward, batch, sd64, **{k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in kw.items()})
+    got = run(model_for(sd32), batch, **kw)
+    assert torch.equal(got[9].cpu(), mel_lens)
+    lens = mel_lens.tolist()
+    for i, name in ((0, "mel"), (1, "postnet")):
+        mx, mean = err_stats(valid_rows(got[i].cpu().numpy(), lens), valid_rows(want[i].numpy(), lens))
+        log_diag(f"pad widths 0..12 {name}: max {mx:.3e} mean {mean:.3e}")
+        assert mx <= TOL_MEL_MAX and mean <= TOL_MEL_MEAN
+        # the last two frames of every utterance are where a wrong tail rule would show
+        tail = np.stack([got[i][b, lens[b] - 2: lens[b]].cpu().numpy() for b in range(n)])
+        tail_w = np.stack([want[i][b, lens[b] - 2: lens[b]].numpy() for b in range(n)])
+        assert np.abs(tail - tail_w).max() <= TOL_MEL_MAX
