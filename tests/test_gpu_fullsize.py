@@ -84,3 +84,38 @@ def test_sharded_batch_matches_oracle_per_shard(sd32, syn):
         T = want["mel_lens"].tolist()
         mx, mean = err_stats(valid_rows(got[1].cpu().numpy(), T), valid_rows(want["postnet"].numpy(), T))
         assert mx <= 3e-3 and mean <= 4e-4
+
+
+def test_config5_control_sweep_batch32(sd32, syn):
+    """BASELINE config 5: pitch / energy / duration controls over 0.5 .. 2.0 on a batch of 32.
+    Size-independent properties on the GPU results of the full sweep, plus two corners against the fp32 oracle:
+      * e_control never changes anything; energy follows p_control (model/modules.py:123-125);
+      * log-durations are control independent; d_rounded = clamp(round(exp(logd) - 1) * d_control) exactly;
+      * pitch scales linearly with p_control while the bucket embedding changes (so energy and mel do change);
+      * mel_lens = sum trunc(d_rounded) for every d_control."""
+    model = model_for(sd32)
+    batch = syn.make_batch(syn.random_lengths(32, seed=5), seed=55)
+    base = run(model, batch)
+    pad = base[6]
+    for d in (0.5, 0.75, 1.0, 1.5, 2.0):
+        out = run(model, batch, d_control=d, e_control=0.5 + d)
+        assert torch.equal(out[4], base[4]) and torch.equal(out[2], base[2]) and torch.equal(out[3], base[3])
+        want_d = torch.clamp(torch.round(torch.exp(out[4]) - 1) * d, min=0) * (~pad)
+        assert torch.equal(out[5], want_d)
+        assert torch.equal(out[9], torch.clamp(torch.trunc(out[5]), min=0).sum(1).long())
+        assert torch.isfinite(out[1]).all()
+    raw_pitch = base[2]
+    for p in (0.5, 0.75, 1.5, 2.0):
+        out = run(model, batch, p_control=p, e_control=2.5 - p)
+        ref = run(model, batch, p_control=p)
+        for x, y in zip(out, ref):
+            assert torch.equal(x, y), "e_control changed the output"
+        assert torch.allclose(out[2], raw_pitch * p, rtol=0, atol=1e-6)      # pitch = raw * p_control (pads stay 0)
+        assert torch.equal(out[4], base[4])                                   # durations are computed before the pitch add
+        assert not torch.equal(out[3], base[3])                               # energy sees the new pitch buckets and p_control
+    want = call(O.forward, batch, sd32, p_control=2.0, d_control=0.5)
+    got = run(model, batch, p_control=2.0, d_control=0.5)
+    n = batch["src_lens"].tolist()
+    for i in (2, 4):
+        mx, _ = err_stats(valid_rows(got[i].cpu().numpy(), n), valid_rows(want[i].numpy(), n))
+        assert mx <= 5e-3
