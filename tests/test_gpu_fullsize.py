@@ -119,3 +119,29 @@ def test_config5_control_sweep_batch32(sd32, syn):
     for i in (2, 4):
         mx, _ = err_stats(valid_rows(got[i].cpu().numpy(), n), valid_rows(want[i].numpy(), n))
         assert mx <= 5e-3
+
+
+def test_config3_batch512_properties(sd32, syn):
+    """BASELINE config 3 on one GPU: 512 utterances, ~200 k frames.  At this size the forward selects the fused FFN kernel
+    by itself (>= 4 waves of row tiles), so this is also its end-to-end check: integer bookkeeping, finiteness, and a slice
+    of the batch against the fp64 oracle with the batch's L_max / T_max forced."""
+    model = model_for(sd32)
+    batch = syn.config2_batch(seed=3, batch=512)
+    out = run(model, batch)
+    mel, post, pitch, energy, log_d, d_round, src_mask, mel_mask, src_lens, mel_lens = out
+    T = int(mel_lens.max())
+    assert int(mel_lens.sum()) > 150_000 and mel.shape == (512, T, 80)
+    assert all(torch.isfinite(t).all() for t in (mel, post, pitch, energy, log_d))
+    assert torch.equal(mel_lens, torch.clamp(torch.trunc(d_round), min=0).sum(1).long())
+    assert torch.equal(mel_mask, torch.arange(T, device=DEV)[None, :] >= mel_lens[:, None])
+    forced = dict(d_targets=d_round.cpu(), p_targets=pitch.cpu(), e_targets=energy.cpu())
+    a = run(model, batch, **forced)
+    idx = [3, 250, 511]
+    sub = {k: (v[idx] if torch.is_tensor(v) else v) for k, v in batch.items()}
+    want = dict(zip(OUT_NAMES, call(O.forward, sub, O.cast_state_dict(sd32, torch.float64), d_targets=d_round.cpu()[idx].double(),
+                                    p_targets=pitch.cpu()[idx].double(), e_targets=energy.cpu()[idx].double(),
+                                    mel_lens=mel_lens.cpu()[idx], max_mel_len=T)))
+    lens = mel_lens.cpu()[idx].tolist()
+    for i, n in ((0, "mel"), (1, "postnet")):
+        mx, mean = err_stats(valid_rows(a[i][idx].cpu().numpy(), lens), valid_rows(want[n].numpy(), lens))
+        assert mx <= 3e-3 and mean <= 4e-4, (n, mx, mean)
