@@ -958,6 +958,7 @@ int fs2_debug_set_flag(int which, int value) {
   if (which == 3) fs2::tc2::a_resident_flag() = value ? 1 : 0;
   if (which == 4) fs2::ffn::enabled_flag() = value;   // 0 off, 1 on, 2 automatic
   if (which == 5) fs2::tc2::n_split_flag() = value ? 1 : 0;
+  if (which == 6) fs2::tc2::two_sm_flag() = value ? 1 : 0;
   if (which == 1) {
     g_trace_on = value;
     if (value && g_trace_buf == nullptr) cudaMalloc(reinterpret_cast<void**>(&g_trace_buf), 64 * sizeof(long long));

@@ -19,6 +19,8 @@
 
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm_mma.cuh"
 #include "tc_ptx.cuh"
@@ -44,12 +46,14 @@ constexpr int AR_ROWS = 192;      // 128 + (taps - 1) * dil <= 192  (k = 11, dil
 constexpr int AR_STAGE_BYTES = 16384;
 
 // AR = 0: activations stream with the weights; AR = 1 / 2: resident activation tile of 1 / 2 K chunks (K <= 32 / 64)
-template <int BN, int AR = 0, int NS = 1>
+// TWO: the CTA pair issues ONE tcgen05.mma.cta_group::2 (M = 256) per K slice; each CTA then keeps only ITS half of the
+// weight tile (BN/2 rows) in shared memory, so a stage is 32 KB instead of 48 and four of them fit.
+template <int BN, int AR = 0, int NS = 1, bool TWO = false>
 struct Cfg {
   // narrow streaming tiles (single utterances) are TMA-latency bound: a fifth 24 KB stage is 25 % more bytes in flight
-  static constexpr int STAGES = AR == 2 ? 3 : (BN > 128 ? 3 : ((BN <= 64 && AR == 0) ? 5 : 4));
+  static constexpr int STAGES = TWO ? 4 : (AR == 2 ? 3 : (BN > 128 ? 3 : ((BN <= 64 && AR == 0) ? 5 : 4)));
   static constexpr int A_BYTES = AR ? 0 : BM * 128;
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * 128;
   static constexpr int STAGE_BYTES = AR ? AR_STAGE_BYTES : A_BYTES + B_BYTES;
   static constexpr int UNITS = AR ? AR_STAGE_BYTES / B_BYTES : 1;          // (tap, K chunk) weight tiles per ring stage
   static constexpr int AR_CHUNK_BYTES = AR_ROWS * 128;
@@ -127,6 +131,39 @@ __device__ __forceinline__ uint64_t umma_desc_rowshift(uint32_t saddr) {
   return d;
 }
 
+// ---- cta_group::2 forms (a CTA pair acting as one 256-row MMA unit; syntax as in CUTLASS cute/arch/*_sm100*.hpp)
+// TMA load executed by BOTH CTAs of the pair into their own shared memory; the transaction bytes are counted on the
+// mbarrier of the pair's even-ranked CTA (the MMA issuer): clearing bit 24 of the shared::cluster address selects it.
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar) & 0xFEFFFFFFu)
+      : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on this barrier in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)0x3)
+               : "memory");
+}
+
 // ---- distributed shared memory helpers (N-split LayerNorm statistics)
 __device__ __forceinline__ uint32_t dsmem_addr(const void* local, int cta_rank) {   // same offset in a peer CTA's smem
   uint32_t r;
@@ -160,12 +197,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 // weight columns, and the LayerNorm statistics of the row are combined across the cluster through distributed shared
 // memory (two floats per row and CTA).  For a handful of row tiles (single utterances) this puts NS SMs on a K loop
 // that one CTA would walk alone: the fused-LN GEMMs were 40 % of the single-utterance latency.
-template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1>
+template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1, bool TWO = false>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                      const __grid_constant__ CUtensorMap tmC2, ConvGemmArgs p) {
-  using C = Cfg<BN, AR, NS>;
+  using C = Cfg<BN, AR, NS, TWO>;
+  static_assert(!TWO || (CL == 2 && !LN && AR == 0 && NS == 1 && BN == 256), "2-SM MMA: CTA pairs, plain epilogue, 256 columns");
   static_assert(!(AR && LN), "A-resident mode: plain epilogue");
   static_assert(!(AR == 2 && BF), "bf16 A-resident tiles hold 64 channels in one K chunk: AR = 1");
   static_assert(NS == 1 || (LN && CL == 1 && !AR && BN * NS == 256), "N-split: fused LayerNorm over 256 columns, cluster along N");
@@ -220,11 +258,12 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (has_res) asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CSIZE);   // a stage is refilled by every CTA of the cluster: all consumers must release it
+      mbar_init(&empty[s], TWO ? 1 : CSIZE);   // a stage is refilled by every CTA of the cluster: all consumers must release
+                                               // it (2-SM: the one issuer's commit covers both CTAs' operands)
     }
     for (int u = 0; u < 2; ++u) {
       mbar_init(&acc_full[u], 1);
-      mbar_init(&acc_empty[u], 128);
+      mbar_init(&acc_empty[u], TWO ? 256 : 128);   // 2-SM: the issuer waits for the epilogue threads of both CTAs
     }
     for (int u = 0; u < 8; ++u) mbar_init(&res_full[u], 1);
     for (int u = 0; u < 3; ++u) {
@@ -235,10 +274,17 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    if (TWO) {   // the same warp of both CTAs, the same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -328,6 +374,15 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
         const int tap = i / kchunks, kc = i - tap * kchunks;
         uint8_t* a_s = ring + s * C::STAGE_BYTES;
+        if (TWO) {   // own activation rows + own half of the weight tile; both CTAs' bytes are counted on the issuer's barrier
+          if (leader) {
+            if (rank == 0) mbar_expect_tx(&full[s], 2 * C::STAGE_BYTES);
+            tma_load_2d_2sm(a_s, &tmA, kc * BKE, m0 + tap * dil - p.pad, &full[s]);
+            tma_load_2d_2sm(a_s + C::A_BYTES, &tmW, kc * BKE, tap * p.N + n0 + rank * (BN / 2), &full[s]);
+          }
+          __syncwarp();
+          continue;
+        }
         if (leader) {
           mbar_expect_tx(&full[s], C::STAGE_BYTES);
           if (NS > 1) {   // this CTA's 128/NS rows of the shared activation tile, delivered to every CTA of the cluster
@@ -348,9 +403,32 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (warp == 1) {
     // ---------------- MMA issuer (whole warp runs the loop, one elected lane issues)
     const bool leader = elect_one();
-    constexpr uint32_t idesc = BF ? umma_idesc_bf16(BM, BN) : umma_idesc_tf32(BM, BN);
+    constexpr uint32_t idesc = BF ? umma_idesc_bf16(TWO ? 2 * BM : BM, BN) : umma_idesc_tf32(TWO ? 2 * BM : BM, BN);
     int it = 0, lt = 0;
-    for (int w = w_first; w < total_items; w += w_step, ++lt) {
+    for (int w = w_first; TWO && rank == 0 && w < total_items; w += w_step, ++lt) {
+      // 2-SM: the even CTA issues for the pair.  One MMA covers the pair's 256 rows (each CTA's 128 rows of A from its own
+      // shared memory, its half of the weight tile from its own shared memory, its 128 accumulator rows in its own TMEM).
+      const int u = lt & 1;
+      mbar_wait_cluster(&acc_empty[u], ((lt >> 1) & 1) ^ 1);   // the epilogue threads of BOTH CTAs drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + u * C::ACC_COLS;
+      for (int i = 0; i < iters; ++i, ++it) {
+        const int s = it % C::STAGES;
+        mbar_wait_cluster(&full[s], (it / C::STAGES) & 1);     // both CTAs' operands of this stage have landed
+        tc_fence_after();
+        const uint8_t* a_s = ring + s * C::STAGE_BYTES;
+        const uint64_t da = umma_desc(a_s), db = umma_desc(a_s + C::A_BYTES);
+        if (leader) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_2sm<BF>(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty[s]);
+        }
+        __syncwarp();
+      }
+      if (leader) umma_commit_2sm(&acc_full[u]);
+      __syncwarp();
+    }
+    for (int w = w_first; !TWO && w < total_items; w += w_step, ++lt) {
       const int u = lt & 1;
       if (lt < 6) stamp(8 + lt * 4 + 0);
       mbar_wait(&acc_empty[u], ((lt >> 1) & 1) ^ 1);   // epilogue drained this accumulator
@@ -634,7 +712,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
           if (c == C::NCHUNK - 1) {   // all TMEM reads of this tile are done: release the accumulator
             tc_fence_before();
-            mbar_arrive(&acc_empty[u]);
+            if (TWO && rank != 0) mbar_arrive_remote(dsmem_addr(&acc_empty[u], 0));   // the issuer lives in the even CTA
+            else mbar_arrive(&acc_empty[u]);
           }
           if (has_out) stage_out(v, c0, width);
           if (has_out2) stage_out_b(v, c0, width);
@@ -764,8 +843,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   if (CSIZE > 1) cluster_sync_all();   // the peers may still multicast commits into this CTA's barriers until they are done too
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
+    if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
     stamp(7);
   }
 }
@@ -783,14 +862,14 @@ inline int& cluster_size_flag() {   // 2 = weight tiles multicast across CTA pai
   return f;
 }
 
-template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1>
+template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1, bool TWO = false>
 inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
-  using C = Cfg<BN, AR, NS>;
+  using C = Cfg<BN, AR, NS, TWO>;
   static bool configured[64] = {};
   int dev = 0;
   FS2_CUDA_OK(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
     configured[dev & 63] = true;
   }
   constexpr CUtensorMapSwizzle SW128 = CU_TENSOR_MAP_SWIZZLE_128B;
@@ -807,7 +886,7 @@ inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
   constexpr int CSIZE = CL > 1 ? CL : NS;
   const int items = NS > 1 ? (a.rows + BM - 1) / BM : (((a.rows + BM - 1) / BM + CL - 1) / CL) * ((a.N + BN - 1) / BN);
   const int grid = std::min(items, sm_count() / CSIZE) * CSIZE;
-  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS>, dim3(grid), dim3(THREADS), C::TOTAL, stream, CSIZE, tmA, tmW, tmC, tmR, tmC2, a);
+  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS, TWO>, dim3(grid), dim3(THREADS), C::TOTAL, stream, CSIZE, tmA, tmW, tmC, tmR, tmC2, a);
   FS2_LAUNCHED();
 }
 
@@ -833,10 +912,28 @@ inline void launch_ar(const ConvGemmArgs& a, cudaStream_t stream) {
   }
 }
 
+// 1 (default) = cta_group::2 MMAs for the 256-column plain GEMMs with a long K loop (conv9, PostNet 512 -> 512, the
+// vocoder's 256-channel stage), 0 = off (FS2_TWO_SM / debug flag 6).  Measured at config 2: conv9 754 -> 834 TFLOP/s TF32,
+// PostNet 0.327 -> 0.288 ms, forward 8.82 -> 9.26 M frames/s; the K = 256 single-tap QKV GEMM is 4 % slower with it and
+// stays on the multicast form.
+inline int& two_sm_flag() {
+  static int f = [] {
+    const char* e = std::getenv("FS2_TWO_SM");
+    return e != nullptr ? std::atoi(e) : 1;
+  }();
+  return f;
+}
+
 template <int BN, bool LN>
 inline void launch_bn(const ConvGemmArgs& a, cudaStream_t stream) {
   // a single row tile has no partner to share weights with
   const bool pair = cluster_size_flag() == 2 && a.rows > BM;
+  if constexpr (BN == 256 && !LN) {
+    if (pair && two_sm_flag() && a.N % 256 == 0 && a.taps * a.K >= 512) {
+      if (a.a_bf16) launch_bn_cl<256, false, 2, true, 0, 1, true>(a, stream); else launch_bn_cl<256, false, 2, false, 0, 1, true>(a, stream);
+      return;
+    }
+  }
   if (a.a_bf16) {
     if (pair) launch_bn_cl<BN, LN, 2, true>(a, stream); else launch_bn_cl<BN, LN, 1, true>(a, stream);
   } else {
