@@ -203,7 +203,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                      const __grid_constant__ CUtensorMap tmC2, ConvGemmArgs p) {
   using C = Cfg<BN, AR, NS, TWO>;
-  static_assert(!TWO || (CL == 2 && !LN && AR == 0 && NS == 1 && BN == 256), "2-SM MMA: CTA pairs, plain epilogue, 256 columns");
+  static_assert(!TWO || (CL == 2 && AR == 0 && NS == 1 && BN == 256), "2-SM MMA: CTA pairs, 256 columns");
   static_assert(!(AR && LN), "A-resident mode: plain epilogue");
   static_assert(!(AR == 2 && BF), "bf16 A-resident tiles hold 64 channels in one K chunk: AR = 1");
   static_assert(NS == 1 || (LN && CL == 1 && !AR && BN * NS == 256), "N-split: fused LayerNorm over 256 columns, cluster along N");
@@ -824,7 +824,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             tmem_ld32_issue(acc + (c + 2) * 32, va);
           } else {                      // the last TMEM read of this tile has landed: release the accumulator
             tc_fence_before();
-            mbar_arrive(&acc_empty[u]);
+            if (TWO && rank != 0) mbar_arrive_remote(dsmem_addr(&acc_empty[u], 0));
+            else mbar_arrive(&acc_empty[u]);
           }
           pass2(vb, c + 1);
         }
@@ -965,6 +966,9 @@ inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
       if (a.a_bf16) launch_bn_cl<64, true, 1, true, 0, 4>(a, stream); else launch_bn_cl<64, true, 1, false, 0, 4>(a, stream);
     } else if (ns == 2) {
       if (a.a_bf16) launch_bn_cl<128, true, 1, true, 0, 2>(a, stream); else launch_bn_cl<128, true, 1, false, 0, 2>(a, stream);
+    } else if (two_sm_flag() && cluster_size_flag() == 2 && a.rows > BM && a.taps * a.K >= 512) {
+      // long K loop (w2 + LayerNorm, K = 1024): operand-delivery bound; the 2-SM form halves the weight bytes each CTA takes in
+      if (a.a_bf16) launch_bn_cl<256, true, 2, true, 0, 1, true>(a, stream); else launch_bn_cl<256, true, 2, false, 0, 1, true>(a, stream);
     } else {
       launch_bn<256, true>(a, stream);
     }
