@@ -383,9 +383,10 @@ def main():
                          # the same against the BURST cuBLAS rate (a kernel timed alone): never above 1
                          "frac_of_burst_peak": achieved / (peaks["bf16_burst"] * (0.5 if args.math == "tf32" else 1.0)),
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed
-                         # `ncu --set full` captures profiles/r01_ncu_full_dec_layer_{tf32,bf16}_raw.csv
-                         # (TF32: 37.06 MB + 56.37 MB; BF16: 18.52 MB + 6.74 MB -- the bf16 hidden tensor mostly stays in L2)
-                         "traffic": ({"tf32": 93.43e6, "bf16": 25.26e6}[args.math]
+                         # `ncu --set full` captures profiles/r01_ncu_full_dec_layer_tf32_2sm_raw.csv (the 2-SM kernel: 37.10 MB
+                         # read + 55.87 MB written) and ..._dec_layer_bf16_raw.csv (18.52 MB + 6.74 MB -- the bf16 hidden tensor
+                         # mostly stays in L2)
+                         "traffic": ({"tf32": 92.97e6, "bf16": 25.26e6}[args.math]
                                      if (args.engine == "tcgen05" and args.batch == 64) else None),
                          "algorithmic_bytes_per_launch": 4 * (frames * 256 + 9 * 1024 * 256 + frames * 1024),
                          "per_launch_ms": per_launch_ms, "launches_per_step": n_dom // PROF_RUNS,
