@@ -348,3 +348,34 @@ def test_attention_growing_scores(lens):
     assert err < 0.5, f"max abs err {err}"
     rel = ((got[live] - want[live]).abs().sum() / want[live].abs().sum()).item()
     assert rel < 0.1, f"relative L1 error {rel}"
+
+
+@pytest.mark.parametrize("shape", [(25765, 256, 1024, 9, 1), (12900, 512, 512, 5, 2), (257, 256, 1024, 9, 1)],
+                         ids=["conv9_odd_tiles", "postnet_mid", "two_tiles_plus_one_row"])
+def test_conv_gemm_two_sm(shape):
+    """cta_group::2 MMAs (one 256-row MMA per CTA pair, each CTA holding half of the weight tile) against float64 and
+    against the single-CTA MMA form (debug flag 6 = 0): same products, same accumulation order per row -> bit-equal."""
+    rows, K, N, taps, act = shape
+    g = torch.Generator().manual_seed(rows + K)
+    A = round_tf32(torch.randn(rows, K, generator=g))
+    W = round_tf32(torch.randn(taps, N, K, generator=g) / np.sqrt(K * taps))
+    bias = torch.randn(N, generator=g)
+    dA, dW, db = A.to(DEV), W.to(DEV), bias.to(DEV)
+    outs = []
+    L = lib()
+    try:
+        for flag in (1, 0):
+            L.fs2_debug_set_flag(6, flag)
+            out = torch.full((rows, N), float("nan"), device=DEV)
+            code = L.fs2_op_conv_gemm(stream(), 1, 0, ptr(dA), K, rows, ptr(dW), ptr(db), taps, (taps - 1) // 2, K, N, act,
+                                      None, N, None, None, 0, ptr(out), N)
+            assert code == 0, L.fs2_last_error(None)
+            torch.cuda.synchronize()
+            outs.append(out.cpu())
+    finally:
+        L.fs2_debug_set_flag(6, 1)
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]), "2-SM and 1-SM forms must agree bit for bit"
+    idx = torch.cat([torch.arange(0, min(rows, 300)), torch.arange(max(rows - 300, 0), rows)]).unique()
+    want = conv_ref(A, W, bias, (taps - 1) // 2, act, None, None, None, 0)[idx]
+    assert (outs[0][idx].double() - want).abs().max().item() < 2e-4
