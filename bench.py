@@ -2,7 +2,7 @@
 """bench.py -- mel frames/s of the FastSpeech2 inference forward on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--engine tcgen05|mma_sync] [--math tf32|bf16]
+                    [--math tf32|bf16|parity]
 
 A step is one forward pass over one synthetic batch of BASELINE config 2 (64 utterances of
 20-120 phonemes, mixed speakers / emotions / arousal-valence, controls 1.0) per GPU; with N > 1
@@ -187,8 +187,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("FS2_ENGINE", "tcgen05"), choices=["tcgen05", "tcgen05_v1", "mma_sync"])
-    ap.add_argument("--math", default=os.environ.get("FS2_MATH", "tf32"), choices=["tf32", "bf16"])
+    ap.add_argument("--math", default=os.environ.get("FS2_MATH", "tf32"), choices=["tf32", "bf16", "parity"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -217,7 +216,7 @@ def main():
     sd = syn.synthetic_state_dict(seed=0)
     jsons = syn.write_fixture_jsons(tempfile.mkdtemp(prefix="fs2_json_"))
     model = fs2_b200.FastSpeech2B200(fs2_b200.config.default_preprocess_config(jsons),
-                                     fs2_b200.config.default_model_config(), math_mode=args.math, engine=args.engine)
+                                     fs2_b200.config.default_model_config(), math_mode=args.math)
     model.load_state_dict(sd)
     model = model.to(dev)
 
@@ -272,9 +271,9 @@ def main():
 
     # the second arithmetic mode of the north star (bf16 operands), same workload, reported beside the headline
     other = None
-    if args.math == "tf32" and args.engine == "tcgen05":
+    if args.math == "tf32":
         m16 = fs2_b200.FastSpeech2B200(fs2_b200.config.default_preprocess_config(jsons),
-                                       fs2_b200.config.default_model_config(), math_mode="bf16", engine=args.engine)
+                                       fs2_b200.config.default_model_config(), math_mode="bf16")
         m16.load_state_dict(sd)
         m16 = m16.to(dev)
         for _ in range(args.warmup):
@@ -290,7 +289,7 @@ def main():
     # the step after the path: HiFi-GAN generator on the mel this batch produced, reported beside
     # the headline (device-resident mel, L2 flushed); never part of `value`
     voc_line = None
-    if args.engine == "tcgen05" and world == 1:
+    if world == 1:
         try:
             mel_t, lens_t = out[1].transpose(1, 2), out[9]
             voc_line = {"workload": "HiFi-GAN V1 generator (hifigan/config.json) on the postnet mel of the same batch, "
@@ -370,7 +369,7 @@ def main():
             "config": {"workload": f"config2: batch {args.batch} per GPU, 20-120 phonemes, mixed speakers/emotions/"
                                    "arousal-valence, controls 1.0, random-init weights (seed 0)",
                        "frames_per_step_per_gpu": frames, "phonemes_per_step_per_gpu": int(batch["src_lens"].sum()),
-                       "engine": args.engine, "l2": "256 MB buffer written between timed iterations (L2 flushed)",
+                       "l2": "256 MB buffer written between timed iterations (L2 flushed)",
                        "algorithmic_tflop_per_step": syn.algorithmic_flops(batch["src_lens"].tolist(), mel_lens) / 1e12},
             "e2e": {"value": frames_all * args.steps / (e2e_total_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": e2e_bytes.get("h2d", 0), "d2h_bytes_per_step": e2e_bytes.get("d2h", 0),
@@ -387,7 +386,7 @@ def main():
                          # read + 55.87 MB written) and ..._dec_layer_bf16_raw.csv (18.52 MB + 6.74 MB -- the bf16 hidden tensor
                          # mostly stays in L2)
                          "traffic": ({"tf32": 92.97e6, "bf16": 25.26e6}[args.math]
-                                     if (args.engine == "tcgen05" and args.batch == 64) else None),
+                                     if (args.math in ("tf32", "bf16") and args.batch == 64) else None),
                          "algorithmic_bytes_per_launch": 4 * (frames * 256 + 9 * 1024 * 256 + frames * 1024),
                          "per_launch_ms": per_launch_ms, "launches_per_step": n_dom // PROF_RUNS,
                          "flops_per_launch": flops_per_launch,

@@ -5,8 +5,7 @@ import os
 from .build import LIB_PATH
 
 FS2_OK = 0
-MATH_TF32, MATH_BF16 = 0, 1
-ENGINE_MMA_SYNC, ENGINE_TCGEN05, ENGINE_TCGEN05_V1 = 0, 1, 2
+MATH_TF32, MATH_BF16, MATH_TF32X3 = 0, 1, 2
 
 c_i64p = C.POINTER(C.c_int64)
 c_i32p = C.POINTER(C.c_int32)
@@ -17,7 +16,7 @@ c_u8p = C.POINTER(C.c_uint8)
 class Config(C.Structure):
     _fields_ = [("n_src_vocab", C.c_int32), ("n_speaker", C.c_int32), ("n_emotion", C.c_int32),
                 ("n_arousal", C.c_int32), ("n_valence", C.c_int32), ("max_seq_len", C.c_int32),
-                ("math_mode", C.c_int32), ("engine", C.c_int32),
+                ("math_mode", C.c_int32),
                 ("pitch_frame_level", C.c_int32), ("energy_frame_level", C.c_int32)]
 
 
@@ -59,10 +58,10 @@ SIGNATURES = {
     "fs2_debug_read_trace": (C.c_int, [c_i64p, C.c_int]),
     "fs2_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "fs2_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
-    "fs2_op_conv_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+    "fs2_op_conv_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
-    "fs2_op_conv_gemm_ln": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+    "fs2_op_conv_gemm_ln": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fs2_op_ffn_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -73,10 +72,8 @@ SIGNATURES = {
     "fs2_op_conv_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
-    "fs2_op_attention": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+    "fs2_op_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_void_p]),
-    "fs2_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fs2_op_durations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "fs2_op_bucketize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),

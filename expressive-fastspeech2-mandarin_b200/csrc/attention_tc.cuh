@@ -14,8 +14,10 @@
 
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
-#include "gemm_tcgen05.cuh"
+#include "tc_ptx.cuh"
 
 namespace fs2 {
 namespace attn_tc {
@@ -62,10 +64,13 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                    const __grid_constant__ CUtensorMap tmV, const int32_t* __restrict__ starts, const int32_t* __restrict__ lens, float* __restrict__ out,
+                    const __grid_constant__ CUtensorMap tmV, const int32_t* __restrict__ starts, const int32_t* __restrict__ lens,
+                    const uint32_t* __restrict__ work, const int32_t* __restrict__ work_count, float* __restrict__ out,
                     __nv_bfloat16* __restrict__ out_b, int dbg) {
   extern __shared__ uint8_t smem_raw[];
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  // work item = 128 queries of one (utterance, head), taken from the longest-first work list (rowops.cuh): CTAs are
+  // dispatched in blockIdx order, so the expensive items start first and the grid's tail is made of short utterances
+  const int item = blockIdx.x >> 1, h = blockIdx.x & 1;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_s = smem;
@@ -115,15 +120,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   // lens / starts / qkv are produced by earlier kernels of this forward
   pdl_trigger();
   pdl_wait();
-  const int len = lens[b];
-  const bool active = q0 < len;              // CTAs beyond the utterance only tear down
-  const int row0 = starts[b];
+  const bool active = item < *work_count;     // the grid is sized from a host-side bound: surplus CTAs only tear down
+  const uint32_t wi = active ? work[item] : 0u;
+  const int b = (int)(wi >> 16), q0 = (int)(wi & 0xFFFFu) * BQ;
+  const int len = active ? lens[b] : 0;
+  const int row0 = active ? starts[b] : 0;
   const int n_tiles = (len + BKV - 1) / BKV;
   const uint32_t tmem_s = tmem_base;          // + u*64
   const uint32_t tmem_o = tmem_base + 128;    // + u*128
   const uint32_t tmem_q = tmem_base + 384;    // 128 columns
 #ifdef FS2_TRACE_BUILD   // phase timestamps for tools/trace_attention.py (block 0 only, dbg == 4)
-  const bool trace = dbg == 4 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const bool trace = dbg == 4 && blockIdx.x == 0;
   const long long t_start = clock64();
   float* tr = out + (size_t)row0 * D_MODEL;
 #define FS2_TRACE(tile, k) do { if (trace && (threadIdx.x & 31) == 0) tr[(tile) * 16 + (k)] = (float)(clock64() - t_start); } while (0)
@@ -378,9 +385,15 @@ inline int& debug_flag() {
   return f;
 }
 
-inline void launch(const float* qkv, int rows, const int32_t* starts, const int32_t* lens, int batch, int max_len,
-                   float* out, cudaStream_t stream, void* out_bf16 = nullptr) {
-  if (batch <= 0 || max_len <= 0 || rows <= 0) return;
+// Upper bound of the work-list length known on the host: sum_b ceil(len_b / 128) <= total_rows / 128 + batch.
+inline int work_bound(int64_t total_len, int batch, int max_len) {
+  const int64_t a = total_len / BQ + batch, b = (int64_t)batch * ((max_len + BQ - 1) / BQ);
+  return (int)std::min(a, b);
+}
+
+inline void launch(const float* qkv, int rows, const int32_t* starts, const int32_t* lens, const uint32_t* work,
+                   const int32_t* work_count, int work_cap, float* out, cudaStream_t stream, void* out_bf16 = nullptr) {
+  if (work_cap <= 0 || rows <= 0) return;
   static bool configured[64] = {};
   int dev = 0;
   FS2_CUDA_OK(cudaGetDevice(&dev));
@@ -391,9 +404,8 @@ inline void launch(const float* qkv, int rows, const int32_t* starts, const int3
   const CUtensorMap tmQ = make_map(qkv, rows, LDQKV, LDQKV, BQ, true, false);
   const CUtensorMap tmKV = make_map(qkv, rows, LDQKV, LDQKV, BKV, true, true);
   const CUtensorMap tmV = make_map(qkv, rows, LDQKV, LDQKV, BKV, true, true, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  dim3 grid((max_len + BQ - 1) / BQ, N_HEAD, batch);
-  launch_pdl(attention_tc_kernel, grid, dim3(THREADS), SMEM_TOTAL, stream, 1, tmQ, tmKV, tmV, starts, lens, out,
-             static_cast<__nv_bfloat16*>(out_bf16), debug_flag());
+  launch_pdl(attention_tc_kernel, dim3(N_HEAD * work_cap), dim3(THREADS), SMEM_TOTAL, stream, 1, tmQ, tmKV, tmV, starts, lens,
+             work, work_count, out, static_cast<__nv_bfloat16*>(out_bf16), debug_flag());
   FS2_LAUNCHED();
 }
 

@@ -6,11 +6,8 @@
 #include <cmath>
 #include <cstring>
 
-#include "attention.cuh"
 #include "attention_tc.cuh"
 #include "common.cuh"
-#include "gemm_mma.cuh"
-#include "gemm_tcgen05.cuh"
 #include "gemm_tc2.cuh"
 #include "ffn_fused.cuh"
 #include "rowops.cuh"
@@ -42,6 +39,9 @@ struct RowSide {  // metadata of one packed row space (phoneme side or frame sid
   int32_t *starts = nullptr, *lens = nullptr;       // [B+1], [B]
   int32_t *utt = nullptr, *vpos = nullptr, *room = nullptr, *slot = nullptr;  // [rows_alloc]
   int64_t* totals = nullptr;                         // device [3]
+  uint32_t* work = nullptr;                          // attention work list (rowops.cuh: build_attention_work)
+  int32_t* work_count = nullptr;                     // device [1]
+  int work_alloc = 0, work_cap = 0;                  // allocated entries / the bound the current batch launches with
   int rows_alloc = 0, batch_alloc = 0;
   RowMeta meta() const { return RowMeta{utt, vpos, room}; }
 };
@@ -79,6 +79,8 @@ struct fs2_ctx {
   float *mel_w = nullptr, *mel_b = nullptr;
   float* pe_long = nullptr;  // generated sinusoid table for sequences beyond max_seq_len
   int pe_long_rows = 0;
+  float* split_buf = nullptr;  // FS2_MATH_TF32X3: [rows, hi | lo] copy of the activations of the contraction being launched
+  size_t split_cap = 0;
 
   RowSide ps, fs;
   Pool pp, fp;
@@ -93,8 +95,9 @@ struct fs2_ctx {
   // state carried from stage 1 to stage 2
   bool stage1_done = false;
   int batch = 0, max_src_len = 0, max_mel_len = 0, phon_rows = 0;
-  int64_t frame_rows = 0;
+  int64_t frame_rows = 0, total_frames = 0;
   const float* lr_input = nullptr;
+  float* va_spare = nullptr;
   const float *p_targets = nullptr, *e_targets = nullptr;  // frame_level teacher forcing: consumed in stage 2
   float p_control = 1.f;
   int64_t scratch_bt = 0;                                   // frame_level: raw predictions [B, T_max]
@@ -144,11 +147,14 @@ static T* dalloc(size_t n) {
   FS2_CUDA_OK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
   return static_cast<T*>(p);
 }
+// Replace a workspace buffer by a larger, zero-filled one.  cudaFree waits for the device, so no kernel still reads the
+// old buffer; the fill is enqueued on the caller's stream, i.e. ordered before every kernel the forward enqueues next
+// (the legacy default stream is not ordered against a caller's non-blocking stream).
 template <typename T>
-static void regrow(T*& p, size_t n) {
+static void regrow(T*& p, size_t n, cudaStream_t s) {
   if (p) FS2_CUDA_OK(cudaFree(p));
   p = dalloc<T>(n);
-  FS2_CUDA_OK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  FS2_CUDA_OK(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), s));
 }
 
 static const DevTensor& W(fs2_ctx* c, const std::string& key, std::initializer_list<int64_t> shape) {
@@ -166,25 +172,29 @@ static float* keep(fs2_ctx* c, size_t n) {
 
 // [Cout][Cin][k] -> [k][Cout][Cin], optional per-Cout scale, TF32-rounded operands
 // In FS2_MATH_BF16 the result is a bf16 array behind the float* (ConvGemmArgs::a_bf16 tells the kernel).
-static void repack_into(fs2_ctx* c, const float* w, int cout, int cin, int k, const float* scale, float* out, cudaStream_t s) {
+static void repack_into(fs2_ctx* c, const float* w, int cout, int cin, int k, const float* scale, float* out, cudaStream_t s,
+                        int64_t lo_off = 0) {
   const int64_t n = (int64_t)cout * cin * k;
   if (c->cfg.math_mode == FS2_MATH_BF16) {
     repack_conv_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, cout, cin, k, scale,
                                                                         reinterpret_cast<__nv_bfloat16*>(out));
+  } else if (c->cfg.math_mode == FS2_MATH_TF32X3) {   // [hi block ; lo block]
+    repack_conv_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, cout, cin, k, scale, out, lo_off > 0 ? lo_off : n);
   } else {
     repack_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, cout, cin, k, scale, 1, out);
   }
   FS2_LAUNCHED();
 }
 static float* repack_conv(fs2_ctx* c, const float* w, int cout, int cin, int k, const float* scale, cudaStream_t s) {
-  float* out = keep(c, (size_t)cout * cin * k);
+  float* out = keep(c, (size_t)cout * cin * k * (c->cfg.math_mode == FS2_MATH_TF32X3 ? 2 : 1));
   repack_into(c, w, cout, cin, k, scale, out, s);
   return out;
 }
 
 static void prepare_fft(fs2_ctx* c, const std::string& p, FFTLayer& L, cudaStream_t s) {
   const int d = D_MODEL;
-  L.wqkv = keep(c, 3 * d * d);
+  const bool x3 = c->cfg.math_mode == FS2_MATH_TF32X3;
+  L.wqkv = keep(c, 3 * d * d * (x3 ? 2 : 1));   // split operands: [Q K V hi ; Q K V lo]
   L.bqkv = keep(c, 3 * d);
   const char* names[3] = {"w_qs", "w_ks", "w_vs"};
   for (int i = 0; i < 3; ++i) {
@@ -194,7 +204,7 @@ static void prepare_fft(fs2_ctx* c, const std::string& p, FFTLayer& L, cudaStrea
     const size_t off = (size_t)i * d * d;   // in elements of the operand type
     repack_into(c, w.ptr, d, d, 1, nullptr,
                 c->cfg.math_mode == FS2_MATH_BF16 ? reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(L.wqkv) + off)
-                                                  : L.wqkv + off, s);
+                                                  : L.wqkv + off, s, 3 * d * d);
     FS2_CUDA_OK(cudaMemcpyAsync(L.bqkv + i * d, b.ptr, d * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
   L.wfc = repack_conv(c, W(c, p + ".slf_attn.fc.weight", {d, d}).ptr, d, d, 1, nullptr, s);
@@ -238,7 +248,7 @@ static const float* position_rows(fs2_ctx* c, const char* key, int n_rows, cudaS
   if (c->pe_long_rows < n_rows) {
     const int rows = round_up(n_rows, 1024);
     FS2_CUDA_OK(cudaStreamSynchronize(s));
-    regrow(c->pe_long, (size_t)rows * D_MODEL);
+    regrow(c->pe_long, (size_t)rows * D_MODEL, s);
     sinusoid_kernel<<<(unsigned)(((int64_t)rows * D_MODEL + 255) / 256), 256, 0, s>>>(c->pe_long, rows);
     FS2_LAUNCHED();
     c->pe_long_rows = rows;
@@ -256,26 +266,31 @@ static void tap(fs2_ctx* c, cudaStream_t s, const char* name, const void* ptr, i
   slot = {p, {rows, cols, elt}};
 }
 
-// ---------------------------------------------------------------------------- GEMM dispatch
-static void conv_gemm(int engine, int math, const ConvGemmArgs& a, cudaStream_t s) {
-  if (engine == FS2_ENGINE_TCGEN05) {
-    tc2::launch(a, math, s);
-  } else if (engine == FS2_ENGINE_TCGEN05_V1) {
-    require(a.ln_gamma == nullptr && !a.a_bf16 && a.C2 == nullptr, FS2_ERR_UNSUPPORTED,
-            "the non-persistent tcgen05 engine has no fused LayerNorm and no bf16 mode");
-    tc::launch(a, math, s);
-  } else {
-    require(a.ln_gamma == nullptr && !a.a_bf16 && a.C2 == nullptr, FS2_ERR_UNSUPPORTED,
-            "the mma.sync engine has no fused LayerNorm and no bf16 mode");
-    require(math == FS2_MATH_TF32, FS2_ERR_UNSUPPORTED, "the mma.sync engine implements TF32 only");
-    mma::launch(a, s);
+// ---------------------------------------------------------------------------- GEMM entry
+// FS2_MATH_TF32X3: the activations are split into [rows, hi | lo] (both exactly representable in TF32) in the context's
+// scratch buffer and the contraction runs three terms against the [hi ; lo] weight blocks prepared by fs2_prepare.
+static void conv_gemm(fs2_ctx* c, ConvGemmArgs a, cudaStream_t s) {
+  if (c->cfg.math_mode == FS2_MATH_TF32X3 && a.rows > 0) {
+    const size_t need = (size_t)a.rows * 2 * a.K;
+    if (need > c->split_cap) {
+      FS2_CUDA_OK(cudaStreamSynchronize(s));
+      regrow(c->split_buf, need, s);
+      c->split_cap = need;
+    }
+    const int64_t n4 = (int64_t)a.rows * (a.K / 4);
+    split_tf32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(a.A, a.rows, a.K, a.lda, c->split_buf);
+    FS2_LAUNCHED();
+    a.A = c->split_buf;
+    a.lda = 2 * a.K;
+    a.terms = 3;
   }
+  tc2::launch(a, s);
 }
 
-static void attention(int engine, const float* qkv, int rows, const int32_t* starts, const int32_t* lens, int batch,
-                      int max_len, float* out, cudaStream_t s, void* out_bf16 = nullptr) {
-  if (engine != FS2_ENGINE_MMA_SYNC) attn_tc::launch(qkv, rows, starts, lens, batch, max_len, out, s, out_bf16);
-  else attn::launch(qkv, starts, lens, batch, max_len, out, s);
+static void attention(const float* qkv, int rows, const RowSide& side, int batch, int max_len, float* out, cudaStream_t s,
+                      void* out_bf16 = nullptr) {
+  (void)batch; (void)max_len;
+  attn_tc::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, out, s, out_bf16);
 }
 
 // bf16-operand variant: A and W are bf16 behind the float* fields
@@ -297,160 +312,125 @@ static ConvGemmArgs gemm_args_b(const void* A, int lda, int rows, const float* W
   return a;
 }
 
-static void layernorm(cudaStream_t s, const float* x, int rows, const float* g, const float* b, const RowSide* side,
-                      int extra, float* y, const float* hw = nullptr, const float* hb = nullptr, float* hout = nullptr) {
-  if (rows == 0) return;
-  layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, rows, g, b, side ? side->vpos : nullptr, side ? side->room : nullptr,
-                                                   extra, y, hw, hb, hout, side ? side->slot : nullptr);
-  FS2_LAUNCHED();
-}
-
 // One FFT block in place on x (transformer/Layers.py:21-30).  t1, t2 are [rows,256] temporaries.
 static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSide& side, Pool& pool, int rows, int batch,
                       int max_len, float* x, float* t1, float* t2, bool frame) {
-  const int eng = c->cfg.engine, math = c->cfg.math_mode;
+  const int math = c->cfg.math_mode;
+  const int32_t* live = reinterpret_cast<const int32_t*>(side.totals);   // low word of totals[0] (little endian)
   if (math == FS2_MATH_BF16) {
     // Same five launches; every A operand is the bf16 mirror written by the producing epilogue, the residual
     // stream (x, t2) and the attention inputs (qkv) stay fp32.
     __nv_bfloat16 *xb = pool.actb[0], *t1b = pool.actb[1], *t2b = pool.actb[2];
-    const int32_t* live = reinterpret_cast<const int32_t*>(side.totals);
     ConvGemmArgs a = gemm_args_b(xb, D_MODEL, rows, L.wqkv, L.bqkv, 1, D_MODEL, 3 * D_MODEL, ACT_NONE, pool.qkv, 3 * D_MODEL,
                                  nullptr, 0);
     a.live_rows = live;
-    { ProfScope ps(c, s, frame ? "dec.gemm_qkv" : "enc.gemm_qkv"); conv_gemm(eng, math, a, s); }
+    { ProfScope ps(c, s, frame ? "dec.gemm_qkv" : "enc.gemm_qkv"); conv_gemm(c, a, s); }
     { ProfScope ps(c, s, frame ? "dec.attention" : "enc.attention");
-      attention(eng, pool.qkv, rows, side.starts, side.lens, batch, max_len, t1, s, t1b); }
+      attention(pool.qkv, rows, side, batch, max_len, t1, s, t1b); }
     a = gemm_args_b(t1b, D_MODEL, rows, L.wfc, L.bfc, 1, D_MODEL, D_MODEL, ACT_NONE, t2, D_MODEL, t2b, D_MODEL);
     a.residual = x; a.ldr = D_MODEL; a.live_rows = live;
     a.ln_gamma = L.ln1_g; a.ln_beta = L.ln1_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
-    { ProfScope ps(c, s, frame ? "dec.gemm_fc_ln" : "enc.gemm_fc_ln"); conv_gemm(eng, math, a, s); }
+    { ProfScope ps(c, s, frame ? "dec.gemm_fc_ln" : "enc.gemm_fc_ln"); conv_gemm(c, a, s); }
     a = gemm_args_b(t2b, D_MODEL, rows, L.w1, L.b1, FFN_TAPS, D_MODEL, D_INNER, ACT_RELU, nullptr, 0, pool.hidb, D_INNER);
     a.live_rows = live;
-    { ProfScope ps(c, s, frame ? "dec.gemm_conv9" : "enc.gemm_conv9"); conv_gemm(eng, math, a, s); }
+    { ProfScope ps(c, s, frame ? "dec.gemm_conv9" : "enc.gemm_conv9"); conv_gemm(c, a, s); }
     a = gemm_args_b(pool.hidb, D_INNER, rows, L.w2, L.b2, 1, D_INNER, D_MODEL, ACT_NONE, x, D_MODEL, xb, D_MODEL);
     a.residual = t2; a.ldr = D_MODEL; a.live_rows = live;
     a.ln_gamma = L.ln2_g; a.ln_beta = L.ln2_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
-    { ProfScope ps(c, s, frame ? "dec.gemm_w2_ln" : "enc.gemm_w2_ln"); conv_gemm(eng, math, a, s); }
+    { ProfScope ps(c, s, frame ? "dec.gemm_w2_ln" : "enc.gemm_w2_ln"); conv_gemm(c, a, s); }
     return;
   }
   ConvGemmArgs a = gemm_args(x, D_MODEL, rows, L.wqkv, L.bqkv, 1, D_MODEL, 3 * D_MODEL, ACT_NONE, pool.qkv, 3 * D_MODEL);
-  a.live_rows = reinterpret_cast<const int32_t*>(side.totals);  // low word of totals[0] (little endian)
-  { ProfScope ps(c, s, frame ? "dec.gemm_qkv" : "enc.gemm_qkv"); conv_gemm(eng, math, a, s); }
+  a.live_rows = live;
+  { ProfScope ps(c, s, frame ? "dec.gemm_qkv" : "enc.gemm_qkv"); conv_gemm(c, a, s); }
   { ProfScope ps(c, s, frame ? "dec.attention" : "enc.attention");
-    attention(eng, pool.qkv, rows, side.starts, side.lens, batch, max_len, t1, s); }
-  if (eng == FS2_ENGINE_TCGEN05) {
-    // fused: LayerNorm(fc(ctx) + x) with the row mask, then LayerNorm(w2(relu(conv9(.))) + .) (SubLayers.py:54-55,87-91)
-    a = gemm_args(t1, D_MODEL, rows, L.wfc, L.bfc, 1, D_MODEL, D_MODEL, ACT_NONE, t2, D_MODEL);
-    a.residual = x; a.ldr = D_MODEL; a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
-    a.ln_gamma = L.ln1_g; a.ln_beta = L.ln1_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
-    { ProfScope ps(c, s, frame ? "dec.gemm_fc_ln" : "enc.gemm_fc_ln"); conv_gemm(eng, math, a, s); }
-    if (ffn::use_fused(rows)) {
-      // conv9 -> ReLU -> w2 -> +residual -> LayerNorm -> mask in one kernel; the hidden tensor stays in tensor memory
-      ffn::Args f{};
-      f.x = t2; f.rows = rows; f.w1 = L.w1; f.b1 = L.b1; f.w2 = L.w2; f.b2 = L.b2; f.gamma = L.ln2_g; f.beta = L.ln2_b;
-      f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 0;
-      f.live_rows = reinterpret_cast<const int32_t*>(side.totals); f.y = x;
-      ProfScope ps(c, s, frame ? "dec.ffn_fused" : "enc.ffn_fused");
-      ffn::launch(f, s);
-      return;
-    }
-    a = gemm_args(t2, D_MODEL, rows, L.w1, L.b1, FFN_TAPS, D_MODEL, D_INNER, ACT_RELU, pool.hid, D_INNER);
-    a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
-    { ProfScope ps(c, s, frame ? "dec.gemm_conv9" : "enc.gemm_conv9"); conv_gemm(eng, math, a, s); }
-    a = gemm_args(pool.hid, D_INNER, rows, L.w2, L.b2, 1, D_INNER, D_MODEL, ACT_NONE, x, D_MODEL);
-    a.residual = t2; a.ldr = D_MODEL; a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
-    a.ln_gamma = L.ln2_g; a.ln_beta = L.ln2_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
-    { ProfScope ps(c, s, frame ? "dec.gemm_w2_ln" : "enc.gemm_w2_ln"); conv_gemm(eng, math, a, s); }
+    attention(pool.qkv, rows, side, batch, max_len, t1, s); }
+  // fused: LayerNorm(fc(ctx) + x) with the row mask, then LayerNorm(w2(relu(conv9(.))) + .) (SubLayers.py:54-55,87-91)
+  a = gemm_args(t1, D_MODEL, rows, L.wfc, L.bfc, 1, D_MODEL, D_MODEL, ACT_NONE, t2, D_MODEL);
+  a.residual = x; a.ldr = D_MODEL; a.live_rows = live;
+  a.ln_gamma = L.ln1_g; a.ln_beta = L.ln1_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
+  { ProfScope ps(c, s, frame ? "dec.gemm_fc_ln" : "enc.gemm_fc_ln"); conv_gemm(c, a, s); }
+  if (math == FS2_MATH_TF32 && ffn::use_fused(rows)) {
+    // conv9 -> ReLU -> w2 -> +residual -> LayerNorm -> mask in one kernel; the hidden tensor stays in tensor memory
+    ffn::Args f{};
+    f.x = t2; f.rows = rows; f.w1 = L.w1; f.b1 = L.b1; f.w2 = L.w2; f.b2 = L.b2; f.gamma = L.ln2_g; f.beta = L.ln2_b;
+    f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 0;
+    f.live_rows = live; f.y = x;
+    ProfScope ps(c, s, frame ? "dec.ffn_fused" : "enc.ffn_fused");
+    ffn::launch(f, s);
     return;
   }
-  a = gemm_args(t1, D_MODEL, rows, L.wfc, L.bfc, 1, D_MODEL, D_MODEL, ACT_NONE, t2, D_MODEL);
-  a.residual = x; a.ldr = D_MODEL; a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
-  { ProfScope ps(c, s, frame ? "dec.gemm_fc" : "enc.gemm_fc"); conv_gemm(eng, math, a, s); }
-  { ProfScope ps(c, s, frame ? "dec.layernorm" : "enc.layernorm"); layernorm(s, t2, rows, L.ln1_g, L.ln1_b, &side, 0, t1); }
-  a = gemm_args(t1, D_MODEL, rows, L.w1, L.b1, FFN_TAPS, D_MODEL, D_INNER, ACT_RELU, pool.hid, D_INNER);
-  a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
-  { ProfScope ps(c, s, frame ? "dec.gemm_conv9" : "enc.gemm_conv9"); conv_gemm(eng, math, a, s); }
-  a = gemm_args(pool.hid, D_INNER, rows, L.w2, L.b2, 1, D_INNER, D_MODEL, ACT_NONE, t2, D_MODEL);
-  a.residual = t1; a.ldr = D_MODEL; a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
-  { ProfScope ps(c, s, frame ? "dec.gemm_w2" : "enc.gemm_w2"); conv_gemm(eng, math, a, s); }
-  { ProfScope ps(c, s, frame ? "dec.layernorm" : "enc.layernorm"); layernorm(s, t2, rows, L.ln2_g, L.ln2_b, &side, 0, x); }
+  a = gemm_args(t2, D_MODEL, rows, L.w1, L.b1, FFN_TAPS, D_MODEL, D_INNER, ACT_RELU, pool.hid, D_INNER);
+  a.live_rows = live;
+  { ProfScope ps(c, s, frame ? "dec.gemm_conv9" : "enc.gemm_conv9"); conv_gemm(c, a, s); }
+  a = gemm_args(pool.hid, D_INNER, rows, L.w2, L.b2, 1, D_INNER, D_MODEL, ACT_NONE, x, D_MODEL);
+  a.residual = t2; a.ldr = D_MODEL; a.live_rows = live;
+  a.ln_gamma = L.ln2_g; a.ln_beta = L.ln2_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
+  { ProfScope ps(c, s, frame ? "dec.gemm_w2_ln" : "enc.gemm_w2_ln"); conv_gemm(c, a, s); }
 }
 
 // VariancePredictor (model/modules.py:242-250) over the packed rows; head_out is [B, Lmax], pre-zeroed.
 static void predictor(fs2_ctx* c, cudaStream_t s, const Predictor& P, const RowSide& side, int rows, const float* x,
-                      float* t1, float* t2, float* head_out, const __nv_bfloat16* xb = nullptr, __nv_bfloat16* t1b = nullptr) {
+                      float* t1, float* head_out, const __nv_bfloat16* xb = nullptr, __nv_bfloat16* t1b = nullptr) {
   ProfScope ps(c, s, "predictor");
-  const int eng = c->cfg.engine, math = c->cfg.math_mode;
-  if (math == FS2_MATH_BF16) {
-    ConvGemmArgs f = gemm_args_b(xb, D_MODEL, rows, P.w1, P.b1, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, nullptr, 0, t1b, D_MODEL);
-    f.live_rows = reinterpret_cast<const int32_t*>(side.totals);
-    f.ln_gamma = P.ln1_g; f.ln_beta = P.ln1_b; f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 1;
-    conv_gemm(eng, math, f, s);
-    f = gemm_args_b(t1b, D_MODEL, rows, P.w2, P.b2, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, nullptr, 0, nullptr, 0);
-    f.live_rows = reinterpret_cast<const int32_t*>(side.totals);
-    f.ln_gamma = P.ln2_g; f.ln_beta = P.ln2_b; f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 0;
-    f.head_w = P.head_w; f.head_b = P.head_b; f.head_out = head_out; f.slot = side.slot;
-    conv_gemm(eng, math, f, s);
-    return;
-  }
-  if (eng == FS2_ENGINE_TCGEN05) {
-    ConvGemmArgs f = gemm_args(x, D_MODEL, rows, P.w1, P.b1, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, t1, D_MODEL);
-    f.live_rows = reinterpret_cast<const int32_t*>(side.totals);
-    f.ln_gamma = P.ln1_g; f.ln_beta = P.ln1_b; f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 1;
-    conv_gemm(eng, math, f, s);
-    f = gemm_args(t1, D_MODEL, rows, P.w2, P.b2, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, nullptr, D_MODEL);
-    f.live_rows = reinterpret_cast<const int32_t*>(side.totals);
-    f.ln_gamma = P.ln2_g; f.ln_beta = P.ln2_b; f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 0;
-    f.head_w = P.head_w; f.head_b = P.head_b; f.head_out = head_out; f.slot = side.slot;
-    conv_gemm(eng, math, f, s);
-    return;
-  }
-  ConvGemmArgs a = gemm_args(x, D_MODEL, rows, P.w1, P.b1, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, t1, D_MODEL);
-  a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
-  conv_gemm(eng, math, a, s);
-  layernorm(s, t1, rows, P.ln1_g, P.ln1_b, &side, 1, t2);  // the hidden row at t = L_b is live when L_b < L_max
-  a = gemm_args(t2, D_MODEL, rows, P.w2, P.b2, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, t1, D_MODEL);
-  a.live_rows = reinterpret_cast<const int32_t*>(side.totals);
-  conv_gemm(eng, math, a, s);
-  layernorm(s, t1, rows, P.ln2_g, P.ln2_b, &side, 0, nullptr, P.head_w, P.head_b, head_out);
+  const int32_t* live = reinterpret_cast<const int32_t*>(side.totals);
+  const bool bf = c->cfg.math_mode == FS2_MATH_BF16;
+  ConvGemmArgs f = bf ? gemm_args_b(xb, D_MODEL, rows, P.w1, P.b1, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, nullptr, 0, t1b, D_MODEL)
+                      : gemm_args(x, D_MODEL, rows, P.w1, P.b1, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, t1, D_MODEL);
+  f.live_rows = live;
+  // the hidden row at t = L_b is live when L_b < L_max (the reference's second conv reads it)
+  f.ln_gamma = P.ln1_g; f.ln_beta = P.ln1_b; f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 1;
+  conv_gemm(c, f, s);
+  f = bf ? gemm_args_b(t1b, D_MODEL, rows, P.w2, P.b2, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, nullptr, 0, nullptr, 0)
+         : gemm_args(t1, D_MODEL, rows, P.w2, P.b2, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, nullptr, D_MODEL);
+  f.live_rows = live;
+  f.ln_gamma = P.ln2_g; f.ln_beta = P.ln2_b; f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 0;
+  f.head_w = P.head_w; f.head_b = P.head_b; f.head_out = head_out; f.slot = side.slot;
+  conv_gemm(c, f, s);
 }
 
-static void ensure_side(RowSide& sd, int batch, int rows) {
+static void ensure_side(RowSide& sd, int batch, int rows, cudaStream_t s, int work_cap = 0) {
   if (batch + 1 > sd.batch_alloc) {
-    regrow(sd.starts, batch + 1);
-    regrow(sd.lens, batch);
+    regrow(sd.starts, batch + 1, s);
+    regrow(sd.lens, batch, s);
     sd.batch_alloc = batch + 1;
   }
   if (rows > sd.rows_alloc) {
-    regrow(sd.utt, rows);
-    regrow(sd.vpos, rows);
-    regrow(sd.room, rows);
-    regrow(sd.slot, rows);
+    regrow(sd.utt, rows, s);
+    regrow(sd.vpos, rows, s);
+    regrow(sd.room, rows, s);
+    regrow(sd.slot, rows, s);
     sd.rows_alloc = rows;
   }
-  if (!sd.totals) regrow(sd.totals, 3);
+  if (work_cap > sd.work_alloc) {
+    regrow(sd.work, work_cap, s);
+    sd.work_alloc = work_cap;
+  }
+  if (work_cap > 0) sd.work_cap = work_cap;
+  if (!sd.totals) regrow(sd.totals, 3, s);
+  if (!sd.work_count) regrow(sd.work_count, 1, s);
 }
 
-static void ensure_pool(Pool& p, int rows, bool frame_side, bool bf16) {
+static void ensure_pool(Pool& p, int rows, bool frame_side, bool bf16, cudaStream_t s) {
   if (rows <= p.rows) return;
-  for (auto& a : p.act) regrow(a, (size_t)rows * D_MODEL);
-  regrow(p.qkv, (size_t)rows * 3 * D_MODEL);
+  for (auto& a : p.act) regrow(a, (size_t)rows * D_MODEL, s);
+  regrow(p.qkv, (size_t)rows * 3 * D_MODEL, s);
   if (bf16) {
-    for (auto& a : p.actb) regrow(a, (size_t)rows * D_MODEL);
-    regrow(p.hidb, (size_t)rows * D_INNER);
+    for (auto& a : p.actb) regrow(a, (size_t)rows * D_MODEL, s);
+    regrow(p.hidb, (size_t)rows * D_INNER, s);
   } else {
-    regrow(p.hid, (size_t)rows * D_INNER);
+    regrow(p.hid, (size_t)rows * D_INNER, s);
   }
   if (frame_side) {
-    regrow(p.mel, (size_t)rows * N_MEL);
-    regrow(p.post, (size_t)rows * N_MEL);
+    regrow(p.mel, (size_t)rows * N_MEL, s);
+    regrow(p.post, (size_t)rows * N_MEL, s);
     if (bf16) {
-      regrow(p.melb, (size_t)rows * N_MEL);
-      regrow(p.pnb[0], (size_t)rows * PN_DIM);
-      regrow(p.pnb[1], (size_t)rows * PN_DIM);
+      regrow(p.melb, (size_t)rows * N_MEL, s);
+      regrow(p.pnb[0], (size_t)rows * PN_DIM, s);
+      regrow(p.pnb[1], (size_t)rows * PN_DIM, s);
     } else {
-      regrow(p.pn[0], (size_t)rows * PN_DIM);
-      regrow(p.pn[1], (size_t)rows * PN_DIM);
+      regrow(p.pn[0], (size_t)rows * PN_DIM, s);
+      regrow(p.pn[1], (size_t)rows * PN_DIM, s);
     }
   }
   p.rows = rows;
@@ -489,40 +469,37 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   const int64_t bound = (int64_t)GAP_PHON + (int64_t)B * (L + GAP_PHON);
   require(bound < (1LL << 30), FS2_ERR_INVALID, "batch * max_src_len too large");
   const int rows = round_up((int)bound, 128);
-  ensure_side(c->ps, B, rows);
-  ensure_side(c->fs, B, 0);
+  ensure_side(c->ps, B, rows, s, attn_tc::work_bound((int64_t)B * L, B, L));
+  ensure_side(c->fs, B, 0, s);
   const bool bf = c->cfg.math_mode == FS2_MATH_BF16;
-  ensure_pool(c->pp, rows, false, bf);
+  ensure_pool(c->pp, rows, false, bf, s);
   const int64_t BL = (int64_t)B * L;
   if (BL > c->scratch_bl) {
-    regrow(c->cum, BL);
-    regrow(c->raw_pitch, BL);
-    regrow(c->raw_energy, BL);
+    regrow(c->cum, BL, s);
+    regrow(c->raw_pitch, BL, s);
+    regrow(c->raw_energy, BL, s);
     c->scratch_bl = BL;
   }
   if (B > c->scratch_b) {
-    regrow(c->mel_lens32, B);
-    regrow(c->cond_spk, (size_t)B * D_MODEL);
-    regrow(c->cond_emo, (size_t)B * D_MODEL);
+    regrow(c->mel_lens32, B, s);
+    regrow(c->cond_spk, (size_t)B * D_MODEL, s);
+    regrow(c->cond_emo, (size_t)B * D_MODEL, s);
     c->scratch_b = B;
   }
 
   RowSide& ps = c->ps;
   Pool& pp = c->pp;
-  FS2_CUDA_OK(cudaMemsetAsync(c->status, 0, sizeof(int32_t), s));
-  FS2_CUDA_OK(cudaMemsetAsync(out->pitch, 0, BL * sizeof(float), s));
-  FS2_CUDA_OK(cudaMemsetAsync(out->energy, 0, BL * sizeof(float), s));
-  FS2_CUDA_OK(cudaMemsetAsync(out->log_d, 0, BL * sizeof(float), s));
-  FS2_CUDA_OK(cudaMemsetAsync(out->d_rounded, 0, BL * sizeof(float), s));
-  FS2_CUDA_OK(cudaMemsetAsync(c->raw_pitch, 0, BL * sizeof(float), s));
-  FS2_CUDA_OK(cudaMemsetAsync(c->raw_energy, 0, BL * sizeof(float), s));
-
+  // (the status word is zero on entry: fs2_create clears it and every stage 1 clears it again after reading it back)
   layout_scan_kernel<int64_t><<<1, 1024, 0, s>>>(in->src_lens, B, GAP_PHON, L, L, ps.starts, ps.lens, ps.totals, c->status);
   FS2_LAUNCHED();
+  // row metadata + attention work list + zero fill of the [B, L] outputs that are written at real positions only
+  // + the source padding mask: one launch
+  SlotInit init{};
+  init.zero[0] = out->pitch; init.zero[1] = out->energy; init.zero[2] = out->log_d; init.zero[3] = out->d_rounded;
+  init.zero[4] = c->raw_pitch; init.zero[5] = c->raw_energy;
+  init.n = BL; init.src_mask = out->src_mask; init.src_lens = in->src_lens; init.max_src_len = L;
   row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(ps.starts, ps.lens, B, GAP_PHON, L, nullptr, rows, ps.utt, ps.vpos,
-                                                     ps.room, ps.slot);
-  FS2_LAUNCHED();
-  src_mask_kernel<<<(unsigned)((BL + 255) / 256), 256, 0, s>>>(in->src_lens, B, L, out->src_mask);
+                                                     ps.room, ps.slot, ps.work, ps.work_cap, ps.work_count, init);
   FS2_LAUNCHED();
 
   // ---- Encoder (transformer/Models.py:73-100)
@@ -551,13 +528,13 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   tap(c, s, "cond_x", xc, rows, D_MODEL);
 
   // ---- VarianceAdaptor (model/modules.py:102-135)
-  predictor(c, s, c->pred[0], ps, rows, xc, t1, t2, out->log_d, pp.actb[3], pp.actb[1]);
+  predictor(c, s, c->pred[0], ps, rows, xc, t1, out->log_d, pp.actb[3], pp.actb[1]);
   // phoneme_level features run here (modules.py:114-125); frame_level ones after the LengthRegulator in stage 2
   const bool pitch_here = !c->cfg.pitch_frame_level, energy_here = !c->cfg.energy_frame_level;
   float* cur = xc;                       // lives in act[3]
   __nv_bfloat16* curb = pp.actb[3];
   if (pitch_here) {
-    predictor(c, s, c->pred[1], ps, rows, cur, t1, t2, c->raw_pitch, curb, pp.actb[1]);
+    predictor(c, s, c->pred[1], ps, rows, cur, t1, c->raw_pitch, curb, pp.actb[1]);
     float* xe = x;  // encoder output is no longer needed
     bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
         cur, ps.meta(), ps.slot, 2, rows, c->raw_pitch, in->p_targets, in->p_control,
@@ -567,26 +544,22 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
     cur = xe;
     curb = pp.actb[0];
   }
-  if (energy_here) {
-    predictor(c, s, c->pred[2], ps, rows, cur, t1, t2, c->raw_energy, curb, pp.actb[1]);
-    float* xf = cur == t3 ? x : t3;
-    bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
-        cur, ps.meta(), ps.slot, 0, rows, c->raw_energy, in->e_targets, in->p_control /* sic: modules.py:123-125 */,
-        c->raw.at("variance_adaptor.energy_bins").ptr, N_BINS - 1,
-        c->raw.at("variance_adaptor.energy_embedding.weight").ptr, out->energy, nullptr, xf);
-    FS2_LAUNCHED();
-    cur = xf;
-  }
+  // phoneme_level energy: only the predictor runs here; its bucketize + embedding add (modules.py:93-100,126) is fused
+  // into the length regulator of stage 2, and the returned prediction is written by the durations kernel below
+  if (energy_here) predictor(c, s, c->pred[2], ps, rows, cur, t1, c->raw_energy, curb, pp.actb[1]);
   float* xf = cur;
+  c->va_spare = cur == t3 ? x : t3;   // free [rows,256] buffer (debug tap of the fused energy add)
   c->p_targets = in->p_targets;
   c->e_targets = in->e_targets;
   c->p_control = in->p_control;
-  tap(c, s, "va_x", xf, rows, D_MODEL);
+  if (!energy_here) tap(c, s, "va_x", xf, rows, D_MODEL);
 
   const bool forced = in->d_targets != nullptr;
   durations_kernel<<<(B + 7) / 8, 256, 0, s>>>(forced ? in->d_targets : out->log_d, forced ? 1 : 0, in->d_control,
                                                in->src_lens, B, L, forced ? nullptr : out->d_rounded, c->cum,
-                                               out->mel_lens, c->mel_lens32);
+                                               out->mel_lens, c->mel_lens32, energy_here ? c->raw_energy : nullptr,
+                                               in->e_targets != nullptr ? 1.f : in->p_control /* sic: modules.py:123-125 */,
+                                               energy_here ? out->energy : nullptr);
   FS2_LAUNCHED();
   layout_scan_kernel<int32_t><<<1, 1024, 0, s>>>(c->mel_lens32, B, GAP_FRAME, 0, in->max_mel_len, c->fs.starts, c->fs.lens,
                                                  c->fs.totals, c->status);
@@ -597,6 +570,7 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   // ---- the one blocking point: sizes of the frame side
   FS2_CUDA_OK(cudaMemcpyAsync(c->h_totals, c->fs.totals, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   FS2_CUDA_OK(cudaMemcpyAsync(c->h_totals + 3, c->status, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  FS2_CUDA_OK(cudaMemsetAsync(c->status, 0, sizeof(int32_t), s));   // clean for the next forward
   FS2_CUDA_OK(cudaStreamSynchronize(s));
   if (timing) {
     const auto t_end = std::chrono::steady_clock::now();
@@ -607,7 +581,7 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   check_status(c, *reinterpret_cast<int32_t*>(c->h_totals + 3));
   c->frame_rows = c->h_totals[0];
   c->max_mel_len = (int)c->h_totals[1];
-  out->total_frames = c->h_totals[2];
+  out->total_frames = c->total_frames = c->h_totals[2];
   out->max_mel_len = c->max_mel_len;
   require(c->frame_rows < (1LL << 30), FS2_ERR_INVALID, "expanded batch too large");
   c->batch = B;
@@ -627,16 +601,16 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
   g_launches = 0;
   const int B = c->batch, L = c->max_src_len, T = c->max_mel_len;
   const int rows = round_up((int)c->frame_rows, 128);
-  const int eng = c->cfg.engine, math = c->cfg.math_mode;
-  ensure_side(c->fs, B, rows);
+  const int math = c->cfg.math_mode;
+  ensure_side(c->fs, B, rows, s, attn_tc::work_bound(c->total_frames, B, T));
   const bool bf = math == FS2_MATH_BF16;
-  ensure_pool(c->fp, rows, true, bf);
+  ensure_pool(c->fp, rows, true, bf, s);
   RowSide& fsd = c->fs;
   Pool& fp = c->fp;
 
   if (T > 0) {
     row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(fsd.starts, fsd.lens, B, GAP_FRAME, T, nullptr, rows, fsd.utt,
-                                                       fsd.vpos, fsd.room, fsd.slot);
+                                                       fsd.vpos, fsd.room, fsd.slot, fsd.work, fsd.work_cap, fsd.work_count);
     FS2_LAUNCHED();
     // ---- LengthRegulator + decoder positional encoding (modules.py:167-194, Models.py:145-162)
     float *x = fp.act[0], *t1 = fp.act[1], *t2 = fp.act[2];
@@ -649,10 +623,21 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
       const int rows_p = c->phon_rows;                                 // phoneme rows laid out by stage 1
       const int reserved = (B + 1) * GAP_FRAME + 128;                  // gaps + the round-up tail
       const int warps = rows_p + reserved;
+      EnergyAdd en{};
+      if (!energy_f) {   // phoneme_level energy: bucketize + embedding add applied to the row on its way through
+        en.raw = c->raw_energy; en.target = c->e_targets; en.control = c->p_control;
+        en.bins = c->raw.at("variance_adaptor.energy_bins").ptr; en.n_bins = N_BINS - 1;
+        en.table = c->raw.at("variance_adaptor.energy_embedding.weight").ptr;
+        if (c->debug) {
+          en.va_out = c->va_spare;
+          FS2_CUDA_OK(cudaMemsetAsync(en.va_out, 0, (size_t)rows_p * D_MODEL * sizeof(float), s));
+        }
+      }
       length_regulate_scatter_kernel<<<(warps + 7) / 8, 256, 0, s>>>(
           c->lr_input, c->ps.meta(), c->ps.lens, rows_p, c->cum, L, fsd.starts, fsd.lens, B, GAP_FRAME, fsd.totals,
-          (pitch_f || energy_f) ? nullptr : pe, rows, x, fp.actb[0]);
+          (pitch_f || energy_f) ? nullptr : pe, rows, x, fp.actb[0], en);
       FS2_LAUNCHED();
+      if (en.va_out != nullptr) tap(c, s, "va_x", en.va_out, rows_p, D_MODEL);
     }
     if (pitch_f || energy_f) {
       // frame_level predictors (modules.py:139-148) on the expanded rows: padding rows of the LengthRegulator output
@@ -661,8 +646,8 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
       // afterwards and every reserved row returns to zero for the decoder.
       const int64_t BT = (int64_t)B * T;
       if (BT > c->scratch_bt) {
-        regrow(c->raw_pitch_f, BT);
-        regrow(c->raw_energy_f, BT);
+        regrow(c->raw_pitch_f, BT, s);
+        regrow(c->raw_energy_f, BT, s);
         c->scratch_bt = BT;
       }
       float* cur = x;                    // act[0]
@@ -671,7 +656,7 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
         require(io->pitch_frames != nullptr, FS2_ERR_INVALID, "pitch is frame_level: stage-2 io needs pitch_frames");
         FS2_CUDA_OK(cudaMemsetAsync(io->pitch_frames, 0, BT * sizeof(float), s));
         FS2_CUDA_OK(cudaMemsetAsync(c->raw_pitch_f, 0, BT * sizeof(float), s));
-        predictor(c, s, c->pred[1], fsd, rows, cur, t1, t2, c->raw_pitch_f, curb, fp.actb[1]);
+        predictor(c, s, c->pred[1], fsd, rows, cur, t1, c->raw_pitch_f, curb, fp.actb[1]);
         bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
             cur, fsd.meta(), fsd.slot, energy_f ? 2 : 0, rows, c->raw_pitch_f, c->p_targets, c->p_control,
             c->raw.at("variance_adaptor.pitch_bins").ptr, N_BINS - 1,
@@ -684,7 +669,7 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
         require(io->energy_frames != nullptr, FS2_ERR_INVALID, "energy is frame_level: stage-2 io needs energy_frames");
         FS2_CUDA_OK(cudaMemsetAsync(io->energy_frames, 0, BT * sizeof(float), s));
         FS2_CUDA_OK(cudaMemsetAsync(c->raw_energy_f, 0, BT * sizeof(float), s));
-        predictor(c, s, c->pred[2], fsd, rows, cur, t1, t2, c->raw_energy_f, curb, fp.actb[1]);
+        predictor(c, s, c->pred[2], fsd, rows, cur, t1, c->raw_energy_f, curb, fp.actb[1]);
         float* dst = cur == x ? fp.act[3] : x;
         bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
             cur, fsd.meta(), fsd.slot, 0, rows, c->raw_energy_f, c->e_targets, c->p_control /* sic */,
@@ -708,7 +693,7 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
                                       fp.melb, N_MEL)
                         : gemm_args(x, D_MODEL, rows, c->mel_w, c->mel_b, 1, D_MODEL, N_MEL, ACT_NONE, fp.mel, N_MEL);
     a.row_vpos = fsd.vpos; a.row_room = fsd.room; a.extra = PN_VIRTUAL;
-    { ProfScope ps(c, s, "mel_linear"); conv_gemm(eng, math, a, s); }
+    { ProfScope ps(c, s, "mel_linear"); conv_gemm(c, a, s); }
     tap(c, s, "mel_p", fp.mel, rows, N_MEL);
     // ---- PostNet (Layers.py:129-137) + residual (fastspeech2.py:136), BatchNorm folded
     const float* src = fp.mel;
@@ -729,7 +714,7 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
       a.row_vpos = fsd.vpos; a.row_room = fsd.room; a.extra = PN_VIRTUAL - 2 * (j + 1);
       if (last) { a.residual = fp.mel; a.ldr = N_MEL; }
       { ProfScope ps(c, s, j == 0 ? "postnet.conv_80_512" : (last ? "postnet.conv_512_80" : "postnet.conv_512_512"));
-        conv_gemm(eng, math, a, s); }
+        conv_gemm(c, a, s); }
       src = dst;
       ld = pc.cout;
     }
@@ -817,11 +802,8 @@ int fs2_version(void) { return 100; }
 int fs2_create(const fs2_config* cfg, int device, fs2_ctx** out) {
   return guarded(nullptr, [&] {
     require(cfg && out, FS2_ERR_INVALID, "null argument");
-    require(cfg->math_mode == FS2_MATH_TF32 || cfg->math_mode == FS2_MATH_BF16, FS2_ERR_UNSUPPORTED, "unknown math_mode");
-    require(cfg->engine == FS2_ENGINE_MMA_SYNC || cfg->engine == FS2_ENGINE_TCGEN05 ||
-                cfg->engine == FS2_ENGINE_TCGEN05_V1, FS2_ERR_UNSUPPORTED, "unknown engine");
-    require(cfg->math_mode == FS2_MATH_TF32 || cfg->engine == FS2_ENGINE_TCGEN05, FS2_ERR_UNSUPPORTED,
-            "FS2_MATH_BF16 is implemented by the persistent tcgen05 engine only");
+    require(cfg->math_mode == FS2_MATH_TF32 || cfg->math_mode == FS2_MATH_BF16 || cfg->math_mode == FS2_MATH_TF32X3,
+            FS2_ERR_UNSUPPORTED, "unknown math_mode");
     require(cfg->n_src_vocab > 0 && cfg->n_speaker > 0 && cfg->n_emotion > 0 && cfg->n_arousal > 0 && cfg->n_valence > 0 &&
                 cfg->max_seq_len > 0, FS2_ERR_INVALID, "table sizes must be positive");
     int n_dev = 0;
@@ -836,6 +818,7 @@ int fs2_create(const fs2_config* cfg, int device, fs2_ctx** out) {
     c->device = device;
     c->cfg = *cfg;
     c->status = dalloc<int32_t>(1);
+    FS2_CUDA_OK(cudaMemset(c->status, 0, sizeof(int32_t)));
     FS2_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&c->h_totals), 8 * sizeof(int64_t)));
     *out = c;
   });
@@ -852,7 +835,7 @@ void fs2_destroy(fs2_ctx* c) {
   for (auto& e : c->event_pool) cudaEventDestroy(e);
   for (RowSide* sd : {&c->ps, &c->fs}) {
     cudaFree(sd->starts); cudaFree(sd->lens); cudaFree(sd->utt); cudaFree(sd->vpos); cudaFree(sd->room); cudaFree(sd->slot);
-    cudaFree(sd->totals);
+    cudaFree(sd->totals); cudaFree(sd->work); cudaFree(sd->work_count);
   }
   for (Pool* p : {&c->pp, &c->fp}) {
     for (float* a : p->act) cudaFree(a);
@@ -861,7 +844,7 @@ void fs2_destroy(fs2_ctx* c) {
     cudaFree(p->hidb); cudaFree(p->melb); cudaFree(p->pnb[0]); cudaFree(p->pnb[1]);
   }
   cudaFree(c->status); cudaFree(c->cum); cudaFree(c->mel_lens32); cudaFree(c->raw_pitch); cudaFree(c->raw_energy);
-  cudaFree(c->cond_spk); cudaFree(c->cond_emo); cudaFree(c->pe_long); cudaFree(c->raw_pitch_f); cudaFree(c->raw_energy_f);
+  cudaFree(c->cond_spk); cudaFree(c->cond_emo); cudaFree(c->pe_long); cudaFree(c->split_buf); cudaFree(c->raw_pitch_f); cudaFree(c->raw_energy_f);
   cudaFreeHost(c->h_totals);
   delete c;
 }
@@ -883,6 +866,9 @@ int fs2_set_weight(fs2_ctx* c, const char* key, const void* dev_ptr, const int64
       t.numel *= shape[i];
     }
     t.ptr = dalloc<float>(t.numel);
+    // the source may have been produced on any stream (a caller's non-blocking stream is not ordered against the legacy
+    // stream this blocking copy runs on): wait for the device first.  Weight upload is rare; this costs nothing that matters.
+    FS2_CUDA_OK(cudaDeviceSynchronize());
     FS2_CUDA_OK(cudaMemcpy(t.ptr, dev_ptr, t.numel * sizeof(float), cudaMemcpyDeviceToDevice));
     auto it = c->raw.find(k);
     if (it != c->raw.end()) cudaFree(it->second.ptr);
@@ -1006,20 +992,40 @@ int fs2_profile_read(fs2_ctx* c, char* buf, int64_t buf_bytes) {
 // ---------------------------------------------------------------------------- single operators
 static thread_local std::string g_op_error;
 
-int fs2_op_conv_gemm(fs2_stream stream, int engine, int math_mode, const float* A, int lda, int rows, const float* Wt,
+int fs2_op_conv_gemm(fs2_stream stream, int math_mode, const float* A, int lda, int rows, const float* Wt,
                      const float* bias, int taps, int pad, int K, int N, int act, const float* residual, int ldr,
                      const int32_t* row_vpos, const int32_t* row_room, int extra, float* C, int ldc) {
   return guarded(nullptr, [&] {
     require(A && Wt && bias && C && rows >= 0 && taps >= 1 && K > 0 && N > 0, FS2_ERR_INVALID, "bad conv_gemm argument");
+    require(math_mode == FS2_MATH_TF32 || math_mode == FS2_MATH_TF32X3, FS2_ERR_INVALID, "conv_gemm: TF32 or TF32X3 (bf16 has its own entry)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
     ConvGemmArgs a{};
     a.A = A; a.lda = lda; a.rows = rows; a.W = Wt; a.bias = bias; a.taps = taps; a.pad = pad; a.K = K; a.N = N; a.act = act;
     a.residual = residual; a.ldr = ldr; a.row_vpos = row_vpos; a.row_room = row_room; a.extra = extra; a.C = C; a.ldc = ldc;
     if (g_trace_on) { a.trace = g_trace_buf + 8 * ((g_trace_on - 1) % 8); ++g_trace_on; }
-    conv_gemm(engine, math_mode, a, static_cast<cudaStream_t>(stream));
+    if (math_mode == FS2_MATH_TF32X3 && rows > 0) {
+      // Wt is the plain fp32 weight [taps][N][K] here: both operands are split into temporaries for this one call
+      require(K % 4 == 0 && lda % 4 == 0, FS2_ERR_INVALID, "conv_gemm: K and lda must be multiples of 4");
+      const int64_t nw = (int64_t)taps * N * K, n4 = (int64_t)rows * (K / 4);
+      float* ws = dalloc<float>(2 * nw);
+      float* as = dalloc<float>((size_t)rows * 2 * K);
+      // a [taps][N][K] tensor is the [Cout = taps*N][Cin = K][k = 1] case of the repack
+      repack_conv_split_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(Wt, taps * N, K, 1, nullptr, ws, nw);
+      FS2_LAUNCHED();
+      split_tf32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(A, rows, K, lda, as);
+      FS2_LAUNCHED();
+      a.A = as; a.lda = 2 * K; a.W = ws; a.terms = 3;
+      tc2::launch(a, s);
+      FS2_CUDA_OK(cudaStreamSynchronize(s));
+      cudaFree(ws);
+      cudaFree(as);
+      return;
+    }
+    tc2::launch(a, s);
   });
 }
 
-int fs2_op_conv_gemm_ln(fs2_stream stream, int engine, const float* A, int lda, int rows, const float* Wt, const float* bias,
+int fs2_op_conv_gemm_ln(fs2_stream stream, const float* A, int lda, int rows, const float* Wt, const float* bias,
                         int taps, int pad, int K, int act, const float* residual, int ldr, const float* gamma,
                         const float* beta, const int32_t* row_vpos, const int32_t* row_room, int extra, float* C, int ldc,
                         const float* head_w, const float* head_b, float* head_out) {
@@ -1030,7 +1036,7 @@ int fs2_op_conv_gemm_ln(fs2_stream stream, int engine, const float* A, int lda, 
     a.residual = residual; a.ldr = ldr; a.row_vpos = row_vpos; a.row_room = row_room; a.extra = extra; a.C = C; a.ldc = ldc;
     a.ln_gamma = gamma; a.ln_beta = beta; a.head_w = head_w; a.head_b = head_b; a.head_out = head_out;
     if (g_trace_on) { a.trace = g_trace_buf + 8 * ((g_trace_on - 1) % 8); ++g_trace_on; }
-    conv_gemm(engine, FS2_MATH_TF32, a, static_cast<cudaStream_t>(stream));
+    tc2::launch(a, static_cast<cudaStream_t>(stream));
   });
 }
 
@@ -1058,7 +1064,7 @@ int fs2_op_conv_gemm_ex(fs2_stream stream, const float* A, int lda, int rows, co
     a.K = K; a.N = N; a.act = act; a.slope = slope; a.residual = residual; a.ldr = ldr; a.res_inv_lrelu = res_inv_lrelu;
     a.act2 = act2; a.row_vpos = row_vpos; a.row_room = row_room; a.extra = extra; a.mask_shift = mask_shift; a.C = C; a.ldc = ldc;
     if (g_trace_on) { a.trace = g_trace_buf + 8 * ((g_trace_on - 1) % 8); ++g_trace_on; }
-    conv_gemm(FS2_ENGINE_TCGEN05, FS2_MATH_TF32, a, static_cast<cudaStream_t>(stream));
+    tc2::launch(a, static_cast<cudaStream_t>(stream));
   });
 }
 
@@ -1074,27 +1080,25 @@ int fs2_op_conv_gemm_bf16(fs2_stream stream, const void* A, int lda, int rows, c
     a.taps = taps; a.pad = pad; a.K = K; a.N = N; a.act = act; a.residual = residual; a.ldr = ldr;
     a.row_vpos = row_vpos; a.row_room = row_room; a.extra = extra; a.C = C; a.ldc = ldc; a.C2 = C2; a.ldc2 = ldc2;
     a.ln_gamma = gamma; a.ln_beta = beta; a.a_bf16 = 1;
-    conv_gemm(FS2_ENGINE_TCGEN05, FS2_MATH_BF16, a, static_cast<cudaStream_t>(stream));
+    tc2::launch(a, static_cast<cudaStream_t>(stream));
   });
 }
 
-int fs2_op_attention(fs2_stream stream, int engine, const float* qkv, int rows, const int32_t* starts, const int32_t* lens,
+int fs2_op_attention(fs2_stream stream, const float* qkv, int rows, const int32_t* starts, const int32_t* lens,
                      int batch, int max_len, float* out) {
   return guarded(nullptr, [&] {
-    require(qkv && starts && lens && out && rows > 0, FS2_ERR_INVALID, "bad attention argument");
-    attention(engine, qkv, rows, starts, lens, batch, max_len, out, static_cast<cudaStream_t>(stream));
-  });
-}
-
-int fs2_op_layernorm(fs2_stream stream, const float* x, int rows, const float* gamma, const float* beta,
-                     const int32_t* row_vpos, const int32_t* row_room, int extra, float* y, const float* head_w,
-                     const float* head_b, float* dot) {
-  return guarded(nullptr, [&] {
-    require(x && gamma && beta && rows >= 0, FS2_ERR_INVALID, "bad layernorm argument");
-    if (rows == 0) return;
-    layernorm_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, gamma, beta, row_vpos, row_room,
-                                                                                    extra, y, head_w, head_b, dot, nullptr);
+    require(qkv && starts && lens && out && rows > 0 && batch > 0 && max_len > 0, FS2_ERR_INVALID, "bad attention argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // the longest-first work list the forward builds in row_meta_kernel, into a temporary
+    const int cap = attn_tc::work_bound((int64_t)batch * max_len, batch, max_len);
+    uint32_t* work = dalloc<uint32_t>(cap);
+    int32_t* count = dalloc<int32_t>(1);
+    attention_work_kernel<<<1, 256, 0, s>>>(lens, batch, work, cap, count);
     FS2_LAUNCHED();
+    attn_tc::launch(qkv, rows, starts, lens, work, count, cap, out, s);
+    FS2_CUDA_OK(cudaStreamSynchronize(s));
+    cudaFree(work);
+    cudaFree(count);
   });
 }
 
@@ -1224,8 +1228,8 @@ static void forward(fs2_voc* c, cudaStream_t s, const float* mel, int64_t sb, in
   g_launches = 0;
   const int64_t bound = (int64_t)VOC_GAP + (int64_t)B * (T + VOC_GAP);
   RowSide& sd = c->side;
-  ensure_side(sd, B, 0);
-  if (c->lens64 == nullptr) regrow(c->lens64, 65536);
+  ensure_side(sd, B, 0, s);
+  if (c->lens64 == nullptr) regrow(c->lens64, 65536, s);
   if (c->h_totals == nullptr) FS2_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&c->h_totals), 4 * sizeof(int64_t)));
   FS2_CUDA_OK(cudaMemsetAsync(c->status, 0, sizeof(int32_t), s));
   FS2_CUDA_OK(cudaMemsetAsync(wav, 0, (size_t)B * T * HOP * sizeof(float), s));
@@ -1249,11 +1253,11 @@ static void forward(fs2_voc* c, cudaStream_t s, const float* mel, int64_t sb, in
   }
   require(used * HOP < (1LL << 31), FS2_ERR_INVALID, "vocoder batch too large (2^31 audio rows)");
   const int rows = round_up((int)used, 128);
-  ensure_side(sd, B, rows);
+  ensure_side(sd, B, rows, s);
   if (rows > c->rows_alloc) {
-    regrow(c->melp, (size_t)rows * N_MEL);
-    regrow(c->a0, (size_t)rows * UP_INITIAL);
-    for (auto& b : c->buf) regrow(b, (size_t)rows * 8192);
+    regrow(c->melp, (size_t)rows * N_MEL, s);
+    regrow(c->a0, (size_t)rows * UP_INITIAL, s);
+    for (auto& b : c->buf) regrow(b, (size_t)rows * 8192, s);
     c->rows_alloc = rows;
   }
   row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(sd.starts, sd.lens, B, VOC_GAP, T, nullptr, rows, sd.utt, sd.vpos, sd.room,
@@ -1273,7 +1277,7 @@ static void forward(fs2_voc* c, cudaStream_t s, const float* mel, int64_t sb, in
     a.act2 = act2; a.row_vpos = sd.vpos; a.row_room = sd.room; a.extra = 0; a.mask_shift = shift;
     a.live_rows = live;
     if (bf) { a.a_bf16 = 1; a.res_bf16 = 1; a.C2 = C; a.ldc2 = ldc; } else { a.C = C; a.ldc = ldc; }
-    tc2::launch(a, c->math_mode, s);
+    tc2::launch(a, s);
   };
 
   // conv_pre (models.py:149) with the leaky ReLU of the first upsampling stage (:151) applied on the way out
@@ -1369,7 +1373,7 @@ void fs2_voc_destroy(fs2_voc* c) {
   for (void* p : c->owned) cudaFree(p);
   RowSide* sd = &c->side;
   cudaFree(sd->starts); cudaFree(sd->lens); cudaFree(sd->utt); cudaFree(sd->vpos); cudaFree(sd->room); cudaFree(sd->slot);
-  cudaFree(sd->totals);
+  cudaFree(sd->totals); cudaFree(sd->work); cudaFree(sd->work_count);
   cudaFree(c->lens64); cudaFree(c->melp); cudaFree(c->a0); cudaFree(c->status);
   if (c->h_totals) cudaFreeHost(c->h_totals);
   for (float* b : c->buf) cudaFree(b);
@@ -1391,6 +1395,7 @@ int fs2_voc_set_weight(fs2_voc* c, const char* key, const void* dev_ptr, const i
       t.numel *= shape[i];
     }
     t.ptr = dalloc<float>(t.numel);
+    FS2_CUDA_OK(cudaDeviceSynchronize());   // see fs2_set_weight
     FS2_CUDA_OK(cudaMemcpy(t.ptr, dev_ptr, t.numel * sizeof(float), cudaMemcpyDeviceToDevice));
     auto it = c->raw.find(key);
     if (it != c->raw.end()) cudaFree(it->second.ptr);

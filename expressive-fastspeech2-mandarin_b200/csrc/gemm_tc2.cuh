@@ -22,7 +22,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
-#include "gemm_mma.cuh"
+#include "conv_args.cuh"
 #include "tc_ptx.cuh"
 
 namespace fs2 {
@@ -243,7 +243,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int warp = warp_index(), lane = threadIdx.x & 31;
   const int kchunks = (p.K + BKE - 1) / BKE;
   const bool half_chunk = BF && p.K <= 32;   // A-resident bf16 convs with 32 channels: only two of the four K slices hold data
-  const int iters = p.taps * kchunks;
+  // FS2_MATH_TF32X3: the K loop runs three terms over split operands (A = [hi | lo] columns, W = hi block then lo block)
+  const int terms = p.terms > 1 ? p.terms : 1;
+  const int iters1 = p.taps * kchunks;
+  const int iters = terms * iters1;
   const int n_tiles_n = (p.N + BN - 1) / BN;
   const bool has_res = p.residual != nullptr;
   const bool has_out = p.C != nullptr;
@@ -372,13 +375,17 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int i = 0; i < iters; ++i, ++it) {
         const int s = it % C::STAGES;
         mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
-        const int tap = i / kchunks, kc = i - tap * kchunks;
+        int term = 0, i1 = i;
+        if (terms > 1) { term = i / iters1; i1 = i - term * iters1; }
+        const int tap = i1 / kchunks, kc = i1 - tap * kchunks;
+        const int a_col = kc * BKE + (term == 1 ? p.K : 0);                 // term 1 reads the lo half of the activations
+        const int w_row = tap * p.N + n0 + (term == 2 ? p.taps * p.N : 0);  // term 2 reads the lo block of the weights
         uint8_t* a_s = ring + s * C::STAGE_BYTES;
         if (TWO) {   // own activation rows + own half of the weight tile; both CTAs' bytes are counted on the issuer's barrier
           if (leader) {
             if (rank == 0) mbar_expect_tx(&full[s], 2 * C::STAGE_BYTES);
-            tma_load_2d_2sm(a_s, &tmA, kc * BKE, m0 + tap * dil - p.pad, &full[s]);
-            tma_load_2d_2sm(a_s + C::A_BYTES, &tmW, kc * BKE, tap * p.N + n0 + rank * (BN / 2), &full[s]);
+            tma_load_2d_2sm(a_s, &tmA, a_col, m0 + tap * dil - p.pad, &full[s]);
+            tma_load_2d_2sm(a_s + C::A_BYTES, &tmW, kc * BKE, w_row + rank * (BN / 2), &full[s]);
           }
           __syncwarp();
           continue;
@@ -386,14 +393,14 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (leader) {
           mbar_expect_tx(&full[s], C::STAGE_BYTES);
           if (NS > 1) {   // this CTA's 128/NS rows of the shared activation tile, delivered to every CTA of the cluster
-            tma_load_2d_mc(a_s + rank * (C::A_BYTES / NS), &tmA, kc * BKE, m0 + tap * dil - p.pad + rank * (BM / NS), &full[s], CMASK);
+            tma_load_2d_mc(a_s + rank * (C::A_BYTES / NS), &tmA, a_col, m0 + tap * dil - p.pad + rank * (BM / NS), &full[s], CMASK);
           } else {
-            tma_load_2d(a_s, &tmA, kc * BKE, m0 + tap * dil - p.pad, &full[s]);
+            tma_load_2d(a_s, &tmA, a_col, m0 + tap * dil - p.pad, &full[s]);
           }
           if (CL == 1) {
-            tma_load_2d(a_s + C::A_BYTES, &tmW, kc * BKE, tap * p.N + n0, &full[s]);
+            tma_load_2d(a_s + C::A_BYTES, &tmW, kc * BKE, w_row, &full[s]);
           } else {   // this CTA's half of the weight tile, delivered to both CTAs of the cluster
-            tma_load_2d_mc(a_s + C::A_BYTES + rank * (C::B_BYTES / 2), &tmW, kc * BKE, tap * p.N + n0 + rank * (BN / 2), &full[s],
+            tma_load_2d_mc(a_s + C::A_BYTES + rank * (C::B_BYTES / 2), &tmW, kc * BKE, w_row + rank * (BN / 2), &full[s],
                            (uint16_t)0x3);
           }
         }
@@ -874,10 +881,11 @@ inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
     configured[dev & 63] = true;
   }
   constexpr CUtensorMapSwizzle SW128 = CU_TENSOR_MAP_SWIZZLE_128B;
+  const int split = a.terms > 1 ? 2 : 1;   // 3xTF32: activations [rows, hi | lo], weights [hi block ; lo block]
   const CUtensorMap tmA = BF ? make_map_any(a.A, a.rows, a.K, a.lda, AR ? AR_ROWS : BM / NS, 64, MAP_BF16, SW128)
-                             : make_map(a.A, a.rows, a.K, a.lda, AR ? AR_ROWS : BM / NS, /*round_tf32=*/true, false);
+                             : make_map(a.A, a.rows, (int64_t)a.K * split, a.lda, AR ? AR_ROWS : BM / NS, /*round_tf32=*/true, false);
   const CUtensorMap tmW = BF ? make_map_any(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN / CL, 64, MAP_BF16, SW128)
-                             : make_map(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN / CL, false, true);
+                             : make_map(a.W, (int64_t)a.taps * a.N * split, a.K, a.K, BN / CL, false, true);
   const CUtensorMap tmC = a.C != nullptr ? make_map(a.C, a.rows, a.N, a.ldc, 32, false, false) : tmA;
   const CUtensorMap tmR = a.residual == nullptr ? tmA
                           : a.res_bf16 ? make_map_any(a.residual, a.rows, a.N, a.ldr, 32, 32, MAP_BF16, CU_TENSOR_MAP_SWIZZLE_64B)
@@ -942,8 +950,8 @@ inline void launch_bn(const ConvGemmArgs& a, cudaStream_t stream) {
   }
 }
 
-inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
-  (void)math_mode;   // the operand type travels with the arguments (a_bf16)
+inline void launch(const ConvGemmArgs& a, cudaStream_t stream) {   // the operand type travels with the arguments (a_bf16, terms)
+  require(a.terms <= 1 || (a.terms == 3 && !a.a_bf16), FS2_ERR_INVALID, "split-operand contraction: three TF32 terms");
   const int am = a.a_bf16 ? 8 : 4;   // elements per 16 bytes of the A / W rows
   require(a.K % am == 0 && a.lda % am == 0 && (a.C == nullptr || a.ldc % 4 == 0) && (a.residual == nullptr || a.ldr % (a.res_bf16 ? 8 : 4) == 0) &&
               (a.C2 == nullptr || a.ldc2 % 8 == 0), FS2_ERR_INVALID,
@@ -961,7 +969,9 @@ inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
     require(a.head_out == nullptr || (a.head_w != nullptr && a.head_b != nullptr), FS2_ERR_INVALID, "head needs weight and bias");
     // few row tiles (single utterances, the encoder of a small batch): split the 256 columns over a cluster of 4 or 2 CTAs
     const int m_tiles_ln = (a.rows + BM - 1) / BM;
-    const int ns = (n_split_flag() == 0 || a.head_out != nullptr) ? 1 : (m_tiles_ln * 4 <= sm_count() ? 4 : (m_tiles_ln * 2 <= sm_count() ? 2 : 1));
+    static const int ns_force = [] { const char* e = std::getenv("FS2_LN_NS"); return e != nullptr ? std::atoi(e) : 0; }();
+    int ns = (n_split_flag() == 0 || a.head_out != nullptr) ? 1 : (m_tiles_ln * 4 <= sm_count() ? 4 : (m_tiles_ln * 2 <= sm_count() ? 2 : 1));
+    if (ns_force > 0 && a.head_out == nullptr && m_tiles_ln * 2 > sm_count()) ns = ns_force;   // experiment: N-split beyond one wave
     if (ns == 4) {
       if (a.a_bf16) launch_bn_cl<64, true, 1, true, 0, 4>(a, stream); else launch_bn_cl<64, true, 1, false, 0, 4>(a, stream);
     } else if (ns == 2) {
@@ -977,7 +987,7 @@ inline void launch(const ConvGemmArgs& a, int math_mode, cudaStream_t stream) {
   require(a.C != nullptr || a.C2 != nullptr, FS2_ERR_INVALID, "conv_gemm: null output");
   {   // small K, several taps: keep the activation tile resident and shift the descriptor per tap
     const int d = a.dil > 0 ? a.dil : 1;
-    if (a_resident_flag() && a.taps > 1 && a.K <= 64 && BM + (a.taps - 1) * d <= AR_ROWS) {
+    if (a_resident_flag() && a.terms <= 1 && a.taps > 1 && a.K <= 64 && BM + (a.taps - 1) * d <= AR_ROWS) {
       if (a.N == 32) { launch_ar<32>(a, stream); return; }
       if (a.N == 64) { launch_ar<64>(a, stream); return; }
     }

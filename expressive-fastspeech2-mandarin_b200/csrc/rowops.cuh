@@ -99,13 +99,84 @@ __global__ void layout_scan_kernel(const LenT* __restrict__ lens, int batch, int
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Work list of the attention kernel (transformer/SubLayers.py:42-52 runs every utterance padded to the batch maximum;
+// here one entry = 128 queries of one utterance).  Entries are (utterance << 16 | query tile), utterances in DESCENDING
+// order of their key-tile count -- the cost of each of their entries -- so that the hardware's in-order CTA dispatch is a
+// longest-processing-time-first schedule: long items go out first and the tail of the grid is made of short ones.
+// Counting sort over 1024 cost classes with shared-memory atomics; the order inside a class is arbitrary (the entries are
+// independent, the results do not depend on it).  Called by every thread of ONE block; bins = 1024 ints of shared memory.
+__device__ inline void build_attention_work(const int32_t* __restrict__ lens32, int batch, uint32_t* __restrict__ work,
+                                            int cap, int32_t* __restrict__ count, int* bins) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < 1024; i += nt) bins[i] = 0;
+  __syncthreads();
+  for (int b = tid; b < batch; b += nt) {
+    const int l = lens32[b];
+    if (l > 0) atomicAdd(&bins[1023 - min((l + 63) >> 6, 1023)], (l + 127) >> 7);
+  }
+  __syncthreads();
+  if (tid < 32) {   // exclusive scan of the 1024 classes by one warp: 32 consecutive classes per lane
+    int v[32], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { v[i] = bins[tid * 32 + i]; sum += v[i]; }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (tid >= o) inc += t;
+    }
+    int run = inc - sum;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { bins[tid * 32 + i] = run; run += v[i]; }
+    if (tid == 31) *count = min(inc, cap);
+  }
+  __syncthreads();
+  for (int b = tid; b < batch; b += nt) {
+    const int l = lens32[b];
+    if (l <= 0) continue;
+    const int q = (l + 127) >> 7;
+    const int pos = atomicAdd(&bins[1023 - min((l + 63) >> 6, 1023)], q);
+    for (int t = 0; t < q; ++t)
+      if (pos + t < cap) work[pos + t] = ((uint32_t)b << 16) | (uint32_t)t;
+  }
+}
+
+__global__ void attention_work_kernel(const int32_t* __restrict__ lens32, int batch, uint32_t* __restrict__ work, int cap,
+                                      int32_t* __restrict__ count) {
+  __shared__ int bins[1024];
+  build_attention_work(lens32, batch, work, cap, count, bins);
+}
+
+// [B, L] arrays the forward fills only at real positions (predictions scattered through `slot`) start from zero, and the
+// source padding mask (utils/tools.py:152-160) is written, by the same grid that builds the row metadata: one launch
+// instead of a memset per array.
+struct SlotInit {
+  float* zero[6];            // each [n] or nullptr
+  int64_t n;                 // B * L
+  uint8_t* src_mask;         // [n] or nullptr: 1 = padding
+  const int64_t* src_lens;   // [B]
+  int max_src_len;
+};
+
 // Per-row metadata from the starts.  max_len comes from a device scalar (totals[1]) when
 // max_len_dev != nullptr (frame side: T_max is only known on the device when this is enqueued).
 __global__ void row_meta_kernel(const int32_t* __restrict__ starts, const int32_t* __restrict__ lens, int batch,
                                 int gap, int max_len_host, const int64_t* __restrict__ max_len_dev, int rows_alloc,
                                 int32_t* __restrict__ utt, int32_t* __restrict__ vpos, int32_t* __restrict__ room,
-                                int32_t* __restrict__ slot) {
+                                int32_t* __restrict__ slot, uint32_t* __restrict__ work = nullptr, int work_cap = 0,
+                                int32_t* __restrict__ work_count = nullptr, SlotInit init = SlotInit{}) {
+  if (work != nullptr && blockIdx.x == gridDim.x - 1) {   // the last block also builds the attention work list of this side
+    __shared__ int bins[1024];
+    build_attention_work(lens, batch, work, work_cap, work_count, bins);
+  }
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = r; i < init.n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (init.zero[k] != nullptr) init.zero[k][i] = 0.f;
+    if (init.src_mask != nullptr) init.src_mask[i] = (i % init.max_src_len) >= init.src_lens[i / init.max_src_len] ? 1 : 0;
+  }
   if (r >= rows_alloc) return;
   const int max_len = max_len_dev ? (int)*max_len_dev : max_len_host;
   int u = -1, vp = VPOS_DEAD, rm = 0, sl = -1;
@@ -240,56 +311,6 @@ __global__ void add_cond_kernel(const float* __restrict__ x, RowMeta meta, const
 }
 
 // ---------------------------------------------------------------------------------------
-// LayerNorm over 256 columns (eps 1e-5, biased variance), optional row mask, optional fused
-// 256->1 head (VariancePredictor.linear_layer, model/modules.py:245-250) scattered to
-// head_out[slot[row]] for real rows.  Warp per row, two-pass in registers.
-__global__ void layernorm_kernel(const float* __restrict__ x, int rows, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, const int32_t* __restrict__ vpos,
-                                 const int32_t* __restrict__ room, int extra, float* __restrict__ y,
-                                 const float* __restrict__ head_w, const float* __restrict__ head_b,
-                                 float* __restrict__ head_out, const int32_t* __restrict__ slot) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const bool live = vpos == nullptr || row_live(vpos[row], room[row], extra);
-  if (!live) {
-    if (y != nullptr) {
-      st4(y + (size_t)row * D_MODEL + lane * 4, make_float4(0, 0, 0, 0));
-      st4(y + (size_t)row * D_MODEL + 128 + lane * 4, make_float4(0, 0, 0, 0));
-    }
-    return;
-  }
-  const float* src = x + (size_t)row * D_MODEL;
-  const float4 a = ld4(src + lane * 4), b = ld4(src + 128 + lane * 4);
-  const float mean = warp_sum(a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w) * (1.f / D_MODEL);
-  float4 ca = make_float4(a.x - mean, a.y - mean, a.z - mean, a.w - mean);
-  float4 cb = make_float4(b.x - mean, b.y - mean, b.z - mean, b.w - mean);
-  const float var = warp_sum(ca.x * ca.x + ca.y * ca.y + ca.z * ca.z + ca.w * ca.w + cb.x * cb.x + cb.y * cb.y +
-                             cb.z * cb.z + cb.w * cb.w) * (1.f / D_MODEL);
-  const float rstd = 1.f / sqrtf(var + 1e-5f);
-  const float4 ga = ld4(gamma + lane * 4), gb = ld4(gamma + 128 + lane * 4);
-  const float4 ba = ld4(beta + lane * 4), bb = ld4(beta + 128 + lane * 4);
-  const float4 ya = make_float4(ca.x * rstd * ga.x + ba.x, ca.y * rstd * ga.y + ba.y, ca.z * rstd * ga.z + ba.z,
-                                ca.w * rstd * ga.w + ba.w);
-  const float4 yb = make_float4(cb.x * rstd * gb.x + bb.x, cb.y * rstd * gb.y + bb.y, cb.z * rstd * gb.z + bb.z,
-                                cb.w * rstd * gb.w + bb.w);
-  if (y != nullptr) {
-    st4(y + (size_t)row * D_MODEL + lane * 4, ya);
-    st4(y + (size_t)row * D_MODEL + 128 + lane * 4, yb);
-  }
-  if (head_out != nullptr) {
-    const float4 wa = ld4(head_w + lane * 4), wb = ld4(head_w + 128 + lane * 4);
-    float d = ya.x * wa.x + ya.y * wa.y + ya.z * wa.z + ya.w * wa.w + yb.x * wb.x + yb.y * wb.y + yb.z * wb.z +
-              yb.w * wb.w;
-    d = warp_sum(d) + head_b[0];
-    if (lane == 0) {
-      const int dst = slot ? slot[row] : row;
-      if (dst >= 0) head_out[dst] = d;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------
 // torch.bucketize(v, bins, right=False): number of boundaries strictly below v; NaN -> n_bins.
 __device__ __forceinline__ int bucket_of(float v, const float* __restrict__ bins, int n_bins) {
   int lo = 0, hi = n_bins;
@@ -352,10 +373,15 @@ __global__ void bucket_embed_add_kernel(const float* __restrict__ x, RowMeta met
 // ---------------------------------------------------------------------------------------
 // Durations (model/modules.py:132-135) -> repeat counts max(int(d),0) (modules.py:186-187) ->
 // inclusive scan per utterance.  Warp per utterance.  Padding positions expand to nothing.
+// When energy_out != nullptr the same pass also writes the energy prediction the forward returns (modules.py:93-100:
+// raw * control, or the raw prediction when a target is embedded instead; 0 at padding) -- its bucketize + embedding add
+// happens inside the length regulator.
 __global__ void durations_kernel(const float* __restrict__ d_in, int is_target, float d_control,
                                  const int64_t* __restrict__ src_lens, int batch, int max_src_len,
                                  float* __restrict__ d_rounded, int32_t* __restrict__ cum,
-                                 int64_t* __restrict__ mel_lens, int32_t* __restrict__ mel_lens32) {
+                                 int64_t* __restrict__ mel_lens, int32_t* __restrict__ mel_lens32,
+                                 const float* __restrict__ energy_raw = nullptr, float energy_scale = 1.f,
+                                 float* __restrict__ energy_out = nullptr) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= batch) return;
@@ -379,6 +405,7 @@ __global__ void durations_kernel(const float* __restrict__ d_in, int is_target, 
         const float t = truncf(d);
         reps = t > 0.f ? (t < 1048576.f ? (int)t : 1048576) : 0;
       }
+      if (energy_out != nullptr) energy_out[i] = j < len ? energy_raw[i] * energy_scale : 0.f;
     }
     int inc = reps;
 #pragma unroll
@@ -446,6 +473,18 @@ __global__ void length_regulate_kernel(const float* __restrict__ x, const int32_
   }
 }
 
+// Phoneme-level energy (model/modules.py:122-126): the bucketize + embedding add of the energy feature is applied to the
+// phoneme row while it sits in registers, instead of in a pass of its own.  table == nullptr: off.
+struct EnergyAdd {
+  const float* raw;      // [B, L] raw predictions (0 at padding)
+  const float* target;   // [B, L] or nullptr
+  float control;         // p_control (sic: modules.py:123-125)
+  const float* bins;
+  int n_bins;
+  const float* table;    // [256, 256]
+  float* va_out;         // optional [rows_p, 256] copy of x + embedding (debug tap "va_x")
+};
+
 // The same expansion driven from the SOURCE side (the product path): a warp owns one phoneme row, keeps its 1 KB in
 // registers and streams it to the frames [cum[j-1], cum[j]) it expands to, adding the positional row of each frame.  No
 // per-frame binary search and one dependent load chain per phoneme instead of per frame, so the kernel is bound by the
@@ -456,7 +495,7 @@ __global__ void length_regulate_scatter_kernel(const float* __restrict__ x, RowM
                                                const int32_t* __restrict__ f_starts, const int32_t* __restrict__ f_lens,
                                                int batch, int gap, const int64_t* __restrict__ f_totals,
                                                const float* __restrict__ pe, int rows_f, float* __restrict__ y,
-                                               __nv_bfloat16* __restrict__ yb) {
+                                               __nv_bfloat16* __restrict__ yb, EnergyAdd en = EnergyAdd{}) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const float4 zero = make_float4(0, 0, 0, 0);
@@ -472,7 +511,18 @@ __global__ void length_regulate_scatter_kernel(const float* __restrict__ x, RowM
     const int t0 = j > 0 ? c[j - 1] : 0, t1 = c[j];
     if (t1 <= t0) return;
     const float* src = x + (size_t)w * D_MODEL;
-    const float4 a = ld4(src + lane * 4), b = ld4(src + 128 + lane * 4);
+    float4 a = ld4(src + lane * 4), b = ld4(src + 128 + lane * 4);
+    if (en.table != nullptr) {   // x + energy_embedding[bucketize(energy)] (model/modules.py:93-100,126), fused into the expansion
+      const size_t sl = (size_t)u * max_src_len + j;
+      const float value = en.target != nullptr ? en.target[sl] : en.raw[sl] * en.control;
+      const float* e = en.table + (size_t)bucket_of(value, en.bins, en.n_bins) * D_MODEL;
+      a = add4(a, ld4(e + lane * 4));
+      b = add4(b, ld4(e + 128 + lane * 4));
+      if (en.va_out != nullptr) {   // debug tap: the variance adaptor's output row
+        st4(en.va_out + (size_t)w * D_MODEL + lane * 4, a);
+        st4(en.va_out + (size_t)w * D_MODEL + 128 + lane * 4, b);
+      }
+    }
     const int base = f_starts[u];
     if (pe == nullptr) {                               // a frame_level predictor runs first: plain copies
       for (int t = t0; t < t1; ++t) {
@@ -571,13 +621,6 @@ __global__ void unpack_mel_kernel(const float* __restrict__ mel_p, const float* 
   st4(post + i * 4, p);
 }
 
-__global__ void src_mask_kernel(const int64_t* __restrict__ src_lens, int batch, int max_src_len,
-                                uint8_t* __restrict__ mask) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)batch * max_src_len) return;
-  mask[i] = (i % max_src_len) >= src_lens[i / max_src_len] ? 1 : 0;
-}
-
 // ---------------------------------------------------------------------------------------
 // Weight repack (once, in fs2_prepare).
 __device__ __forceinline__ float round_tf32(float x) {
@@ -598,6 +641,36 @@ __global__ void repack_conv_kernel(const float* __restrict__ w, int cout, int ci
   float v = w[((size_t)co * cin + ci) * k + t];
   if (scale != nullptr) v *= scale[co];
   out[i] = round_operand ? round_tf32(v) : v;
+}
+
+// FS2_MATH_TF32X3: w = hi + lo with both parts exactly representable in TF32; out = [hi block ; lo block], each [k][Cout][Cin].
+__global__ void repack_conv_split_kernel(const float* __restrict__ w, int cout, int cin, int k,
+                                         const float* __restrict__ scale, float* __restrict__ out, int64_t lo_off) {
+  const int64_t n = (int64_t)cout * cin * k;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int ci = (int)(i % cin);
+  const int co = (int)((i / cin) % cout);
+  const int t = (int)(i / ((int64_t)cin * cout));
+  float v = w[((size_t)co * cin + ci) * k + t];
+  if (scale != nullptr) v *= scale[co];
+  const float hi = round_tf32(v);
+  out[i] = hi;
+  out[lo_off + i] = round_tf32(v - hi);   // lo_off = distance from a hi element to its lo element (>= n)
+}
+
+// Activations of a split-operand contraction: x [rows, K] (pitch ldx) -> out [rows, 2K] = [hi | lo].
+__global__ void split_tf32_kernel(const float* __restrict__ x, int rows, int K, int ldx, float* __restrict__ out) {
+  const int k4 = K >> 2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * k4) return;
+  const int64_t r = i / k4;
+  const int c = (int)(i - r * k4) * 4;
+  const float4 v = ld4(x + r * ldx + c);
+  const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+  const float4 lo = make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
+  st4(out + r * 2 * K + c, hi);
+  st4(out + r * 2 * K + K + c, lo);
 }
 
 // The same repack with the operands rounded to bf16 (round to nearest even) -- FS2_MATH_BF16.

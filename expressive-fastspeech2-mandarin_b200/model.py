@@ -68,7 +68,7 @@ def _schema(n_speaker, n_emotion, n_arousal, n_valence, max_seq_len):
 class FastSpeech2B200(nn.Module):
     """Drop-in for `FastSpeech2(preprocess_config, model_config)` in eval mode on one B200."""
 
-    def __init__(self, preprocess_config, model_config, math_mode="tf32", engine="tcgen05", init_seed=0):
+    def __init__(self, preprocess_config, model_config, math_mode="tf32", init_seed=0):
         super().__init__()
         check_supported(preprocess_config, model_config)
         self.model_config = model_config
@@ -85,9 +85,9 @@ class FastSpeech2B200(nn.Module):
         pp = preprocess_config["preprocessing"]                    # model/modules.py:28-35
         self.pitch_frame_level = pp["pitch"]["feature"] == "frame_level"
         self.energy_frame_level = pp["energy"]["feature"] == "frame_level"
-        self.math_mode = {"tf32": _lib.MATH_TF32, "bf16": _lib.MATH_BF16}[math_mode]
-        self.engine = {"mma_sync": _lib.ENGINE_MMA_SYNC, "tcgen05": _lib.ENGINE_TCGEN05,
-                       "tcgen05_v1": _lib.ENGINE_TCGEN05_V1}[engine]
+        # "tf32" (default), "bf16" (bf16 operands) or "parity" (split-operand 3xTF32 contractions, ~1e-4 of fp64)
+        self.math_mode = {"tf32": _lib.MATH_TF32, "bf16": _lib.MATH_BF16, "parity": _lib.MATH_TF32X3,
+                          "tf32x3": _lib.MATH_TF32X3}[math_mode]
 
         # Parameter tree built from the schema; values: deterministic tables where the reference
         # computes them (position_enc, bins), seeded random elsewhere (the reference random-inits).
@@ -165,7 +165,7 @@ class FastSpeech2B200(nn.Module):
             lib.fs2_destroy(self._ctx)
             self._ctx = None
         if self._ctx is None:
-            cfg = _lib.Config(math_mode=self.math_mode, engine=self.engine, pitch_frame_level=int(self.pitch_frame_level),
+            cfg = _lib.Config(math_mode=self.math_mode, pitch_frame_level=int(self.pitch_frame_level),
                               energy_frame_level=int(self.energy_frame_level), **self._dims)
             ctx = C.c_void_p()
             code = lib.fs2_create(C.byref(cfg), dev.index if dev.index is not None else torch.cuda.current_device(),

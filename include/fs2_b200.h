@@ -35,14 +35,14 @@ enum {
   FS2_ERR_UNSUPPORTED = -4  /* hyper-parameters the kernels are not compiled for */
 };
 
-/* Arithmetic of the tensor-core contractions (accumulation, LayerNorm and softmax are fp32 in both).
- * TF32: fp32 activations, operands rounded to TF32.  BF16: every Conv1d/Linear takes bf16 operands (weights
- * rounded once, activations written as bf16 by the producing epilogue); the residual stream, the attention
- * (TF32), LayerNorm, softmax and all outputs stay fp32.  BF16 needs FS2_ENGINE_TCGEN05. */
-enum { FS2_MATH_TF32 = 0, FS2_MATH_BF16 = 1 };
-/* GEMM engines: the product path is TCGEN05; MMA_SYNC is the legacy-tensor-core cross-check
- * used by the unit tests and for bring-up. */
-enum { FS2_ENGINE_MMA_SYNC = 0, FS2_ENGINE_TCGEN05 = 1, FS2_ENGINE_TCGEN05_V1 = 2 /* non-persistent bring-up variant */ };
+/* Arithmetic of the tensor-core contractions (accumulation, LayerNorm and softmax are fp32 in all modes).
+ * TF32: fp32 activations, operands rounded to TF32 -- the arithmetic class of the reference's own GPU run (cuDNN convs
+ * use TF32 by default).  BF16: every Conv1d/Linear takes bf16 operands (weights rounded once, activations written as
+ * bf16 by the producing epilogue); the residual stream, LayerNorm, softmax and all outputs stay fp32.
+ * TF32X3 ("parity" mode): every Conv1d/Linear runs as a split-operand contraction a_hi*w_hi + a_lo*w_hi + a_hi*w_lo on
+ * the same tensor-core kernel (three times the MMAs), which brings the mel to ~1e-4 of the fp64 reference
+ * (tests/test_gpu_forward.py states the tolerance); the attention products stay TF32. */
+enum { FS2_MATH_TF32 = 0, FS2_MATH_BF16 = 1, FS2_MATH_TF32X3 = 2 };
 
 /* Model dimensions that are data (table sizes); the layer structure is fixed to
  * config/ESD-Chinese-Singing-MFA/model.yaml (d_model 256, 2 heads, 4+6 FFT blocks,
@@ -55,7 +55,6 @@ typedef struct {
   int32_t n_valence;    /* model/fastspeech2.py:54    */
   int32_t max_seq_len;  /* model.yaml:27; position_enc has max_seq_len+1 rows */
   int32_t math_mode;    /* FS2_MATH_*  */
-  int32_t engine;       /* FS2_ENGINE_* */
   /* preprocess.yaml preprocessing.{pitch,energy}.feature (model/modules.py:28-35): 0 = phoneme_level (the
    * predictor runs before the LengthRegulator, modules.py:114-125), 1 = frame_level (after it, :139-148). */
   int32_t pitch_frame_level;
@@ -74,7 +73,9 @@ typedef struct {
   const int64_t* src_lens; /* device [B] */
   const float* p_targets;  /* device [B, max_src_len] or NULL (model/modules.py:82-83); [B, max_mel_len] when the
                               feature is frame_level (must stay valid until fs2_forward_stage2 has been enqueued) */
-  const float* e_targets;  /* device [B, max_src_len] or NULL (model/modules.py:93-94); frame_level: as above */
+  const float* e_targets;  /* device [B, max_src_len] or NULL (model/modules.py:93-94); frame_level: as above.  Must stay
+                              valid until fs2_forward_stage2 has been enqueued in every configuration: the energy
+                              bucketize + embedding add runs inside the length regulator of stage 2 */
   const float* d_targets;  /* device [B, max_src_len] or NULL (model/modules.py:128-130) */
   float p_control;         /* scales pitch AND energy (model/modules.py:118-125) */
   float e_control;         /* accepted and ignored, as in the reference */
@@ -161,16 +162,17 @@ int fs2_profile_read(fs2_ctx* ctx, char* buf, int64_t buf_bytes);
  * rows outside [0,rows) read as zero; then rows with row_vpos[r] >= min(extra,row_room[r]) are
  * zeroed when row_vpos != NULL.  act: 0 none, 1 relu, 2 tanh.  This is every Conv1d / Linear of
  * the path in token-major layout (SubLayers.py:39-41,54,87-88; modules.py:243-247;
- * fastspeech2.py:134; Layers.py:129-137). */
-int fs2_op_conv_gemm(fs2_stream stream, int engine, int math_mode, const float* A, int lda, int rows,
+ * fastspeech2.py:134; Layers.py:129-137).  math_mode FS2_MATH_TF32: W holds TF32-rounded values;
+ * FS2_MATH_TF32X3: W is the plain fp32 weight and both operands are split (hi + lo) inside the call. */
+int fs2_op_conv_gemm(fs2_stream stream, int math_mode, const float* A, int lda, int rows,
                      const float* W, const float* bias, int taps, int pad, int K, int N, int act,
                      const float* residual, int ldr, const int32_t* row_vpos, const int32_t* row_room,
                      int extra, float* C, int ldc);
-/* The same contraction with the fused post-LayerNorm epilogue of the persistent tcgen05 engine
+/* The same contraction with the fused post-LayerNorm epilogue
  * (N = 256): y = LayerNorm(act(conv + bias) + residual) * gamma + beta, masked rows -> 0
  * (SubLayers.py:54-55,87-91; modules.py:243-247), optional head dot[r] = y[r,:].head_w + head_b
  * (modules.py:245-246).  C may be NULL when only `head_out` ([rows]) is wanted. */
-int fs2_op_conv_gemm_ln(fs2_stream stream, int engine, const float* A, int lda, int rows, const float* W,
+int fs2_op_conv_gemm_ln(fs2_stream stream, const float* A, int lda, int rows, const float* W,
                         const float* bias, int taps, int pad, int K, int act, const float* residual, int ldr,
                         const float* gamma, const float* beta, const int32_t* row_vpos, const int32_t* row_room,
                         int extra, float* C, int ldc, const float* head_w, const float* head_b, float* head_out);
@@ -182,7 +184,7 @@ int fs2_op_conv_gemm_ln(fs2_stream stream, int engine, const float* A, int lda, 
 int fs2_op_ffn_fused(fs2_stream stream, const float* x, int rows, const float* w1, const float* b1, const float* w2,
                      const float* b2, const float* gamma, const float* beta, const int32_t* row_vpos,
                      const int32_t* row_room, int extra, float* y);
-/* The vocoder's form of the contraction (persistent tcgen05 engine, TF32): dilated taps (tap t reads row
+/* The vocoder's form of the contraction (TF32): dilated taps (tap t reads row
  * r + (t - (taps-1)/2) * dil; hifigan/models.py:27-55), leaky ReLU (act = 3, `slope`) before and/or after (`act2`) the
  * residual add, a residual buffer that holds lrelu(x) and is inverted on the fly (`res_inv_lrelu`), and a row mask
  * looked up at row >> mask_shift (rows of an upsampled stage share the mask of their mel frame).  Small-K multi-tap
@@ -202,15 +204,10 @@ int fs2_op_conv_gemm_bf16(fs2_stream stream, const void* A, int lda, int rows, c
                           int extra, float* C, int ldc, void* C2, int ldc2);
 /* Varlen 2-head self-attention over packed rows (SubLayers.py:42-52, Modules.py:14-25):
  * qkv [rows,768] = [q | k | v], heads are 128-wide halves; utterance b owns rows
- * [starts[b], starts[b]+lens[b]); rows = rows of the qkv buffer.  out [rows,256]. */
-int fs2_op_attention(fs2_stream stream, int engine, const float* qkv, int rows, const int32_t* starts,
+ * [starts[b], starts[b]+lens[b]); rows = rows of the qkv buffer.  out [rows,256].  The call builds the
+ * longest-utterance-first work list the forward keeps per batch (one entry per 128 queries). */
+int fs2_op_attention(fs2_stream stream, const float* qkv, int rows, const int32_t* starts,
                      const int32_t* lens, int batch, int max_len, float* out);
-/* y = LayerNorm(x) * gamma + beta over 256 columns, eps 1e-5, biased variance
- * (SubLayers.py:55,91; modules.py:224,234); masked rows -> 0; optional fused head
- * dot[r] = y[r,:]·head_w + head_b (modules.py:245-246). */
-int fs2_op_layernorm(fs2_stream stream, const float* x, int rows, const float* gamma, const float* beta,
-                     const int32_t* row_vpos, const int32_t* row_room, int extra,
-                     float* y, const float* head_w, const float* head_b, float* dot);
 /* Durations -> repeat counts -> per-utterance inclusive scan (modules.py:132-135,186-187).
  * d_in: log-durations (is_target=0) or target durations (is_target=1), [B,L].  Writes
  * d_rounded [B,L] (fp32), cum [B,L] (int32 inclusive prefix sums of the repeat counts) and

@@ -19,16 +19,15 @@ def lib():
     return _lib.load_library()
 
 
-def model_for(sd, math_mode="tf32", engine=None, key="seed0", pitch_level="phoneme_level", energy_level="phoneme_level"):
-    engine = engine or os.environ.get("FS2_ENGINE", "tcgen05")
-    k = (key, math_mode, engine, pitch_level, energy_level)
+def model_for(sd, math_mode="tf32", key="seed0", pitch_level="phoneme_level", energy_level="phoneme_level"):
+    k = (key, math_mode, pitch_level, energy_level)
     if k not in _MODELS:
         d = fs2_b200.synthetic.write_fixture_jsons(tempfile.mkdtemp(prefix="fs2_json_"))
         pre = fs2_b200.config.default_preprocess_config(d)
         pre["preprocessing"]["pitch"]["feature"] = pitch_level
         pre["preprocessing"]["energy"]["feature"] = energy_level
         m = fs2_b200.FastSpeech2B200(pre,
-                                     fs2_b200.config.default_model_config(), math_mode=math_mode, engine=engine)
+                                     fs2_b200.config.default_model_config(), math_mode=math_mode)
         m.load_state_dict(sd)
         _MODELS[k] = m.to(DEV)
     return _MODELS[k]

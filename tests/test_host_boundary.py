@@ -77,7 +77,7 @@ def test_library_exports_every_declared_symbol(library):
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
 def test_create_fails_loudly_without_a_gpu(library):
     cfg = _lib.Config(n_src_vocab=139, n_speaker=10, n_emotion=5, n_arousal=4, n_valence=5, max_seq_len=2000,
-                      math_mode=0, engine=0)
+                      math_mode=0)
     ctx = ctypes.c_void_p()
     code = library.fs2_create(ctypes.byref(cfg), 0, ctypes.byref(ctx))
     assert code != 0

@@ -6,7 +6,7 @@ import numpy as np, torch
 from gpu_util import DEV, lib, ptr, stream
 torch.set_printoptions(precision=3, linewidth=220, sci_mode=False)
 
-def run(qkv, lens, engine=1):
+def run(qkv, lens):
     gap = 4
     starts, r = [], gap
     for n in lens:
@@ -17,7 +17,7 @@ def run(qkv, lens, engine=1):
     out = torch.zeros(rows, 256, device=DEV)
     ds = torch.tensor(starts, dtype=torch.int32, device=DEV)
     dl = torch.tensor(lens, dtype=torch.int32, device=DEV)
-    code = lib().fs2_op_attention(stream(), engine, ptr(dq), rows, ptr(ds), ptr(dl), len(lens), max(lens), ptr(out))
+    code = lib().fs2_op_attention(stream(), ptr(dq), rows, ptr(ds), ptr(dl), len(lens), max(lens), ptr(out))
     assert code == 0, lib().fs2_last_error(None)
     torch.cuda.synchronize()
     return out.cpu(), starts

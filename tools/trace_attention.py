@@ -14,14 +14,14 @@ qkv = torch.randn(rows, 768, device=DEV)
 out = torch.zeros(rows, 256, device=DEV)
 ds = torch.tensor(starts, dtype=torch.int32, device=DEV); dl = torch.tensor(lens, dtype=torch.int32, device=DEV)
 for _ in range(3):
-    L.fs2_op_attention(stream(), 1, ptr(qkv), rows, ptr(ds), ptr(dl), len(lens), max(lens), ptr(out))
+    L.fs2_op_attention(stream(), ptr(qkv), rows, ptr(ds), ptr(dl), len(lens), max(lens), ptr(out))
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); L.fs2_op_attention(stream(), 1, ptr(qkv), rows, ptr(ds), ptr(dl), len(lens), max(lens), ptr(out)); e1.record(); torch.cuda.synchronize()
+e0.record(); L.fs2_op_attention(stream(), ptr(qkv), rows, ptr(ds), ptr(dl), len(lens), max(lens), ptr(out)); e1.record(); torch.cuda.synchronize()
 print("attention 64x640: %.1f us" % (e0.elapsed_time(e1) * 1e3), "CTAs", 64 * 2 * 5)
 L.fs2_debug_set_flag(0, 4)
 out.zero_()
-L.fs2_op_attention(stream(), 1, ptr(qkv), rows, ptr(ds), ptr(dl), len(lens), max(lens), ptr(out))
+L.fs2_op_attention(stream(), ptr(qkv), rows, ptr(ds), ptr(dl), len(lens), max(lens), ptr(out))
 torch.cuda.synchronize()
 L.fs2_debug_set_flag(0, 0)
 t = out[starts[0]].cpu().numpy()[:160].reshape(10, 16)

@@ -7,7 +7,7 @@ L = lib()
 for rows, K, N, taps in [(128, 256, 768, 1), (128, 256, 1024, 9), (26788, 256, 768, 1)]:
     A = torch.randn(rows, K, device=DEV); W = torch.randn(taps, N, K, device=DEV) / 16; bias = torch.randn(N, device=DEV)
     out = torch.empty(rows, N, device=DEV)
-    call = lambda: L.fs2_op_conv_gemm(stream(), 1, 0, ptr(A), K, rows, ptr(W), ptr(bias), taps, (taps - 1) // 2, K, N, 0, None, N, None, None, 0, ptr(out), N)
+    call = lambda: L.fs2_op_conv_gemm(stream(), 0, ptr(A), K, rows, ptr(W), ptr(bias), taps, (taps - 1) // 2, K, N, 0, None, N, None, None, 0, ptr(out), N)
     for _ in range(3): call()
     torch.cuda.synchronize()
     L.fs2_debug_set_flag(1, 1)
@@ -25,7 +25,7 @@ print("==== back-to-back launches: gap between exit of kernel i and entry of ker
 rows, K, N, taps = 128, 256, 768, 1
 A = torch.randn(rows, K, device=DEV); W = torch.randn(taps, N, K, device=DEV) / 16; bias = torch.randn(N, device=DEV)
 out = torch.empty(rows, N, device=DEV)
-call = lambda: L.fs2_op_conv_gemm(stream(), 1, 0, ptr(A), K, rows, ptr(W), ptr(bias), taps, 0, K, N, 0, None, N, None, None, 0, ptr(out), N)
+call = lambda: L.fs2_op_conv_gemm(stream(), 0, ptr(A), K, rows, ptr(W), ptr(bias), taps, 0, K, N, 0, None, N, None, None, 0, ptr(out), N)
 for _ in range(3): call()
 torch.cuda.synchronize()
 L.fs2_debug_set_flag(1, 1)
@@ -45,7 +45,7 @@ for rows, K in [(128, 256), (128, 1024), (26788, 256), (26788, 1024)]:
     A = torch.randn(rows, K, device=DEV); W = torch.randn(1, 256, K, device=DEV) / 16; bias = torch.randn(256, device=DEV)
     res = torch.randn(rows, 256, device=DEV); gm = torch.ones(256, device=DEV); bt = torch.zeros(256, device=DEV)
     out = torch.empty(rows, 256, device=DEV)
-    call = lambda: L.fs2_op_conv_gemm_ln(stream(), 1, ptr(A), K, rows, ptr(W), ptr(bias), 1, 0, K, 0, ptr(res), 256, ptr(gm), ptr(bt), None, None, 0, ptr(out), 256, None, None, None)
+    call = lambda: L.fs2_op_conv_gemm_ln(stream(), ptr(A), K, rows, ptr(W), ptr(bias), 1, 0, K, 0, ptr(res), 256, ptr(gm), ptr(bt), None, None, 0, ptr(out), 256, None, None, None)
     for _ in range(3): call()
     torch.cuda.synchronize()
     L.fs2_debug_set_flag(1, 1)
@@ -63,9 +63,9 @@ for name, K, N, taps, ln in [("qkv", 256, 768, 1, False), ("fc_ln", 256, 256, 1,
     res = torch.randn(rows, N, device=DEV); gm = torch.ones(256, device=DEV); bt = torch.zeros(256, device=DEV)
     out = torch.empty(rows, N, device=DEV)
     if ln:
-        call = lambda: L.fs2_op_conv_gemm_ln(stream(), 1, ptr(A), K, rows, ptr(W), ptr(bias), taps, (taps-1)//2, K, 0, ptr(res), 256, ptr(gm), ptr(bt), None, None, 0, ptr(out), 256, None, None, None)
+        call = lambda: L.fs2_op_conv_gemm_ln(stream(), ptr(A), K, rows, ptr(W), ptr(bias), taps, (taps-1)//2, K, 0, ptr(res), 256, ptr(gm), ptr(bt), None, None, 0, ptr(out), 256, None, None, None)
     else:
-        call = lambda: L.fs2_op_conv_gemm(stream(), 1, 0, ptr(A), K, rows, ptr(W), ptr(bias), taps, (taps-1)//2, K, N, 0, None, N, None, None, 0, ptr(out), N)
+        call = lambda: L.fs2_op_conv_gemm(stream(), 0, ptr(A), K, rows, ptr(W), ptr(bias), taps, (taps-1)//2, K, N, 0, None, N, None, None, 0, ptr(out), N)
     for _ in range(3): call()
     torch.cuda.synchronize()
     L.fs2_debug_set_flag(1, 1)
