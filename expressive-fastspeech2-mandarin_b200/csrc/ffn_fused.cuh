@@ -23,7 +23,8 @@ namespace ffn {
 using namespace tc2;   // (which itself brings in the PTX helpers of namespace tc)
 
 constexpr int BM = tc2::BM;              // local names win over the same-named constants of the older engines
-constexpr int THREADS = tc2::THREADS;
+constexpr int THREADS = 192;             // TMA producer, MMA issuer, four epilogue warps
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
 constexpr int HC = 256;                       // hidden columns per chunk = N of the first MMA = K of the second
 constexpr int N_CHUNKS = D_INNER / HC;        // 4
 constexpr int KC1 = D_MODEL / 32;             // 8 K chunks of the conv

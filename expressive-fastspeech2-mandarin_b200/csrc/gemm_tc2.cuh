@@ -32,7 +32,6 @@ using namespace tc;
 
 constexpr int BM = 128;
 constexpr int BK = 32;
-constexpr int THREADS = 192;
 constexpr int WCHUNK = 32 * 128;        // one warp's [32 rows x 32 fp32] swizzled sub-tile (4 KB)
 constexpr int MAX_N = 2048;
 
@@ -63,12 +62,13 @@ struct Cfg {
   // Three 24 KB buffers (requested two tiles ahead) fit; three 48 KB buffers do not.
   static constexpr int AR_BUFS = AR == 1 ? 3 : 2;
   static constexpr int OFF_RING = AR_BUFS * AR_BUF_BYTES;
-  static constexpr int OFF_CST = OFF_RING + STAGES * STAGE_BYTES;      // 4 warps x 2 output staging sub-tiles
-  static constexpr int OFF_RES = OFF_CST + 8 * WCHUNK;      // 4 warps x 2 residual sub-tiles
+  static constexpr int OFF_CST = OFF_RING + STAGES * STAGE_BYTES;      // 4 warps x 2 (or 8 warps x 1) output staging sub-tiles
+  static constexpr int OFF_RES = OFF_CST + 8 * WCHUNK;      // 4 warps x 2 (or 8 warps x 1) residual sub-tiles
   static constexpr int OFF_PAR = OFF_RES + 8 * WCHUNK;      // bias[2048] | gamma[256] | beta[256] | head_w[256]
   static constexpr int OFF_BAR = OFF_PAR + 12288;
   static constexpr int OFF_STAT = OFF_BAR + 256;            // N-split: float2 [2 parities][4 source ranks][128 rows]
-  static constexpr int TOTAL = OFF_STAT + (NS > 1 ? 8192 : 0) + 1024;
+  static constexpr int OFF_PAIR = OFF_STAT + (NS > 1 ? 8192 : 0);   // two LayerNorm warps per lane quarter: float2 [2][2][128]
+  static constexpr int TOTAL = OFF_PAIR + (NS > 1 ? 0 : 4096) + 1024;
   static constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static constexpr int NCHUNK = (BN + 31) / 32;
@@ -89,7 +89,6 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
 
 // explicit shared-space 16-byte accesses (the generic pointers derived from the aligned dynamic
 // smem base would otherwise compile to generic LD/ST)
@@ -197,8 +196,8 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 // weight columns, and the LayerNorm statistics of the row are combined across the cluster through distributed shared
 // memory (two floats per row and CTA).  For a handful of row tiles (single utterances) this puts NS SMs on a K loop
 // that one CTA would walk alone: the fused-LN GEMMs were 40 % of the single-utterance latency.
-template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1, bool TWO = false>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1, bool TWO = false, int EW = 4>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                      const __grid_constant__ CUtensorMap tmC2, ConvGemmArgs p) {
@@ -207,6 +206,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   static_assert(!(AR && LN), "A-resident mode: plain epilogue");
   static_assert(!(AR == 2 && BF), "bf16 A-resident tiles hold 64 channels in one K chunk: AR = 1");
   static_assert(NS == 1 || (LN && CL == 1 && !AR && BN * NS == 256), "N-split: fused LayerNorm over 256 columns, cluster along N");
+  static_assert(EW == 4 || (EW == 8 && NS == 1), "epilogue warps: one or two per TMEM lane quarter");
+  static_assert(!LN || EW == 4 || BN == 256, "two LayerNorm warps per quarter split 8 sub-tiles");
   constexpr int CSIZE = CL > 1 ? CL : NS;          // CTAs per cluster
   constexpr uint16_t CMASK = (uint16_t)((1u << CSIZE) - 1);
   constexpr int BKE = BF ? 64 : 32;   // operand elements per 128-byte swizzle row
@@ -238,6 +239,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* stat_full = a_empty + 3;        // [2]  NS: the peers' LayerNorm statistics of this tile parity have arrived
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_full + 2);
   float2* stat_s = reinterpret_cast<float2*>(smem + C::OFF_STAT);        // NS: [2 parities][4 source ranks][128 rows]
+  float2* pair_stat = reinterpret_cast<float2*>(smem + C::OFF_PAIR);     // EW = 8: [2 parities][2 halves][128 rows]
   uint8_t* ring = smem + C::OFF_RING;
 
   const int warp = warp_index(), lane = threadIdx.x & 31;
@@ -266,7 +268,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int u = 0; u < 2; ++u) {
       mbar_init(&acc_full[u], 1);
-      mbar_init(&acc_empty[u], TWO ? 256 : 128);   // 2-SM: the issuer waits for the epilogue threads of both CTAs
+      mbar_init(&acc_empty[u], (TWO ? 2 : 1) * EW * 32);   // 2-SM: the issuer waits for the epilogue threads of both CTAs
     }
     for (int u = 0; u < 8; ++u) mbar_init(&res_full[u], 1);
     for (int u = 0; u < 3; ++u) {
@@ -552,33 +554,48 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (lt == 0) stamp(3);
     }
   } else {
-    // ---------------- epilogue (4 independent warps; thread = one accumulator row)
+    // ---------------- epilogue: EW warps, thread = one accumulator row, every warp independent of the others.
+    // EW = 8: two warps share each TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31) and split the tile's
+    // 32-column sub-tiles between them, so every scheduler has TWO epilogue warps whose TMEM loads, shared-memory round
+    // trips, fences and TMA issues overlap.  Measured with one warp per scheduler (tools/trace_ln.py): ~0.45 us per
+    // sub-tile at ~0.2 instructions per cycle -- pure latency -- i.e. 7.7 us per 128 x 256 LayerNorm tile against a
+    // 4.5 us main loop.  Each warp then keeps ONE staging and ONE residual buffer (same shared memory as 4 x 2).
+    constexpr int EH = EW / 4;                       // warps per lane quarter
+    constexpr int NB = EH == 2 ? 1 : 2;              // staging / residual buffers per warp
+    constexpr int ET = EW * 32;                      // epilogue threads
     const int et = threadIdx.x - 64;
-    const int q = warp & 3;
+    const int ew = warp - 2;                         // 0 .. EW-1
+    const int q = warp & 3;                          // TMEM lane quarter of this warp
+    const int h = EH == 2 ? (ew >> 2) : 0;           // which share of the sub-tiles
     const int r = q * 32 + lane;                     // row inside the tile
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    uint8_t* my_cst = cst + q * 2 * WCHUNK;
-    uint8_t* my_res = res + q * 2 * WCHUNK;
-    uint64_t* my_res_full = res_full + q * 2;
+    constexpr int C_SPLIT = EH == 2 ? (C::NCHUNK + 1) / 2 : C::NCHUNK;
+    const int c_lo = h * C_SPLIT, c_hi = h == 0 ? C_SPLIT : C::NCHUNK;   // this warp's sub-tiles [c_lo, c_hi)
+    uint8_t* my_cst = cst + ew * NB * WCHUNK;
+    uint8_t* my_res = res + ew * NB * WCHUNK;
+    uint64_t* my_res_full = res_full + ew * NB;
     const uint32_t bias_sa = smem_u32(bias_s), gamma_sa = smem_u32(gamma_s), beta_sa = smem_u32(beta_s),
                    headw_sa = smem_u32(headw_s), cst_sa = smem_u32(my_cst), res_sa = smem_u32(my_res);
     const uint32_t swz_x = (uint32_t)(lane & 7) << 4;
     const int act = p.act;
-    for (int i = et; i < p.N; i += 128) bias_s[i] = p.bias[i];
+    for (int i = et; i < p.N; i += ET) bias_s[i] = p.bias[i];
     if (LN) {
-      for (int i = et; i < 256; i += 128) {
+      for (int i = et; i < 256; i += ET) {
         gamma_s[i] = p.ln_gamma[i];
         beta_s[i] = p.ln_beta[i];
         headw_s[i] = p.head_w != nullptr ? p.head_w[i] : 0.f;
       }
     }
-    epi_barrier();   // the only CTA-level epilogue barrier: parameters are in smem
-    int g_res = 0;   // residual sub-tiles consumed so far (buffer = g & 1, parity = (g >> 1) & 1)
+    asm volatile("bar.sync 1, %0;\n" ::"n"(ET) : "memory");   // the only CTA-level epilogue barrier: parameters are in smem
+#ifdef FS2_TRACE_BUILD
+    long long res_wait_cycles = 0;   // cycles this thread spent waiting for residual sub-tiles (tools/trace_ln.py)
+#endif
+    int g_res = 0;   // residual sub-tiles consumed so far (buffer = g % NB, parity = (g / NB) & 1)
     int g_st = 0;    // staging sub-tiles produced so far
     const uint32_t res_bytes = p.res_bf16 ? WCHUNK / 2 : WCHUNK;   // [32 rows x 32 columns] fp32 or bf16
-    if (has_res && lane == 0 && w_first < total_items) {  // first residual sub-tile of the first tile
+    if (has_res && lane == 0 && w_first < total_items && c_lo < c_hi) {  // first residual sub-tile of the first tile
       mbar_expect_tx(&my_res_full[0], res_bytes);
-      tma_load_2d(my_res, &tmR, item_n0(w_first), item_m0(w_first) + q * 32, &my_res_full[0]);
+      tma_load_2d(my_res, &tmR, item_n0(w_first) + c_lo * 32, item_m0(w_first) + q * 32, &my_res_full[0]);
     }
     int lt = 0;
     for (int w = w_first; w < total_items; w += w_step, ++lt) {
@@ -597,20 +614,28 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_after();
       const uint32_t acc = tmem_base + lane_sel + u * C::ACC_COLS;
       const int w_next = w + w_step;
+      auto release_acc = [&]() {   // this thread has read its last accumulator value of the tile
+        tc_fence_before();
+        if (TWO && rank != 0) mbar_arrive_remote(dsmem_addr(&acc_empty[u], 0));   // the issuer lives in the even CTA
+        else mbar_arrive(&acc_empty[u]);
+      };
 
-      // prefetch the residual sub-tile after (tile t, chunk c): next chunk of this tile or chunk 0 of
-      // the next tile.  Called by the whole warp AFTER a __syncwarp that follows the previous reads.
+      // Request the residual sub-tile that follows (tile w, sub-tile c) in this warp's sequence: its next sub-tile of this
+      // tile or its first one of the next tile.  Two buffers: called (by the whole warp, after a __syncwarp that follows
+      // the reads of the other buffer) when sub-tile c is taken up; one buffer: called right after sub-tile c's residual
+      // has been read.
       auto prefetch_res = [&](int c) {
         if (!has_res || lane != 0) return;
         int ww = w, cc = c + 1;
-        if (cc >= C::NCHUNK) { ww = w_next; cc = 0; }
+        if (cc >= c_hi) { ww = w_next; cc = c_lo; }
         if (ww >= total_items) return;
-        const int buf = (g_res + 1) & 1;
+        const int buf = (g_res + 1) % NB;
         mbar_expect_tx(&my_res_full[buf], res_bytes);
         tma_load_2d(my_res + buf * WCHUNK, &tmR, item_n0(ww) + cc * 32, item_m0(ww) + q * 32, &my_res_full[buf]);
       };
       // v = act(acc + bias) (+ residual from this warp's smem sub-tile)
-      auto finish = [&](float (&v)[32], int c0, int width) {
+      auto finish = [&](float (&v)[32], int c, int width) {
+        const int c0 = c * 32;
         const uint32_t ba = bias_sa + (uint32_t)(n0 + c0) * 4;
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
@@ -619,76 +644,106 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             v[cc * 4 + 0] += b4.x; v[cc * 4 + 1] += b4.y; v[cc * 4 + 2] += b4.z; v[cc * 4 + 3] += b4.w;
           }
         }
+        // (the fused-LayerNorm kernels serve the FFT blocks and the predictors only: no tanh, no vocoder options)
         if (act == ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        } else if (act == ACT_TANH) {
+        } else if (!LN && act == ACT_TANH) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-        } else if (act == ACT_LRELU) {
+        } else if (!LN && act == ACT_LRELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * p.slope;
         }
         if (has_res) {
-          mbar_wait(&my_res_full[g_res & 1], (g_res >> 1) & 1);
-          const float inv = p.res_inv_lrelu ? 1.f / p.slope : 1.f;   // residual stored as lrelu(x): undo it
-          if (p.res_bf16) {   // [32 rows x 64 B], SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3; bf16 -> fp32 is a 16-bit shift
-            const uint32_t rb = res_sa + (g_res & 1) * WCHUNK + lane * 64;
-            const uint32_t sx64 = (uint32_t)((lane >> 1) & 3) << 4;
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              if (cc * 8 < width) {
-                const float4 r4 = lds4(rb + ((cc << 4) ^ sx64));
-                const uint32_t w[4] = {__float_as_uint(r4.x), __float_as_uint(r4.y), __float_as_uint(r4.z), __float_as_uint(r4.w)};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xFFFF0000u);
-                  v[cc * 8 + 2 * e] += lo >= 0.f ? lo : lo * inv;
-                  v[cc * 8 + 2 * e + 1] += hi >= 0.f ? hi : hi * inv;
-                }
-              }
-            }
-          } else {
-            const uint32_t rb = res_sa + (g_res & 1) * WCHUNK + lane * 128;
+#ifdef FS2_TRACE_BUILD
+          const long long tw0 = clock64();
+#endif
+          mbar_wait(&my_res_full[g_res % NB], (g_res / NB) & 1);
+#ifdef FS2_TRACE_BUILD
+          res_wait_cycles += clock64() - tw0;
+#endif
+          const uint32_t rbase = res_sa + (g_res % NB) * WCHUNK;
+          if (LN || !(p.res_inv_lrelu || p.res_bf16)) {   // plain fp32 residual
+            const uint32_t rb = rbase + lane * 128;
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {
               if (cc * 4 < width) {
                 const float4 r4 = lds4(rb + ((cc << 4) ^ swz_x));
-                v[cc * 4 + 0] += r4.x >= 0.f ? r4.x : r4.x * inv; v[cc * 4 + 1] += r4.y >= 0.f ? r4.y : r4.y * inv;
-                v[cc * 4 + 2] += r4.z >= 0.f ? r4.z : r4.z * inv; v[cc * 4 + 3] += r4.w >= 0.f ? r4.w : r4.w * inv;
+                v[cc * 4 + 0] += r4.x; v[cc * 4 + 1] += r4.y; v[cc * 4 + 2] += r4.z; v[cc * 4 + 3] += r4.w;
+              }
+            }
+          } else {   // vocoder forms: bf16 residual and / or a residual stored as lrelu(x), undone on the fly
+            const float inv = p.res_inv_lrelu ? 1.f / p.slope : 1.f;
+            if (p.res_bf16) {   // [32 rows x 64 B], SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3; bf16 -> fp32 is a 16-bit shift
+              const uint32_t rb = rbase + lane * 64;
+              const uint32_t sx64 = (uint32_t)((lane >> 1) & 3) << 4;
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                if (cc * 8 < width) {
+                  const float4 r4 = lds4(rb + ((cc << 4) ^ sx64));
+                  const uint32_t wv[4] = {__float_as_uint(r4.x), __float_as_uint(r4.y), __float_as_uint(r4.z), __float_as_uint(r4.w)};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float lo = __uint_as_float(wv[e] << 16), hi = __uint_as_float(wv[e] & 0xFFFF0000u);
+                    v[cc * 8 + 2 * e] += lo >= 0.f ? lo : lo * inv;
+                    v[cc * 8 + 2 * e + 1] += hi >= 0.f ? hi : hi * inv;
+                  }
+                }
+              }
+            } else {
+              const uint32_t rb = rbase + lane * 128;
+#pragma unroll
+              for (int cc = 0; cc < 8; ++cc) {
+                if (cc * 4 < width) {
+                  const float4 r4 = lds4(rb + ((cc << 4) ^ swz_x));
+                  v[cc * 4 + 0] += r4.x >= 0.f ? r4.x : r4.x * inv; v[cc * 4 + 1] += r4.y >= 0.f ? r4.y : r4.y * inv;
+                  v[cc * 4 + 2] += r4.z >= 0.f ? r4.z : r4.z * inv; v[cc * 4 + 3] += r4.w >= 0.f ? r4.w : r4.w * inv;
+                }
               }
             }
           }
+          if (NB == 1) {   // the single buffer is free again once every lane has read it
+            __syncwarp();
+            prefetch_res(c);
+          }
+          ++g_res;
         }
-        if (p.act2 == ACT_LRELU) {
+        if (!LN && p.act2 == ACT_LRELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * p.slope;
         }
       };
       // this warp's [32 x 32] sub-tile -> swizzled staging -> TMA store
       auto stage_out = [&](const float (&v)[32], int c0, int width) {
-        if (lane == 0) bulk_wait_read<1>();   // the store that used this staging buffer two sub-tiles ago is done
+        const bool tr = lt == 0 && warp == 2 && c0 == 64;   // trace build: phases of the third sub-tile's store
+        if (tr) stamp(49);
+        if (lane == 0) bulk_wait_read<NB - 1>();   // the store that last used this staging buffer has read it
         __syncwarp();
-        uint8_t* sb = my_cst + (g_st & 1) * WCHUNK;
-        const uint32_t sa = cst_sa + (g_st & 1) * WCHUNK + lane * 128;
+        if (tr) stamp(50);
+        uint8_t* sb = my_cst + (g_st % NB) * WCHUNK;
+        const uint32_t sa = cst_sa + (g_st % NB) * WCHUNK + lane * 128;
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
           if (cc * 4 < width) sts4(sa + ((cc << 4) ^ swz_x), make_float4(v[cc * 4], v[cc * 4 + 1], v[cc * 4 + 2], v[cc * 4 + 3]));
         }
+        if (tr) stamp(51);
         fence_async_smem();
         __syncwarp();
+        if (tr) stamp(52);
         if (lane == 0) {
           tma_store_2d(&tmC, sb, n0 + c0, m0 + q * 32);
           bulk_commit();
         }
+        if (tr) stamp(53);
         ++g_st;
       };
       // the same sub-tile rounded to bf16: [32 rows x 64 B], SWIZZLE_64B (16-byte chunk ^= (row >> 1) & 3)
       auto stage_out_b = [&](const float (&v)[32], int c0, int width) {
-        if (lane == 0) bulk_wait_read<1>();
+        if (lane == 0) bulk_wait_read<NB - 1>();
         __syncwarp();
-        uint8_t* sb = my_cst + (g_st & 1) * WCHUNK;
-        const uint32_t sa = cst_sa + (g_st & 1) * WCHUNK + lane * 64;
+        uint8_t* sb = my_cst + (g_st % NB) * WCHUNK;
+        const uint32_t sa = cst_sa + (g_st % NB) * WCHUNK + lane * 64;
         const uint32_t sx = (uint32_t)((lane >> 1) & 3) << 4;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
@@ -704,24 +759,20 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       };
 
       if (!LN) {
+        if (c_lo >= c_hi) release_acc();   // (a narrow tile leaves the second warp of a quarter without sub-tiles)
 #pragma unroll 1
-        for (int c = 0; c < C::NCHUNK; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
           const int c0 = c * 32;
           const int width = (BN - c0) >= 32 ? 32 : 16;
           float v[32];
           if (width == 32) tmem_ld32(acc + c0, v); else tmem_ld16(acc + c0, v);
-          prefetch_res(c);            // all lanes passed the __syncwarp of the previous stage_out
-          finish(v, c0, width);
-          if (has_res) ++g_res;
+          if (NB == 2) prefetch_res(c);   // all lanes passed the __syncwarp of the previous stage_out
+          finish(v, c, width);
           if (!live) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
-          if (c == C::NCHUNK - 1) {   // all TMEM reads of this tile are done: release the accumulator
-            tc_fence_before();
-            if (TWO && rank != 0) mbar_arrive_remote(dsmem_addr(&acc_empty[u], 0));   // the issuer lives in the even CTA
-            else mbar_arrive(&acc_empty[u]);
-          }
+          if (c == c_hi - 1) release_acc();   // all TMEM reads of this tile are done: release the accumulator
           if (has_out) stage_out(v, c0, width);
           if (has_out2) stage_out_b(v, c0, width);
         }
@@ -733,12 +784,11 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         float va[32], vb[32];          // double-buffered chunk registers: the TMEM load of chunk c+1 is in
                                        // flight while chunk c is processed
         auto pass1 = [&](float (&v)[32], int c) {
-          if (has_res) {
+          if (has_res && NB == 2) {
             __syncwarp();             // every lane finished reading the other residual buffer
             prefetch_res(c);
           }
-          finish(v, c * 32, 32);
-          if (has_res) ++g_res;
+          finish(v, c, 32);
           float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -753,22 +803,38 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
           const float cm2 = (q4[0] + q4[1]) + (q4[2] + q4[3]);
           const float delta = cm - mean;
-          const float n_old = 32.f * c, n_new = 32.f * (c + 1);
-          mean = fmaf(delta, 32.f / n_new, mean);
-          var += cm2 + delta * delta * (n_old * 32.f / n_new);
+          const int k = c - c_lo;                                  // chunks this warp has merged before this one
+          const float inv_n = __frcp_rn((float)(k + 1));           // (no division in the loop)
+          mean = fmaf(delta, inv_n, mean);
+          var += cm2 + delta * delta * (32.f * (float)k * inv_n);
           tmem_st32(acc + c * 32, v);
+          if (lt == 0 && warp == 2) stamp(32 + c);
         };
-        tmem_ld32_issue(acc, va);
+        if (lt == 0 && warp == 2) stamp(31);
+        tmem_ld32_issue(acc + c_lo * 32, va);
 #pragma unroll 1
-        for (int c = 0; c < C::NCHUNK; c += 2) {
+        for (int c = c_lo; c < c_hi; c += 2) {
           tmem_ld_wait();
           tmem_ld32_issue(acc + (c + 1) * 32, vb);
           pass1(va, c);
           tmem_ld_wait();
-          if (c + 2 < C::NCHUNK) tmem_ld32_issue(acc + (c + 2) * 32, va);
+          if (c + 2 < c_hi) tmem_ld32_issue(acc + (c + 2) * 32, va);
           pass1(vb, c + 1);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        if (EH == 2) {
+          // the two warps of a lane quarter hold (mean, M2) over 128 columns each: exchange through shared memory and merge
+          // in the order (first half, second half), so that both normalise with bit-identical statistics
+          float2* mine = pair_stat + ((lt & 1) * 2 + h) * BM + r;
+          const float2* other = pair_stat + ((lt & 1) * 2 + (h ^ 1)) * BM + r;
+          *mine = make_float2(mean, var);
+          asm volatile("bar.sync %0, 64;\n" ::"r"(2 + q) : "memory");
+          const float2 o = *other;
+          const float m_a = h == 0 ? mean : o.x, q_a = h == 0 ? var : o.y, m_b = h == 0 ? o.x : mean, q_b = h == 0 ? o.y : var;
+          const float d = m_b - m_a;
+          mean = fmaf(d, 0.5f, m_a);
+          var = (q_a + q_b) + d * d * 64.f;   // n_a n_b / (n_a + n_b) = 128 * 128 / 256
+        }
         if (NS > 1) {
           // (mean, M2) over this CTA's BN columns -> every peer; then merge the NS groups in rank order (Chan), so all
           // CTAs of the cluster normalise with bit-identical statistics
@@ -819,31 +885,35 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
           if (has_out) stage_out(v, c * 32, 32);
           if (has_out2) stage_out_b(v, c * 32, 32);
+          if (lt == 0 && warp == 2) stamp(40 + c);
         };
-        tmem_ld32_issue(acc, va);
+        tmem_ld32_issue(acc + c_lo * 32, va);
 #pragma unroll 1
-        for (int c = 0; c < C::NCHUNK; c += 2) {
+        for (int c = c_lo; c < c_hi; c += 2) {
           tmem_ld_wait();
           tmem_ld32_issue(acc + (c + 1) * 32, vb);
           pass2(va, c);
           tmem_ld_wait();
-          if (c + 2 < C::NCHUNK) {
-            tmem_ld32_issue(acc + (c + 2) * 32, va);
-          } else {                      // the last TMEM read of this tile has landed: release the accumulator
-            tc_fence_before();
-            if (TWO && rank != 0) mbar_arrive_remote(dsmem_addr(&acc_empty[u], 0));
-            else mbar_arrive(&acc_empty[u]);
-          }
+          if (c + 2 < c_hi) tmem_ld32_issue(acc + (c + 2) * 32, va);
+          else release_acc();           // the last TMEM read of this tile has landed: release the accumulator
           pass2(vb, c + 1);
         }
         if (p.head_out != nullptr && live) {
           const int dst = p.slot != nullptr ? p.slot[row] : row;
-          if (dst >= 0) p.head_out[dst] = dot + p.head_b[0];
+          if (dst >= 0) {
+            // two warps per row: each adds its half of the dot product to the zero-initialised slot (two terms: the
+            // result does not depend on the order)
+            if (EH == 2) atomicAdd(&p.head_out[dst], h == 0 ? dot + p.head_b[0] : dot);
+            else p.head_out[dst] = dot + p.head_b[0];
+          }
         }
       }
       if (lt < 6 && warp == 2) stamp(8 + lt * 4 + 3);
     }
     if (warp == 2) stamp(5);
+#ifdef FS2_TRACE_BUILD
+    if (p.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0) p.trace[48] = res_wait_cycles;
+#endif
     if (lane == 0) bulk_wait_read<0>();   // smem must outlive the last TMA stores
     if (warp == 2) stamp(6);
   }
@@ -870,14 +940,30 @@ inline int& cluster_size_flag() {   // 2 = weight tiles multicast across CTA pai
   return f;
 }
 
-template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1, bool TWO = false>
+inline int& epi_warps_flag() {   // 8 (default) = two epilogue warps per TMEM lane quarter where the variant has them, 4 = one
+  static int f = [] {
+    const char* e = std::getenv("FS2_EPI_WARPS");
+    return e != nullptr ? std::atoi(e) : 8;
+  }();
+  return f;
+}
+
+template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1, bool TWO = false, int EW = 0>
 inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
+  if constexpr (EW == 0) {   // pick the epilogue width: 8 warps for the full-width streaming variants
+    constexpr bool CAN8 = NS == 1 && AR == 0 && (!LN || BN == 256) && BN >= 64;
+    if constexpr (CAN8) {
+      if (epi_warps_flag() == 8) { launch_bn_cl<BN, LN, CL, BF, AR, NS, TWO, 8>(a, stream); return; }
+    }
+    launch_bn_cl<BN, LN, CL, BF, AR, NS, TWO, 4>(a, stream);
+    return;
+  } else {
   using C = Cfg<BN, AR, NS, TWO>;
   static bool configured[64] = {};
   int dev = 0;
   FS2_CUDA_OK(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS, TWO, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
     configured[dev & 63] = true;
   }
   constexpr CUtensorMapSwizzle SW128 = CU_TENSOR_MAP_SWIZZLE_128B;
@@ -895,8 +981,9 @@ inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
   constexpr int CSIZE = CL > 1 ? CL : NS;
   const int items = NS > 1 ? (a.rows + BM - 1) / BM : (((a.rows + BM - 1) / BM + CL - 1) / CL) * ((a.N + BN - 1) / BN);
   const int grid = std::min(items, sm_count() / CSIZE) * CSIZE;
-  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS, TWO>, dim3(grid), dim3(THREADS), C::TOTAL, stream, CSIZE, tmA, tmW, tmC, tmR, tmC2, a);
+  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS, TWO, EW>, dim3(grid), dim3(64 + 32 * EW), C::TOTAL, stream, CSIZE, tmA, tmW, tmC, tmR, tmC2, a);
   FS2_LAUNCHED();
+  }
 }
 
 inline int& n_split_flag() {   // 1 = N-split fused-LN GEMMs for small row counts (default), 0 = always one CTA per row tile

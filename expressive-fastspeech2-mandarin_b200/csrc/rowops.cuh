@@ -509,7 +509,7 @@ __global__ void length_regulate_scatter_kernel(const float* __restrict__ x, RowM
     const int j = vp + p_lens[u];
     const int32_t* c = cum + (size_t)u * max_src_len;
     const int t0 = j > 0 ? c[j - 1] : 0, t1 = c[j];
-    if (t1 <= t0) return;
+    if (t1 <= t0 && en.va_out == nullptr) return;      // (the debug tap wants the row even when it expands to nothing)
     const float* src = x + (size_t)w * D_MODEL;
     float4 a = ld4(src + lane * 4), b = ld4(src + 128 + lane * 4);
     if (en.table != nullptr) {   // x + energy_embedding[bucketize(energy)] (model/modules.py:93-100,126), fused into the expansion
@@ -523,6 +523,7 @@ __global__ void length_regulate_scatter_kernel(const float* __restrict__ x, RowM
         st4(en.va_out + (size_t)w * D_MODEL + 128 + lane * 4, b);
       }
     }
+    if (t1 <= t0) return;
     const int base = f_starts[u];
     if (pe == nullptr) {                               // a frame_level predictor runs first: plain copies
       for (int t = t0; t < t1; ++t) {

@@ -348,7 +348,7 @@ def test_attention_growing_scores(lens):
     out = torch.zeros(rows, 256, device=DEV)
     ds = torch.tensor(starts, dtype=torch.int32, device=DEV)
     dl = torch.tensor(lens, dtype=torch.int32, device=DEV)
-    code = lib().fs2_op_attention(stream(), 1, ptr(dq), rows, ptr(ds), ptr(dl), len(lens), max(lens), ptr(out))
+    code = lib().fs2_op_attention(stream(), ptr(dq), rows, ptr(ds), ptr(dl), len(lens), max(lens), ptr(out))
     assert code == 0, lib().fs2_last_error(None)
     torch.cuda.synchronize()
     got = out.cpu().double()
