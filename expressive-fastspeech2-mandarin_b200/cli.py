@@ -94,10 +94,22 @@ def single_batch(args, preprocess_config):
             np.array([len(ids)]), int(len(ids)))
 
 
-def source_batches(path, preprocess_config, batch_size=8):
+def expand(values, durations):
+    """utils/tools.py:163-167: per-phoneme values repeated max(0, int(d)) times -> per-frame array."""
+    reps = np.maximum(np.trunc(np.asarray(durations, dtype=np.float64)).astype(np.int64), 0)
+    return np.repeat(np.asarray(values), reps)
+
+
+def source_batches(path, preprocess_config, batch_size=8, max_seq_len=None, mel_filter=True):
     """Batch mode: lines `basename|speaker|{p1 p2 ...}|raw_text|...|emotion|arousal|valence`
-    (dataset_chinese.py:246-262,221-232); texts zero-padded per batch (:264-276)."""
+    (dataset_chinese.py:236-262,221-232); texts zero-padded per batch (:264-276).
+    The reference's TextDataset.process_meta loads `<preprocessed_path>/mel/<speaker>-mel-<basename>.npy` for every
+    line and drops the utterances whose recorded mel is longer than model_config["max_seq_len"] (:244-255; a missing
+    file raises there).  mel_filter=True reproduces that whenever the mel directory exists; synthesis from a bare
+    phoneme list (no preprocessed corpus on disk) simply has nothing to filter."""
     root = preprocess_config["path"]["preprocessed_path"]
+    mel_dir = os.path.join(root, "mel")
+    use_filter = mel_filter and max_seq_len is not None and os.path.isdir(mel_dir)
     with open(os.path.join(root, "speakers.json")) as f:
         speaker_map = json.load(f)
     with open(os.path.join(root, "emotions.json")) as f:
@@ -109,6 +121,10 @@ def source_batches(path, preprocess_config, batch_size=8):
             if len(parts) < 4:
                 continue
             emotion, arousal, valence = parts[-3], parts[-2], parts[-1]
+            if use_filter:
+                mel = np.load(os.path.join(mel_dir, "{}-mel-{}.npy".format(parts[1], parts[0])), mmap_mode="r")
+                if mel.shape[0] > max_seq_len:
+                    continue
             rows.append((parts[0], parts[3], speaker_map[parts[1]], emo["emotion_dict"][emotion],
                          emo["arousal_dict"][arousal], emo["valence_dict"][valence],
                          phonemes_to_ids(text_to_phonemes(parts[2]))))
@@ -141,8 +157,12 @@ def build_parser():
     p.add_argument("--random_init", action="store_true", help="seeded synthetic weights instead of the checkpoints")
     p.add_argument("--vocoder_ckpt", type=str, default=None, help="generator checkpoint (default hifigan/generator_<speaker>.pth.tar)")
     p.add_argument("--no_vocoder", action="store_true", help="write the mel only")
-    p.add_argument("--math_mode", type=str, default="tf32", choices=["tf32", "bf16"],
-                   help="arithmetic of the contractions of both networks (bf16: faster, tolerance in tests/test_gpu_bf16.py)")
+    p.add_argument("--math_mode", type=str, default="tf32", choices=["tf32", "bf16", "parity"],
+                   help="arithmetic of the contractions (bf16: faster, tolerance in tests/test_gpu_bf16.py; parity: split-operand "
+                        "3xTF32 acoustic model, ~1e-4 of the fp64 reference)")
+    p.add_argument("--ragged_vocoder", action="store_true",
+                   help="skip the padded frames in the vocoder (each utterance generated as if alone; about a third of the work "
+                        "at batch 64) instead of the reference's run-padded-then-trim")
     return p
 
 
@@ -160,18 +180,38 @@ def load_model(args, preprocess_config, model_config, train_config, device="cuda
     return model.to(device).eval()
 
 
+def _voc_mode(args):
+    return "bf16" if args.math_mode == "bf16" else "tf32"    # the parity mode is the acoustic model's
+
+
 def load_vocoder(args, model_config, device="cuda"):
     """utils/model.py:37-71.  Returns None when no generator weights can be found (the reference ships none)."""
     if args.no_vocoder:
         return None
     from .vocoder import get_vocoder
     if args.random_init:
-        return get_vocoder(model_config, device, random_init=True, math_mode=args.math_mode)
+        return get_vocoder(model_config, device, random_init=True, math_mode=_voc_mode(args))
     path = args.vocoder_ckpt or os.path.join("hifigan", f"generator_{model_config['vocoder']['speaker']}.pth.tar")
     if not os.path.exists(path):
         print(f"[fs2_b200] no vocoder weights at {path}: writing mel spectrograms only")
         return None
-    return get_vocoder(model_config, device, ckpt_path=path, math_mode=args.math_mode)
+    return get_vocoder(model_config, device, ckpt_path=path, math_mode=_voc_mode(args))
+
+
+def _plot(out_dir, name, mel, feats, i, n_src, n_mel, pp):
+    """The spectrogram figure of synth_samples (utils/tools.py:247-256) when matplotlib is importable (it is not part of
+    this image; the curves are always written as .npy next to the mel)."""
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+    except ImportError:
+        return
+    fig, ax = plt.subplots(1, 1)
+    ax.imshow(np.asarray(mel).T, origin="lower", aspect="auto")
+    ax.set_title("Synthetized Spectrogram")
+    fig.savefig(os.path.join(out_dir, f"{name}.png"))
+    plt.close(fig)
 
 
 def write_wavs(out_dir, ids, wavs, sampling_rate):
@@ -198,7 +238,8 @@ def main(argv=None):
     hop = preprocess_config["preprocessing"]["stft"]["hop_length"]
     sampling_rate = preprocess_config["preprocessing"]["audio"]["sampling_rate"]
     batches = [single_batch(args, preprocess_config)] if args.mode == "single" else \
-        source_batches(args.source, preprocess_config)
+        source_batches(args.source, preprocess_config, max_seq_len=int(model_config["max_seq_len"]))
+    pp = preprocess_config["preprocessing"]
     out_dir = train_config["path"]["result_path"]
     os.makedirs(out_dir, exist_ok=True)
     for ids, raw_texts, speakers, emotions, arousals, valences, texts, text_lens, max_len in batches:
@@ -209,10 +250,22 @@ def main(argv=None):
         if vocoder is not None:        # utils/tools.py:258-271
             from .vocoder import vocoder_infer
             mels_dev = model.last_postnet.transpose(1, 2)
-            wavs = vocoder_infer(mels_dev, vocoder, model_config, preprocess_config, lengths=[int(n) * hop for n in mel_lens])
-            write_wavs(out_dir, ids, wavs, sampling_rate)
+            if mels_dev.shape[2] > 0:
+                wavs = vocoder_infer(mels_dev, vocoder, model_config, preprocess_config, lengths=[int(n) * hop for n in mel_lens],
+                                     skip_padding=args.ragged_vocoder)
+                write_wavs(out_dir, ids, wavs, sampling_rate)
+        feats = model.last_host
         for i, name in enumerate(ids):
-            np.save(os.path.join(out_dir, f"{name}.npy"), np.array(mel[i]))   # packed per-utterance view -> own array
+            np.save(os.path.join(out_dir, f"{name}.npy"), mel[i])
+            # the per-frame pitch / energy curves synth_samples draws under the spectrogram (utils/tools.py:229-243):
+            # phoneme_level predictions are expanded by the durations, frame_level ones are cut at mel_len
+            n_src, n_mel = int(text_lens[i]), int(mel_lens[i])
+            dur = feats["durations"][i, :n_src]
+            for key in ("pitch", "energy"):
+                v = feats[key][i]
+                curve = expand(v[:n_src], dur) if pp[key]["feature"] == "phoneme_level" else v[:n_mel]
+                np.save(os.path.join(out_dir, f"{name}.{key}.npy"), np.asarray(curve, dtype=np.float32))
+            _plot(out_dir, name, mel[i], feats, i, n_src, n_mel, pp)
             with open(os.path.join(out_dir, f"{name}.json"), "w", encoding="utf-8") as f:
                 json.dump({"text": raw_texts[i], "n_phonemes": int(text_lens[i]), "n_frames": int(mel_lens[i])}, f,
                           ensure_ascii=False)

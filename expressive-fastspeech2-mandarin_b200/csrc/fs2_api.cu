@@ -242,6 +242,8 @@ __global__ void sinusoid_kernel(float* pe, int rows) {
   pe[i] = (float)((j & 1) ? cos(ang) : sin(ang));
 }
 
+static void tap(fs2_ctx* c, cudaStream_t s, const char* name, const void* ptr, int64_t rows, int64_t cols, int64_t elt);
+
 static const float* position_rows(fs2_ctx* c, const char* key, int n_rows, cudaStream_t s) {
   // Stored table for n_rows <= max_seq_len, regenerated formula beyond (Models.py:82-91,145-162)
   if (n_rows <= c->cfg.max_seq_len) return c->raw.at(key).ptr;
@@ -253,10 +255,12 @@ static const float* position_rows(fs2_ctx* c, const char* key, int n_rows, cudaS
     FS2_LAUNCHED();
     c->pe_long_rows = rows;
   }
+  if (c->debug) tap(c, s, "pe_long", c->pe_long, c->pe_long_rows, D_MODEL, 4);
   return c->pe_long;
 }
 
-static void tap(fs2_ctx* c, cudaStream_t s, const char* name, const void* ptr, int64_t rows, int64_t cols, int64_t elt = 4) {
+static void tap(fs2_ctx* c, cudaStream_t s, const char* name, const void* ptr, int64_t rows, int64_t cols, int64_t elt = 4);
+static void tap(fs2_ctx* c, cudaStream_t s, const char* name, const void* ptr, int64_t rows, int64_t cols, int64_t elt) {
   if (!c->debug) return;
   auto& slot = c->taps[name];
   if (slot.first) cudaFree(slot.first);
@@ -490,24 +494,33 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   RowSide& ps = c->ps;
   Pool& pp = c->pp;
   // (the status word is zero on entry: fs2_create clears it and every stage 1 clears it again after reading it back)
-  layout_scan_kernel<int64_t><<<1, 1024, 0, s>>>(in->src_lens, B, GAP_PHON, L, L, ps.starts, ps.lens, ps.totals, c->status);
-  FS2_LAUNCHED();
+  {
+    ProfScope pr(c, s, "layout_scan");
+    layout_scan_kernel<int64_t><<<1, 1024, 0, s>>>(in->src_lens, B, GAP_PHON, L, L, ps.starts, ps.lens, ps.totals, c->status);
+    FS2_LAUNCHED();
+  }
   // row metadata + attention work list + zero fill of the [B, L] outputs that are written at real positions only
   // + the source padding mask: one launch
   SlotInit init{};
   init.zero[0] = out->pitch; init.zero[1] = out->energy; init.zero[2] = out->log_d; init.zero[3] = out->d_rounded;
   init.zero[4] = c->raw_pitch; init.zero[5] = c->raw_energy;
   init.n = BL; init.src_mask = out->src_mask; init.src_lens = in->src_lens; init.max_src_len = L;
-  row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(ps.starts, ps.lens, B, GAP_PHON, L, nullptr, rows, ps.utt, ps.vpos,
-                                                     ps.room, ps.slot, ps.work, ps.work_cap, ps.work_count, init);
-  FS2_LAUNCHED();
+  {
+    ProfScope pr(c, s, "row_meta");
+    row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(ps.starts, ps.lens, B, GAP_PHON, L, nullptr, rows, ps.utt, ps.vpos,
+                                                       ps.room, ps.slot, ps.work, ps.work_cap, ps.work_count, init);
+    FS2_LAUNCHED();
+  }
 
   // ---- Encoder (transformer/Models.py:73-100)
   float *x = pp.act[0], *t1 = pp.act[1], *t2 = pp.act[2], *t3 = pp.act[3];
   const float* pe = position_rows(c, "encoder.position_enc", L, s);
-  embed_pe_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in->texts, L, c->raw.at("encoder.src_word_emb.weight").ptr,
-                                                 c->cfg.n_src_vocab, pe, ps.meta(), ps.lens, rows, x, c->status, pp.actb[0]);
-  FS2_LAUNCHED();
+  {
+    ProfScope pr(c, s, "embed_pe");
+    embed_pe_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in->texts, L, c->raw.at("encoder.src_word_emb.weight").ptr,
+                                                   c->cfg.n_src_vocab, pe, ps.meta(), ps.lens, rows, x, c->status, pp.actb[0]);
+    FS2_LAUNCHED();
+  }
   tap(c, s, "p_start", ps.starts, 1, B + 1);
   tap(c, s, "enc_in", x, rows, D_MODEL);
   for (int i = 0; i < ENC_LAYERS; ++i) {
@@ -523,8 +536,11 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
                                 c->raw.at("emotion_linear.0.bias").ptr, c->cond_spk, c->cond_emo, c->status);
   FS2_LAUNCHED();
   float* xc = t3;
-  add_cond_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, ps.meta(), c->cond_spk, c->cond_emo, 2, rows, xc, pp.actb[3]);
-  FS2_LAUNCHED();
+  {
+    ProfScope pr(c, s, "add_cond");
+    add_cond_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, ps.meta(), c->cond_spk, c->cond_emo, 2, rows, xc, pp.actb[3]);
+    FS2_LAUNCHED();
+  }
   tap(c, s, "cond_x", xc, rows, D_MODEL);
 
   // ---- VarianceAdaptor (model/modules.py:102-135)
@@ -536,6 +552,7 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   if (pitch_here) {
     predictor(c, s, c->pred[1], ps, rows, cur, t1, c->raw_pitch, curb, pp.actb[1]);
     float* xe = x;  // encoder output is no longer needed
+    ProfScope pr(c, s, "bucket_embed_add");
     bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
         cur, ps.meta(), ps.slot, 2, rows, c->raw_pitch, in->p_targets, in->p_control,
         c->raw.at("variance_adaptor.pitch_bins").ptr, N_BINS - 1, c->raw.at("variance_adaptor.pitch_embedding.weight").ptr,

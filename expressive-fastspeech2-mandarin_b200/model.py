@@ -251,8 +251,10 @@ class FastSpeech2B200(nn.Module):
         d_t = self._target(d_targets, "d_targets", (B, L))
 
         f32 = dict(dtype=torch.float32, device=dev)
-        pitch, energy = torch.empty(B, L, **f32), torch.empty(B, L, **f32)
-        log_d, d_round = torch.empty(B, L, **f32), torch.empty(B, L, **f32)
+        # one allocation for the four [B, L] prediction tensors: the host-buffer entry reads them back with one copy
+        pred = torch.empty(4, B, L, **f32)
+        pitch, energy, log_d, d_round = pred[0], pred[1], pred[2], pred[3]
+        self._last_pred = pred
         src_mask = torch.empty(B, L, dtype=torch.bool, device=dev)
         out_lens = torch.empty(B, dtype=torch.int64, device=dev)
 
@@ -290,22 +292,36 @@ class FastSpeech2B200(nn.Module):
                 src_lens, out_lens)
 
     # ------------------------------------------------------------------ host-buffer entry (what the CLI does)
-    def synthesize_host(self, batch, p_control=1.0, e_control=1.0, d_control=1.0, padded=False):
-        """`to_device(batch)` (utils/tools.py:117-127) + forward + the device->host reads that
-        `synth_samples` performs (utils/tools.py:228-266), on pinned staging buffers.
-        `batch` holds host numpy arrays: speakers, emotions, arousals, valences, texts, src_lens,
-        max_src_len.  Returns (mels, mel_lens numpy, h2d_bytes, d2h_bytes) where `mels` is a list of per-utterance
-        [mel_len, 80] numpy views into one pinned buffer of PACKED rows (what `synth_samples` slices out of the padded
-        tensor; a third of its bytes at batch 64), or with padded=True the padded [B, T, 80] array itself."""
+    def _pinned_buf(self, role, dtype, numel):
+        """One grow-only pinned staging buffer per ROLE (never per shape): a server with dynamic batch sizes keeps a
+        handful of buffers sized for the largest request seen, instead of one buffer per distinct shape."""
+        buf = self._pinned.get(role)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            cap = max(int(numel), int(buf.numel() * 1.5) if buf is not None else 0, 16)
+            buf = torch.empty(cap, dtype=dtype).pin_memory()
+            self._pinned[role] = buf
+        return buf[:numel]
+
+    def synthesize_host(self, batch, p_control=1.0, e_control=1.0, d_control=1.0, padded=False, copy=True):
+        """`to_device(batch)` (utils/tools.py:117-127) + forward + the device->host reads that `synth_samples`
+        performs (utils/tools.py:228-243: predictions[1] mel rows, [2] pitch, [3] energy, [5] durations, [9] mel_lens),
+        on pinned staging buffers.  `batch` holds host numpy arrays: speakers, emotions, arousals, valences, texts,
+        src_lens, max_src_len.
+
+        Returns (mels, mel_lens, h2d_bytes, d2h_bytes): `mels` is a list of per-utterance [mel_len, 80] arrays (the PACKED
+        rows `synth_samples` slices out of the padded tensor; a third of its bytes at batch 64), or with padded=True the
+        padded [B, T, 80] array itself.  The pitch / energy / duration predictions of the same call are in
+        `self.last_host` (dict of numpy arrays `pitch`, `energy`, `log_d`, `durations`).
+
+        copy=True (default): every returned array owns its memory.  copy=False returns VIEWS into the pinned staging
+        buffers, which the NEXT call to synthesize_host overwrites -- only for callers that consume the result before
+        calling again (the benchmark does)."""
         dev = self._device()
         names = ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")
         # one pinned staging buffer and ONE host->device copy for the six int64 inputs; the device tensors are views of it
         arrays = [np.ascontiguousarray(batch[n], dtype=np.int64) for n in names]
         total = sum(a.size for a in arrays)
-        key = ("inputs", total)
-        if key not in self._pinned:
-            self._pinned[key] = torch.empty(total, dtype=torch.int64).pin_memory()
-        stage = self._pinned[key]
+        stage = self._pinned_buf("inputs", torch.int64, total)
         stage_np, off = stage.numpy(), 0
         for a in arrays:
             stage_np[off: off + a.size] = a.reshape(-1)
@@ -320,39 +336,48 @@ class FastSpeech2B200(nn.Module):
                            dev_t["src_lens"], int(batch["max_src_len"]), p_control=p_control, e_control=e_control,
                            d_control=d_control)
         post, lens = out[1], out[9]
-        B = int(post.shape[0])
+        B, L = int(post.shape[0]), int(batch["max_src_len"])
         self.last_postnet = post      # device tensor [B, T, 80]: what the vocoder consumes next (utils/tools.py:258-262)
-        if ("lens", B) not in self._pinned:
-            self._pinned[("lens", B)] = torch.empty(B, dtype=torch.int64).pin_memory()
-        hl = self._pinned[("lens", B)]
         stream = torch.cuda.current_stream(dev)
-        if padded:
-            key = ("post", tuple(post.shape))
-            if key not in self._pinned:
-                self._pinned[key] = torch.empty(post.shape, dtype=torch.float32).pin_memory()
-            hp = self._pinned[key]
-            hp.copy_(post, non_blocking=True)
-            hl.copy_(lens, non_blocking=True)
-            stream.synchronize()
-            return hp.numpy(), hl.numpy(), h2d, post.numel() * 4 + lens.numel() * 8
-        # packed rows straight out of the library's frame-side buffer: rows = sum(mel_lens) + 12 reserved per utterance
-        rows_cap = int(self.last_total_frames) + 12 * (B + 1)
-        cap = self._pinned.get("packed_cap", 0)
-        if rows_cap > cap or ("starts", B) not in self._pinned:
-            cap = max(rows_cap, int(cap * 1.5))
-            self._pinned["packed"] = torch.empty(cap, 80, dtype=torch.float32).pin_memory()
-            self._pinned["packed_cap"] = cap
-            self._pinned[("starts", B)] = torch.empty(B + 1, dtype=torch.int32).pin_memory()
-        hp, hs = self._pinned["packed"], self._pinned[("starts", B)]
-        rows = C.c_int64()
-        lib = _lib.load_library()
-        _lib.check(lib, self._ctx, lib.fs2_read_packed_postnet(self._ctx, stream.cuda_stream, hp.data_ptr(), cap, hs.data_ptr(),
-                                                                C.byref(rows)))
+        hl = self._pinned_buf("lens", torch.int64, B)
         hl.copy_(lens, non_blocking=True)
-        stream.synchronize()
-        packed, starts, lens_h = hp.numpy(), hs.numpy(), hl.numpy()
-        mels = [packed[int(starts[b]): int(starts[b]) + int(lens_h[b])] for b in range(B)]
-        return mels, lens_h, h2d, int(rows.value) * 80 * 4 + (B + 1) * 4 + B * 8
+        # pitch / energy / log-duration / rounded duration: one copy of the [4, B, L] block the forward allocated
+        # (frame_level features live on the frame axis and are read separately)
+        hpred = self._pinned_buf("pred", torch.float32, 4 * B * L).view(4, B, L)
+        hpred.copy_(self._last_pred, non_blocking=True)
+        d2h = 4 * B * L * 4 + B * 8
+        frame_feats = {}
+        for key, idx, flag in (("pitch", 2, self.pitch_frame_level), ("energy", 3, self.energy_frame_level)):
+            if flag:
+                t = out[idx]
+                hb = self._pinned_buf("frame_" + key, torch.float32, t.numel()).view(t.shape)
+                hb.copy_(t, non_blocking=True)
+                frame_feats[key] = hb
+                d2h += t.numel() * 4
+        own = (lambda a: np.array(a)) if copy else (lambda a: a)
+        if padded:
+            hp = self._pinned_buf("post", torch.float32, post.numel()).view(post.shape)
+            hp.copy_(post, non_blocking=True)
+            stream.synchronize()
+            mels, d2h = own(hp.numpy()), d2h + post.numel() * 4
+        else:
+            # packed rows straight out of the library's frame-side buffer: rows = sum(mel_lens) + 12 reserved per utterance
+            rows_cap = int(self.last_total_frames) + 12 * (B + 1)
+            hp = self._pinned_buf("packed", torch.float32, rows_cap * 80).view(rows_cap, 80)
+            hs = self._pinned_buf("starts", torch.int32, B + 1)
+            rows = C.c_int64()
+            lib = _lib.load_library()
+            _lib.check(lib, self._ctx, lib.fs2_read_packed_postnet(self._ctx, stream.cuda_stream, hp.data_ptr(), rows_cap,
+                                                                    hs.data_ptr(), C.byref(rows)))
+            stream.synchronize()
+            packed, starts, lens_np = hp.numpy(), hs.numpy(), hl.numpy()
+            mels = [own(packed[int(starts[b]): int(starts[b]) + int(lens_np[b])]) for b in range(B)]
+            d2h += int(rows.value) * 80 * 4 + (B + 1) * 4
+        pred_np = hpred.numpy()
+        self.last_host = {"pitch": own(frame_feats["pitch"].numpy() if "pitch" in frame_feats else pred_np[0]),
+                          "energy": own(frame_feats["energy"].numpy() if "energy" in frame_feats else pred_np[1]),
+                          "log_d": own(pred_np[2]), "durations": own(pred_np[3])}
+        return mels, own(hl.numpy()), h2d, d2h
 
 
 def get_model(preprocess_config, model_config, state_dict=None, device="cuda", **kw):

@@ -126,7 +126,57 @@ def frame_level_fixtures(out_dir, sd):
         print("frame_both_forced mel_lens", out[9].tolist())
 
 
+LOG_STATS = {"pitch": [0.35, 9.0, 2.0, 1.0], "energy": [0.2, 8.0, 2.0, 1.0]}    # positive minima: log bins need them
+
+
+def log_quantisation_fixture(out_dir, sd):
+    """variance_embedding.{pitch,energy}_quantization = "log" (model/modules.py:48-54,60-66): bins =
+    exp(linspace(log(min), log(max), n_bins - 1)) from a stats.json with positive minima.  The predictor head biases are
+    raised so that the predictions land inside the bins.  The bins the reference constructs are recorded (the facade
+    must build the same ones from the same configuration) and loaded back through the state dict as usual."""
+    import json
+    import fs2_b200
+    FastSpeech2 = import_reference()
+    syn = fs2_b200.synthetic
+    cfg_dir = os.path.join(REF, "config", "ESD-Chinese-Singing-MFA")
+    preprocess = yaml.load(open(os.path.join(cfg_dir, "preprocess.yaml")), Loader=yaml.FullLoader)
+    model_cfg = yaml.load(open(os.path.join(cfg_dir, "model.yaml")), Loader=yaml.FullLoader)
+    model_cfg["variance_embedding"]["pitch_quantization"] = "log"
+    model_cfg["variance_embedding"]["energy_quantization"] = "log"
+    tmp = tempfile.mkdtemp(prefix="fs2_fixture_")
+    syn.write_fixture_jsons(tmp)
+    with open(os.path.join(tmp, "stats.json"), "w") as f:
+        json.dump(LOG_STATS, f)
+    preprocess["path"]["preprocessed_path"] = tmp
+    model = FastSpeech2(preprocess, model_cfg)
+    bins = {k: model.state_dict()[f"variance_adaptor.{k}_bins"].clone() for k in ("pitch", "energy")}
+    sd = dict(sd)
+    for k in ("pitch", "energy"):
+        sd[f"variance_adaptor.{k}_bins"] = bins[k]
+        sd[f"variance_adaptor.{k}_predictor.linear_layer.bias"] = torch.tensor([2.0])
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().to(torch.float64)
+    batch = syn.make_batch([19, 8, 23, 15], seed=33)
+    kw = {"p_control": 1.25}
+    out = run_reference(model, batch, **kw)
+    rec = {f"in_{k}": (v.numpy() if torch.is_tensor(v) else np.array(v)) for k, v in batch.items()}
+    rec["kw_p_control"] = np.array(kw["p_control"])
+    for n, v in zip(NAMES, out):
+        rec[f"out_{n}"] = v.numpy()
+    for k in ("pitch", "energy"):
+        rec[f"ref_{k}_bins"] = bins[k].numpy()
+        rec[f"cfg_stats_{k}"] = np.array(LOG_STATS[k])
+        idx = torch.bucketize(out[2 if k == "pitch" else 3], bins[k].double())
+        print("log_bins", k, "bucket range", int(idx.min()), int(idx.max()), "distinct", len(torch.unique(idx)))
+    np.savez_compressed(os.path.join(out_dir, "log_bins.npz"), **rec)
+    print("log_bins mel_lens", out[9].tolist())
+
+
 def main():
+    if "--log-bins-only" in sys.argv:
+        import fs2_b200
+        log_quantisation_fixture(os.path.dirname(os.path.abspath(__file__)), fs2_b200.synthetic.synthetic_state_dict(seed=0))
+        return
     if "--frame-level-only" in sys.argv:    # adds the frame_level fixtures without rewriting the others
         import fs2_b200
         frame_level_fixtures(os.path.dirname(os.path.abspath(__file__)), fs2_b200.synthetic.synthetic_state_dict(seed=0))
@@ -185,6 +235,7 @@ def main():
     np.savez_compressed(os.path.join(out_dir, "longform.npz"), **rec)
     print("longform mel_lens", out[9].tolist())
     frame_level_fixtures(out_dir, sd)
+    log_quantisation_fixture(out_dir, sd)
 
 
 if __name__ == "__main__":

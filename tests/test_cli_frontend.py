@@ -78,3 +78,36 @@ def test_batch_source_file():
     assert ids == ["0001_000001", "0002_000002"] and mx == 6 and lens.tolist() == [6, 2]
     assert texts[1].tolist() == [76, 66, 0, 0, 0, 0] and spk.tolist() == [0, 1] and emo.tolist() == [1, 3]
     assert aro.tolist() == [1, 3] and val.tolist() == [1, 3]
+
+
+def test_batch_source_drops_utterances_longer_than_max_seq_len():
+    """TextDataset.process_meta (dataset_chinese.py:244-255): a line whose recorded mel has more than max_seq_len rows is
+    skipped; a listed utterance without a mel file raises, as np.load does there."""
+    d = synthetic.write_fixture_jsons(tempfile.mkdtemp(prefix="fs2_json_"))
+    os.makedirs(os.path.join(d, "mel"))
+    np.save(os.path.join(d, "mel", "0001-mel-short.npy"), np.zeros((30, 80), dtype=np.float32))
+    np.save(os.path.join(d, "mel", "0002-mel-long.npy"), np.zeros((41, 80), dtype=np.float32))
+    src = os.path.join(d, "val.txt")
+    with open(src, "w", encoding="utf-8") as f:
+        f.write("short|0001|{j i n}|今|x|Happy|0.8|0.8\n")
+        f.write("long|0002|{h ao}|好|x|Sad|0.3|0.2\n")
+    cfg = {"path": {"preprocessed_path": d}}
+    (ids, *_), = list(cli.source_batches(src, cfg, max_seq_len=40))
+    assert ids == ["short"]
+    (ids, *_), = list(cli.source_batches(src, cfg, max_seq_len=41))
+    assert ids == ["short", "long"]
+    (ids, *_), = list(cli.source_batches(src, cfg, max_seq_len=40, mel_filter=False))
+    assert ids == ["short", "long"]
+    with open(src, "a", encoding="utf-8") as f:
+        f.write("absent|0001|{h ao}|好|x|Sad|0.3|0.2\n")
+    with pytest.raises(FileNotFoundError):
+        list(cli.source_batches(src, cfg, max_seq_len=40))
+
+
+def test_expand_matches_the_reference_rule():
+    """utils/tools.py:163-167: value j repeated max(0, int(d_j)) times."""
+    vals, durs = np.array([1.5, -2.0, 3.0, 4.0]), np.array([2.0, 0.0, 3.9, -1.0])
+    want = []
+    for v, dd in zip(vals, durs):
+        want += [v] * max(0, int(dd))
+    assert cli.expand(vals, durs).tolist() == want

@@ -6,7 +6,8 @@ all outputs stay fp32.
 
 Stated tolerances, max-abs on valid rows against the fp64 reference (SURVEY.md §8(c) budget for bf16 operands:
 predictions 1.3e-2, mel 8.7e-3, postnet 1.0e-2, mean 1.6e-3):
-    log-duration / pitch / energy <= 3e-2;  mel / postnet mel <= 3e-2, mean-abs <= 3e-3.
+    log-duration / pitch / energy <= 1.5e-2;  mel / postnet mel <= 1.2e-2, mean-abs <= 2.2e-3
+(measured on B200: predictions <= 1.02e-2, mel / postnet <= 9.3e-3, mean 1.6e-3 -- profiles/r02_parity_*.txt).
 Integer stages are the same kernels as in TF32 mode and stay bit-exact given equal inputs (teacher forcing).
 Operator level: against float64 on the SAME bf16-rounded operands only the fp32 accumulation order differs.
 """
@@ -21,9 +22,9 @@ from test_gpu_ops import conv_ref
 
 pytestmark = pytest.mark.gpu
 
-TOL_PRED = 3e-2
-TOL_MEL_MAX = 3e-2
-TOL_MEL_MEAN = 3e-3
+TOL_PRED = 1.5e-2
+TOL_MEL_MAX = 1.2e-2
+TOL_MEL_MEAN = 2.2e-3
 
 CASES = [
     # rows, K, N, taps, act, residual, mask, ln, fp32 out, bf16 out, name

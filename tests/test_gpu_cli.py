@@ -28,6 +28,10 @@ def test_cli_single_sentence(sd32):
     mel = np.load(os.path.join(d, "result", "synthesis_0001_Happy.npy"))
     meta = json.load(open(os.path.join(d, "result", "synthesis_0001_Happy.json")))
     assert mel.ndim == 2 and mel.shape[1] == 80 and mel.shape[0] == meta["n_frames"] > 16
+    # the per-frame pitch / energy curves of synth_samples (utils/tools.py:229-243): phoneme values expanded by the durations
+    for key in ("pitch", "energy"):
+        curve = np.load(os.path.join(d, "result", f"synthesis_0001_Happy.{key}.npy"))
+        assert curve.shape == (meta["n_frames"],) and np.isfinite(curve).all()
     assert meta["n_phonemes"] == 16 and np.isfinite(mel).all()
     # the vocoder step of the reference script (utils/tools.py:258-271): an int16 wav of n_frames * hop samples
     from scipy.io import wavfile
@@ -76,3 +80,31 @@ def test_host_entry_packed_equals_padded(sd32):
     for i, n in enumerate(lens):
         assert mels[i].shape == (int(n), 80)
         assert np.array_equal(mels[i], padded[i, : int(n)])
+
+
+def test_host_entry_reads_what_synth_samples_reads(sd32):
+    """utils/tools.py:228-243 reads predictions[2] (pitch), [3] (energy), [5] (durations) and [9] besides the mel: the
+    host entry returns them too, equal to the device tensors of a plain forward; results own their memory by default
+    (a second call must not change them) and the pinned staging does not grow with the number of distinct batch shapes."""
+    from gpu_util import model_for, run
+    syn = fs2_b200.synthetic
+    model = model_for(sd32)
+    b = syn.make_batch([30, 7, 19, 30], seed=12)
+    host = {k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in b.items()}
+    mels, lens, _, d2h = model.synthesize_host(host)
+    feats = {k: v.copy() for k, v in model.last_host.items()}
+    snapshot = [m.copy() for m in mels]
+    out = run(model, b)
+    assert np.array_equal(feats["pitch"], out[2].cpu().numpy()) and np.array_equal(feats["energy"], out[3].cpu().numpy())
+    assert np.array_equal(feats["log_d"], out[4].cpu().numpy()) and np.array_equal(feats["durations"], out[5].cpu().numpy())
+    assert np.array_equal(lens, out[9].cpu().numpy())
+    assert d2h >= sum(int(n) for n in lens) * 320 + 3 * 4 * 30 * 4
+    n_bufs = len(model._pinned)
+    for n in (1, 2, 3, 5, 4):          # other batch shapes, then the first again
+        other = syn.make_batch([11 + n] * n, seed=n)
+        model.synthesize_host({k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in other.items()})
+    assert len(model._pinned) == n_bufs, "one staging buffer per role, not per shape"
+    for m, s0 in zip(mels, snapshot):
+        assert np.array_equal(m, s0), "results of an earlier call must survive later calls"
+    views, _, _, _ = model.synthesize_host(host, copy=False)
+    assert all(np.array_equal(v, s0) for v, s0 in zip(views, snapshot))

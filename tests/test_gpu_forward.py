@@ -2,11 +2,15 @@
 (1) the committed golden outputs of the unmodified reference and (2) the CPU oracle on fresh
 batches, using the staged / teacher-forced protocol of SURVEY.md §8(c).
 
-Stated tolerances, TF32 mode (operands rounded to TF32, fp32 accumulate / LayerNorm / softmax),
-max-abs on valid rows:   log-duration, pitch, energy  <= 5e-3;   mel, postnet mel <= 3e-3
-(mean-abs <= 4e-4).  Integer results (durations given equal log-durations, bucket indices,
-frame->phoneme maps, mel_lens) are bit-exact; free-running durations may differ only at a
-reported rounding boundary.
+Stated tolerances, max-abs on valid rows (measured values: profiles/r02_parity_*.txt):
+  TF32 mode (operands rounded to TF32, fp32 accumulate / LayerNorm / softmax):
+      log-duration, pitch, energy <= 2.5e-3;   mel, postnet mel <= 1.5e-3 (mean-abs <= 3e-4)
+  parity mode (FS2_MATH_TF32X3: split-operand contractions; the north star's "<= 1e-3 on normalised mel" with margin):
+      log-duration, pitch, energy <= 2.5e-4;   mel, postnet mel <= 3e-4   (mean-abs <= 5e-5)
+      (measured: predictions <= 1.2e-4, mel <= 1.7e-4, mean 2.6e-5 -- what remains is the TF32 attention and the
+      tensor core's accumulation; tools/error_budget.py predicts 1.1e-4 from the attention alone)
+Integer results (durations given equal log-durations, bucket indices, frame->phoneme maps, mel_lens) are bit-exact;
+free-running durations may differ only at a reported rounding boundary.
 """
 import os
 
@@ -16,13 +20,12 @@ import torch
 
 from oracle import fs2_oracle as O
 from gpu_util import DEV, err_stats, model_for, packed_to_padded, run
-from helpers import OUT_NAMES, call, golden_names, load_golden, valid_rows
+from helpers import OUT_NAMES, call, golden_names, load_golden, log_bins_case, log_bins_model, valid_rows
 
 pytestmark = pytest.mark.gpu
 
-TOL_PRED = 5e-3
-TOL_MEL_MAX = 3e-3
-TOL_MEL_MEAN = 4e-4
+TOLS = {"tf32": dict(pred=2.5e-3, mel_max=1.5e-3, mel_mean=3e-4), "parity": dict(pred=2.5e-4, mel_max=3e-4, mel_mean=5e-5)}
+TOL_PRED, TOL_MEL_MAX, TOL_MEL_MEAN = TOLS["tf32"]["pred"], TOLS["tf32"]["mel_max"], TOLS["tf32"]["mel_mean"]
 DIAG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_diag.txt")
 
 
@@ -40,11 +43,11 @@ def teacher_kwargs(ref_out, src_lens):
                 e_targets=torch.as_tensor(ref_out["energy"]).float(), mel_lens=mel_lens, max_mel_len=int(mel_lens.max()))
 
 
-def check_phoneme_side(tag, got, want, src_lens):
+def check_phoneme_side(tag, got, want, src_lens, mode="tf32"):
     for i, n in ((4, "log_d"), (2, "pitch")):
         mx, mean = err_stats(valid_rows(got[i].cpu().numpy(), src_lens), valid_rows(want[n], src_lens))
         log_diag(f"{tag} {n}: max {mx:.3e} mean {mean:.3e}")
-        assert mx <= TOL_PRED, (tag, n, mx)
+        assert mx <= TOLS[mode]["pred"], (tag, n, mx)
     assert np.array_equal(got[6].cpu().numpy(), want["src_mask"])
     pad = want["src_mask"]
     for i in (2, 3, 4, 5):
@@ -63,7 +66,7 @@ def check_durations(tag, got, want, d_control):
     return not bad.any()
 
 
-def check_frame_side(tag, got, want, mel_lens, stride=1):
+def check_frame_side(tag, got, want, mel_lens, stride=1, mode="tf32"):
     for i, n in ((0, "mel"), (1, "postnet")):
         g = got[i].cpu().numpy()
         if stride > 1:
@@ -73,13 +76,16 @@ def check_frame_side(tag, got, want, mel_lens, stride=1):
             lens = mel_lens
         mx, mean = err_stats(valid_rows(g, lens), valid_rows(want[n], lens))
         log_diag(f"{tag} {n}: max {mx:.3e} mean {mean:.3e}")
-        assert mx <= TOL_MEL_MAX and mean <= TOL_MEL_MEAN, (tag, n, mx, mean)
+        assert mx <= TOLS[mode]["mel_max"] and mean <= TOLS[mode]["mel_mean"], (tag, n, mx, mean)
 
 
+@pytest.mark.parametrize("mode", ["tf32", "parity"])
 @pytest.mark.parametrize("name", golden_names(frame_level=False))
-def test_golden_fixture(name, sd32):
-    """The reference's own outputs (tests/golden/*.npz, float64 run of the unmodified module)."""
-    model = model_for(sd32)
+def test_golden_fixture(name, mode, sd32):
+    """The reference's own outputs (tests/golden/*.npz, float64 run of the unmodified module), in the default TF32 mode
+    and in the split-operand parity mode."""
+    model = model_for(sd32, math_mode=mode)
+    tag = name if mode == "tf32" else f"{name}[{mode}]"
     batch, kw, want, stride = load_golden(name)
     src_lens = batch["src_lens"].tolist()
     mel_lens = want["mel_lens"].tolist()
@@ -87,25 +93,25 @@ def test_golden_fixture(name, sd32):
         got = run(model, batch, **{k: (v.float() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in kw.items()})
         assert np.array_equal(got[9].cpu().numpy(), want["mel_lens"])
         assert np.array_equal(got[7].cpu().numpy(), want["mel_mask"])
-        check_frame_side(name, got, want, mel_lens)
+        check_frame_side(tag, got, want, mel_lens, mode=mode)
         return
     # stage A: free-running phoneme side
     free = run(model, batch, **kw)
-    check_phoneme_side(name, free, want, src_lens)
-    same = check_durations(name, free, want, kw.get("d_control", 1.0))
+    check_phoneme_side(tag, free, want, src_lens, mode)
+    same = check_durations(tag, free, want, kw.get("d_control", 1.0))
     if same:
         assert np.array_equal(free[9].cpu().numpy(), want["mel_lens"])
     # energy depends on the pitch buckets: compare it with the reference's pitch forced
     forced_p = run(model, batch, p_targets=torch.as_tensor(want["pitch"]).float(), **kw)
     mx, mean = err_stats(valid_rows(forced_p[3].cpu().numpy(), src_lens), valid_rows(want["energy"], src_lens))
-    log_diag(f"{name} energy (pitch forced): max {mx:.3e} mean {mean:.3e}")
-    assert mx <= TOL_PRED
+    log_diag(f"{tag} energy (pitch forced): max {mx:.3e} mean {mean:.3e}")
+    assert mx <= TOLS[mode]["pred"]
     # stage B: frame side with durations / pitch / energy forced
     tk = teacher_kwargs(want, src_lens)
     got = run(model, batch, **tk)
     assert np.array_equal(got[9].cpu().numpy(), want["mel_lens"])
     assert np.array_equal(got[7].cpu().numpy(), want["mel_mask"])
-    check_frame_side(name, got, want, mel_lens, stride)
+    check_frame_side(tag, got, want, mel_lens, stride, mode)
     # padding rows of mel carry mel_linear.bias, as in the reference (fastspeech2.py:134)
     mel = got[0].cpu().numpy()
     bias = sd32["mel_linear.bias"].numpy()
@@ -138,7 +144,7 @@ def test_per_layer_taps_against_oracle(sd32, sd64, syn):
             mx, mean = err_stats(valid_rows(mine, lens), valid_rows(ref, lens))
             log_diag(f"tap {key}: max {mx:.3e} mean {mean:.3e}")
             worst = max(worst, mx)
-        assert worst <= 5e-3
+        assert worst <= 2.5e-3      # measured: 1.8e-3 after the sixth decoder block
     finally:
         model.debug_taps(False)
 
@@ -213,13 +219,46 @@ def test_input_validation(sd32, syn):
     run(model, batch)  # still usable afterwards
 
 
-def test_long_position_table_matches_formula():
-    """The device-generated sinusoid rows beyond max_seq_len equal the numpy float64 evaluation
-    of transformer/Models.py:10-30."""
-    import fs2_b200
-    # exercised through the longform golden fixture; here only the table itself
-    want = fs2_b200.synthetic.sinusoid_table(3000, 256).numpy()
-    assert want.shape == (3000, 256)
+def test_long_position_table_is_bitwise_the_reference_formula(sd32, syn):
+    """Beyond max_seq_len the reference rebuilds the sinusoid table per call (transformer/Models.py:145-152, :10-30:
+    float64 numpy, cast to fp32).  The library generates the rows on the device in float64 (CUDA pow / sin / cos) and
+    keeps them as fp32: the table must equal the numpy evaluation BIT FOR BIT."""
+    model = model_for(sd32)
+    batch = syn.make_batch([400], seed=9)               # ~2.7 k frames > max_seq_len = 2000
+    model.debug_taps(True)
+    try:
+        out = run(model, batch)
+        T = int(out[9].max())
+        assert T > 2000
+        table = model.fetch_tap("pe_long")
+    finally:
+        model.debug_taps(False)
+    want = O.sinusoid_rows(table.shape[0], 256).numpy()
+    assert table.shape[0] >= T and table.shape[1] == 256
+    diff = table.view(np.int32) != want.view(np.int32)
+    assert not diff.any(), f"{int(diff.sum())} of {diff.size} table entries differ from the float64 numpy formula"
+
+
+def test_log_quantisation_fixture_on_gpu(sd32):
+    """variance_embedding.*_quantization = "log" (model/modules.py:48-54,60-66): the facade builds the bins from the model
+    config + stats.json (bit-equal to the reference's, tests/test_oracle_golden.py) and the forward runs the fixture the
+    unmodified reference produced with them -- staged protocol, bucket indices spread over ~200 of the 256 bins."""
+    batch, kw, want, sd, stats = log_bins_case(sd32)
+    sd = {k: v for k, v in sd.items() if not k.endswith("_bins")}          # keep the facade's own bins
+    model = log_bins_model(stats)
+    missing = model.load_state_dict(sd, strict=False)
+    assert sorted(missing.missing_keys) == ["variance_adaptor.energy_bins", "variance_adaptor.pitch_bins"]
+    model = model.to(DEV)
+    src_lens = batch["src_lens"].tolist()
+    free = run(model, batch, **kw)
+    check_phoneme_side("log_bins", free, want, src_lens)
+    check_durations("log_bins", free, want, 1.0)
+    forced_p = run(model, batch, p_targets=torch.as_tensor(want["pitch"]).float(), **kw)
+    mx, _ = err_stats(valid_rows(forced_p[3].cpu().numpy(), src_lens), valid_rows(want["energy"], src_lens))
+    assert mx <= TOL_PRED
+    got = run(model, batch, **teacher_kwargs(want, src_lens))
+    assert np.array_equal(got[9].cpu().numpy(), want["mel_lens"])
+    check_frame_side("log_bins", got, want, want["mel_lens"].tolist())
 
 
 @pytest.mark.parametrize("name", ["pads", "controls", "longform"])

@@ -380,7 +380,7 @@ def test_conv_gemm_two_sm(shape):
         for flag in (1, 0):
             L.fs2_debug_set_flag(6, flag)
             out = torch.full((rows, N), float("nan"), device=DEV)
-            code = L.fs2_op_conv_gemm(stream(), 1, 0, ptr(dA), K, rows, ptr(dW), ptr(db), taps, (taps - 1) // 2, K, N, act,
+            code = L.fs2_op_conv_gemm(stream(), 0, ptr(dA), K, rows, ptr(dW), ptr(db), taps, (taps - 1) // 2, K, N, act,
                                       None, N, None, None, 0, ptr(out), N)
             assert code == 0, L.fs2_last_error(None)
             torch.cuda.synchronize()
