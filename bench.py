@@ -1,20 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- mel frames/s of the FastSpeech2 inference forward on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--math tf32|bf16|parity]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--math tf32|bf16|parity]
 
-A step is one forward pass over one synthetic batch of BASELINE config 2 (64 utterances of
-20-120 phonemes, mixed speakers / emotions / arousal-valence, controls 1.0) per GPU; with N > 1
-(launched by torchrun, one rank per GPU) every rank runs its own copy of that batch (utterances
-are independent: no collective on the data path, weak scaling) and rank 0 prints ONE JSON line.
-`value` is timed with inputs resident in HBM; `e2e` goes through the host-buffer entry
-(`FastSpeech2B200.synthesize_host`: pinned H2D of the int64 inputs, forward, D2H of the postnet
-mel rows -- packed, as `synth_samples` slices them -- and mel_lens) with the copies inside the timed region.  `--impl reference` times the CPU
-oracle port of the reference forward (oracle/fs2_oracle.py; the reference itself is Python and
-/root/reference does not exist on the GPU box) on the host cores.
+A step is one forward pass over one synthetic batch of BASELINE config 2 (64 utterances of 20-120 phonemes, mixed
+speakers / emotions / arousal-valence, controls 1.0) per GPU; with N > 1 (launched by torchrun, one rank per GPU) every
+rank runs its own copy of that batch (utterances are independent: no collective on the data path, weak scaling) and rank 0
+prints ONE JSON line.  `value` is timed with inputs resident in HBM; `e2e` goes through the host-buffer entry
+(`FastSpeech2B200.synthesize_host`: pinned H2D of the int64 inputs, forward, D2H of everything `synth_samples` reads --
+the packed postnet mel rows, pitch, energy, durations, mel_lens) with the copies inside the timed region.
+
+Beside the headline the line carries: `roofline` (dominant kernel against the measured burst peak), `kernel_ms_per_step`,
+`hbm_kernels` (every memory-bound kernel at batch 512, where the data no longer fits L2), `latency` (config 1),
+`bf16_mode`, `vocoder`, `config3_strong` (BASELINE config 3: ONE batch of 512 sharded over the N GPUs, by phonemes and
+re-balanced by frames), `cpu_baseline`.  `--impl reference` times the CPU oracle port of the reference forward
+(oracle/fs2_oracle.py; the reference itself is Python and /root/reference does not exist on the GPU box) on the host cores.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -35,6 +38,7 @@ UNIT = "frames/s"
 CPU_SAMPLE_UTTS = 64      # the whole config-2 batch per CPU step (about 3-4 s on 16 cores)
 CPU_SAMPLE_STEPS = 3      # cpu_baseline leg of the default run: about 10 s of CPU work
 FLOPS_CONV9_PER_ROW = 2 * 9 * 256 * 1024
+NAMES = ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")
 
 
 def measured_peaks():
@@ -47,22 +51,32 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
 
 
-def hbm_kernels(prof, runs, frames, phonemes, batch, t_max, peak_gbs):
-    """Achieved GB/s of the memory-bound kernels from their algorithmic bytes."""
-    algo = {
-        # LengthRegulator + PE add: read one 1 KB phoneme row per frame (L2-served repeats counted once:
-        # 1024*P), the PE row (L2) and write 1024*F
-        "length_regulator": 1024 * phonemes + 4 * phonemes + 1024 * frames,
-        # unpack: read 2 x 320 B per valid frame, write 2 x 320 B per padded frame + 1 B mask
-        "unpack": 2 * 320 * frames + (2 * 320 + 1) * batch * t_max,
-    }
-    out = {}
-    for k, nbytes in algo.items():
-        if k in prof and prof[k][1] > 0:
-            ms = prof[k][1] / prof[k][0]
-            gbs = nbytes / (ms * 1e-3) / 1e9
-            out[k] = {"bytes": nbytes, "ms": ms, "achieved_gbs": gbs, "frac_of_measured_hbm": gbs / peak_gbs}
-    return out
+def measure_tf32_peak(dev):
+    """Calibration only (cuBLAS, never on the product path): the burst TF32 rate of this GPU, measured the way
+    MEASURED_PEAKS.json measures bf16 -- torch.matmul 8192^3, best of 10, CUDA events."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(2):
+            torch.matmul(a, b)
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del a, b
+        torch.cuda.empty_cache()
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 class ClockSampler:
@@ -125,7 +139,7 @@ def oracle_cpu_run(sd, batch, n_utts, steps, warmup):
     L = int(sub["src_lens"].max())
     sub["texts"] = sub["texts"][:, :L].contiguous()
     sub["max_src_len"] = L
-    args = [sub[k] for k in ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")]
+    args = [sub[k] for k in NAMES]
     small = [a[:2] for a in args]
     L2 = int(small[5].max())
     small[4] = small[4][:, :L2].contiguous()
@@ -174,11 +188,49 @@ def run_reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config2: batch 64, 20-120 phonemes, mixed speakers/emotions, controls 1.0",
+            "config": {"workload": "config2: batch 64 per GPU, 20-120 phonemes, mixed speakers/emotions/arousal-valence, "
+                                   "controls 1.0, random-init weights (seed 0)",
                        "timed_sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def profile_forward(lib, model, dev_args, L, flush, runs):
+    """Per-kernel-class CUDA-event timing through the library's own profiling hooks (events bracket each launch on the
+    launching stream, so the programmatic-dependent-launch overlap between kernels is serialised away: the classes sum
+    to MORE than the step time).  Returns {label: (launches per forward, median ms per forward)}."""
+    lib.fs2_profile_enable(model._ctx, 1)
+    acc = {}
+    for _ in range(runs):
+        flush.zero_()
+        model(*dev_args, L)
+        buf = (ctypes.c_char * 16384)()
+        lib.fs2_profile_read(model._ctx, buf, 16384)
+        for line in buf.value.decode().splitlines():
+            label, n, ms = line.split()
+            acc.setdefault(label, []).append((int(n), float(ms)))
+    lib.fs2_profile_enable(model._ctx, 0)
+    return {k: (v[0][0], float(np.median([x[1] for x in v]))) for k, v in acc.items()}
+
+
+def hbm_kernel_table(prof, frames, phonemes, batch, t_max, peak_gbs):
+    """Achieved GB/s of the memory-bound kernels from their ALGORITHMIC bytes (fp32 rows of 1 KB)."""
+    P, F = phonemes, frames
+    algo = {
+        "embed_pe": 8 * P + 1024 * P,                         # ids in, rows out (embedding / PE tables are L2 resident)
+        "add_cond": 2048 * P,                                 # read x, write x + spk + emo
+        "bucket_embed_add": 2048 * P + 8 * P,                 # read x (+ raw prediction), write x + embedding (+ prediction)
+        "length_regulator": 1024 * P + 8 * P + 1024 * F,      # one 1 KB row + cum + energy per phoneme in, 1 KB per frame out
+        "unpack": 2 * 320 * F + (2 * 320 + 1) * batch * t_max,
+    }
+    out = {}
+    for k, nbytes in algo.items():
+        if k in prof and prof[k][1] > 0:
+            ms = prof[k][1] / max(prof[k][0], 1)
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            out[k] = {"bytes": nbytes, "us": ms * 1e3, "achieved_gbs": gbs, "frac_of_measured_hbm": gbs / peak_gbs}
+    return out
 
 
 def main():
@@ -190,6 +242,7 @@ def main():
     ap.add_argument("--math", default=os.environ.get("FS2_MATH", "tf32"), choices=["tf32", "bf16", "parity"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline, e2e, roofline and latency only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -202,7 +255,7 @@ def main():
 
     import torch.distributed as dist
     import fs2_b200
-    from fs2_b200 import _lib
+    from fs2_b200 import _lib, partition
     syn = fs2_b200.synthetic
 
     if not torch.cuda.is_available():
@@ -215,17 +268,21 @@ def main():
 
     sd = syn.synthetic_state_dict(seed=0)
     jsons = syn.write_fixture_jsons(tempfile.mkdtemp(prefix="fs2_json_"))
-    model = fs2_b200.FastSpeech2B200(fs2_b200.config.default_preprocess_config(jsons),
-                                     fs2_b200.config.default_model_config(), math_mode=args.math)
-    model.load_state_dict(sd)
-    model = model.to(dev)
+
+    def new_model(math):
+        m = fs2_b200.FastSpeech2B200(fs2_b200.config.default_preprocess_config(jsons), fs2_b200.config.default_model_config(),
+                                     math_mode=math)
+        m.load_state_dict(sd)
+        return m.to(dev)
+
+    model = new_model(args.math)
+    tf32_peak = measure_tf32_peak(dev) if rank == 0 else None
 
     # weak scaling: every rank runs the SAME config-2 batch (seed 0), so the per-GPU work is identical by construction
     # and the max-over-ranks time measures the hardware, not the luck of a rank's length draw
     batch = syn.config2_batch(seed=0, batch=args.batch)
-    names = ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")
-    dev_args = [batch[k].to(dev) for k in names]
-    host_batch = {k: batch[k].numpy() for k in names}
+    dev_args = [batch[k].to(dev) for k in NAMES]
+    host_batch = {k: batch[k].numpy() for k in NAMES}
     host_batch["max_src_len"] = batch["max_src_len"]
     L = batch["max_src_len"]
 
@@ -237,11 +294,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(step_fn, steps):
+    def timed_loop(step_fn, steps, sync_each=False):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         for beg, end in evs:
             flush.zero_()                      # evict L2 between timed iterations (outside the event pair)
+            if sync_each:
+                barrier()                      # collectives inside the step: every rank starts the step together
             beg.record()
             step_fn()
             end.record()
@@ -251,7 +310,7 @@ def main():
     out = None
     for _ in range(args.warmup):
         out = model(*dev_args, L)
-        model.synthesize_host(host_batch)
+        model.synthesize_host(host_batch, copy=False)
     torch.cuda.synchronize()
     frames = int(out[9].sum())
     mel_lens = out[9].tolist()
@@ -264,36 +323,33 @@ def main():
     e2e_bytes = {}
 
     def e2e_step():
-        _, _, h2d, d2h = model.synthesize_host(host_batch)
+        _, _, h2d, d2h = model.synthesize_host(host_batch, copy=False)   # (consumed before the next call: views suffice)
         e2e_bytes["h2d"], e2e_bytes["d2h"] = h2d, d2h
 
     e2e_ms = timed_loop(e2e_step, args.steps)
 
     # the second arithmetic mode of the north star (bf16 operands), same workload, reported beside the headline
     other = None
-    if args.math == "tf32":
-        m16 = fs2_b200.FastSpeech2B200(fs2_b200.config.default_preprocess_config(jsons),
-                                       fs2_b200.config.default_model_config(), math_mode="bf16")
-        m16.load_state_dict(sd)
-        m16 = m16.to(dev)
+    if args.math == "tf32" and not args.no_extras:
+        m16 = new_model("bf16")
         for _ in range(args.warmup):
             o16 = m16(*dev_args, L)
-            m16.synthesize_host(host_batch)
+            m16.synthesize_host(host_batch, copy=False)
         torch.cuda.synchronize()
         f16 = int(o16[9].sum())
         ms16 = timed_loop(lambda: m16(*dev_args, L), args.steps)
-        e16 = timed_loop(lambda: m16.synthesize_host(host_batch), args.steps)
+        e16 = timed_loop(lambda: m16.synthesize_host(host_batch, copy=False), args.steps)
         other = (f16, float(sum(ms16)), float(sum(e16)))
         del m16
 
     # the step after the path: HiFi-GAN generator on the mel this batch produced, reported beside
     # the headline (device-resident mel, L2 flushed); never part of `value`
     voc_line = None
-    if world == 1:
+    if world == 1 and not args.no_extras:
         try:
             mel_t, lens_t = out[1].transpose(1, 2), out[9]
             voc_line = {"workload": "HiFi-GAN V1 generator (hifigan/config.json) on the postnet mel of the same batch, "
-                                    "random-init weights"}
+                                    "random-init weights, ragged (frames beyond mel_lens skipped)"}
             for mode in ("tf32", "bf16"):
                 voc = fs2_b200.HiFiGANGeneratorB200(math_mode=mode)
                 voc.load_state_dict(syn.synthetic_vocoder_state_dict(0))
@@ -311,25 +367,66 @@ def main():
 
     # per-kernel-class CUDA-event timing (same workload, same process, after the timed region)
     lib = _lib.load_library()
-    lib.fs2_profile_enable(model._ctx, 1)
-    runs = {}
     PROF_RUNS = 7
-    for _ in range(PROF_RUNS):
-        flush.zero_()
-        model(*dev_args, L)
-        buf = (__import__("ctypes").c_char * 8192)()
-        lib.fs2_profile_read(model._ctx, buf, 8192)
-        for line in buf.value.decode().splitlines():
-            label, n, ms = line.split()
-            runs.setdefault(label, []).append((int(n), float(ms)))
-    lib.fs2_profile_enable(model._ctx, 0)
-    # per label: launches per forward and the MEDIAN over the runs of the summed duration, scaled back to
-    # PROF_RUNS forwards so that the consumers below keep dividing by PROF_RUNS (robust to one slow run)
-    prof = {k: [v[0][0] * PROF_RUNS, float(np.median([x[1] for x in v])) * PROF_RUNS] for k, v in runs.items()}
+    prof = profile_forward(lib, model, dev_args, L, flush, PROF_RUNS)
+
+    # the memory-bound kernels where they actually reach HBM: one batch of 512 (the batch-64 tensors live in the 126 MB L2)
+    hbm = None
+    c3 = None
+    if not args.no_extras:
+        big = syn.config2_batch(seed=0, batch=512)
+        if world == 1:
+            big_args = [big[k].to(dev) for k in NAMES]
+            for _ in range(2):
+                ob = model(*big_args, big["max_src_len"])
+            torch.cuda.synchronize()
+            prof_big = profile_forward(lib, model, big_args, big["max_src_len"], flush, 5)
+            hbm = {"workload": "config-3 batch (512 utterances) on one GPU, L2 flushed before each forward",
+                   "kernels": hbm_kernel_table(prof_big, int(ob[9].sum()), int(big["src_lens"].sum()), 512, int(ob[0].shape[1]),
+                                               measured_peaks()["hbm_gbs"])}
+            del ob
+        # ---- BASELINE config 3: ONE batch of 512 utterances sharded over the N GPUs (strong scaling)
+        parts = partition.lpt_partition(big["src_lens"].tolist(), world)
+        mine = partition.take(big, parts[rank])
+        mine_args = [mine[k].to(dev) for k in NAMES]
+        steps3 = max(3, min(args.steps, 10))
+        for _ in range(2):
+            o3 = model(*mine_args, mine["max_src_len"])
+        torch.cuda.synchronize()
+        t_plain = float(np.median(timed_loop(lambda: model(*mine_args, mine["max_src_len"]), steps3, sync_each=world > 1)))
+        f_plain = float(o3[9].sum())
+        t_reb, f_reb = None, None
+        if world > 1:
+            for _ in range(2):
+                r3 = partition.rebalanced_forward(model, big, parts, rank)
+            torch.cuda.synchronize()
+            t_reb = float(np.median(timed_loop(lambda: partition.rebalanced_forward(model, big, parts, rank), steps3, sync_each=True)))
+            f_reb = float(r3["mel_lens"].sum()) if r3["ids"] else 0.0
+        v = torch.tensor([t_plain, f_plain, t_reb or 0.0, f_reb or 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            vmax, vmin, vsum = v.clone(), v.clone(), v.clone()
+            dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(vmin, op=dist.ReduceOp.MIN)
+            dist.all_reduce(vsum, op=dist.ReduceOp.SUM)
+        else:
+            vmax = vmin = vsum = v
+        c3 = {"workload": "config3: ONE batch of 512 utterances (20-120 phonemes, seed 0) sharded over the GPUs; step = the "
+                          "slowest rank (CUDA events, every rank starts each step at a barrier, L2 flushed)",
+              "n_gpus": world, "total_frames": float(vsum[1]),
+              "lpt_by_phonemes": {"ms_per_step": float(vmax[0]), "frames_per_s": float(vsum[1]) / float(vmax[0]) * 1e3,
+                                  "frames_per_rank_min_max": [float(vmin[1]), float(vmax[1])],
+                                  "note": "shards balanced on phoneme counts (all that is known before stage 1); no collective"}}
+        if world > 1:
+            c3["rebalanced_by_frames"] = {
+                "ms_per_step": float(vmax[2]), "frames_per_s": float(vsum[3]) / float(vmax[2]) * 1e3,
+                "frames_per_rank_min_max": [float(vmin[3]), float(vmax[3])],
+                "note": "stage 1 on the phoneme shards, all-gather of mel_lens, LPT on the true stage-2 cost, one NCCL "
+                        "all-to-all of the phoneme rows that change owner, stage 2 where the utterance landed "
+                        "(partition.rebalanced_forward); the collectives and the host planning are inside the timed step"}
 
     # p50 single-utterance latency (BASELINE config 1), device-resident inputs, host sync included
     c1 = syn.config1_batch()
-    c1_args = [c1[k].to(dev) for k in names]
+    c1_args = [c1[k].to(dev) for k in NAMES]
     lat = []
     for i in range(230):
         t0 = time.perf_counter()
@@ -355,13 +452,19 @@ def main():
 
     if rank == 0:
         peaks = measured_peaks()
-        tensor_peak = peaks["bf16_sustained"] * (0.5 if args.math == "tf32" else 1.0)
+        half = 0.5 if args.math in ("tf32", "parity") else 1.0
+        # the dominant kernel is timed ALONE between two events (155 us): the burst peak is its denominator.  TF32 burst
+        # peak: measured in this run with cuBLAS (calibration only); MEASURED_PEAKS.json's bf16 burst / 2 as the fallback
+        burst = tf32_peak if (half == 0.5 and tf32_peak) else peaks["bf16_burst"] * half
+        peak_source = ("torch.matmul TF32 8192^3 burst, measured in this run (calibration only)" if (half == 0.5 and tf32_peak)
+                       else f"{peaks['source']} bf16_tflops (burst)" + (" / 2" if half == 0.5 else ""))
         dom = "dec.gemm_conv9"
-        n_dom, ms_dom = prof.get(dom, [0, 0.0])
+        n_dom, ms_dom = prof.get(dom, (0, 0.0))
         per_launch_ms = ms_dom / max(n_dom, 1)
+        terms = 3 if args.math == "parity" else 1
         flops_per_launch = FLOPS_CONV9_PER_ROW * frames
         achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
-        kernel_ms = {k: round(v[1] / PROF_RUNS, 4) for k, v in sorted(prof.items())}
+        kernel_ms = {k: round(v[1], 4) for k, v in sorted(prof.items())}
         line = {
             "metric": METRIC, "value": frames_all * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -373,35 +476,34 @@ def main():
                        "algorithmic_tflop_per_step": syn.algorithmic_flops(batch["src_lens"].tolist(), mel_lens) / 1e12},
             "e2e": {"value": frames_all * args.steps / (e2e_total_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": e2e_bytes.get("h2d", 0), "d2h_bytes_per_step": e2e_bytes.get("d2h", 0),
-                    "ms_per_step": e2e_total_ms / args.steps},
+                    "ms_per_step": e2e_total_ms / args.steps,
+                    "reads": "packed postnet mel rows, pitch, energy, log-duration, durations, mel_lens (utils/tools.py:228-243)"},
             "gpu_launches": launches * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": dom + " (decoder FFN Conv1d k=9 implicit GEMM, 256->1024)",
-                         "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tensor_peak if tensor_peak else None,
-                         # the same against the BURST cuBLAS rate (a kernel timed alone): never above 1
-                         "frac_of_burst_peak": achieved / (peaks["bf16_burst"] * (0.5 if args.math == "tf32" else 1.0)),
+                         "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
+                         "frac": achieved / burst if burst else None,
+                         "peak_source": peak_source,
+                         "frac_of_half_measured_bf16_burst": achieved / (peaks["bf16_burst"] * half),
+                         "tensor_flops_issued_per_launch": flops_per_launch * terms,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed
-                         # `ncu --set full` captures profiles/r01_ncu_full_dec_layer_tf32_2sm_raw.csv (the 2-SM kernel: 37.10 MB
-                         # read + 55.87 MB written) and ..._dec_layer_bf16_raw.csv (18.52 MB + 6.74 MB -- the bf16 hidden tensor
-                         # mostly stays in L2)
-                         "traffic": ({"tf32": 92.97e6, "bf16": 25.26e6}[args.math]
-                                     if (args.math in ("tf32", "bf16") and args.batch == 64) else None),
+                         # `ncu --set full` captures (profiles/): 37.10 MB read + 55.87 MB written in TF32 (the 110 MB
+                         # hidden tensor mostly stays in L2), 18.52 MB + 6.74 MB in bf16
+                         "traffic": ({"tf32": 92.97e6, "bf16": 25.26e6}.get(args.math) if args.batch == 64 else None),
                          "algorithmic_bytes_per_launch": 4 * (frames * 256 + 9 * 1024 * 256 + frames * 1024),
-                         "per_launch_ms": per_launch_ms, "launches_per_step": n_dom // PROF_RUNS,
-                         "flops_per_launch": flops_per_launch,
-                         "peak_source": f"{peaks['source']} bf16_tflops_sustained" +
-                                        (" / 2 (TF32 runs at half the bf16 tensor rate)" if args.math == "tf32" else "")},
+                         "per_launch_ms": per_launch_ms, "launches_per_step": n_dom,
+                         "flops_per_launch": flops_per_launch},
             "kernel_ms_per_step": kernel_ms,
+            "kernel_ms_note": "CUDA events around every launch: the programmatic-dependent-launch overlap between consecutive "
+                              "kernels is serialised away, so the classes sum to more than ms_per_step",
             "latency": {"workload": "config1: single utterance, 16 phonemes, controls 1.0", "p50_ms": float(np.percentile(lat, 50)),
                         "p90_ms": float(np.percentile(lat, 90)), "frames": c1_frames, "gpu_launches": c1_launches,
                         "calls": len(lat)},
-            "hbm_kernels": hbm_kernels(prof, PROF_RUNS, frames, int(batch["src_lens"].sum()), args.batch,
-                                       int(out[0].shape[1]), peaks["hbm_gbs"]),
-            "hbm_kernels_note": "at batch 64 these kernels move 27-67 MB, live in the 126 MB L2 and run 12-15 us (launch-latency "
-                                "bound); run with --batch 512 for figures that reach HBM (profiles/r01_bench_batch512_scatter_lr.json: "
-                                "length regulator 0.68, unpack 0.93 of the measured copy peak)",
         }
+        if hbm is not None:
+            line["hbm_kernels"] = hbm
+        if c3 is not None:
+            line["config3_strong"] = c3
         if other is not None:
             line["bf16_mode"] = {"value": o[0] * args.steps / (o[1] * 1e-3), "e2e": o[0] * args.steps / (o[2] * 1e-3),
                                  "unit": UNIT, "ms_per_step": o[1] / args.steps,

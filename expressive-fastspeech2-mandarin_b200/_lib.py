@@ -50,6 +50,9 @@ SIGNATURES = {
     "fs2_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fs2_forward_stage1": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Inputs), C.POINTER(Stage1Out)]),
     "fs2_forward_stage2": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Stage2IO)]),
+    "fs2_export_stage1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fs2_import_stage1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, c_i64p, C.POINTER(C.c_int32)]),
     "fs2_last_launch_count": (C.c_int, [C.c_void_p]),
     "fs2_read_packed_postnet": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, c_i64p]),
     "fs2_debug_enable": (C.c_int, [C.c_void_p, C.c_int]),

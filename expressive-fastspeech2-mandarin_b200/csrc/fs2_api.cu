@@ -98,6 +98,7 @@ struct fs2_ctx {
   int64_t frame_rows = 0, total_frames = 0;
   const float* lr_input = nullptr;
   float* va_spare = nullptr;
+  bool lr_adds_energy = true;    // false after fs2_import_stage1: the imported rows already carry the energy embedding
   const float *p_targets = nullptr, *e_targets = nullptr;  // frame_level teacher forcing: consumed in stage 2
   float p_control = 1.f;
   int64_t scratch_bt = 0;                                   // frame_level: raw predictions [B, T_max]
@@ -605,6 +606,7 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   c->phon_rows = rows;
   c->max_src_len = L;
   c->lr_input = xf;
+  c->lr_adds_energy = true;
   c->stage1_done = true;
   c->last_launches = g_launches;
 }
@@ -641,7 +643,7 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
       const int reserved = (B + 1) * GAP_FRAME + 128;                  // gaps + the round-up tail
       const int warps = rows_p + reserved;
       EnergyAdd en{};
-      if (!energy_f) {   // phoneme_level energy: bucketize + embedding add applied to the row on its way through
+      if (!energy_f && c->lr_adds_energy) {   // phoneme_level energy: bucketize + embedding add applied to the row on its way through
         en.raw = c->raw_energy; en.target = c->e_targets; en.control = c->p_control;
         en.bins = c->raw.at("variance_adaptor.energy_bins").ptr; en.n_bins = N_BINS - 1;
         en.table = c->raw.at("variance_adaptor.energy_embedding.weight").ptr;
@@ -795,6 +797,86 @@ static void prepare(fs2_ctx* c, cudaStream_t s) {
   c->prepared = true;
 }
 
+// ---- hand-over of the length regulator's input between contexts (rebalancing a sharded batch by frames)
+static void export_stage1(fs2_ctx* c, cudaStream_t s, float* hidden, int32_t* reps) {
+  require(c->stage1_done && c->lr_adds_energy, FS2_ERR_STATE, "fs2_export_stage1 needs a completed fs2_forward_stage1 of this context");
+  require(hidden && reps, FS2_ERR_INVALID, "null argument");
+  require(!c->cfg.pitch_frame_level && !c->cfg.energy_frame_level, FS2_ERR_UNSUPPORTED,
+          "export / import of stage 1 is implemented for phoneme_level features");
+  FS2_CUDA_OK(cudaSetDevice(c->device));
+  const int B = c->batch, L = c->max_src_len;
+  EnergyAdd en{};
+  en.raw = c->raw_energy; en.target = c->e_targets; en.control = c->p_control;
+  en.bins = c->raw.at("variance_adaptor.energy_bins").ptr; en.n_bins = N_BINS - 1;
+  en.table = c->raw.at("variance_adaptor.energy_embedding.weight").ptr;
+  const int warps = B * L;
+  export_rows_kernel<<<(warps + 7) / 8, 256, 0, s>>>(c->lr_input, c->ps.starts, c->ps.lens, c->cum, B, L, en, hidden, reps);
+  FS2_LAUNCHED();
+}
+
+static void import_stage1(fs2_ctx* c, cudaStream_t s, const float* hidden, const int32_t* reps, const int64_t* src_lens, int B,
+                          int L, int max_mel_len, int64_t* mel_lens, int64_t* total_frames, int32_t* max_mel_len_out) {
+  require(c->prepared, FS2_ERR_STATE, "fs2_import_stage1 called before fs2_prepare");
+  require(hidden && reps && src_lens && mel_lens && total_frames && max_mel_len_out, FS2_ERR_INVALID, "null argument");
+  require(B > 0 && B <= 65535 && L > 0, FS2_ERR_INVALID, "batch must be in [1,65535] and max_src_len > 0");
+  require(!c->cfg.pitch_frame_level && !c->cfg.energy_frame_level, FS2_ERR_UNSUPPORTED,
+          "export / import of stage 1 is implemented for phoneme_level features");
+  FS2_CUDA_OK(cudaSetDevice(c->device));
+  g_launches = 0;
+  c->stage1_done = false;
+  const int64_t bound = (int64_t)GAP_PHON + (int64_t)B * (L + GAP_PHON);
+  require(bound < (1LL << 30), FS2_ERR_INVALID, "batch * max_src_len too large");
+  const int rows = round_up((int)bound, 128);
+  ensure_side(c->ps, B, rows, s, attn_tc::work_bound((int64_t)B * L, B, L));
+  ensure_side(c->fs, B, 0, s);
+  ensure_pool(c->pp, rows, false, c->cfg.math_mode == FS2_MATH_BF16, s);
+  const int64_t BL = (int64_t)B * L;
+  if (BL > c->scratch_bl) {
+    regrow(c->cum, BL, s);
+    regrow(c->raw_pitch, BL, s);
+    regrow(c->raw_energy, BL, s);
+    c->scratch_bl = BL;
+  }
+  if (B > c->scratch_b) {
+    regrow(c->mel_lens32, B, s);
+    regrow(c->cond_spk, (size_t)B * D_MODEL, s);
+    regrow(c->cond_emo, (size_t)B * D_MODEL, s);
+    c->scratch_b = B;
+  }
+  RowSide& ps = c->ps;
+  layout_scan_kernel<int64_t><<<1, 1024, 0, s>>>(src_lens, B, GAP_PHON, L, L, ps.starts, ps.lens, ps.totals, c->status);
+  FS2_LAUNCHED();
+  row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(ps.starts, ps.lens, B, GAP_PHON, L, nullptr, rows, ps.utt, ps.vpos, ps.room,
+                                                     ps.slot);
+  FS2_LAUNCHED();
+  float* x = c->pp.act[3];
+  import_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(hidden, ps.meta(), ps.lens, L, rows, x);
+  FS2_LAUNCHED();
+  reps_scan_kernel<<<(B + 7) / 8, 256, 0, s>>>(reps, src_lens, B, L, c->cum, mel_lens, c->mel_lens32);
+  FS2_LAUNCHED();
+  layout_scan_kernel<int32_t><<<1, 1024, 0, s>>>(c->mel_lens32, B, GAP_FRAME, 0, max_mel_len, c->fs.starts, c->fs.lens,
+                                                 c->fs.totals, c->status);
+  FS2_LAUNCHED();
+  FS2_CUDA_OK(cudaMemcpyAsync(c->h_totals, c->fs.totals, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  FS2_CUDA_OK(cudaMemcpyAsync(c->h_totals + 3, c->status, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  FS2_CUDA_OK(cudaMemsetAsync(c->status, 0, sizeof(int32_t), s));
+  FS2_CUDA_OK(cudaStreamSynchronize(s));
+  check_status(c, *reinterpret_cast<int32_t*>(c->h_totals + 3));
+  c->frame_rows = c->h_totals[0];
+  c->max_mel_len = (int)c->h_totals[1];
+  *total_frames = c->total_frames = c->h_totals[2];
+  *max_mel_len_out = c->max_mel_len;
+  require(c->frame_rows < (1LL << 30), FS2_ERR_INVALID, "expanded batch too large");
+  c->batch = B;
+  c->phon_rows = rows;
+  c->max_src_len = L;
+  c->lr_input = x;
+  c->lr_adds_energy = false;
+  c->p_targets = c->e_targets = nullptr;
+  c->stage1_done = true;
+  c->last_launches = g_launches;
+}
+
 template <typename F>
 static int guarded(fs2_ctx* c, F&& f) {
   try {
@@ -907,6 +989,21 @@ int fs2_forward_stage1(fs2_ctx* c, fs2_stream stream, const fs2_inputs* in, fs2_
 int fs2_forward_stage2(fs2_ctx* c, fs2_stream stream, const fs2_stage2_io* io) {
   if (!c) return FS2_ERR_INVALID;
   return guarded(c, [&] { stage2(c, static_cast<cudaStream_t>(stream), io); });
+}
+
+int fs2_export_stage1(fs2_ctx* c, fs2_stream stream, float* hidden, int32_t* reps) {
+  if (!c) return FS2_ERR_INVALID;
+  return guarded(c, [&] { export_stage1(c, static_cast<cudaStream_t>(stream), hidden, reps); });
+}
+
+int fs2_import_stage1(fs2_ctx* c, fs2_stream stream, const float* hidden, const int32_t* reps, const int64_t* src_lens,
+                      int batch, int max_src_len, int max_mel_len, int64_t* mel_lens, int64_t* total_frames,
+                      int32_t* max_mel_len_out) {
+  if (!c) return FS2_ERR_INVALID;
+  return guarded(c, [&] {
+    import_stage1(c, static_cast<cudaStream_t>(stream), hidden, reps, src_lens, batch, max_src_len, max_mel_len, mel_lens,
+                  total_frames, max_mel_len_out);
+  });
 }
 
 int fs2_last_launch_count(const fs2_ctx* c) { return c ? c->last_launches : 0; }

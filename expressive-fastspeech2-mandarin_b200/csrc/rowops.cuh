@@ -569,6 +569,81 @@ __global__ void length_regulate_scatter_kernel(const float* __restrict__ x, RowM
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Hand-over of the length regulator's input between contexts (multi-GPU rebalancing by FRAMES: the durations are only
+// known after stage 1).  export: padded [B, L, 256] rows = x + energy_embedding[bucketize(energy)]
+// (what model/modules.py:126 feeds the LengthRegulator) and the integer repeat counts; import: the inverse.
+__global__ void export_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ p_starts,
+                                   const int32_t* __restrict__ p_lens, const int32_t* __restrict__ cum, int batch,
+                                   int max_src_len, EnergyAdd en, float* __restrict__ hidden, int32_t* __restrict__ reps) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= batch * max_src_len) return;
+  const int b = w / max_src_len, j = w - b * max_src_len;
+  float* dst = hidden + (size_t)w * D_MODEL;
+  if (j >= p_lens[b]) {
+    st4(dst + lane * 4, make_float4(0, 0, 0, 0));
+    st4(dst + 128 + lane * 4, make_float4(0, 0, 0, 0));
+    if (lane == 0) reps[w] = 0;
+    return;
+  }
+  const float* src = x + (size_t)(p_starts[b] + j) * D_MODEL;
+  float4 a = ld4(src + lane * 4), c = ld4(src + 128 + lane * 4);
+  if (en.table != nullptr) {
+    const float value = en.target != nullptr ? en.target[w] : en.raw[w] * en.control;
+    const float* e = en.table + (size_t)bucket_of(value, en.bins, en.n_bins) * D_MODEL;
+    a = add4(a, ld4(e + lane * 4));
+    c = add4(c, ld4(e + 128 + lane * 4));
+  }
+  st4(dst + lane * 4, a);
+  st4(dst + 128 + lane * 4, c);
+  if (lane == 0) reps[w] = cum[w] - (j > 0 ? cum[w - 1] : 0);
+}
+
+__global__ void import_rows_kernel(const float* __restrict__ hidden, RowMeta meta, const int32_t* __restrict__ p_lens,
+                                   int max_src_len, int rows, float* __restrict__ x) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int u = meta.utt[row], vp = meta.vpos[row];
+  float* dst = x + (size_t)row * D_MODEL;
+  if (u < 0 || vp >= 0) {
+    st4(dst + lane * 4, make_float4(0, 0, 0, 0));
+    st4(dst + 128 + lane * 4, make_float4(0, 0, 0, 0));
+    return;
+  }
+  const float* src = hidden + ((size_t)u * max_src_len + (vp + p_lens[u])) * D_MODEL;
+  st4(dst + lane * 4, ld4(src + lane * 4));
+  st4(dst + 128 + lane * 4, ld4(src + 128 + lane * 4));
+}
+
+// Inclusive scan of given repeat counts per utterance (the second half of durations_kernel).  Warp per utterance.
+__global__ void reps_scan_kernel(const int32_t* __restrict__ reps, const int64_t* __restrict__ src_lens, int batch,
+                                 int max_src_len, int32_t* __restrict__ cum, int64_t* __restrict__ mel_lens,
+                                 int32_t* __restrict__ mel_lens32) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= batch) return;
+  long long len = src_lens[b];
+  len = len < 0 ? 0 : (len > max_src_len ? max_src_len : len);
+  int run = 0;
+  for (int j0 = 0; j0 < max_src_len; j0 += 32) {
+    const int j = j0 + lane;
+    int inc = (j < len) ? max(reps[(size_t)b * max_src_len + j], 0) : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (j < max_src_len) cum[(size_t)b * max_src_len + j] = run + inc;
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) {
+    if (mel_lens != nullptr) mel_lens[b] = run;
+    mel_lens32[b] = run;
+  }
+}
+
 // Decoder input when a frame_level predictor sits between the LengthRegulator and the decoder
 // (model/modules.py:139-148, transformer/Models.py:154-162): real rows get x + position_enc[t], every
 // reserved row returns to zero (the FFT stacks need zero gaps).  In place is fine (row-wise).

@@ -226,10 +226,10 @@ class FastSpeech2B200(nn.Module):
             raise RuntimeError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
         return t.to(torch.float32).contiguous()
 
-    @torch.no_grad()
-    def forward(self, speakers, emotions, arousals, valences, texts, src_lens, max_src_len, mels=None, mel_lens=None,
-                max_mel_len=None, p_targets=None, e_targets=None, d_targets=None, p_control=1.0, e_control=1.0,
-                d_control=1.0):
+    def _stage1(self, speakers, emotions, arousals, valences, texts, src_lens, max_src_len, max_mel_len, p_targets, e_targets,
+                d_targets, p_control, e_control, d_control):
+        """fs2_forward_stage1: masks, encoder, conditioning, variance adaptor up to the durations.  Returns the phoneme-side
+        tensors and the frame-side sizes (the call blocks for them)."""
         if self.training:
             raise RuntimeError("FastSpeech2B200.forward is inference-only")
         lib = self._ensure_ctx()
@@ -268,11 +268,18 @@ class FastSpeech2B200(nn.Module):
         s1 = _lib.Stage1Out(pitch=ptr(pitch), energy=ptr(energy), log_d=ptr(log_d), d_rounded=ptr(d_round),
                             src_mask=ptr(src_mask), mel_lens=ptr(out_lens))
         stream = torch.cuda.current_stream(dev).cuda_stream
+        # the targets must outlive stage 2 (frame_level features and the fused energy add read them there)
+        self._keep = (spk, emo, aro, val, txt, lens, p_t, e_t, d_t)
         _lib.check(lib, self._ctx, lib.fs2_forward_stage1(self._ctx, stream, C.byref(inp), C.byref(s1)))
-        T = int(s1.max_mel_len)
-        if d_targets is not None and mel_lens is not None:
-            if not torch.equal(mel_lens.to(out_lens.device, torch.int64), out_lens):
-                raise RuntimeError("mel_lens must equal the row sums of trunc(d_targets) (inconsistent teacher forcing)")
+        self.last_total_frames = int(s1.total_frames)
+        return dict(B=B, L=L, T=int(s1.max_mel_len), pitch=pitch, energy=energy, log_d=log_d, d_round=d_round,
+                    src_mask=src_mask, mel_lens=out_lens, p_t=p_t, e_t=e_t)
+
+    def _stage2(self, B, T, pitch=None, energy=None, p_t=None, e_t=None):
+        """fs2_forward_stage2: length regulator, decoder, mel_linear, PostNet into freshly allocated outputs."""
+        lib = self._ensure_ctx()
+        dev = self._device()
+        f32 = dict(dtype=torch.float32, device=dev)
         mel = torch.empty(B, T, 80, **f32)
         post = torch.empty(B, T, 80, **f32)
         mel_mask = torch.empty(B, T, dtype=torch.bool, device=dev)
@@ -283,13 +290,66 @@ class FastSpeech2B200(nn.Module):
             pitch = torch.empty(B, T, **f32)
         if self.energy_frame_level:                                 # model/modules.py:144-148
             energy = torch.empty(B, T, **f32)
-        io = _lib.Stage2IO(mel=ptr(mel), postnet=ptr(post), mel_mask=ptr(mel_mask),
-                           pitch_frames=ptr(pitch) if self.pitch_frame_level else None,
-                           energy_frames=ptr(energy) if self.energy_frame_level else None)
+        io = _lib.Stage2IO(mel=mel.data_ptr(), postnet=post.data_ptr(), mel_mask=mel_mask.data_ptr(),
+                           pitch_frames=pitch.data_ptr() if self.pitch_frame_level else None,
+                           energy_frames=energy.data_ptr() if self.energy_frame_level else None)
+        stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib, self._ctx, lib.fs2_forward_stage2(self._ctx, stream, C.byref(io)))
-        self.last_total_frames = int(s1.total_frames)
-        return (mel, post, pitch, energy, log_d, d_targets if d_targets is not None else d_round, src_mask, mel_mask,
-                src_lens, out_lens)
+        return mel, post, mel_mask, pitch, energy
+
+    @torch.no_grad()
+    def forward(self, speakers, emotions, arousals, valences, texts, src_lens, max_src_len, mels=None, mel_lens=None,
+                max_mel_len=None, p_targets=None, e_targets=None, d_targets=None, p_control=1.0, e_control=1.0,
+                d_control=1.0):
+        s1 = self._stage1(speakers, emotions, arousals, valences, texts, src_lens, max_src_len, max_mel_len, p_targets,
+                          e_targets, d_targets, p_control, e_control, d_control)
+        if d_targets is not None and mel_lens is not None:
+            if not torch.equal(mel_lens.to(s1["mel_lens"].device, torch.int64), s1["mel_lens"]):
+                raise RuntimeError("mel_lens must equal the row sums of trunc(d_targets) (inconsistent teacher forcing)")
+        mel, post, mel_mask, pitch, energy = self._stage2(s1["B"], s1["T"], s1["pitch"], s1["energy"], s1["p_t"], s1["e_t"])
+        return (mel, post, pitch, energy, s1["log_d"], d_targets if d_targets is not None else s1["d_round"], s1["src_mask"],
+                mel_mask, src_lens, s1["mel_lens"])
+
+    # ------------------------------------------------------------------ sharded batches re-balanced by frames (partition.py)
+    @torch.no_grad()
+    def encode(self, speakers, emotions, arousals, valences, texts, src_lens, max_src_len, p_control=1.0, e_control=1.0,
+               d_control=1.0):
+        """Stage 1 only (model/fastspeech2.py:92-131 up to the durations).  Returns a dict with the phoneme-side outputs
+        (`pitch`, `energy`, `log_d`, `d_round`, `src_mask`), `mel_lens` [B] (device) and what the length regulator consumes,
+        exported for another context: `hidden` [B, L, 256] (x + pitch embedding + energy embedding) and `reps` [B, L] int32."""
+        s1 = self._stage1(speakers, emotions, arousals, valences, texts, src_lens, max_src_len, None, None, None, None,
+                          p_control, e_control, d_control)
+        dev = self._device()
+        hidden = torch.empty(s1["B"], s1["L"], 256, dtype=torch.float32, device=dev)
+        reps = torch.empty(s1["B"], s1["L"], dtype=torch.int32, device=dev)
+        lib = _lib.load_library()
+        _lib.check(lib, self._ctx, lib.fs2_export_stage1(self._ctx, torch.cuda.current_stream(dev).cuda_stream,
+                                                          hidden.data_ptr(), reps.data_ptr()))
+        s1["hidden"], s1["reps"] = hidden, reps
+        return s1
+
+    @torch.no_grad()
+    def decode(self, hidden, reps, src_lens, max_mel_len=None):
+        """Stage 2 from exported rows (model/modules.py:136-137, fastspeech2.py:133-136) -- possibly of utterances another
+        GPU encoded.  hidden [B, L, 256] fp32, reps [B, L] int32, src_lens [B] int64, all on this module's device.
+        Returns (mel, postnet, mel_mask, mel_lens)."""
+        lib = self._ensure_ctx()
+        dev = self._device()
+        B, L = int(hidden.shape[0]), int(hidden.shape[1])
+        if tuple(hidden.shape) != (B, L, 256) or tuple(reps.shape) != (B, L) or hidden.device != dev or reps.device != dev:
+            raise RuntimeError(f"decode: hidden [B, L, 256] and reps [B, L] must live on {dev}")
+        hidden = hidden.to(torch.float32).contiguous()
+        reps = reps.to(torch.int32).contiguous()
+        lens = self._idx(src_lens, "src_lens", (B,))
+        mel_lens = torch.empty(B, dtype=torch.int64, device=dev)
+        total, t_max = C.c_int64(), C.c_int32()
+        self._keep = (hidden, reps, lens)
+        _lib.check(lib, self._ctx, lib.fs2_import_stage1(self._ctx, torch.cuda.current_stream(dev).cuda_stream, hidden.data_ptr(),
+                                                          reps.data_ptr(), lens.data_ptr(), B, L, int(max_mel_len) if max_mel_len else 0,
+                                                          mel_lens.data_ptr(), C.byref(total), C.byref(t_max)))
+        self.last_total_frames = int(total.value)
+        mel, post, mel_mask, _, _ = self._stage2(B, int(t_max.value))
+        return mel, post, mel_mask, mel_lens
 
     # ------------------------------------------------------------------ host-buffer entry (what the CLI does)
     def _pinned_buf(self, role, dtype, numel):

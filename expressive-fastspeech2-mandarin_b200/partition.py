@@ -1,8 +1,17 @@
 """Multi-GPU inference = utterance sharding: utterances are independent, every
-GPU holds a full weight replica and runs its own context, and there is NO collective on the hot
-path.  This module is the host logic: a length-balanced LPT partition and an optional gather of
-the padded outputs over torch.distributed (NCCL over NVLink on the GPU box, gloo in CPU tests).
+GPU holds a full weight replica and runs its own context.  This module is the host logic:
+  * `lpt_partition`: a length-balanced LPT partition by phoneme counts -- all that is known before stage 1; a forward
+    on such shards needs NO collective;
+  * `rebalanced_forward`: the same batch re-balanced by FRAMES once stage 1 has produced the durations (the decoder,
+    mel_linear and PostNet are 90 % of the work and follow the frames, not the phonemes): one small all-gather of
+    mel_lens, a deterministic LPT on the true stage-2 cost, ONE all-to-all of the phoneme rows that change owner
+    (P x 1 KB over NVLink), stage 2 where the utterance landed;
+  * `gather_padded`: an optional gather of the padded outputs AFTER the forward.
+torch.distributed: NCCL over NVLink on the GPU box, gloo (with point-to-point exchange) in the CPU tests.
 """
+import heapq
+
+import numpy as np
 import torch
 
 FRAMES_PER_PHONEME = 5.0   # planning value only: T_i is unknown before stage 1
@@ -31,6 +40,144 @@ def lpt_partition(src_lens, n_parts, frames_per_phoneme=FRAMES_PER_PHONEME):
     for p in parts:
         p.sort()
     return parts
+
+
+def stage2_cost(n_frames):
+    """FLOP proxy (MFLOP) of the frame side of one utterance: decoder + mel_linear + PostNet
+    rows and the quadratic decoder attention."""
+    T = np.asarray(n_frames, dtype=np.float64)
+    return T * 43.33 + 0.006144 * T * T
+
+
+def lpt_by_cost(costs, n_parts):
+    """Longest-processing-time-first on given costs (ties by index): n_parts sorted index lists, identical on every
+    rank.  A heap keeps the greedy step O(log n_parts)."""
+    costs = np.asarray(costs, dtype=np.float64)
+    order = np.lexsort((np.arange(len(costs)), -costs))
+    heap = [(0.0, k) for k in range(n_parts)]
+    parts = [[] for _ in range(n_parts)]
+    for i in order.tolist():
+        load, k = heapq.heappop(heap)
+        parts[k].append(i)
+        heapq.heappush(heap, (load + float(costs[i]), k))
+    for p in parts:
+        p.sort()
+    return parts
+
+
+def _exchange(send, send_splits, recv_splits, width, dtype, device, group):
+    """All-to-all of row blocks: `send` [sum(send_splits), width] ordered by destination rank.  NCCL: one
+    all_to_all_single; gloo (CPU tests) has no all-to-all: point-to-point isend / irecv with the same semantics."""
+    import torch.distributed as dist
+    recv = torch.empty(int(sum(recv_splits)), width, dtype=dtype, device=device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(recv, send, list(recv_splits), list(send_splits), group=group)
+        return recv
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    so, ro = np.concatenate(([0], np.cumsum(send_splits))), np.concatenate(([0], np.cumsum(recv_splits)))
+    recv[ro[rank]: ro[rank + 1]] = send[so[rank]: so[rank + 1]]
+    ops = []
+    for r in range(world):
+        if r == rank:
+            continue
+        if send_splits[r]:
+            ops.append(dist.P2POp(dist.isend, send[so[r]: so[r + 1]].contiguous(), r, group))
+        if recv_splits[r]:
+            ops.append(dist.P2POp(dist.irecv, recv[ro[r]: ro[r + 1]], r, group))
+    for w in (dist.batch_isend_irecv(ops) if ops else []):
+        w.wait()
+    return recv
+
+
+def plan_rebalance(parts, src_lens, mel_lens, n_parts):
+    """Given the phoneme shards `parts` (owner of every utterance during stage 1), all src_lens and the mel_lens stage 1
+    produced, returns (new_parts, moves): new_parts = LPT of the TRUE stage-2 cost; moves[src][dst] = sorted utterance
+    ids that rank src sends to rank dst (src == dst: stay).  Pure host arithmetic, identical on every rank."""
+    new_parts = lpt_by_cost(stage2_cost(mel_lens), n_parts)
+    owner = np.empty(len(src_lens), dtype=np.int64)
+    for r, p in enumerate(parts):
+        owner[p] = r
+    moves = [[[] for _ in range(n_parts)] for _ in range(n_parts)]
+    for dst, p in enumerate(new_parts):
+        for i in p:
+            moves[int(owner[i])][dst].append(i)
+    return new_parts, moves
+
+
+def exchange_rows(hidden, reps, local_ids, src_lens_all, moves, rank, group=None):
+    """Move the exported stage-1 rows to their stage-2 owners.  hidden [B_local, L_local, 256] fp32 and reps
+    [B_local, L_local] int32 are this rank's stage-1 export for the utterances `local_ids` (sorted global ids);
+    src_lens_all: every utterance's phoneme count (host list).  Returns (hidden', reps', src_lens', ids') for the
+    utterances this rank now owns, padded to their own maximum, ids' in the order of the rows."""
+    world = len(moves)
+    dev = hidden.device
+    lens = np.asarray(src_lens_all, dtype=np.int64)
+    pos = {g: j for j, g in enumerate(local_ids)}
+    # send side: for every destination the (local utterance, position) pairs of the real rows, in id order
+    send_ids = [moves[rank][d] for d in range(world)]
+    flat = [g for ids in send_ids for g in ids]
+    if flat:
+        b_idx = np.repeat(np.array([pos[g] for g in flat], dtype=np.int64), lens[flat])
+        j_idx = np.concatenate([np.arange(lens[g]) for g in flat])
+    else:
+        b_idx = j_idx = np.zeros(0, dtype=np.int64)
+    bi, ji = torch.from_numpy(b_idx).to(dev, non_blocking=True), torch.from_numpy(j_idx).to(dev, non_blocking=True)
+    # one message per peer: 256 fp32 columns of the row + its repeat count, bit-cast into a 257th column
+    send = torch.cat([hidden[bi, ji], reps[bi, ji].contiguous().view(torch.float32).unsqueeze(1)], dim=1)
+    send_splits = [int(lens[ids].sum()) if ids else 0 for ids in send_ids]
+    recv_ids = [moves[s][rank] for s in range(world)]
+    recv_splits = [int(lens[ids].sum()) if ids else 0 for ids in recv_ids]
+    recv = send if world == 1 else _exchange(send, send_splits, recv_splits, 257, torch.float32, dev, group)
+    ids = [g for r_ids in recv_ids for g in r_ids]
+    my_lens = lens[ids] if ids else np.zeros(0, dtype=np.int64)
+    B, L = len(ids), int(my_lens.max()) if len(ids) else 0
+    out_h = torch.zeros(B, L, 256, dtype=torch.float32, device=dev)
+    out_r = torch.zeros(B, L, dtype=torch.int32, device=dev)
+    if B:
+        rb = torch.from_numpy(np.repeat(np.arange(B), my_lens)).to(dev, non_blocking=True)
+        rj = torch.from_numpy(np.concatenate([np.arange(n) for n in my_lens])).to(dev, non_blocking=True)
+        out_h[rb, rj] = recv[:, :256]
+        out_r[rb, rj] = recv[:, 256].contiguous().view(torch.int32)
+    return out_h, out_r, torch.from_numpy(my_lens).to(dev), ids
+
+
+def rebalanced_forward(model, batch, parts, rank, group=None, p_control=1.0, e_control=1.0, d_control=1.0):
+    """One sharded forward with the frames re-balanced after stage 1.  `batch` is the WHOLE batch (host tensors, known to
+    every rank), `parts` its phoneme partition (`lpt_partition`).  Returns a dict: `ids` (global ids of the utterances this
+    rank decoded), `mel`, `postnet`, `mel_mask`, `mel_lens` for them, `stage1` (this rank's phoneme-side outputs for
+    parts[rank]) and `new_parts`.  Collectives: one all_gather of mel_lens, one all-to-all of rows."""
+    import torch.distributed as dist
+    world = len(parts)
+    dev = model._device()
+    mine = parts[rank]
+    sub = take(batch, mine)
+    s1 = model.encode(*[sub[k].to(dev, non_blocking=True) for k in ("speakers", "emotions", "arousals", "valences", "texts",
+                                                                       "src_lens")], sub["max_src_len"],
+                      p_control=p_control, e_control=e_control, d_control=d_control)
+    n = len(batch["src_lens"])
+    b_max = max(len(p) for p in parts)
+    local = torch.full((b_max,), -1, dtype=torch.int64, device=dev)
+    local[: len(mine)] = s1["mel_lens"]
+    if world > 1:
+        gathered = torch.empty(world * b_max, dtype=torch.int64, device=dev)
+        if dist.get_backend(group) == "nccl":
+            dist.all_gather_into_tensor(gathered, local, group=group)
+        else:
+            chunks = [torch.empty_like(local) for _ in range(world)]
+            dist.all_gather(chunks, local, group=group)
+            gathered = torch.cat(chunks)
+    else:
+        gathered = local
+    g = gathered.cpu().numpy().reshape(world, b_max)          # (the only host sync besides the two stage read-backs)
+    mel_lens = np.zeros(n, dtype=np.int64)
+    for r, p in enumerate(parts):
+        mel_lens[p] = g[r, : len(p)]
+    new_parts, moves = plan_rebalance(parts, batch["src_lens"].tolist(), mel_lens, world)
+    hidden, reps, lens, ids = exchange_rows(s1["hidden"], s1["reps"], mine, batch["src_lens"].tolist(), moves, rank, group)
+    out = {"ids": ids, "stage1": s1, "new_parts": new_parts, "mel_lens_all": mel_lens}
+    if ids:
+        out["mel"], out["postnet"], out["mel_mask"], out["mel_lens"] = model.decode(hidden, reps, lens)
+    return out
 
 
 def take(batch, indices):

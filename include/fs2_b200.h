@@ -134,6 +134,22 @@ int fs2_forward_stage2(fs2_ctx* ctx, fs2_stream stream, const fs2_stage2_io* io)
  * should be pinned; `*rows_out` (written before the call returns) = rows to expect; max_rows = capacity of host_rows. */
 int fs2_read_packed_postnet(fs2_ctx* ctx, fs2_stream stream, float* host_rows, int64_t max_rows, int32_t* host_starts,
                             int64_t* rows_out);
+/* --- hand-over between contexts: one batch sharded over several GPUs, re-balanced by FRAMES ---------------------
+ * The shards of a batch can only be balanced by phonemes before stage 1 (the durations are its result); the decoder's
+ * cost follows the frames.  A caller that owns one context per GPU therefore runs stage 1 on
+ * phoneme-balanced shards, exchanges utterances so that the frames are balanced, and runs stage 2 where the utterance
+ * landed (expressive-fastspeech2-mandarin_b200/partition.py does this over torch.distributed / NCCL).
+ * fs2_export_stage1: after fs2_forward_stage1, writes what the LengthRegulator consumes (model/modules.py:126-137):
+ *   hidden [B, max_src_len, 256] = x + pitch embedding + energy embedding (zero at padding) and reps [B, max_src_len] =
+ *   max(int(d), 0), the integer repeat counts.  phoneme_level features only.
+ * fs2_import_stage1: takes the place of fs2_forward_stage1 on the receiving context: lays the given utterances out,
+ *   computes mel_lens = row sums of reps, and blocks for the sizes exactly like stage 1; fs2_forward_stage2 follows.
+ *   max_mel_len: 0 = maximum over the batch.  Results equal the reference's forward on the RECEIVING batch with
+ *   d_targets / p_targets / e_targets forced (the PostNet tails follow that batch's T_max). */
+int fs2_export_stage1(fs2_ctx* ctx, fs2_stream stream, float* hidden, int32_t* reps);
+int fs2_import_stage1(fs2_ctx* ctx, fs2_stream stream, const float* hidden, const int32_t* reps, const int64_t* src_lens,
+                      int batch, int max_src_len, int max_mel_len, int64_t* mel_lens, int64_t* total_frames,
+                      int32_t* max_mel_len_out);
 /* Number of kernels the last stage1+stage2 pair launched. */
 int fs2_last_launch_count(const fs2_ctx* ctx);
 

@@ -167,3 +167,57 @@ def test_config3_batch512_properties(sd32, syn):
     for i, n in ((0, "mel"), (1, "postnet")):
         mx, mean = err_stats(valid_rows(a[i][idx].cpu().numpy(), lens), valid_rows(want[n].numpy(), lens))
         assert mx <= TOL_MEL_MAX and mean <= TOL_MEL_MEAN, (n, mx, mean)
+
+
+def test_export_import_of_stage1_is_bit_exact_and_matches_oracle_after_regrouping(sd32, syn):
+    """fs2_export_stage1 / fs2_import_stage1 (the hand-over partition.rebalanced_forward uses to balance a sharded batch by
+    FRAMES): (1) decoding the exported rows on the same batch equals the plain forward bit for bit; (2) utterances encoded
+    in two phoneme shards and REGROUPED into two other batches decode to the oracle's result on the receiving batch with
+    the durations / pitch / energy of stage 1 forced."""
+    from fs2_b200 import partition
+    model = model_for(sd32)
+    batch = syn.make_batch(syn.random_lengths(10, lo=10, hi=60, seed=13), seed=71)
+    names = ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")
+    plain = run(model, batch)
+    b = {k: v.to(DEV) for k, v in batch.items() if torch.is_tensor(v)}
+    s1 = model.encode(*[b[k] for k in names], batch["max_src_len"])
+    mel, post, mask, lens = model.decode(s1["hidden"], s1["reps"], b["src_lens"])
+    torch.cuda.synchronize()
+    assert torch.equal(lens, plain[9]) and torch.equal(mel, plain[0]) and torch.equal(post, plain[1]) and torch.equal(mask, plain[7])
+    assert torch.equal(s1["pitch"], plain[2]) and torch.equal(s1["energy"], plain[3]) and torch.equal(s1["d_round"], plain[5])
+    # (2) two stage-1 shards -> regrouped stage-2 shards
+    parts = partition.lpt_partition(batch["src_lens"].tolist(), 2)
+    enc = []
+    for p in parts:
+        sub = partition.take(batch, p)
+        sb = {k: v.to(DEV) for k, v in sub.items() if torch.is_tensor(v)}
+        enc.append((p, sub, model.encode(*[sb[k] for k in names], sub["max_src_len"])))
+        enc[-1][2]["hidden"] = enc[-1][2]["hidden"].clone()      # (the same context encodes both shards here)
+    mel_lens_all = [0] * 10
+    for p, _, e in enc:
+        for j, g in enumerate(p):
+            mel_lens_all[g] = int(e["mel_lens"][j])
+    new_parts, moves = partition.plan_rebalance(parts, batch["src_lens"].tolist(), mel_lens_all, 2)
+    sd64 = O.cast_state_dict(sd32, torch.float64)
+    where = {g: (r, j) for r, (p, _, _) in enumerate(enc) for j, g in enumerate(p)}
+    for new in new_parts:
+        L = max(int(batch["src_lens"][g]) for g in new)
+        hid = torch.zeros(len(new), L, 256, device=DEV)
+        rep = torch.zeros(len(new), L, dtype=torch.int32, device=DEV)
+        d_t, p_t, e_t = (torch.zeros(len(new), L, dtype=torch.float64) for _ in range(3))
+        for i, g in enumerate(new):
+            r, j = where[g]
+            n = int(batch["src_lens"][g])
+            e = enc[r][2]
+            hid[i, :n], rep[i, :n] = e["hidden"][j, :n], e["reps"][j, :n]
+            d_t[i, :n], p_t[i, :n], e_t[i, :n] = e["d_round"][j, :n].cpu(), e["pitch"][j, :n].cpu(), e["energy"][j, :n].cpu()
+        sub = partition.take(batch, new)
+        got = model.decode(hid, rep, sub["src_lens"].to(DEV))
+        want = dict(zip(OUT_NAMES, call(O.forward, sub, sd64, d_targets=d_t, p_targets=p_t, e_targets=e_t,
+                                        mel_lens=got[3].cpu(), max_mel_len=int(got[3].max()))))
+        assert torch.equal(got[3].cpu(), want["mel_lens"])
+        T = want["mel_lens"].tolist()
+        for i, n in ((0, "mel"), (1, "postnet")):
+            mx, mean = err_stats(valid_rows(got[i].cpu().numpy(), T), valid_rows(want[n].numpy(), T))
+            log_diag(f"regrouped stage 2 {n}: max {mx:.3e} mean {mean:.3e}")
+            assert mx <= TOL_MEL_MAX and mean <= TOL_MEL_MEAN

@@ -32,6 +32,61 @@ def test_take_repads_to_the_shards_own_max(syn):
     assert torch.equal(sub["src_lens"], torch.tensor([7, 12]))
 
 
+def test_rebalance_plan_is_a_permutation_and_balances_frames(syn):
+    lens = syn.random_lengths(512, seed=100)
+    g = torch.Generator().manual_seed(1)
+    mel_lens = [int(n * (4.0 + 5.0 * float(torch.rand(1, generator=g)))) for n in lens]      # 4 .. 9 frames per phoneme
+    for world in (2, 8):
+        parts = partition.lpt_partition(lens, world)
+        new_parts, moves = partition.plan_rebalance(parts, lens, mel_lens, world)
+        assert sorted(i for p in new_parts for i in p) == list(range(512))
+        for src in range(world):
+            assert sorted(i for dst in range(world) for i in moves[src][dst]) == parts[src]
+        for dst in range(world):
+            assert sorted(i for src in range(world) for i in moves[src][dst]) == new_parts[dst]
+        cost = lambda p: float(sum(partition.stage2_cost(mel_lens[i]) for i in p))
+        before = max(cost(p) for p in parts) / (sum(cost(p) for p in parts) / world)
+        after = max(cost(p) for p in new_parts) / (sum(cost(p) for p in new_parts) / world)
+        assert after < 1.002 and after < before, (before, after)
+    assert partition.lpt_by_cost([3, 1, 2, 3], 2) == [[0, 2], [1, 3]]        # ties by index, deterministic
+
+
+def _rebalance_worker(rank, world, port, lens, mel_lens):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        parts = partition.lpt_partition(lens, world)
+        mine = parts[rank]
+        L = max(lens[i] for i in mine)
+        hidden = torch.zeros(len(mine), L, 256)
+        reps = torch.zeros(len(mine), L, dtype=torch.int32)
+        for b, gid in enumerate(mine):            # row (utterance g, position j) carries g * 1000 + j + column / 1000
+            n = lens[gid]
+            hidden[b, :n] = (gid * 1000 + torch.arange(n).float()).unsqueeze(1) + torch.arange(256).float() / 1000
+            reps[b, :n] = (gid + torch.arange(n)).int()
+        new_parts, moves = partition.plan_rebalance(parts, lens, mel_lens, world)
+        h2, r2, l2, ids = partition.exchange_rows(hidden, reps, mine, lens, moves, rank)
+        assert sorted(ids) == new_parts[rank]
+        assert l2.tolist() == [lens[g] for g in ids] and h2.shape[1] == max(lens[g] for g in ids)
+        for b, gid in enumerate(ids):
+            n = lens[gid]
+            want = (gid * 1000 + torch.arange(n).float()).unsqueeze(1) + torch.arange(256).float() / 1000
+            assert torch.equal(h2[b, :n], want) and torch.all(h2[b, n:] == 0)
+            assert torch.equal(r2[b, :n], (gid + torch.arange(n)).int()) and torch.all(r2[b, n:] == 0)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_exchange_over_gloo_world_size_2(syn):
+    """The re-partition by frames (partition.plan_rebalance + exchange_rows): every utterance's rows and repeat counts
+    arrive bit-exact at their stage-2 owner."""
+    lens = syn.random_lengths(21, lo=5, hi=40, seed=6)
+    g = torch.Generator().manual_seed(2)
+    mel_lens = [int(n * (3.0 + 6.0 * float(torch.rand(1, generator=g)))) for n in lens]
+    mp.spawn(_rebalance_worker, args=(2, _free_port(), lens, mel_lens), nprocs=2, join=True)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
