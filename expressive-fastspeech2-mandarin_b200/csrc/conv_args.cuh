@@ -51,6 +51,7 @@ struct ConvGemmArgs {
   // FS2_MATH_TF32X3 (split-operand "3xTF32"): A is [rows, 2K] = [hi | lo] (both TF32-exact, written by split_tf32_kernel),
   // W is [2][taps][N][K] = hi block then lo block; the K loop runs three terms  A_hi W_hi + A_lo W_hi + A_hi W_lo.
   int terms;          // 0 / 1 = plain, 3 = split operands
+  float* splitk_ws;   // optional workspace (tc2::SPLITK_WS_BYTES) that allows the K-split form for single-row-tile launches
   long long* trace;   // bring-up only: CTA 0 writes globaltimer stamps of its phases (nullptr in normal operation)
 };
 

@@ -79,6 +79,7 @@ struct fs2_ctx {
   float *mel_w = nullptr, *mel_b = nullptr;
   float* pe_long = nullptr;  // generated sinusoid table for sequences beyond max_seq_len
   int pe_long_rows = 0;
+  float* splitk_ws = nullptr;  // K-split workspace (tc2::SPLITK_WS_BYTES): partial tiles of single-utterance launches
   float* split_buf = nullptr;  // FS2_MATH_TF32X3: [rows, hi | lo] copy of the activations of the contraction being launched
   size_t split_cap = 0;
 
@@ -289,6 +290,7 @@ static void conv_gemm(fs2_ctx* c, ConvGemmArgs a, cudaStream_t s) {
     a.lda = 2 * a.K;
     a.terms = 3;
   }
+  a.splitk_ws = c->splitk_ws;
   tc2::launch(a, s);
 }
 
@@ -918,6 +920,7 @@ int fs2_create(const fs2_config* cfg, int device, fs2_ctx** out) {
     c->cfg = *cfg;
     c->status = dalloc<int32_t>(1);
     FS2_CUDA_OK(cudaMemset(c->status, 0, sizeof(int32_t)));
+    c->splitk_ws = dalloc<float>(tc2::SPLITK_WS_BYTES / sizeof(float));
     FS2_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&c->h_totals), 8 * sizeof(int64_t)));
     *out = c;
   });
@@ -943,7 +946,7 @@ void fs2_destroy(fs2_ctx* c) {
     cudaFree(p->hidb); cudaFree(p->melb); cudaFree(p->pnb[0]); cudaFree(p->pnb[1]);
   }
   cudaFree(c->status); cudaFree(c->cum); cudaFree(c->mel_lens32); cudaFree(c->raw_pitch); cudaFree(c->raw_energy);
-  cudaFree(c->cond_spk); cudaFree(c->cond_emo); cudaFree(c->pe_long); cudaFree(c->split_buf); cudaFree(c->raw_pitch_f); cudaFree(c->raw_energy_f);
+  cudaFree(c->cond_spk); cudaFree(c->cond_emo); cudaFree(c->pe_long); cudaFree(c->split_buf); cudaFree(c->splitk_ws); cudaFree(c->raw_pitch_f); cudaFree(c->raw_energy_f);
   cudaFreeHost(c->h_totals);
   delete c;
 }
@@ -1059,6 +1062,7 @@ int fs2_debug_set_flag(int which, int value) {
   if (which == 4) fs2::ffn::enabled_flag() = value;   // 0 off, 1 on, 2 automatic
   if (which == 5) fs2::tc2::n_split_flag() = value ? 1 : 0;
   if (which == 6) fs2::tc2::two_sm_flag() = value ? 1 : 0;
+  if (which == 7) fs2::tc2::k_split_flag() = value ? 1 : 0;
   if (which == 1) {
     g_trace_on = value;
     if (value && g_trace_buf == nullptr) cudaMalloc(reinterpret_cast<void**>(&g_trace_buf), 64 * sizeof(long long));
@@ -1133,6 +1137,14 @@ int fs2_op_conv_gemm(fs2_stream stream, int math_mode, const float* A, int lda, 
       FS2_CUDA_OK(cudaStreamSynchronize(s));
       cudaFree(ws);
       cudaFree(as);
+      return;
+    }
+    if (rows > 0 && rows <= tc2::BM) {   // single row tile: give the launch the K-split workspace the forward owns
+      float* sk = dalloc<float>(tc2::SPLITK_WS_BYTES / sizeof(float));
+      a.splitk_ws = sk;
+      tc2::launch(a, s);
+      FS2_CUDA_OK(cudaStreamSynchronize(s));
+      cudaFree(sk);
       return;
     }
     tc2::launch(a, s);

@@ -196,7 +196,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 // weight columns, and the LayerNorm statistics of the row are combined across the cluster through distributed shared
 // memory (two floats per row and CTA).  For a handful of row tiles (single utterances) this puts NS SMs on a K loop
 // that one CTA would walk alone: the fused-LN GEMMs were 40 % of the single-utterance latency.
-template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1, bool TWO = false, int EW = 4>
+// KS > 1: K-split.  A cluster of KS CTAs shares ONE output tile and each walks 1/KS of the (tap, K chunk) loop; the partial
+// accumulators of ranks 1..KS-1 travel through a small global (L2-resident) workspace to rank 0, which adds them to its own
+// and runs the epilogue.  For a SINGLE row tile (one utterance) with a long K loop the kernel is otherwise one CTA per
+// column tile pulling megabytes of operands through one SM at ~90 GB/s (measured: 17 us for the k = 9 FFN conv of a
+// 56-frame utterance, 72 ring steps); KS = 8 puts 8 SMs on that loop.
+template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1, bool TWO = false, int EW = 4, int KS = 1>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -208,7 +213,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   static_assert(NS == 1 || (LN && CL == 1 && !AR && BN * NS == 256), "N-split: fused LayerNorm over 256 columns, cluster along N");
   static_assert(EW == 4 || (EW == 8 && NS == 1), "epilogue warps: one or two per TMEM lane quarter");
   static_assert(!LN || EW == 4 || BN == 256, "two LayerNorm warps per quarter split 8 sub-tiles");
-  constexpr int CSIZE = CL > 1 ? CL : NS;          // CTAs per cluster
+  static_assert(KS == 1 || (CL == 1 && NS == 1 && AR == 0 && !TWO && !LN), "K-split: plain epilogue, cluster along K only");
+  constexpr int CSIZE = CL > 1 ? CL : (NS > 1 ? NS : KS);          // CTAs per cluster
   constexpr uint16_t CMASK = (uint16_t)((1u << CSIZE) - 1);
   constexpr int BKE = BF ? 64 : 32;   // operand elements per 128-byte swizzle row
   extern __shared__ uint8_t smem_raw[];
@@ -237,7 +243,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* a_full = res_full + 8;          // [3]  AR: the resident activation tile of buffer lt % AR_BUFS has landed
   uint64_t* a_empty = a_full + 3;           // [3]  AR: every MMA that reads that buffer has completed
   uint64_t* stat_full = a_empty + 3;        // [2]  NS: the peers' LayerNorm statistics of this tile parity have arrived
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_full + 2);
+  uint64_t* sk_full = stat_full + 2;        // [1]  KS: the partial accumulators of every other rank are in the workspace
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sk_full + 1);
   float2* stat_s = reinterpret_cast<float2*>(smem + C::OFF_STAT);        // NS: [2 parities][4 source ranks][128 rows]
   float2* pair_stat = reinterpret_cast<float2*>(smem + C::OFF_PAIR);     // EW = 8: [2 parities][2 halves][128 rows]
   uint8_t* ring = smem + C::OFF_RING;
@@ -263,7 +270,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (has_res) asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], TWO ? 1 : CSIZE);   // a stage is refilled by every CTA of the cluster: all consumers must release
+      mbar_init(&empty[s], (TWO || KS > 1) ? 1 : CSIZE);   // a stage is refilled by every CTA of the cluster: all consumers must release
                                                // it (2-SM: the one issuer's commit covers both CTAs' operands)
     }
     for (int u = 0; u < 2; ++u) {
@@ -276,6 +283,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&a_empty[u], 1);
     }
     for (int u = 0; u < 2; ++u) mbar_init(&stat_full[u], 128 * (NS > 1 ? NS - 1 : 1));
+    mbar_init(sk_full, (KS > 1 ? KS - 1 : 1) * EW);   // one arrival per epilogue WARP of every other rank
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
@@ -308,7 +316,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int m_groups = ((rows_live + BM - 1) / BM + CL - 1) / CL;
   const int total_items = NS > 1 ? m_groups : m_groups * n_tiles_n;       // N-split: one item = one row tile
   const int w_first = blockIdx.x / CSIZE, w_step = gridDim.x / CSIZE;
-  auto item_m0 = [&](int w) { return NS > 1 ? w * BM : ((w / n_tiles_n) * CL + rank) * BM; };
+  auto item_m0 = [&](int w) { return NS > 1 ? w * BM : ((w / n_tiles_n) * CL + (KS > 1 ? 0 : rank)) * BM; };
+  // K-split: this rank's share of the iteration space [it_lo, it_hi)
+  const int it_lo = KS > 1 ? (int)(((long long)rank * iters) / KS) : 0;
+  const int it_hi = KS > 1 ? (int)(((long long)(rank + 1) * iters) / KS) : iters;
   auto item_n0 = [&](int w) { return NS > 1 ? rank * BN : (w % n_tiles_n) * BN; };
 
   if (warp == 0) {
@@ -374,7 +385,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         continue;
       }
-      for (int i = 0; i < iters; ++i, ++it) {
+      for (int i = it_lo; i < it_hi; ++i, ++it) {
         const int s = it % C::STAGES;
         mbar_wait(&empty[s], ((it / C::STAGES) & 1) ^ 1);
         int term = 0, i1 = i;
@@ -531,7 +542,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         __syncwarp();
         continue;
       }
-      for (int i = 0; i < iters; ++i, ++it) {
+      for (int i = it_lo; i < it_hi; ++i, ++it) {
         const int s = it % C::STAGES;
         mbar_wait(&full[s], (it / C::STAGES) & 1);
         if (it == 0) stamp(2);
@@ -542,10 +553,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (leader) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {   // four 32-byte K slices per stage: K = 8 (tf32) or 16 (bf16) each
-            if (BF) umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
-            else umma_tf32(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
+            if (BF) umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i > it_lo || kk != 0) ? 1u : 0u);
+            else umma_tf32(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (i > it_lo || kk != 0) ? 1u : 0u);
           }
-          if (CSIZE == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], CMASK);
+          if (CSIZE == 1 || KS > 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], CMASK);
         }
         __syncwarp();
       }
@@ -593,7 +604,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int g_res = 0;   // residual sub-tiles consumed so far (buffer = g % NB, parity = (g / NB) & 1)
     int g_st = 0;    // staging sub-tiles produced so far
     const uint32_t res_bytes = p.res_bf16 ? WCHUNK / 2 : WCHUNK;   // [32 rows x 32 columns] fp32 or bf16
-    if (has_res && lane == 0 && w_first < total_items && c_lo < c_hi) {  // first residual sub-tile of the first tile
+    if (has_res && lane == 0 && w_first < total_items && c_lo < c_hi && (KS == 1 || rank == 0)) {  // first residual sub-tile of the first tile
       mbar_expect_tx(&my_res_full[0], res_bytes);
       tma_load_2d(my_res, &tmR, item_n0(w_first) + c_lo * 32, item_m0(w_first) + q * 32, &my_res_full[0]);
     }
@@ -760,12 +771,67 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
       if (!LN) {
         if (c_lo >= c_hi) release_acc();   // (a narrow tile leaves the second warp of a quarter without sub-tiles)
+        // K-split: ranks 1.. write their partial tile to the workspace and signal rank 0; rank 0 waits for all of them
+        // Workspace layout [partial][sub-tile][16-byte piece][row]: thread = row on both sides, so a warp's 16-byte accesses
+        // to one piece are 512 contiguous bytes (with a row-major tile every lane touched its own 128-byte line: 32
+        // wavefronts per instruction, and the reduction of 3 partial tiles took 6 us)
+        constexpr size_t SK_TILE = (size_t)C::NCHUNK * 8 * BM * 4;   // floats per partial tile
+        float* sk_ws = KS > 1 ? p.splitk_ws + (size_t)w * (KS - 1) * SK_TILE : nullptr;
+        if (KS > 1 && rank != 0) {
+          float* dst = sk_ws + (size_t)(rank - 1) * SK_TILE + (size_t)r * 4;
+#pragma unroll 1
+          for (int c = c_lo; c < c_hi; ++c) {
+            const int c0 = c * 32;
+            const int width = (BN - c0) >= 32 ? 32 : 16;
+            float v[32];
+            if (width == 32) tmem_ld32(acc + c0, v); else tmem_ld16(acc + c0, v);
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc)
+              if (cc * 4 < width)
+                *reinterpret_cast<float4*>(dst + (size_t)(c * 8 + cc) * BM * 4) = make_float4(v[cc * 4], v[cc * 4 + 1], v[cc * 4 + 2], v[cc * 4 + 3]);
+          }
+          if (c_lo < c_hi) release_acc();
+          // one remote arrival per warp (896 per-thread arrivals on one barrier took 15 us): __syncwarp orders the lanes'
+          // stores before lane 0's release at cluster scope, which makes them visible to rank 0's acquiring wait
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(dsmem_addr(sk_full, 0));
+          continue;
+        }
+        if (KS > 1) {
+          if (warp == 2) stamp(54);
+          mbar_wait_cluster(sk_full, lt & 1);
+          if (warp == 2) stamp(55);
+        }
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; ++c) {
           const int c0 = c * 32;
           const int width = (BN - c0) >= 32 ? 32 : 16;
           float v[32];
           if (width == 32) tmem_ld32(acc + c0, v); else tmem_ld16(acc + c0, v);
+          if constexpr (KS > 1) {
+            // + the other ranks' partial sums.  Every load of the sub-tile is issued before the first add (3 x 8 16-byte
+            // loads per thread in flight): with the loads trickling out eight at a time the reduction was a chain of L2
+            // round trips (measured: 15 us for 7 partial tiles, against 3.3 us for the K loop itself)
+            float4 t4[KS - 1][8];
+#pragma unroll
+            for (int pr = 0; pr < KS - 1; ++pr) {
+              const float* src = sk_ws + (size_t)pr * SK_TILE + (size_t)r * 4;
+#pragma unroll
+              for (int cc = 0; cc < 8; ++cc)   // (first touch of these lines by this SM: nothing stale in L1)
+                if (cc * 4 < width) t4[pr][cc] = *reinterpret_cast<const float4*>(src + (size_t)(c * 8 + cc) * BM * 4);
+            }
+#pragma unroll
+            for (int pr = 0; pr < KS - 1; ++pr) {
+#pragma unroll
+              for (int cc = 0; cc < 8; ++cc) {
+                if (cc * 4 < width) {
+                  v[cc * 4] += t4[pr][cc].x; v[cc * 4 + 1] += t4[pr][cc].y; v[cc * 4 + 2] += t4[pr][cc].z; v[cc * 4 + 3] += t4[pr][cc].w;
+                }
+              }
+            }
+            if (warp == 2) stamp(56);
+          }
           if (NB == 2) prefetch_res(c);   // all lanes passed the __syncwarp of the previous stage_out
           finish(v, c, width);
           if (!live) {
@@ -948,14 +1014,14 @@ inline int& epi_warps_flag() {   // 8 (default) = two epilogue warps per TMEM la
   return f;
 }
 
-template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1, bool TWO = false, int EW = 0>
+template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1, bool TWO = false, int EW = 0, int KS = 1>
 inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
   if constexpr (EW == 0) {   // pick the epilogue width: 8 warps for the full-width streaming variants
     constexpr bool CAN8 = NS == 1 && AR == 0 && (!LN || BN == 256) && BN >= 64;
     if constexpr (CAN8) {
-      if (epi_warps_flag() == 8) { launch_bn_cl<BN, LN, CL, BF, AR, NS, TWO, 8>(a, stream); return; }
+      if (epi_warps_flag() == 8) { launch_bn_cl<BN, LN, CL, BF, AR, NS, TWO, 8, KS>(a, stream); return; }
     }
-    launch_bn_cl<BN, LN, CL, BF, AR, NS, TWO, 4>(a, stream);
+    launch_bn_cl<BN, LN, CL, BF, AR, NS, TWO, 4, KS>(a, stream);
     return;
   } else {
   using C = Cfg<BN, AR, NS, TWO>;
@@ -963,7 +1029,7 @@ inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
   int dev = 0;
   FS2_CUDA_OK(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS, TWO, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS, TWO, EW, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
     configured[dev & 63] = true;
   }
   constexpr CUtensorMapSwizzle SW128 = CU_TENSOR_MAP_SWIZZLE_128B;
@@ -978,16 +1044,26 @@ inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
                                        : make_map(a.residual, a.rows, a.N, a.ldr, 32, false, false);
   const CUtensorMap tmC2 =
       a.C2 != nullptr ? make_map_any(a.C2, a.rows, a.N, a.ldc2, 32, 32, MAP_BF16, CU_TENSOR_MAP_SWIZZLE_64B) : tmA;
-  constexpr int CSIZE = CL > 1 ? CL : NS;
+  constexpr int CSIZE = CL > 1 ? CL : (NS > 1 ? NS : KS);
   const int items = NS > 1 ? (a.rows + BM - 1) / BM : (((a.rows + BM - 1) / BM + CL - 1) / CL) * ((a.N + BN - 1) / BN);
   const int grid = std::min(items, sm_count() / CSIZE) * CSIZE;
-  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS, TWO, EW>, dim3(grid), dim3(64 + 32 * EW), C::TOTAL, stream, CSIZE, tmA, tmW, tmC, tmR, tmC2, a);
+  require(KS == 1 || (items * KS <= sm_count() && a.splitk_ws != nullptr), FS2_ERR_INVALID, "K-split: one resident cluster per tile and a workspace");
+  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS, TWO, EW, KS>, dim3(grid), dim3(64 + 32 * EW), C::TOTAL, stream, CSIZE, tmA, tmW, tmC, tmR, tmC2, a);
   FS2_LAUNCHED();
   }
 }
 
 inline int& n_split_flag() {   // 1 = N-split fused-LN GEMMs for small row counts (default), 0 = always one CTA per row tile
   static int f = 1;
+  return f;
+}
+
+constexpr size_t SPLITK_WS_BYTES = 8u << 20;   // K-split workspace a caller provides (ConvGemmArgs::splitk_ws)
+inline int& k_split_flag() {   // 1 (default) = K-split clusters for single-row-tile GEMMs with long K loops, 0 = off (FS2_K_SPLIT)
+  static int f = [] {
+    const char* e = std::getenv("FS2_K_SPLIT");
+    return e != nullptr ? std::atoi(e) : 1;
+  }();
   return f;
 }
 
@@ -1084,6 +1160,21 @@ inline void launch(const ConvGemmArgs& a, cudaStream_t stream) {   // the operan
   // CTAs whose stages are proportionally shorter.
   const int m_tiles = (a.rows + BM - 1) / BM;
   const int sms = sm_count();
+  if (m_tiles == 1 && a.splitk_ws != nullptr && k_split_flag()) {
+    // one utterance: the K loop is the critical path of the launch -- spread it over a cluster (KS CTAs per column tile)
+    const int ke = a.a_bf16 ? 64 : 32;
+    const int iters = (a.terms > 1 ? a.terms : 1) * a.taps * ((a.K + ke - 1) / ke);
+    if (a.N % 64 == 0 || a.N == 80) {
+      const int tiles = a.N == 80 ? 1 : a.N / 64;
+      constexpr int KSPLIT = 4;   // 3 partial tiles: their loads fit the registers in one round (see the epilogue)
+      const bool fits = (size_t)tiles * (KSPLIT - 1) * BM * (a.N == 80 ? 96 : 64) * sizeof(float) <= SPLITK_WS_BYTES;
+      if (iters >= 32 && tiles * KSPLIT <= sms && fits) {
+        if (a.N == 80) { if (a.a_bf16) launch_bn_cl<80, false, 1, true, 0, 1, false, 0, KSPLIT>(a, stream); else launch_bn_cl<80, false, 1, false, 0, 1, false, 0, KSPLIT>(a, stream); }
+        else { if (a.a_bf16) launch_bn_cl<64, false, 1, true, 0, 1, false, 0, KSPLIT>(a, stream); else launch_bn_cl<64, false, 1, false, 0, 1, false, 0, KSPLIT>(a, stream); }
+        return;
+      }
+    }
+  }
   if (a.N % 256 == 0 && m_tiles * (a.N / 256) * 4 <= sms) { launch_bn<64, false>(a, stream); return; }
   if (a.N % 256 == 0 && m_tiles * (a.N / 256) * 2 <= sms) { launch_bn<128, false>(a, stream); return; }
   if (a.N % 256 == 0) launch_bn<256, false>(a, stream);

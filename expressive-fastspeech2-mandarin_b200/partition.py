@@ -51,9 +51,16 @@ def stage2_cost(n_frames):
 
 def lpt_by_cost(costs, n_parts):
     """Longest-processing-time-first on given costs (ties by index): n_parts sorted index lists, identical on every
-    rank.  A heap keeps the greedy step O(log n_parts)."""
+    rank.  A heap keeps the greedy step O(log n_parts).  With many items per part (>= 16) the greedy loop is replaced by
+    its vectorised cousin -- sort by cost and deal the items out in serpentine order -- which balances a few hundred
+    utterances to within a fraction of a percent and costs microseconds instead of a Python loop on the critical path
+    between the two stages."""
     costs = np.asarray(costs, dtype=np.float64)
     order = np.lexsort((np.arange(len(costs)), -costs))
+    if n_parts > 1 and len(costs) >= 16 * n_parts:
+        k = np.arange(len(order)) % (2 * n_parts)
+        dest = np.where(k < n_parts, k, 2 * n_parts - 1 - k)
+        return [np.sort(order[dest == p]).tolist() for p in range(n_parts)]
     heap = [(0.0, k) for k in range(n_parts)]
     parts = [[] for _ in range(n_parts)]
     for i in order.tolist():
@@ -89,19 +96,37 @@ def _exchange(send, send_splits, recv_splits, width, dtype, device, group):
     return recv
 
 
+class Moves:
+    """Who sends what to whom: owner[i] = stage-1 rank of utterance i, dest[i] = its stage-2 rank.  moves[src][dst] is the
+    sorted list of utterance ids going from src to dst (computed on demand: a rank only needs its own row and column)."""
+
+    def __init__(self, owner, dest, n_parts):
+        self.owner, self.dest, self.n = np.asarray(owner), np.asarray(dest), n_parts
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, src):
+        sel = self.owner == src
+        return [np.nonzero(sel & (self.dest == d))[0].tolist() for d in range(self.n)]
+
+    def column(self, dst):
+        sel = self.dest == dst
+        return [np.nonzero(sel & (self.owner == s))[0].tolist() for s in range(self.n)]
+
+
 def plan_rebalance(parts, src_lens, mel_lens, n_parts):
     """Given the phoneme shards `parts` (owner of every utterance during stage 1), all src_lens and the mel_lens stage 1
     produced, returns (new_parts, moves): new_parts = LPT of the TRUE stage-2 cost; moves[src][dst] = sorted utterance
     ids that rank src sends to rank dst (src == dst: stay).  Pure host arithmetic, identical on every rank."""
     new_parts = lpt_by_cost(stage2_cost(mel_lens), n_parts)
     owner = np.empty(len(src_lens), dtype=np.int64)
+    dest = np.empty(len(src_lens), dtype=np.int64)
     for r, p in enumerate(parts):
         owner[p] = r
-    moves = [[[] for _ in range(n_parts)] for _ in range(n_parts)]
-    for dst, p in enumerate(new_parts):
-        for i in p:
-            moves[int(owner[i])][dst].append(i)
-    return new_parts, moves
+    for r, p in enumerate(new_parts):
+        dest[p] = r
+    return new_parts, Moves(owner, dest, n_parts)
 
 
 def exchange_rows(hidden, reps, local_ids, src_lens_all, moves, rank, group=None):
@@ -114,18 +139,19 @@ def exchange_rows(hidden, reps, local_ids, src_lens_all, moves, rank, group=None
     lens = np.asarray(src_lens_all, dtype=np.int64)
     pos = {g: j for j, g in enumerate(local_ids)}
     # send side: for every destination the (local utterance, position) pairs of the real rows, in id order
-    send_ids = [moves[rank][d] for d in range(world)]
+    send_ids = moves[rank]
     flat = [g for ids in send_ids for g in ids]
     if flat:
-        b_idx = np.repeat(np.array([pos[g] for g in flat], dtype=np.int64), lens[flat])
-        j_idx = np.concatenate([np.arange(lens[g]) for g in flat])
+        fl = lens[flat]
+        b_idx = np.repeat(np.array([pos[g] for g in flat], dtype=np.int64), fl)
+        j_idx = np.arange(int(fl.sum())) - np.repeat(np.cumsum(fl) - fl, fl)       # position inside each utterance
     else:
         b_idx = j_idx = np.zeros(0, dtype=np.int64)
     bi, ji = torch.from_numpy(b_idx).to(dev, non_blocking=True), torch.from_numpy(j_idx).to(dev, non_blocking=True)
     # one message per peer: 256 fp32 columns of the row + its repeat count, bit-cast into a 257th column
     send = torch.cat([hidden[bi, ji], reps[bi, ji].contiguous().view(torch.float32).unsqueeze(1)], dim=1)
     send_splits = [int(lens[ids].sum()) if ids else 0 for ids in send_ids]
-    recv_ids = [moves[s][rank] for s in range(world)]
+    recv_ids = moves.column(rank) if isinstance(moves, Moves) else [moves[s][rank] for s in range(world)]
     recv_splits = [int(lens[ids].sum()) if ids else 0 for ids in recv_ids]
     recv = send if world == 1 else _exchange(send, send_splits, recv_splits, 257, torch.float32, dev, group)
     ids = [g for r_ids in recv_ids for g in r_ids]
@@ -135,7 +161,7 @@ def exchange_rows(hidden, reps, local_ids, src_lens_all, moves, rank, group=None
     out_r = torch.zeros(B, L, dtype=torch.int32, device=dev)
     if B:
         rb = torch.from_numpy(np.repeat(np.arange(B), my_lens)).to(dev, non_blocking=True)
-        rj = torch.from_numpy(np.concatenate([np.arange(n) for n in my_lens])).to(dev, non_blocking=True)
+        rj = torch.from_numpy(np.arange(int(my_lens.sum())) - np.repeat(np.cumsum(my_lens) - my_lens, my_lens)).to(dev, non_blocking=True)
         out_h[rb, rj] = recv[:, :256]
         out_r[rb, rj] = recv[:, 256].contiguous().view(torch.int32)
     return out_h, out_r, torch.from_numpy(my_lens).to(dev), ids

@@ -181,8 +181,11 @@ def test_control_sweep(controls, sd32, sd64, syn):
 
 def test_batch_padding_independence(sd32, syn):
     """The FFT stacks are padding-independent, the predictors / PostNet are not:
-    an utterance alone and inside a batch with the same L_max / T_max must agree bit for bit,
-    because the packed layout reproduces the padded semantics from lengths alone."""
+    an utterance alone and inside a batch with the same L_max / T_max must agree, because the packed layout
+    reproduces the padded semantics from lengths alone.  Bit for bit when both runs use the same kernel forms; a lone
+    short utterance runs its long-K contractions in the K-split form (another fp32 summation order; a last-bit difference
+    there moves TF32 operand roundings downstream), so that comparison uses the TF32 tolerance and the bit-exact one is
+    made with the K-split switched off."""
     model = model_for(sd32)
     batch = syn.make_batch([30, 30, 12], seed=77)
     full = run(model, batch)
@@ -193,6 +196,17 @@ def test_batch_padding_independence(sd32, syn):
     again = run(model, batch, d_targets=d_t.cpu(), p_targets=full[2].cpu(), e_targets=full[3].cpu())
     t1 = int(full[9][1])
     assert t1 > 0
+    assert float((one[1][0, :t1] - again[1][1, :t1]).abs().max()) <= TOL_MEL_MAX
+    assert float((one[0][0, :t1] - again[0][1, :t1]).abs().max()) <= TOL_MEL_MAX
+    from gpu_util import lib
+    L = lib()
+    try:
+        L.fs2_debug_set_flag(7, 0)      # K-split off: the same kernel forms for both runs
+        one = run(model, solo, d_targets=d_t[1:2].cpu(), p_targets=full[2][1:2].cpu(), e_targets=full[3][1:2].cpu(),
+                  max_mel_len=int(full[0].shape[1]))
+        again = run(model, batch, d_targets=d_t.cpu(), p_targets=full[2].cpu(), e_targets=full[3].cpu())
+    finally:
+        L.fs2_debug_set_flag(7, 1)
     assert torch.equal(one[1][0, :t1], again[1][1, :t1])
     assert torch.equal(one[0][0, :t1], again[0][1, :t1])
 

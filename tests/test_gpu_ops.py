@@ -46,6 +46,11 @@ CASES = [
     (333, 512, 512, 5, 2, False, True, "postnet_mid"),
     (129, 512, 80, 5, 0, True, True, "postnet_last"),
     (5, 256, 256, 1, 0, False, False, "tiny"),
+    # single row tile + long K loop: the K-split cluster form (8 CTAs per column tile, partial tiles through the workspace)
+    (56, 256, 1024, 9, 1, False, False, "one_tile_conv9_ksplit"),
+    (100, 512, 512, 5, 2, False, True, "one_tile_postnet_mid_ksplit"),
+    (128, 512, 80, 5, 0, True, True, "one_tile_postnet_last_ksplit"),
+    (77, 1024, 256, 1, 0, True, False, "one_tile_w2_ksplit"),
     (40000, 256, 768, 1, 0, False, False, "qkv_many_tiles"),
     (30011, 1024, 256, 1, 0, True, True, "w2_many_tiles"),
     (25000, 512, 80, 5, 0, True, True, "postnet_last_many_tiles"),
