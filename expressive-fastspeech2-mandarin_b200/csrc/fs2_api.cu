@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "attention_tc.cuh"
+#include "attention_bf16.cuh"
 #include "common.cuh"
 #include "gemm_tc2.cuh"
 #include "ffn_fused.cuh"
@@ -54,6 +55,7 @@ struct Pool {  // activation buffers of one side
   float* pn[2] = {nullptr, nullptr};                     // [rows,512]  (frame side only)
   // FS2_MATH_BF16: bf16 copies that serve as the A operands (the fp32 hid / pn buffers are not allocated)
   __nv_bfloat16* actb[4] = {nullptr, nullptr, nullptr, nullptr};  // mirrors of act[i]
+  __nv_bfloat16* qkvb = nullptr;                                   // [rows,768]: Q | K | V as the attention's bf16 operands
   __nv_bfloat16* hidb = nullptr;                                   // [rows,1024]
   __nv_bfloat16* melb = nullptr;                                   // [rows,80]
   __nv_bfloat16* pnb[2] = {nullptr, nullptr};                      // [rows,512]
@@ -325,15 +327,15 @@ static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSi
   const int math = c->cfg.math_mode;
   const int32_t* live = reinterpret_cast<const int32_t*>(side.totals);   // low word of totals[0] (little endian)
   if (math == FS2_MATH_BF16) {
-    // Same five launches; every A operand is the bf16 mirror written by the producing epilogue, the residual
-    // stream (x, t2) and the attention inputs (qkv) stay fp32.
+    // Same five launches; every A operand is the bf16 mirror written by the producing epilogue (Q, K, V included: the
+    // attention runs kind::f16 MMAs on 128-key tiles), the residual stream (x, t2) stays fp32.
     __nv_bfloat16 *xb = pool.actb[0], *t1b = pool.actb[1], *t2b = pool.actb[2];
-    ConvGemmArgs a = gemm_args_b(xb, D_MODEL, rows, L.wqkv, L.bqkv, 1, D_MODEL, 3 * D_MODEL, ACT_NONE, pool.qkv, 3 * D_MODEL,
-                                 nullptr, 0);
+    ConvGemmArgs a = gemm_args_b(xb, D_MODEL, rows, L.wqkv, L.bqkv, 1, D_MODEL, 3 * D_MODEL, ACT_NONE, nullptr, 0, pool.qkvb,
+                                 3 * D_MODEL);
     a.live_rows = live;
     { ProfScope ps(c, s, frame ? "dec.gemm_qkv" : "enc.gemm_qkv"); conv_gemm(c, a, s); }
     { ProfScope ps(c, s, frame ? "dec.attention" : "enc.attention");
-      attention(pool.qkv, rows, side, batch, max_len, t1, s, t1b); }
+      attn_bf::launch(pool.qkvb, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, nullptr, t1b, s); }
     a = gemm_args_b(t1b, D_MODEL, rows, L.wfc, L.bfc, 1, D_MODEL, D_MODEL, ACT_NONE, t2, D_MODEL, t2b, D_MODEL);
     a.residual = x; a.ldr = D_MODEL; a.live_rows = live;
     a.ln_gamma = L.ln1_g; a.ln_beta = L.ln1_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
@@ -424,6 +426,7 @@ static void ensure_pool(Pool& p, int rows, bool frame_side, bool bf16, cudaStrea
   regrow(p.qkv, (size_t)rows * 3 * D_MODEL, s);
   if (bf16) {
     for (auto& a : p.actb) regrow(a, (size_t)rows * D_MODEL, s);
+    regrow(p.qkvb, (size_t)rows * 3 * D_MODEL, s);
     regrow(p.hidb, (size_t)rows * D_INNER, s);
   } else {
     regrow(p.hid, (size_t)rows * D_INNER, s);
@@ -943,7 +946,7 @@ void fs2_destroy(fs2_ctx* c) {
     for (float* a : p->act) cudaFree(a);
     cudaFree(p->qkv); cudaFree(p->hid); cudaFree(p->mel); cudaFree(p->post); cudaFree(p->pn[0]); cudaFree(p->pn[1]);
     for (auto* a : p->actb) cudaFree(a);
-    cudaFree(p->hidb); cudaFree(p->melb); cudaFree(p->pnb[0]); cudaFree(p->pnb[1]);
+    cudaFree(p->hidb); cudaFree(p->qkvb); cudaFree(p->melb); cudaFree(p->pnb[0]); cudaFree(p->pnb[1]);
   }
   cudaFree(c->status); cudaFree(c->cum); cudaFree(c->mel_lens32); cudaFree(c->raw_pitch); cudaFree(c->raw_energy);
   cudaFree(c->cond_spk); cudaFree(c->cond_emo); cudaFree(c->pe_long); cudaFree(c->split_buf); cudaFree(c->splitk_ws); cudaFree(c->raw_pitch_f); cudaFree(c->raw_energy_f);
@@ -1222,6 +1225,23 @@ int fs2_op_attention(fs2_stream stream, const float* qkv, int rows, const int32_
     attention_work_kernel<<<1, 256, 0, s>>>(lens, batch, work, cap, count);
     FS2_LAUNCHED();
     attn_tc::launch(qkv, rows, starts, lens, work, count, cap, out, s);
+    FS2_CUDA_OK(cudaStreamSynchronize(s));
+    cudaFree(work);
+    cudaFree(count);
+  });
+}
+
+int fs2_op_attention_bf16(fs2_stream stream, const void* qkv, int rows, const int32_t* starts, const int32_t* lens, int batch,
+                          int max_len, float* out) {
+  return guarded(nullptr, [&] {
+    require(qkv && starts && lens && out && rows > 0 && batch > 0 && max_len > 0, FS2_ERR_INVALID, "bad attention argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int cap = attn_tc::work_bound((int64_t)batch * max_len, batch, max_len);
+    uint32_t* work = dalloc<uint32_t>(cap);
+    int32_t* count = dalloc<int32_t>(1);
+    attention_work_kernel<<<1, 256, 0, s>>>(lens, batch, work, cap, count);
+    FS2_LAUNCHED();
+    attn_bf::launch(static_cast<const __nv_bfloat16*>(qkv), rows, starts, lens, work, count, cap, out, nullptr, s);
     FS2_CUDA_OK(cudaStreamSynchronize(s));
     cudaFree(work);
     cudaFree(count);

@@ -225,6 +225,10 @@ int fs2_op_conv_gemm_bf16(fs2_stream stream, const void* A, int lda, int rows, c
  * longest-utterance-first work list the forward keeps per batch (one entry per 128 queries). */
 int fs2_op_attention(fs2_stream stream, const float* qkv, int rows, const int32_t* starts,
                      const int32_t* lens, int batch, int max_len, float* out);
+/* The FS2_MATH_BF16 form: qkv is bf16 [rows,768]; kind::f16 MMAs on 128-key tiles, probabilities rounded to bf16 (packed
+ * in tensor memory), fp32 softmax statistics and output accumulation.  out [rows,256] fp32. */
+int fs2_op_attention_bf16(fs2_stream stream, const void* qkv, int rows, const int32_t* starts, const int32_t* lens,
+                          int batch, int max_len, float* out);
 /* Durations -> repeat counts -> per-utterance inclusive scan (modules.py:132-135,186-187).
  * d_in: log-durations (is_target=0) or target durations (is_target=1), [B,L].  Writes
  * d_rounded [B,L] (fp32), cum [B,L] (int32 inclusive prefix sums of the repeat counts) and

@@ -132,3 +132,41 @@ def test_bf16_close_to_tf32_at_full_size(sd32, syn):
         mx, mean = err_stats(valid_rows(b[i].cpu().numpy(), lens), valid_rows(a[i].cpu().numpy(), lens))
         log_diag(f"bf16 vs tf32 config2 {n}: max {mx:.3e} mean {mean:.3e}")
         assert mx <= TOL_MEL_MAX and mean <= TOL_MEL_MEAN
+
+
+@pytest.mark.parametrize("lens", [[1], [5, 64, 65, 33], [200, 7, 129, 128, 127], [700], [0, 3, 0, 300, 1], [37] * 70 + [513, 2, 1024]])
+def test_attention_bf16(lens):
+    """The bf16 attention kernel (128-key tiles, P as packed bf16 in tensor memory, V as the MN-major operand) against
+    float64 softmax attention on the SAME bf16-rounded q / k / v: what remains is the bf16 rounding of the probabilities
+    (2^-9 relative) and fp32 accumulation order."""
+    g = torch.Generator().manual_seed(sum(lens) + 1)
+    gap = 4
+    starts, r = [], gap
+    for n in lens:
+        starts.append(r)
+        r += n + gap
+    rows = r
+    qkv = torch.randn(rows, 768, generator=g).to(torch.bfloat16)
+    want = torch.zeros(rows, 256, dtype=torch.float64)
+    for s, n in zip(starts, lens):
+        x = qkv[s: s + n].double()
+        for h in range(2):
+            q, k, v = (x[:, i * 256 + h * 128: i * 256 + (h + 1) * 128] for i in range(3))
+            p = torch.softmax(q @ k.T / np.sqrt(128.0), dim=1)
+            want[s: s + n, h * 128: (h + 1) * 128] = p @ v
+    dq = qkv.to(DEV)
+    out = torch.zeros(rows, 256, device=DEV)
+    ds = torch.tensor(starts, dtype=torch.int32, device=DEV)
+    dl = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    code = lib().fs2_op_attention_bf16(stream(), ptr(dq), rows, ptr(ds), ptr(dl), len(lens), max(lens), ptr(out))
+    assert code == 0, lib().fs2_last_error(None)
+    torch.cuda.synchronize()
+    got = out.cpu().double()
+    live = torch.zeros(rows, dtype=torch.bool)
+    for s, n in zip(starts, lens):
+        live[s: s + n] = True
+    assert (got[~live] == 0).all(), "rows outside the utterances must not be written"
+    err = (got[live] - want[live]).abs().max().item()
+    assert torch.isfinite(got).all()
+    print(f"bf16 attention lens={lens[:4]}.. max abs err {err:.3e}")
+    assert err < 1.5e-2, f"max abs err {err}"   # unit-variance data: |p v| sums of up to 1024 terms with 2^-9 relative weights
