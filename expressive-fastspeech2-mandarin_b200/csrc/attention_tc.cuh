@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -25,6 +26,7 @@ namespace attn_tc {
 using namespace tc;
 
 constexpr int BQ = 128, BKV = 64, THREADS = 192;
+constexpr int THREADS2 = 224;   // attention_tc_kernel: + a second MMA-issuing warp
 constexpr int Q_BYTES = BQ * D_HEAD * 4;          // 64 KB: 4 sub-tiles [128 rows x 128 B]
 constexpr int K_BYTES = BKV * D_HEAD * 4;         // 32 KB: 4 sub-tiles [64 rows x 128 B]
 constexpr int KV_STAGES = 3;
@@ -62,7 +64,13 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+// PAIR: the kernel runs as clusters of two CTAs that own two ADJACENT query tiles of the same (utterance, head).  Each CTA
+// loads HALF of every K and V tile (32 of the 64 key rows) and TMA-multicasts it into both CTAs' shared memory, so the L2
+// traffic of the kernel -- every query tile of an utterance re-reads all of its keys and values: 420 MB per launch at batch
+// 64, which the per-tile trace showed as waits for K/V tiles at ~75 GB/s per SM, the chip's aggregate L2 limit -- is
+// halved.  A pair whose second tile lies beyond the utterance keeps its second CTA for the loads only.
+template <bool PAIR>
+__global__ void __launch_bounds__(THREADS2, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                     const __grid_constant__ CUtensorMap tmV, const int32_t* __restrict__ starts, const int32_t* __restrict__ lens,
                     const uint32_t* __restrict__ work, const int32_t* __restrict__ work_count, float* __restrict__ out,
@@ -70,7 +78,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   // work item = 128 queries of one (utterance, head), taken from the longest-first work list (rowops.cuh): CTAs are
   // dispatched in blockIdx order, so the expensive items start first and the grid's tail is made of short utterances
-  const int item = blockIdx.x >> 1, h = blockIdx.x & 1;
+  const int rank = PAIR ? (int)(blockIdx.x & 1) : 0;                    // == %cluster_ctarank (cluster of 2 along x)
+  const int item = PAIR ? blockIdx.x >> 2 : blockIdx.x >> 1, h = PAIR ? (blockIdx.x >> 1) & 1 : blockIdx.x & 1;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_s = smem;
@@ -80,13 +89,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   uint64_t* q_full = bars;            // [1]
   uint64_t* q_moved = bars + 1;       // [1]  Q copied to TMEM: its smem may be overwritten
-  uint64_t* kv_full = bars + 2;       // [3]  K_j and V_j of one tile share a stage and a barrier pair
-  uint64_t* kv_empty = bars + 5;      // [3]  free after P_j V_j (three stages: loads run two tiles ahead)
+  // K and V have their OWN rings: a K stage is free as soon as Q K_j^T has completed, one tile before P_j V_j releases the V
+  // stage.  With one shared barrier pair (the first version) K_{j+3} could only be requested when P_j V_j was done, i.e. one
+  // tile before Q K_{j+3}^T wants it (the Q K^T products run two tiles ahead of the P V products): the per-tile trace showed
+  // ~1,100 cycles of waiting for K on every other tile, at a TMA latency of ~2,100 cycles against a 1,650-cycle tile.
+  uint64_t* k_full = bars + 2;        // [3]
+  uint64_t* k_empty = bars + 5;       // [3]  free after Q K_j^T
+  uint64_t* v_full = bars + 16;       // [3]
+  uint64_t* v_empty = bars + 19;      // [3]  free after P_j V_j
   uint64_t* s_full = bars + 8;        // [2]
   uint64_t* p_full = bars + 10;       // [2]  also implies that O_{j-2} has been accumulated (program order
                                       //      of the softmax threads), so P_j V_j may overwrite that buffer
   uint64_t* o_full = bars + 12;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* q_free = bars + 14;       // [1]  PAIR: the Q staging area of BOTH CTAs is free (stage 2 may be multicast into it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = warp_index(), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -95,9 +111,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
     mbar_init(q_full, 1);
     mbar_init(q_moved, 128);
+    mbar_init(q_free, 256);
     for (int u = 0; u < KV_STAGES; ++u) {
-      mbar_init(&kv_full[u], 1);
-      mbar_init(&kv_empty[u], 1);
+      mbar_init(&k_full[u], 1);
+      mbar_init(&v_full[u], 1);
+      mbar_init(&k_empty[u], PAIR ? 2 : 1);    // PAIR: a stage is refilled by both CTAs: both consumers release it
+      mbar_init(&v_empty[u], PAIR ? 2 : 1);
     }
     for (int u = 0; u < 2; ++u) {
       mbar_init(&s_full[u], 1);
@@ -116,15 +135,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to it
   // ---- the prologue above overlaps the previous kernel's tail (programmatic dependent launch);
   // lens / starts / qkv are produced by earlier kernels of this forward
   pdl_trigger();
   pdl_wait();
-  const bool active = item < *work_count;     // the grid is sized from a host-side bound: surplus CTAs only tear down
-  const uint32_t wi = active ? work[item] : 0u;
-  const int b = (int)(wi >> 16), q0 = (int)(wi & 0xFFFFu) * BQ;
-  const int len = active ? lens[b] : 0;
-  const int row0 = active ? starts[b] : 0;
+  const bool listed = item < *work_count;     // the grid is sized from a host-side bound: surplus CTAs only tear down
+  const uint32_t wi = listed ? work[item] : 0u;
+  // a work-list entry covers BQ queries, or 2 * BQ in the PAIR form (one tile per CTA of the cluster)
+  const int b = (int)(wi >> 16), q0 = ((int)(wi & 0xFFFFu) * (PAIR ? 2 : 1) + rank) * BQ;
+  const int len = listed ? lens[b] : 0;
+  const int row0 = listed ? starts[b] : 0;
+  const bool active = listed && q0 < len;     // PAIR: the second CTA of a pair past the utterance's end only loads
+  const bool loads_only = PAIR && listed && !active;
   const int n_tiles = (len + BKV - 1) / BKV;
   const uint32_t tmem_s = tmem_base;          // + u*64
   const uint32_t tmem_o = tmem_base + 128;    // + u*128
@@ -138,12 +161,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #define FS2_TRACE(tile, k) do { } while (0)
 #endif
 
-  if (!active) {
+  if (!active && !loads_only) {
     // nothing to do
   } else if (warp == 0) {
     // ---- TMA producer (whole warp, one elected lane issues): Q once, then K_j / V_j into 3-stage rings
     const bool leader = elect_one();
-    if (leader) {
+    if (leader && active) {
       mbar_expect_tx(q_full, Q_BYTES);
 #pragma unroll
       for (int dc = 0; dc < 4; ++dc) tma_load_2d(q_s + dc * (BQ * 128), &tmQ, h * D_HEAD + dc * 32, row0 + q0, q_full);
@@ -152,30 +175,76 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int j = 0; j < n_tiles; ++j) {
       const int sk = j % KV_STAGES;
       const uint32_t par = ((j / KV_STAGES) & 1) ^ 1;
-      if (j == 2) mbar_wait(q_moved, 0);      // stage 2 lives where Q was staged
+      // stage 2 lives where Q was staged: its first use waits until Q has been moved to tensor memory -- in BOTH CTAs of a
+      // pair, because this CTA's multicast lands in the peer's staging area too (q_free: 128 arrivals from each CTA)
+      if (j == 2) {
+        if (PAIR) mbar_wait_cluster(q_free, 0);
+        else mbar_wait(q_moved, 0);
+      }
       uint8_t* k_s = k_stage(sk);
       uint8_t* v_s = v_stage(sk);
-      mbar_wait(&kv_empty[sk], par);
+      const int half = rank * (BKV / 2);   // PAIR: this CTA's 32 key rows of every sub-tile, delivered to both CTAs
+      mbar_wait(&k_empty[sk], par);
       if (leader) {
-        mbar_expect_tx(&kv_full[sk], 2 * K_BYTES);
+        mbar_expect_tx(&k_full[sk], K_BYTES);
 #pragma unroll
-        for (int dc = 0; dc < 4; ++dc)
-          tma_load_2d(k_s + dc * (BKV * 128), &tmKV, D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &kv_full[sk]);
+        for (int dc = 0; dc < 4; ++dc) {
+          if (PAIR) tma_load_2d_mc(k_s + dc * (BKV * 128) + half * 128, &tmKV, D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV + half,
+                                   &k_full[sk], (uint16_t)0x3);
+          else tma_load_2d(k_s + dc * (BKV * 128), &tmKV, D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &k_full[sk]);
+        }
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[sk], par);
+      if (leader) {
+        mbar_expect_tx(&v_full[sk], K_BYTES);
 #pragma unroll
-        for (int dc = 0; dc < 4; ++dc)
-          tma_load_2d(v_s + dc * (BKV * 128), &tmV, 2 * D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &kv_full[sk]);
+        for (int dc = 0; dc < 4; ++dc) {
+          if (PAIR) tma_load_2d_mc(v_s + dc * (BKV * 128) + half * 128, &tmV, 2 * D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV + half,
+                                   &v_full[sk], (uint16_t)0x3);
+          else tma_load_2d(v_s + dc * (BKV * 128), &tmV, 2 * D_MODEL + h * D_HEAD + dc * 32, row0 + j * BKV, &v_full[sk]);
+        }
       }
       __syncwarp();
     }
+  } else if (loads_only) {
+    // ---- PAIR, second CTA beyond the utterance's end: it only loads its halves of the K/V tiles for the peer.  Its Q
+    // staging area is free from the start (q_free), and every stage is released, in both CTAs, as soon as its bytes have
+    // landed here.
+    if (warp >= 2 && warp <= 5) {
+      mbar_arrive(q_free);
+      mbar_arrive_remote(dsmem_addr(q_free, rank ^ 1));
+    } else if (warp == 6) {
+      for (int j = 0; j < n_tiles; ++j) {
+        const int sk = j % KV_STAGES;
+        mbar_wait(&k_full[sk], (j / KV_STAGES) & 1);
+        if (lane == 0) {
+          mbar_arrive(&k_empty[sk]);
+          mbar_arrive_remote(dsmem_addr(&k_empty[sk], rank ^ 1));
+        }
+        mbar_wait(&v_full[sk], (j / KV_STAGES) & 1);
+        if (lane == 0) {
+          mbar_arrive(&v_empty[sk]);
+          mbar_arrive_remote(dsmem_addr(&v_empty[sk], rank ^ 1));
+        }
+        __syncwarp();
+      }
+    }
   } else if (warp == 1) {
-    // ---- MMA issuer (whole warp runs the loop, one elected lane issues)
+    // ---- MMA issuer 1: S_j = Q K_j^T.  The per-tile trace (tools/trace_attention.py) showed ONE issuing thread as the
+    // critical path of the kernel: 16 + 8 MMAs and three commits cost it ~1650 cycles per 64-key tile for 1024 cycles of
+    // tensor work (an N = 64 MMA is 32 cycles of work and ~26 cycles to issue).  Q K^T and P V therefore have a warp
+    // each; their order on the tensor pipe is no longer program order, so Q K_j^T waits for P V_{j-2} -- which read P
+    // from the same TMEM columns -- through its completion barrier.
     const bool leader = elect_one();
     constexpr uint32_t idesc_qk = idesc_tf32(BQ, BKV, 0);
-    constexpr uint32_t idesc_pv = idesc_tf32(BQ, D_HEAD, 1);
-    auto issue_qk = [&](int j) {
+    mbar_wait(q_moved, 0);
+    tc_fence_after();
+    for (int j = 0; j < n_tiles; ++j) {
       const int u = j & 1, sk = j % KV_STAGES;
       FS2_TRACE(j, 8);
-      mbar_wait(&kv_full[sk], (j / KV_STAGES) & 1);
+      mbar_wait(&k_full[sk], (j / KV_STAGES) & 1);
+      if (j >= 2) mbar_wait(&o_full[u], ((j - 2) >> 1) & 1);
       FS2_TRACE(j, 9);
       tc_fence_after();
       const uint8_t* k_s = k_stage(sk);
@@ -189,22 +258,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         FS2_TRACE(j, 10);
         umma_commit(&s_full[u]);
+        if (PAIR) umma_commit_mc(&k_empty[sk], (uint16_t)0x3); else umma_commit(&k_empty[sk]);
         FS2_TRACE(j, 11);
       }
       __syncwarp();
-    };
-    mbar_wait(q_moved, 0);
-    tc_fence_after();
-    issue_qk(0);
+    }
+  } else if (warp == 6) {
+    // ---- MMA issuer 2: O_j = P_j V_j (A = P from tensor memory)
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_pv = idesc_tf32(BQ, D_HEAD, 1);
     for (int j = 0; j < n_tiles; ++j) {
       const int u = j & 1;
       const uint32_t par = (j >> 1) & 1;
-      if (j + 1 < n_tiles) issue_qk(j + 1);
       const int sk = j % KV_STAGES;
       FS2_TRACE(j, 4);
-      mbar_wait(&p_full[u], par);      // P_j written; O buffer u drained (see p_full above); V_j landed with K_j
+      mbar_wait(&v_full[sk], (j / KV_STAGES) & 1);
+      mbar_wait(&p_full[u], par);      // P_j written; O buffer u drained (see p_full above)
       FS2_TRACE(j, 5);
-      FS2_TRACE(j, 6);
       tc_fence_after();
       const uint8_t* v_s = v_stage(sk);
       const uint64_t dv = umma_desc_mn(v_s, BKV * 128, 512);
@@ -214,7 +284,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           umma_tf32_ts(tmem_o + u * D_HEAD, tmem_s + u * BKV + k8 * 8, dv + (uint64_t)(k8 * (1024 >> 4)), idesc_pv, k8 != 0);
         FS2_TRACE(j, 12);
         umma_commit(&o_full[u]);
-        umma_commit(&kv_empty[sk]);
+        if (PAIR) umma_commit_mc(&v_empty[sk], (uint16_t)0x3); else umma_commit(&v_empty[sk]);
         FS2_TRACE(j, 13);
       }
       __syncwarp();
@@ -248,6 +318,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads before the TMA overwrites
       tc_fence_before();
       mbar_arrive(q_moved);
+      if (PAIR) {
+        mbar_arrive(q_free);
+        mbar_arrive_remote(dsmem_addr(q_free, rank ^ 1));
+      }
     }
     float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
     float o[D_HEAD];
@@ -374,6 +448,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer may still multicast into this CTA's shared memory / arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
@@ -385,28 +460,57 @@ inline int& debug_flag() {
   return f;
 }
 
-// Upper bound of the work-list length known on the host: sum_b ceil(len_b / 128) <= total_rows / 128 + batch.
-inline int work_bound(int64_t total_len, int batch, int max_len) {
-  const int64_t a = total_len / BQ + batch, b = (int64_t)batch * ((max_len + BQ - 1) / BQ);
+// Upper bound of the work-list length known on the host: sum_b ceil(len_b / q_rows) <= total_rows / q_rows + batch.
+inline int work_bound(int64_t total_len, int batch, int max_len, int q_rows = BQ) {
+  const int64_t a = total_len / q_rows + batch, b = (int64_t)batch * ((max_len + q_rows - 1) / q_rows);
   return (int)std::min(a, b);
 }
 
-inline void launch(const float* qkv, int rows, const int32_t* starts, const int32_t* lens, const uint32_t* work,
-                   const int32_t* work_count, int work_cap, float* out, cudaStream_t stream, void* out_bf16 = nullptr) {
-  if (work_cap <= 0 || rows <= 0) return;
+// Query rows per work-list entry: 256 = the PAIR form (clusters of two CTAs sharing every K/V tile through multicast), chosen
+// when the batch has enough work to fill the machine with pairs; 128 = one CTA per entry (single utterances: a pair
+// would only add a cluster hand-shake).  The work list must be built with the same value (rowops.cuh).
+inline int& pair_force_flag() {   // -1 automatic (default; FS2_ATTN_PAIR overrides), 0 never, 1 always
+  static int f = [] { const char* e = std::getenv("FS2_ATTN_PAIR"); return e != nullptr ? std::atoi(e) : -1; }();
+  return f;
+}
+inline int query_rows_per_entry(int64_t total_len, int batch, int max_len) {
+  const int force = pair_force_flag();
+  if (force == 0) return BQ;
+  if (force == 1) return 2 * BQ;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  (void)sms; (void)total_len; (void)batch; (void)max_len;
+  // Measured at config 2 (profiles/r02_attention_experiments.txt): the paired form is SLOWER (0.40 vs 0.345 ms per step) --
+  // the two CTAs of a pair advance in lock step through every stage -- so the automatic choice is the unpaired kernel;
+  // the form stays selectable (debug flag 8 / FS2_ATTN_PAIR=1) and is covered by tests/test_gpu_ops.py.
+  return BQ;
+}
+
+template <bool PAIR>
+inline void launch_t(const float* qkv, int rows, const int32_t* starts, const int32_t* lens, const uint32_t* work,
+                     const int32_t* work_count, int work_cap, float* out, cudaStream_t stream, void* out_bf16) {
   static bool configured[64] = {};
   int dev = 0;
   FS2_CUDA_OK(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    FS2_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    FS2_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     configured[dev & 63] = true;
   }
+  constexpr int KROWS = PAIR ? BKV / 2 : BKV;   // PAIR: each CTA loads half of the key rows of a tile (and multicasts it)
   const CUtensorMap tmQ = make_map(qkv, rows, LDQKV, LDQKV, BQ, true, false);
-  const CUtensorMap tmKV = make_map(qkv, rows, LDQKV, LDQKV, BKV, true, true);
-  const CUtensorMap tmV = make_map(qkv, rows, LDQKV, LDQKV, BKV, true, true, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  launch_pdl(attention_tc_kernel, dim3(N_HEAD * work_cap), dim3(THREADS), SMEM_TOTAL, stream, 1, tmQ, tmKV, tmV, starts, lens,
-             work, work_count, out, static_cast<__nv_bfloat16*>(out_bf16), debug_flag());
+  const CUtensorMap tmKV = make_map(qkv, rows, LDQKV, LDQKV, KROWS, true, true);
+  const CUtensorMap tmV = make_map(qkv, rows, LDQKV, LDQKV, KROWS, true, true, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  launch_pdl(attention_tc_kernel<PAIR>, dim3(N_HEAD * work_cap * (PAIR ? 2 : 1)), dim3(THREADS2), SMEM_TOTAL, stream, PAIR ? 2 : 1,
+             tmQ, tmKV, tmV, starts, lens, work, work_count, out, static_cast<__nv_bfloat16*>(out_bf16), debug_flag());
   FS2_LAUNCHED();
+}
+
+// q_rows: query rows per work-list entry (128, or 256 = PAIR form); work / work_count / work_cap describe that list.
+inline void launch(const float* qkv, int rows, const int32_t* starts, const int32_t* lens, const uint32_t* work,
+                   const int32_t* work_count, int work_cap, int q_rows, float* out, cudaStream_t stream, void* out_bf16 = nullptr) {
+  if (work_cap <= 0 || rows <= 0) return;
+  if (q_rows == 2 * BQ) launch_t<true>(qkv, rows, starts, lens, work, work_count, work_cap, out, stream, out_bf16);
+  else launch_t<false>(qkv, rows, starts, lens, work, work_count, work_cap, out, stream, out_bf16);
 }
 
 }  // namespace attn_tc

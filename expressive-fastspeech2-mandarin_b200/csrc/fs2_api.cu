@@ -43,6 +43,7 @@ struct RowSide {  // metadata of one packed row space (phoneme side or frame sid
   uint32_t* work = nullptr;                          // attention work list (rowops.cuh: build_attention_work)
   int32_t* work_count = nullptr;                     // device [1]
   int work_alloc = 0, work_cap = 0;                  // allocated entries / the bound the current batch launches with
+  int work_q_rows = 128;                             // query rows per entry: 128, or 256 (paired attention kernel)
   int rows_alloc = 0, batch_alloc = 0;
   RowMeta meta() const { return RowMeta{utt, vpos, room}; }
 };
@@ -299,7 +300,7 @@ static void conv_gemm(fs2_ctx* c, ConvGemmArgs a, cudaStream_t s) {
 static void attention(const float* qkv, int rows, const RowSide& side, int batch, int max_len, float* out, cudaStream_t s,
                       void* out_bf16 = nullptr) {
   (void)batch; (void)max_len;
-  attn_tc::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, out, s, out_bf16);
+  attn_tc::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, side.work_q_rows, out, s, out_bf16);
 }
 
 // bf16-operand variant: A and W are bf16 behind the float* fields
@@ -479,9 +480,11 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   const int64_t bound = (int64_t)GAP_PHON + (int64_t)B * (L + GAP_PHON);
   require(bound < (1LL << 30), FS2_ERR_INVALID, "batch * max_src_len too large");
   const int rows = round_up((int)bound, 128);
-  ensure_side(c->ps, B, rows, s, attn_tc::work_bound((int64_t)B * L, B, L));
-  ensure_side(c->fs, B, 0, s);
   const bool bf = c->cfg.math_mode == FS2_MATH_BF16;
+  // query rows per attention work item: the paired (K/V-multicast) kernel where utterances span several query tiles
+  c->ps.work_q_rows = (bf || L <= attn_tc::BQ) ? attn_tc::BQ : attn_tc::query_rows_per_entry((int64_t)B * L, B, L);
+  ensure_side(c->ps, B, rows, s, attn_tc::work_bound((int64_t)B * L, B, L, c->ps.work_q_rows));
+  ensure_side(c->fs, B, 0, s);
   ensure_pool(c->pp, rows, false, bf, s);
   const int64_t BL = (int64_t)B * L;
   if (BL > c->scratch_bl) {
@@ -514,7 +517,7 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   {
     ProfScope pr(c, s, "row_meta");
     row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(ps.starts, ps.lens, B, GAP_PHON, L, nullptr, rows, ps.utt, ps.vpos,
-                                                       ps.room, ps.slot, ps.work, ps.work_cap, ps.work_count, init);
+                                                       ps.room, ps.slot, ps.work, ps.work_cap, ps.work_count, init, ps.work_q_rows);
     FS2_LAUNCHED();
   }
 
@@ -626,15 +629,17 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
   const int B = c->batch, L = c->max_src_len, T = c->max_mel_len;
   const int rows = round_up((int)c->frame_rows, 128);
   const int math = c->cfg.math_mode;
-  ensure_side(c->fs, B, rows, s, attn_tc::work_bound(c->total_frames, B, T));
   const bool bf = math == FS2_MATH_BF16;
+  c->fs.work_q_rows = (bf || T <= attn_tc::BQ) ? attn_tc::BQ : attn_tc::query_rows_per_entry(c->total_frames, B, T);
+  ensure_side(c->fs, B, rows, s, attn_tc::work_bound(c->total_frames, B, T, c->fs.work_q_rows));
   ensure_pool(c->fp, rows, true, bf, s);
   RowSide& fsd = c->fs;
   Pool& fp = c->fp;
 
   if (T > 0) {
     row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(fsd.starts, fsd.lens, B, GAP_FRAME, T, nullptr, rows, fsd.utt,
-                                                       fsd.vpos, fsd.room, fsd.slot, fsd.work, fsd.work_cap, fsd.work_count);
+                                                       fsd.vpos, fsd.room, fsd.slot, fsd.work, fsd.work_cap, fsd.work_count, SlotInit{},
+                                                       fsd.work_q_rows);
     FS2_LAUNCHED();
     // ---- LengthRegulator + decoder positional encoding (modules.py:167-194, Models.py:145-162)
     float *x = fp.act[0], *t1 = fp.act[1], *t2 = fp.act[2];
@@ -1066,6 +1071,7 @@ int fs2_debug_set_flag(int which, int value) {
   if (which == 5) fs2::tc2::n_split_flag() = value ? 1 : 0;
   if (which == 6) fs2::tc2::two_sm_flag() = value ? 1 : 0;
   if (which == 7) fs2::tc2::k_split_flag() = value ? 1 : 0;
+  if (which == 8) fs2::attn_tc::pair_force_flag() = value;   // -1 automatic, 0 never, 1 always
   if (which == 1) {
     g_trace_on = value;
     if (value && g_trace_buf == nullptr) cudaMalloc(reinterpret_cast<void**>(&g_trace_buf), 64 * sizeof(long long));
@@ -1219,12 +1225,15 @@ int fs2_op_attention(fs2_stream stream, const float* qkv, int rows, const int32_
     require(qkv && starts && lens && out && rows > 0 && batch > 0 && max_len > 0, FS2_ERR_INVALID, "bad attention argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // the longest-first work list the forward builds in row_meta_kernel, into a temporary
-    const int cap = attn_tc::work_bound((int64_t)batch * max_len, batch, max_len);
+    // paired (K/V multicast) form when there is enough multi-tile work, exactly as the forward decides
+    const int q_rows = (max_len <= attn_tc::BQ && attn_tc::pair_force_flag() != 1) ? attn_tc::BQ
+                       : attn_tc::query_rows_per_entry((int64_t)batch * max_len, batch, max_len);
+    const int cap = attn_tc::work_bound((int64_t)batch * max_len, batch, max_len, q_rows);
     uint32_t* work = dalloc<uint32_t>(cap);
     int32_t* count = dalloc<int32_t>(1);
-    attention_work_kernel<<<1, 256, 0, s>>>(lens, batch, work, cap, count);
+    attention_work_kernel<<<1, 256, 0, s>>>(lens, batch, work, cap, count, q_rows);
     FS2_LAUNCHED();
-    attn_tc::launch(qkv, rows, starts, lens, work, count, cap, out, s);
+    attn_tc::launch(qkv, rows, starts, lens, work, count, cap, q_rows, out, s);
     FS2_CUDA_OK(cudaStreamSynchronize(s));
     cudaFree(work);
     cudaFree(count);
@@ -1239,7 +1248,7 @@ int fs2_op_attention_bf16(fs2_stream stream, const void* qkv, int rows, const in
     const int cap = attn_tc::work_bound((int64_t)batch * max_len, batch, max_len);
     uint32_t* work = dalloc<uint32_t>(cap);
     int32_t* count = dalloc<int32_t>(1);
-    attention_work_kernel<<<1, 256, 0, s>>>(lens, batch, work, cap, count);
+    attention_work_kernel<<<1, 256, 0, s>>>(lens, batch, work, cap, count, attn_bf::BQ);
     FS2_LAUNCHED();
     attn_bf::launch(static_cast<const __nv_bfloat16*>(qkv), rows, starts, lens, work, count, cap, out, nullptr, s);
     FS2_CUDA_OK(cudaStreamSynchronize(s));

@@ -163,33 +163,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on
                : "memory");
 }
 
-// ---- distributed shared memory helpers (N-split LayerNorm statistics)
-__device__ __forceinline__ uint32_t dsmem_addr(const void* local, int cta_rank) {   // same offset in a peer CTA's smem
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_u32(local)), "r"(cta_rank));
-  return r;
-}
-__device__ __forceinline__ void dsmem_st2(uint32_t raddr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};\n" ::"r"(raddr), "f"(a), "f"(b) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t rbar) {   // release at cluster scope: the stores above are visible
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(rbar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  const long long t0 = clock64();
-  while (true) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
 
 // NS > 1 (fused-LayerNorm only): N-split.  A cluster of NS CTAs shares ONE row tile, CTA r owns the 256/NS columns
 // [r*BN, (r+1)*BN): each loads 1/NS of the activation tile and multicasts it to the others, streams only its own

@@ -106,14 +106,15 @@ __global__ void layout_scan_kernel(const LenT* __restrict__ lens, int batch, int
 // longest-processing-time-first schedule: long items go out first and the tail of the grid is made of short ones.
 // Counting sort over 1024 cost classes with shared-memory atomics; the order inside a class is arbitrary (the entries are
 // independent, the results do not depend on it).  Called by every thread of ONE block; bins = 1024 ints of shared memory.
+// q_rows = query rows one entry covers: 128, or 256 for the paired attention kernel (attention_tc.cuh).
 __device__ inline void build_attention_work(const int32_t* __restrict__ lens32, int batch, uint32_t* __restrict__ work,
-                                            int cap, int32_t* __restrict__ count, int* bins) {
+                                            int cap, int32_t* __restrict__ count, int* bins, int q_rows) {
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int i = tid; i < 1024; i += nt) bins[i] = 0;
   __syncthreads();
   for (int b = tid; b < batch; b += nt) {
     const int l = lens32[b];
-    if (l > 0) atomicAdd(&bins[1023 - min((l + 63) >> 6, 1023)], (l + 127) >> 7);
+    if (l > 0) atomicAdd(&bins[1023 - min((l + 63) >> 6, 1023)], (l + q_rows - 1) / q_rows);
   }
   __syncthreads();
   if (tid < 32) {   // exclusive scan of the 1024 classes by one warp: 32 consecutive classes per lane
@@ -135,7 +136,7 @@ __device__ inline void build_attention_work(const int32_t* __restrict__ lens32, 
   for (int b = tid; b < batch; b += nt) {
     const int l = lens32[b];
     if (l <= 0) continue;
-    const int q = (l + 127) >> 7;
+    const int q = (l + q_rows - 1) / q_rows;
     const int pos = atomicAdd(&bins[1023 - min((l + 63) >> 6, 1023)], q);
     for (int t = 0; t < q; ++t)
       if (pos + t < cap) work[pos + t] = ((uint32_t)b << 16) | (uint32_t)t;
@@ -143,9 +144,9 @@ __device__ inline void build_attention_work(const int32_t* __restrict__ lens32, 
 }
 
 __global__ void attention_work_kernel(const int32_t* __restrict__ lens32, int batch, uint32_t* __restrict__ work, int cap,
-                                      int32_t* __restrict__ count) {
+                                      int32_t* __restrict__ count, int q_rows) {
   __shared__ int bins[1024];
-  build_attention_work(lens32, batch, work, cap, count, bins);
+  build_attention_work(lens32, batch, work, cap, count, bins, q_rows);
 }
 
 // [B, L] arrays the forward fills only at real positions (predictions scattered through `slot`) start from zero, and the
@@ -165,10 +166,10 @@ __global__ void row_meta_kernel(const int32_t* __restrict__ starts, const int32_
                                 int gap, int max_len_host, const int64_t* __restrict__ max_len_dev, int rows_alloc,
                                 int32_t* __restrict__ utt, int32_t* __restrict__ vpos, int32_t* __restrict__ room,
                                 int32_t* __restrict__ slot, uint32_t* __restrict__ work = nullptr, int work_cap = 0,
-                                int32_t* __restrict__ work_count = nullptr, SlotInit init = SlotInit{}) {
+                                int32_t* __restrict__ work_count = nullptr, SlotInit init = SlotInit{}, int work_q_rows = 128) {
   if (work != nullptr && blockIdx.x == gridDim.x - 1) {   // the last block also builds the attention work list of this side
     __shared__ int bins[1024];
-    build_attention_work(lens, batch, work, work_cap, work_count, bins);
+    build_attention_work(lens, batch, work, work_cap, work_count, bins, work_q_rows);
   }
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   for (int64_t i = r; i < init.n; i += (int64_t)gridDim.x * blockDim.x) {
