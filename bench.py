@@ -322,11 +322,31 @@ def main():
     clocks = sampler.stop()
     e2e_bytes = {}
 
-    def e2e_step():
-        _, _, h2d, d2h = model.synthesize_host(host_batch, copy=False)   # (consumed before the next call: views suffice)
+    def e2e_loop(m, steps):
+        """K host-buffer syntheses as a serving loop would issue them: batch i+1 is submitted (pinned H2D, forward) while
+        the device->host reads of batch i are still landing, and batch i's results are taken right after.  Every step's
+        H2D and D2H copies are inside the timed span: first submit -> last result on the host (device events on the
+        launching stream and on the copy stream).  The L2 flush between steps is inside the span too (~45 us each)."""
+        w0 = m.synthesize_host_async(host_batch, copy=False)     # untimed: both staging slots and the copy stream exist
+        m.synthesize_host_async(host_batch, copy=False).wait()
+        w0.wait()
+        barrier()
+        beg = torch.cuda.Event(enable_timing=True)
+        beg.record()
+        prev = None
+        for i in range(steps):
+            flush.zero_()
+            h = m.synthesize_host_async(host_batch, copy=False)
+            if prev is not None:
+                prev.wait()
+            prev = h
+        _, _, h2d, d2h = prev.wait()
         e2e_bytes["h2d"], e2e_bytes["d2h"] = h2d, d2h
+        span = beg.elapsed_time(prev.done)
+        barrier()
+        return span
 
-    e2e_ms = timed_loop(e2e_step, args.steps)
+    e2e_total = e2e_loop(model, args.steps)
 
     # the second arithmetic mode of the north star (bf16 operands), same workload, reported beside the headline
     other = None
@@ -338,8 +358,7 @@ def main():
         torch.cuda.synchronize()
         f16 = int(o16[9].sum())
         ms16 = timed_loop(lambda: m16(*dev_args, L), args.steps)
-        e16 = timed_loop(lambda: m16.synthesize_host(host_batch, copy=False), args.steps)
-        other = (f16, float(sum(ms16)), float(sum(e16)))
+        other = (f16, float(sum(ms16)), float(e2e_loop(m16, args.steps)))
         del m16
 
     # the step after the path: HiFi-GAN generator on the mel this batch produced, reported beside
@@ -439,7 +458,7 @@ def main():
 
     total_ms = float(sum(step_ms))
     o = other or (0, 0.0, 0.0)
-    t = torch.tensor([total_ms, float(sum(e2e_ms)), float(frames), o[1], o[2], float(o[0])], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, float(e2e_total), float(frames), o[1], o[2], float(o[0])], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -477,7 +496,10 @@ def main():
             "e2e": {"value": frames_all * args.steps / (e2e_total_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": e2e_bytes.get("h2d", 0), "d2h_bytes_per_step": e2e_bytes.get("d2h", 0),
                     "ms_per_step": e2e_total_ms / args.steps,
-                    "reads": "packed postnet mel rows, pitch, energy, log-duration, durations, mel_lens (utils/tools.py:228-243)"},
+                    "reads": "packed postnet mel rows, pitch, energy, log-duration, durations, mel_lens (utils/tools.py:228-243)",
+                    "how": "synthesize_host_async: batch i+1 is submitted while batch i's device->host reads land (double-"
+                           "buffered pinned staging, copy stream); span = first submit -> last result, copies and the "
+                           "per-step L2 flush inside"},
             "gpu_launches": launches * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": dom + " (decoder FFN Conv1d k=9 implicit GEMM, 256->1024)",

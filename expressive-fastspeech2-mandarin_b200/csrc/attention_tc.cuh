@@ -64,6 +64,14 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
+#ifdef FS2_TRACE_BUILD   // per-CTA time stamps for tools/trace_attention_ctas.py: [cta][entry, after pdl_wait, first S, exit, smid, tiles]
+__device__ long long g_attn_cta_trace[2048 * 6];
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define FS2_CTA_STAMP(k) do { if (threadIdx.x == 64 && blockIdx.x < 2048) g_attn_cta_trace[blockIdx.x * 6 + (k)] = gtimer(); } while (0)
+#else
+#define FS2_CTA_STAMP(k) do { } while (0)
+#endif
+
 // PAIR: the kernel runs as clusters of two CTAs that own two ADJACENT query tiles of the same (utterance, head).  Each CTA
 // loads HALF of every K and V tile (32 of the 64 key rows) and TMA-multicasts it into both CTAs' shared memory, so the L2
 // traffic of the kernel -- every query tile of an utterance re-reads all of its keys and values: 420 MB per launch at batch
@@ -76,6 +84,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const uint32_t* __restrict__ work, const int32_t* __restrict__ work_count, float* __restrict__ out,
                     __nv_bfloat16* __restrict__ out_b, int dbg) {
   extern __shared__ uint8_t smem_raw[];
+  FS2_CTA_STAMP(0);
   // work item = 128 queries of one (utterance, head), taken from the longest-first work list (rowops.cuh): CTAs are
   // dispatched in blockIdx order, so the expensive items start first and the grid's tail is made of short utterances
   const int rank = PAIR ? (int)(blockIdx.x & 1) : 0;                    // == %cluster_ctarank (cluster of 2 along x)
@@ -140,6 +149,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   // lens / starts / qkv are produced by earlier kernels of this forward
   pdl_trigger();
   pdl_wait();
+  FS2_CTA_STAMP(1);
   const bool listed = item < *work_count;     // the grid is sized from a host-side bound: surplus CTAs only tear down
   const uint32_t wi = listed ? work[item] : 0u;
   // a work-list entry covers BQ queries, or 2 * BQ in the PAIR form (one tile per CTA of the cluster)
@@ -352,6 +362,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int u = j & 1;
       FS2_TRACE(j, 0);
       mbar_wait(&s_full[u], (j >> 1) & 1);
+      if (j == 0) FS2_CTA_STAMP(2);
       FS2_TRACE(j, 1);
       tc_fence_after();
       float s0[32], s1[32];
@@ -448,6 +459,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+#ifdef FS2_TRACE_BUILD
+  if (threadIdx.x == 64 && blockIdx.x < 2048) {
+    g_attn_cta_trace[blockIdx.x * 6 + 3] = gtimer();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_attn_cta_trace[blockIdx.x * 6 + 4] = smid;
+    g_attn_cta_trace[blockIdx.x * 6 + 5] = n_tiles;
+  }
+#endif
   if (PAIR) cluster_sync_all();   // the peer may still multicast into this CTA's shared memory / arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)

@@ -1080,6 +1080,13 @@ int fs2_debug_set_flag(int which, int value) {
 }
 
 int fs2_debug_read_trace(int64_t* host_dst, int n) {
+#ifdef FS2_TRACE_BUILD
+  if (n > 64) {   // per-CTA stamps of the last attention launch (tools/trace_attention_ctas.py)
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(host_dst, fs2::attn_tc::g_attn_cta_trace, std::min<size_t>(n, 2048 * 6) * sizeof(long long)) ==
+                   cudaSuccess ? FS2_OK : FS2_ERR_CUDA;
+  }
+#endif
   if (g_trace_buf == nullptr || n > 64) return FS2_ERR_INVALID;
   g_trace_on = g_trace_on ? 1 : 0;
   cudaDeviceSynchronize();

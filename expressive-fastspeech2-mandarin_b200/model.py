@@ -290,6 +290,10 @@ class FastSpeech2B200(nn.Module):
             pitch = torch.empty(B, T, **f32)
         if self.energy_frame_level:                                 # model/modules.py:144-148
             energy = torch.empty(B, T, **f32)
+        pending = getattr(self, "_pending_read", None)
+        if pending is not None:       # an asynchronous host read of the previous call's packed rows (synthesize_host_async)
+            torch.cuda.current_stream(dev).wait_event(pending)
+            self._pending_read = None
         io = _lib.Stage2IO(mel=mel.data_ptr(), postnet=post.data_ptr(), mel_mask=mel_mask.data_ptr(),
                            pitch_frames=pitch.data_ptr() if self.pitch_frame_level else None,
                            energy_frames=energy.data_ptr() if self.energy_frame_level else None)
@@ -374,8 +378,17 @@ class FastSpeech2B200(nn.Module):
         `self.last_host` (dict of numpy arrays `pitch`, `energy`, `log_d`, `durations`).
 
         copy=True (default): every returned array owns its memory.  copy=False returns VIEWS into the pinned staging
-        buffers, which the NEXT call to synthesize_host overwrites -- only for callers that consume the result before
-        calling again (the benchmark does)."""
+        buffers, which a later call overwrites (the call after next: the staging is double buffered) -- only for callers
+        that consume the result before calling again (the benchmark does).
+
+        `synthesize_host_async` is the same call without the final wait: it returns a handle whose `.wait()` gives this
+        tuple, so a serving loop can submit batch i+1 while the device->host copies of batch i are still in flight."""
+        return self.synthesize_host_async(batch, p_control, e_control, d_control, padded=padded, copy=copy).wait()
+
+    def synthesize_host_async(self, batch, p_control=1.0, e_control=1.0, d_control=1.0, padded=False, copy=True):
+        """Enqueue one host-buffer synthesis and return a `HostResult` handle.  The device->host reads run on a side
+        stream behind an event, into one of two staging slots, so they overlap the next call's encoder; the next call's
+        stage 2 (which overwrites the library's frame-side buffer the packed rows are read from) waits for them."""
         dev = self._device()
         names = ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")
         # one pinned staging buffer and ONE host->device copy for the six int64 inputs; the device tensors are views of it
@@ -386,7 +399,7 @@ class FastSpeech2B200(nn.Module):
         for a in arrays:
             stage_np[off: off + a.size] = a.reshape(-1)
             off += a.size
-        on_dev = stage.to(dev, non_blocking=True)
+        on_dev = stage.to(dev, non_blocking=True)     # (consumed before stage 1 returns: it ends with a stream sync)
         h2d = total * 8
         dev_t, off = {}, 0
         for n, a in zip(names, arrays):
@@ -398,46 +411,74 @@ class FastSpeech2B200(nn.Module):
         post, lens = out[1], out[9]
         B, L = int(post.shape[0]), int(batch["max_src_len"])
         self.last_postnet = post      # device tensor [B, T, 80]: what the vocoder consumes next (utils/tools.py:258-262)
-        stream = torch.cuda.current_stream(dev)
-        hl = self._pinned_buf("lens", torch.int64, B)
-        hl.copy_(lens, non_blocking=True)
-        # pitch / energy / log-duration / rounded duration: one copy of the [4, B, L] block the forward allocated
-        # (frame_level features live on the frame axis and are read separately)
-        hpred = self._pinned_buf("pred", torch.float32, 4 * B * L).view(4, B, L)
-        hpred.copy_(self._last_pred, non_blocking=True)
-        d2h = 4 * B * L * 4 + B * 8
-        frame_feats = {}
-        for key, idx, flag in (("pitch", 2, self.pitch_frame_level), ("energy", 3, self.energy_frame_level)):
-            if flag:
-                t = out[idx]
-                hb = self._pinned_buf("frame_" + key, torch.float32, t.numel()).view(t.shape)
-                hb.copy_(t, non_blocking=True)
-                frame_feats[key] = hb
-                d2h += t.numel() * 4
-        own = (lambda a: np.array(a)) if copy else (lambda a: a)
-        if padded:
-            hp = self._pinned_buf("post", torch.float32, post.numel()).view(post.shape)
-            hp.copy_(post, non_blocking=True)
-            stream.synchronize()
-            mels, d2h = own(hp.numpy()), d2h + post.numel() * 4
+        compute = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != dev:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        side = self._copy_stream
+        slot = self._host_slot = 1 - getattr(self, "_host_slot", 1)
+        tag = lambda role: f"{role}#{slot}"
+        side.wait_stream(compute)
+        res = HostResult(self, copy, padded, h2d, B)
+        res.keep = (out, self._last_pred)           # the device tensors outlive the copies
+        with torch.cuda.stream(side):
+            res.hl = self._pinned_buf(tag("lens"), torch.int64, B)
+            res.hl.copy_(lens, non_blocking=True)
+            # pitch / energy / log-duration / rounded duration: one copy of the [4, B, L] block the forward allocated
+            # (frame_level features live on the frame axis and are read separately)
+            res.hpred = self._pinned_buf(tag("pred"), torch.float32, 4 * B * L).view(4, B, L)
+            res.hpred.copy_(self._last_pred, non_blocking=True)
+            res.d2h = 4 * B * L * 4 + B * 8
+            for key, idx, flag in (("pitch", 2, self.pitch_frame_level), ("energy", 3, self.energy_frame_level)):
+                if flag:
+                    t = out[idx]
+                    hb = self._pinned_buf(tag("frame_" + key), torch.float32, t.numel()).view(t.shape)
+                    hb.copy_(t, non_blocking=True)
+                    res.frame_feats[key] = hb
+                    res.d2h += t.numel() * 4
+            if padded:
+                res.hp = self._pinned_buf(tag("post"), torch.float32, post.numel()).view(post.shape)
+                res.hp.copy_(post, non_blocking=True)
+                res.d2h += post.numel() * 4
+            else:
+                # packed rows straight out of the library's frame-side buffer: rows = sum(mel_lens) + 12 reserved per utterance
+                rows_cap = int(self.last_total_frames) + 12 * (B + 1)
+                res.hp = self._pinned_buf(tag("packed"), torch.float32, rows_cap * 80).view(rows_cap, 80)
+                res.hs = self._pinned_buf(tag("starts"), torch.int32, B + 1)
+                rows = C.c_int64()
+                lib = _lib.load_library()
+                _lib.check(lib, self._ctx, lib.fs2_read_packed_postnet(self._ctx, side.cuda_stream, res.hp.data_ptr(), rows_cap,
+                                                                        res.hs.data_ptr(), C.byref(rows)))
+                res.d2h += int(rows.value) * 80 * 4 + (B + 1) * 4
+            res.done = torch.cuda.Event(enable_timing=True)
+            res.done.record(side)
+        self._pending_read = res.done          # the next stage 2 must not overwrite the frame-side buffer before this
+        return res
+
+
+class HostResult:
+    """Handle of one `synthesize_host_async` call; `wait()` blocks until the device->host copies have landed and returns
+    (mels, mel_lens, h2d_bytes, d2h_bytes) as `synthesize_host` does (and fills `model.last_host`)."""
+
+    def __init__(self, model, copy, padded, h2d, batch):
+        self.model, self.copy, self.padded, self.h2d, self.B = model, copy, padded, h2d, batch
+        self.frame_feats, self.hs, self.d2h, self.done, self.keep = {}, None, 0, None, None
+
+    def wait(self):
+        self.done.synchronize()
+        own = (lambda a: np.array(a)) if self.copy else (lambda a: a)
+        lens_np = self.hl.numpy()
+        if self.padded:
+            mels = own(self.hp.numpy())
         else:
-            # packed rows straight out of the library's frame-side buffer: rows = sum(mel_lens) + 12 reserved per utterance
-            rows_cap = int(self.last_total_frames) + 12 * (B + 1)
-            hp = self._pinned_buf("packed", torch.float32, rows_cap * 80).view(rows_cap, 80)
-            hs = self._pinned_buf("starts", torch.int32, B + 1)
-            rows = C.c_int64()
-            lib = _lib.load_library()
-            _lib.check(lib, self._ctx, lib.fs2_read_packed_postnet(self._ctx, stream.cuda_stream, hp.data_ptr(), rows_cap,
-                                                                    hs.data_ptr(), C.byref(rows)))
-            stream.synchronize()
-            packed, starts, lens_np = hp.numpy(), hs.numpy(), hl.numpy()
-            mels = [own(packed[int(starts[b]): int(starts[b]) + int(lens_np[b])]) for b in range(B)]
-            d2h += int(rows.value) * 80 * 4 + (B + 1) * 4
-        pred_np = hpred.numpy()
-        self.last_host = {"pitch": own(frame_feats["pitch"].numpy() if "pitch" in frame_feats else pred_np[0]),
-                          "energy": own(frame_feats["energy"].numpy() if "energy" in frame_feats else pred_np[1]),
-                          "log_d": own(pred_np[2]), "durations": own(pred_np[3])}
-        return mels, own(hl.numpy()), h2d, d2h
+            packed, starts = self.hp.numpy(), self.hs.numpy()
+            mels = [own(packed[int(starts[b]): int(starts[b]) + int(lens_np[b])]) for b in range(self.B)]
+        pred_np = self.hpred.numpy()
+        ff = self.frame_feats
+        self.model.last_host = {"pitch": own(ff["pitch"].numpy() if "pitch" in ff else pred_np[0]),
+                                "energy": own(ff["energy"].numpy() if "energy" in ff else pred_np[1]),
+                                "log_d": own(pred_np[2]), "durations": own(pred_np[3])}
+        self.keep = None
+        return mels, own(lens_np), self.h2d, self.d2h
 
 
 def get_model(preprocess_config, model_config, state_dict=None, device="cuda", **kw):

@@ -99,6 +99,7 @@ def test_host_entry_reads_what_synth_samples_reads(sd32):
     assert np.array_equal(feats["log_d"], out[4].cpu().numpy()) and np.array_equal(feats["durations"], out[5].cpu().numpy())
     assert np.array_equal(lens, out[9].cpu().numpy())
     assert d2h >= sum(int(n) for n in lens) * 320 + 3 * 4 * 30 * 4
+    model.synthesize_host(host)        # (the output staging is double buffered: both slots exist after two calls)
     n_bufs = len(model._pinned)
     for n in (1, 2, 3, 5, 4):          # other batch shapes, then the first again
         other = syn.make_batch([11 + n] * n, seed=n)
@@ -108,3 +109,21 @@ def test_host_entry_reads_what_synth_samples_reads(sd32):
         assert np.array_equal(m, s0), "results of an earlier call must survive later calls"
     views, _, _, _ = model.synthesize_host(host, copy=False)
     assert all(np.array_equal(v, s0) for v, s0 in zip(views, snapshot))
+
+
+def test_async_host_entry_overlaps_without_mixing_results(sd32):
+    """synthesize_host_async: two batches in flight (the second submitted before the first is read) give the same arrays
+    as two synchronous calls; views of the first stay intact until its slot is reused."""
+    from gpu_util import model_for
+    syn = fs2_b200.synthetic
+    model = model_for(sd32)
+    mk = lambda lens, seed: {k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in syn.make_batch(lens, seed=seed).items()}
+    a, b = mk([30, 7, 19], 12), mk([11, 40], 13)
+    want_a, la, _, _ = model.synthesize_host(a)
+    want_b, lb, _, _ = model.synthesize_host(b)
+    ha = model.synthesize_host_async(a, copy=False)
+    hb = model.synthesize_host_async(b, copy=False)
+    got_a, ga_l, _, _ = ha.wait()
+    got_b, gb_l, _, _ = hb.wait()
+    assert np.array_equal(ga_l, la) and np.array_equal(gb_l, lb)
+    assert all(np.array_equal(x, y) for x, y in zip(got_a, want_a)) and all(np.array_equal(x, y) for x, y in zip(got_b, want_b))
