@@ -38,6 +38,8 @@ UNIT = "frames/s"
 CPU_SAMPLE_UTTS = 64      # the whole config-2 batch per CPU step (about 3-4 s on 16 cores)
 CPU_SAMPLE_STEPS = 3      # cpu_baseline leg of the default run: about 10 s of CPU work
 FLOPS_CONV9_PER_ROW = 2 * 9 * 256 * 1024
+# dram bytes (read + written) of one dec.ffn_fused launch at batch 64, from the ncu --set full capture; None until captured
+DRAM_TRAFFIC_FUSED = {}
 NAMES = ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")
 
 
@@ -480,11 +482,25 @@ def main():
         burst = tf32_peak if (half == 0.5 and tf32_peak) else peaks["bf16_burst"] * half
         peak_source = ("torch.matmul TF32 8192^3 burst, measured in this run (calibration only)" if (half == 0.5 and tf32_peak)
                        else f"{peaks['source']} bf16_tflops (burst)" + (" / 2" if half == 0.5 else ""))
-        dom = "dec.gemm_conv9"
+        # the decoder FFN: one fused launch per layer (conv9 -> ReLU -> w2 -> +x -> LayerNorm, stream-K over hidden
+        # chunks) once the row tiles fill the machine, else conv9 and w2/LN as two launches with conv9 the dominant one
+        fused = "dec.ffn_fused" in prof
+        dom = "dec.ffn_fused" if fused else "dec.gemm_conv9"
+        dom_what = ("decoder FFN in one launch: Conv1d k=9 256->1024 + ReLU + Conv1d k=1 1024->256 + residual + LayerNorm"
+                    if fused else "decoder FFN Conv1d k=9 implicit GEMM, 256->1024")
         n_dom, ms_dom = prof.get(dom, (0, 0.0))
         per_launch_ms = ms_dom / max(n_dom, 1)
         terms = 3 if args.math == "parity" else 1
-        flops_per_launch = FLOPS_CONV9_PER_ROW * frames
+        flops_per_launch = (FLOPS_CONV9_PER_ROW + (2 * 1024 * 256 if fused else 0)) * frames
+        # algorithmic bytes: activations in, weights once, and the output (hidden [rows,1024] for conv9 alone; the
+        # fused kernel writes only the [rows,256] block output and re-reads x once as the residual)
+        alg_bytes = (4 * (frames * 256 * 3 + 9 * 1024 * 256 + 1024 * 256) if fused
+                     else 4 * (frames * 256 + 9 * 1024 * 256 + frames * 1024))
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed `ncu --set full`
+        # captures (profiles/, batch 64): see profiles/README.md for which file each figure comes from
+        traffic = None
+        if args.batch == 64:
+            traffic = DRAM_TRAFFIC_FUSED.get(args.math) if fused else {"tf32": 92.97e6, "bf16": 25.26e6}.get(args.math)
         achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
         kernel_ms = {k: round(v[1], 4) for k, v in sorted(prof.items())}
         line = {
@@ -505,17 +521,14 @@ def main():
                            "per-step L2 flush inside"},
             "gpu_launches": launches * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": dom + " (decoder FFN Conv1d k=9 implicit GEMM, 256->1024)",
+            "roofline": {"bound": "tensor", "kernel": f"{dom} ({dom_what})",
                          "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
                          "frac": achieved / burst if burst else None,
                          "peak_source": peak_source,
                          "frac_of_half_measured_bf16_burst": achieved / (peaks["bf16_burst"] * half),
                          "tensor_flops_issued_per_launch": flops_per_launch * terms,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed
-                         # `ncu --set full` captures (profiles/): 37.10 MB read + 55.87 MB written in TF32 (the 110 MB
-                         # hidden tensor mostly stays in L2), 18.52 MB + 6.74 MB in bf16
-                         "traffic": ({"tf32": 92.97e6, "bf16": 25.26e6}.get(args.math) if args.batch == 64 else None),
-                         "algorithmic_bytes_per_launch": 4 * (frames * 256 + 9 * 1024 * 256 + frames * 1024),
+                         "traffic": traffic,
+                         "algorithmic_bytes_per_launch": alg_bytes,
                          "per_launch_ms": per_launch_ms, "launches_per_step": n_dom,
                          "flops_per_launch": flops_per_launch},
             "kernel_ms_per_step": kernel_ms,

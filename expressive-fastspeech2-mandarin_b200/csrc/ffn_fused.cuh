@@ -10,6 +10,16 @@
 // operand-delivery-bound main loop: the second contraction's A operand is already on chip.
 // The tensor pipe executes MMAs in issue order, so conv(c+1) overwriting acc1 needs no barrier against GEMM2(c)'s reads;
 // the two hand-offs with the epilogue warps (hidden ready / out drained) are mbarriers.
+//
+// Scheduling ("stream-K" over hidden chunks).  The unit of work is (row-tile group, hidden chunk): 4 units per group.  The
+// launch has one cluster per SM pair and cluster k walks the contiguous unit range [k U / n, (k+1) U / n), so a machine
+// that holds 74 clusters takes 105 groups (batch 64: 26.8 k decoder rows) as 5.7 units each instead of one or two whole
+// groups each (2 rounds for 1.42 rounds of work: the reason the fused kernel lost to the two-launch form at batch 64).
+// A group whose chunks straddle two clusters is finished by the cluster that owns its FIRST chunks: the other cluster
+// (which meets the group's tail at the very start of its range) writes its partial `out` tile to a global workspace and
+// raises a flag; the owner -- which reaches the group at the end of its range, one to five units later -- loads that
+// partial into its `out` accumulator while the conv of its first chunk runs and accumulates on top of it.  No cluster
+// waits for anything it has not produced except at the end of its own range, on work another cluster does first.
 #pragma once
 
 #include <cstdlib>
@@ -53,6 +63,12 @@ struct Args {
   int extra;
   const int32_t* live_rows;
   float* y;              // [rows, 256]
+  // hand-over of a row-tile group split between two clusters (stream-K schedule): partial [rows, 256] fp32 and
+  // flags [flag_count(rows)] int32, each holding the epoch of the launch that last completed the slot (never reset;
+  // zero-initialised, epochs start at 1 and are unique per launch on the stream)
+  float* partial;
+  int32_t* flags;
+  int32_t epoch;
 };
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -68,7 +84,7 @@ template <int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
-                 const __grid_constant__ CUtensorMap tmR, Args p) {
+                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmP, Args p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* cst = smem + OFF_CST;
@@ -84,7 +100,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* out_full = hid_ready + 1;     // [1] the fourth GEMM2 of a tile has completed
   uint64_t* out_empty = out_full + 1;     // [1] 128 epilogue threads have read the out accumulator
   uint64_t* res_full = out_empty + 1;     // [4 warps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 8);
+  uint64_t* par_full = res_full + 8;      // [4 warps][2]  sub-tiles of another cluster's partial `out` tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(par_full + 8);
 
   const int warp = warp_index(), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -93,6 +110,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmW2)) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmP)) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], CL);
@@ -102,6 +120,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     mbar_init(out_full, 1);
     mbar_init(out_empty, 128);
     for (int u = 0; u < 8; ++u) mbar_init(&res_full[u], 1);
+    for (int u = 0; u < 8; ++u) mbar_init(&par_full[u], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
@@ -120,16 +139,21 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   int rows_live = p.rows;
   if (p.live_rows != nullptr) rows_live = min(rows_live, *p.live_rows);
   const int m_groups = ((rows_live + BM - 1) / BM + CL - 1) / CL;
-  const int w_first = blockIdx.x / CL, w_step = gridDim.x / CL;
   auto item_m0 = [&](int w) { return (w * CL + rank) * BM; };
+  // this cluster's contiguous range of (group, hidden chunk) units; at least 4 per cluster, so that a group is shared by
+  // at most two clusters
+  const int n_units = m_groups * N_CHUNKS;
+  const int n_cl = min((int)gridDim.x / CL, m_groups), kcl = (int)blockIdx.x / CL;
+  const int u0 = kcl < n_cl ? (int)(((long long)kcl * n_units) / n_cl) : 0;
+  const int u1 = kcl < n_cl ? (int)(((long long)(kcl + 1) * n_units) / n_cl) : 0;
 
   if (warp == 0) {
     // ---------------- TMA producer
     const bool leader = elect_one();
     int it = 0;
-    for (int w = w_first; w < m_groups; w += w_step) {
-      const int m0 = item_m0(w);
-      for (int c = 0; c < N_CHUNKS; ++c) {
+    for (int u = u0; u < u1; ++u) {
+      const int m0 = item_m0(u / N_CHUNKS), c = u % N_CHUNKS;
+      {
         for (int i = 0; i < STEPS1 + STEPS2; ++i, ++it) {
           const int s = it % STAGES;
           mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
@@ -157,9 +181,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // ---------------- MMA issuer
     const bool leader = elect_one();
     constexpr uint32_t idesc = umma_idesc_tf32(BM, 256);
-    int it = 0, n_h = 0, lt = 0;
-    for (int w = w_first; w < m_groups; w += w_step, ++lt) {
-      for (int c = 0; c < N_CHUNKS; ++c, ++n_h) {
+    int it = 0, n_h = 0, n_seg = 0;
+    for (int u = u0; u < u1; ++u, ++n_h) {
+      const int c = u % N_CHUNKS;
+      // a segment = this cluster's consecutive chunks of one group; `out` is handed over per segment
+      const bool seg_first = u == u0 || c == 0, seg_last = u == u1 - 1 || c == N_CHUNKS - 1;
+      // head segment of a group whose last chunks belong to the next cluster: `out` starts from that cluster's partial
+      const bool preloaded = c == 0 && u1 - u < N_CHUNKS;
+      {
         // conv chunk c -> acc1 (the previous chunk's GEMM2 reads of acc1 precede these writes in the tensor pipe)
         for (int i = 0; i < STEPS1; ++i, ++it) {
           const int s = it % STAGES;
@@ -178,7 +207,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         __syncwarp();
         // GEMM2 chunk c: out += ReLU(hidden chunk) (TMEM) x W2 tile (smem)
         mbar_wait(hid_ready, n_h & 1);
-        if (c == 0) mbar_wait(out_empty, (lt & 1) ^ 1);      // the previous tile's LayerNorm has drained `out`
+        // the previous segment's epilogue has drained `out` (and, for a head segment, loaded the partial into it)
+        if (seg_first) mbar_wait(out_empty, (n_seg & 1) ^ 1);
         tc_fence_after();
         for (int i = 0; i < STEPS2; ++i, ++it) {
           const int s = it % STAGES;
@@ -188,14 +218,17 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if (leader) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_tf32_ts(tmem_out, tmem_hid + i * 32 + kk * 8, db + 2 * kk, idesc, (c | i | kk) != 0 ? 1u : 0u);
+              umma_tf32_ts(tmem_out, tmem_hid + i * 32 + kk * 8, db + 2 * kk, idesc, (!seg_first || preloaded || (i | kk) != 0) ? 1u : 0u);
             if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], (uint16_t)0x3);
           }
           __syncwarp();
         }
       }
-      if (leader) umma_commit(out_full);
-      __syncwarp();
+      if (seg_last) {
+        if (leader) umma_commit(out_full);
+        __syncwarp();
+        ++n_seg;
+      }
     }
   } else {
     // ---------------- epilogue warps: thread = accumulator row
@@ -216,19 +249,67 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       beta_s[i] = p.beta[i];
     }
     epi_barrier();
-    int g_res = 0, g_st = 0, n_h = 0, lt = 0;
-    if (lane == 0 && w_first < m_groups) {
+    int g_res = 0, g_st = 0, g_par = 0, n_h = 0, n_seg = 0;
+    uint64_t* my_par_full = par_full + q * 2;
+    // groups this cluster FINISHES (LayerNorm + store): those whose first chunk lies in its range
+    const int g_fin0 = (u0 + N_CHUNKS - 1) / N_CHUNKS;
+    auto finishes = [&](int g) { return g * N_CHUNKS >= u0 && g * N_CHUNKS < u1; };
+    if (lane == 0 && finishes(g_fin0)) {   // first residual sub-tile of the first group to finish
       mbar_expect_tx(&my_res_full[0], WCHUNK);
-      tma_load_2d(my_res, &tmR, 0, item_m0(w_first) + q * 32, &my_res_full[0]);
+      tma_load_2d(my_res, &tmR, 0, item_m0(g_fin0) + q * 32, &my_res_full[0]);
     }
-    for (int w = w_first; w < m_groups; w += w_step, ++lt) {
+    int32_t* my_flag_base = p.flags + rank;      // slot of group g: flags[g * CL + rank] (each CTA hands over its own rows)
+    // The next group's last chunks belong to the next cluster, which computed them first thing: wait for its flag, load
+    // the partial tile into `out` (TMA -> staging -> tcgen05.st), then hand `out` to the issuer, whose second contraction
+    // accumulates on top of it.  All of this runs under the conv of the group's first chunk.
+    auto preload_partial = [&](int gn) {
+      if (et == 0) {
+        const long long t0 = clock64();
+        int32_t seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(seen) : "l"(my_flag_base + (size_t)gn * CL) : "memory");
+          if (clock64() - t0 > 4000000000LL) __trap();
+        } while (seen != p.epoch);
+      }
+      epi_barrier();
+      asm volatile("fence.proxy.async;\n" ::: "memory");   // the partial was written through the async proxy of another SM
+      if (lane == 0) bulk_wait_read<0>();                   // both staging buffers are free
+      __syncwarp();
+      const int mn = item_m0(gn);
+      auto load_par = [&](int cch) {
+        if (lane != 0) return;
+        const int buf = (g_par + (cch & 1)) & 1;
+        mbar_expect_tx(&my_par_full[buf], WCHUNK);
+        tma_load_2d(my_cst + buf * WCHUNK, &tmP, cch * 32, mn + q * 32, &my_par_full[buf]);
+      };
+      load_par(0);
+      float v[32];
+#pragma unroll 1
+      for (int cch = 0; cch < 8; ++cch) {
+        if (cch + 1 < 8) load_par(cch + 1);
+        const int buf = (g_par + (cch & 1)) & 1;
+        mbar_wait(&my_par_full[buf], ((g_par + cch) >> 1) & 1);
+        const uint32_t pb = cst_sa + buf * WCHUNK + lane * 128;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          const float4 t4 = lds4(pb + ((cc << 4) ^ swz_x));
+          v[cc * 4] = t4.x; v[cc * 4 + 1] = t4.y; v[cc * 4 + 2] = t4.z; v[cc * 4 + 3] = t4.w;
+        }
+        tmem_st32(tmem_out + lane_sel + cch * 32, v);
+        fence_async_smem();         // every lane has read the buffer before the async proxy writes it again
+        __syncwarp();
+      }
+      g_par += 8;
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(out_empty);
+    };
+    for (int u = u0; u < u1; ++u, ++n_h) {
+      const int w = u / N_CHUNKS, c = u % N_CHUNKS;
+      const bool seg_last = u == u1 - 1 || c == N_CHUNKS - 1;
       const int m0 = item_m0(w);
-      const int row = m0 + r;
-      bool live = row < p.rows;
-      if (live && p.row_vpos != nullptr) live = row_live(p.row_vpos[row], p.row_room[row], p.extra);
-      const int w_next = w + w_step;
-      // ---- hidden chunks: acc1 <- tf32(ReLU(acc1 + b1)) in place
-      for (int c = 0; c < N_CHUNKS; ++c, ++n_h) {
+      // ---- hidden chunk: acc1 <- tf32(ReLU(acc1 + b1)) in place
+      {
         mbar_wait(hid_full, n_h & 1);
         tc_fence_after();
         float va[32], vb[32];
@@ -258,25 +339,71 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tc_fence_before();
         mbar_arrive(hid_ready);
       }
-      // ---- LayerNorm(out + b2 + x) -> y   (same two-pass scheme as gemm_tc2.cuh's LN epilogue)
-      mbar_wait(out_full, lt & 1);
+      if (!seg_last) continue;
+      // ---- end of this cluster's segment of group w
+      mbar_wait(out_full, n_seg & 1);
+      ++n_seg;
       tc_fence_after();
       const uint32_t acc = tmem_out + lane_sel;
-      auto prefetch_res = [&](int c) {
+      const int seg_c0 = (u - c >= u0) ? 0 : (u0 % N_CHUNKS);     // first chunk of the segment
+      // the next segment (if any) starts a new group; it is a HEAD segment when the range ends inside that group: its
+      // `out` accumulator must then hold the next cluster's partial before it is handed back to the issuer
+      const bool next_is_head = u + 1 < u1 && u1 - (u + 1) < N_CHUNKS;
+      if (seg_c0 != 0) {
+        // ---- TAIL segment: this cluster met the group at the start of its range; the group is finished by the previous
+        // cluster.  Raw `out` tile -> workspace (TMA stores), then the flag of this CTA's rows.
+        float v[32];
+#pragma unroll 1
+        for (int cc8 = 0; cc8 < 8; ++cc8) {
+          tmem_ld32(acc + cc8 * 32, v);
+          if (cc8 == 7 && !next_is_head) {
+            tc_fence_before();
+            mbar_arrive(out_empty);
+          }
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          uint8_t* sb = my_cst + (g_st & 1) * WCHUNK;
+          const uint32_t sa = cst_sa + (g_st & 1) * WCHUNK + lane * 128;
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) sts4(sa + ((cc << 4) ^ swz_x), make_float4(v[cc * 4], v[cc * 4 + 1], v[cc * 4 + 2], v[cc * 4 + 3]));
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmP, sb, cc8 * 32, m0 + q * 32);
+            bulk_commit();
+          }
+          ++g_st;
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // the stores are COMPLETE, not just read
+        __syncwarp();
+        epi_barrier();
+        if (et == 0) {
+          __threadfence();
+          asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(my_flag_base + (size_t)w * CL), "r"(p.epoch) : "memory");
+        }
+        if (next_is_head) preload_partial(w + 1);
+        continue;
+      }
+      // ---- HEAD (or whole) segment: LayerNorm(out + b2 + x) -> y   (same two-pass scheme as gemm_tc2.cuh's LN epilogue)
+      const int row = m0 + r;
+      bool live = row < p.rows;
+      if (live && p.row_vpos != nullptr) live = row_live(p.row_vpos[row], p.row_room[row], p.extra);
+      const int w_next = w + 1;
+      auto prefetch_res = [&](int cch) {
         if (lane != 0) return;
-        int ww = w, cc = c + 1;
+        int ww = w, cc = cch + 1;
         if (cc >= 8) { ww = w_next; cc = 0; }
-        if (ww >= m_groups) return;
+        if (!finishes(ww)) return;
         const int buf = (g_res + 1) & 1;
         mbar_expect_tx(&my_res_full[buf], WCHUNK);
         tma_load_2d(my_res + buf * WCHUNK, &tmR, cc * 32, item_m0(ww) + q * 32, &my_res_full[buf]);
       };
       float mean = 0.f, m2 = 0.f;
       float va[32], vb[32];
-      auto pass1 = [&](float (&v)[32], int c) {
+      auto pass1 = [&](float (&v)[32], int cch) {
         __syncwarp();
-        prefetch_res(c);
-        const uint32_t ba = b2_sa + (uint32_t)(c * 32) * 4;
+        prefetch_res(cch);
+        const uint32_t ba = b2_sa + (uint32_t)(cch * 32) * 4;
         mbar_wait(&my_res_full[g_res & 1], (g_res >> 1) & 1);
         const uint32_t rb = res_sa + (g_res & 1) * WCHUNK + lane * 128;
 #pragma unroll
@@ -298,27 +425,27 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         const float cm2 = (q4[0] + q4[1]) + (q4[2] + q4[3]);
         const float delta = cm - mean;
-        const float n_old = 32.f * c, n_new = 32.f * (c + 1);
-        mean = fmaf(delta, 32.f / n_new, mean);
-        m2 += cm2 + delta * delta * (n_old * 32.f / n_new);
-        tmem_st32(acc + c * 32, v);
+        const float inv_n = __frcp_rn((float)(cch + 1));
+        mean = fmaf(delta, inv_n, mean);
+        m2 += cm2 + delta * delta * (32.f * (float)cch * inv_n);
+        tmem_st32(acc + cch * 32, v);
       };
       tmem_ld32_issue(acc, va);
 #pragma unroll 1
-      for (int c = 0; c < 8; c += 2) {
+      for (int cch = 0; cch < 8; cch += 2) {
         tmem_ld_wait();
-        tmem_ld32_issue(acc + (c + 1) * 32, vb);
-        pass1(va, c);
+        tmem_ld32_issue(acc + (cch + 1) * 32, vb);
+        pass1(va, cch);
         tmem_ld_wait();
-        if (c + 2 < 8) tmem_ld32_issue(acc + (c + 2) * 32, va);
-        pass1(vb, c + 1);
+        if (cch + 2 < 8) tmem_ld32_issue(acc + (cch + 2) * 32, va);
+        pass1(vb, cch + 1);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
       const float rstd = 1.f / sqrtf(m2 * (1.f / 256.f) + 1e-5f);
-      auto pass2 = [&](float (&v)[32], int c) {
+      auto pass2 = [&](float (&v)[32], int cch) {
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
-          const float4 g4 = lds4(gamma_sa + c * 128 + cc * 16), b4 = lds4(beta_sa + c * 128 + cc * 16);
+          const float4 g4 = lds4(gamma_sa + cch * 128 + cc * 16), b4 = lds4(beta_sa + cch * 128 + cc * 16);
           const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[cc * 4 + e] = live ? fmaf((v[cc * 4 + e] - mean) * rstd, gg[e], bb[e]) : 0.f;
@@ -332,26 +459,27 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmY, sb, c * 32, m0 + q * 32);
+          tma_store_2d(&tmY, sb, cch * 32, m0 + q * 32);
           bulk_commit();
         }
         ++g_st;
       };
       tmem_ld32_issue(acc, va);
 #pragma unroll 1
-      for (int c = 0; c < 8; c += 2) {
+      for (int cch = 0; cch < 8; cch += 2) {
         tmem_ld_wait();
-        tmem_ld32_issue(acc + (c + 1) * 32, vb);
-        pass2(va, c);
+        tmem_ld32_issue(acc + (cch + 1) * 32, vb);
+        pass2(va, cch);
         tmem_ld_wait();
-        if (c + 2 < 8) {
-          tmem_ld32_issue(acc + (c + 2) * 32, va);
-        } else {
+        if (cch + 2 < 8) {
+          tmem_ld32_issue(acc + (cch + 2) * 32, va);
+        } else if (!next_is_head) {        // the last read of `out` has landed: hand it back to the issuer
           tc_fence_before();
           mbar_arrive(out_empty);
         }
-        pass2(vb, c + 1);
+        pass2(vb, cch + 1);
       }
+      if (next_is_head) preload_partial(w + 1);
     }
     if (lane == 0) bulk_wait_read<0>();
   }
@@ -362,9 +490,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 }
 
 // 0 = conv9 + w2/LN as two launches, 1 = always the fused kernel, 2 = automatic (default; FS2_FFN_FUSED overrides).
-// A fused tile costs ~4.65 conv-tile times on ONE SM, the two-launch form 4 + ~1.1 spread over four column tiles: the
-// fused kernel only wins once the row tiles alone fill the machine several times over (measured: batch 64 has 210 row
-// tiles = 1.42 waves of 148 SMs and loses 11 % to the quantisation; batch 512 has 10.6 waves and gains 6 %).
+// A (group, chunk) unit costs ~1.16 conv-tile times on one SM against 1 + ~0.28 for the two-launch form, but a cluster
+// cannot take fewer than the 4 units of one group: the fused kernel wins once there are at least as many row-tile groups
+// as clusters (the stream-K schedule then keeps every SM busy to within one unit), and loses SMs outright below that.
 inline int& enabled_flag() {
   static int f = [] {
     const char* e = std::getenv("FS2_FFN_FUSED");
@@ -375,8 +503,10 @@ inline int& enabled_flag() {
 inline bool use_fused(int rows) {
   const int mode = enabled_flag();
   if (mode != 2) return mode == 1;
-  return (rows + BM - 1) / BM >= 4 * sm_count();
+  return (rows + BM - 1) / BM >= sm_count();
 }
+// int32 hand-over flags a launch over `rows` rows may touch
+inline size_t flag_count(int rows) { return (size_t)((rows + BM - 1) / BM + 2); }
 
 template <int CL>
 inline void launch_cl(const Args& a, cudaStream_t stream) {
@@ -392,15 +522,17 @@ inline void launch_cl(const Args& a, cudaStream_t stream) {
   const CUtensorMap tmW2 = make_map(a.w2, D_MODEL, D_INNER, D_INNER, 256 / CL, false, true);
   const CUtensorMap tmY = make_map(a.y, a.rows, D_MODEL, D_MODEL, 32, false, false);
   const CUtensorMap tmR = make_map(a.x, a.rows, D_MODEL, D_MODEL, 32, false, false);
+  const CUtensorMap tmP = make_map(a.partial, a.rows, D_MODEL, D_MODEL, 32, false, false);
   const int items = ((a.rows + BM - 1) / BM + CL - 1) / CL;
   const int grid = std::min(items, sm_count() / CL) * CL;
-  launch_pdl(ffn_fused_kernel<CL>, dim3(grid), dim3(THREADS), SMEM_TOTAL, stream, CL, tmX, tmW1, tmW2, tmY, tmR, a);
+  launch_pdl(ffn_fused_kernel<CL>, dim3(grid), dim3(THREADS), SMEM_TOTAL, stream, CL, tmX, tmW1, tmW2, tmY, tmR, tmP, a);
   FS2_LAUNCHED();
 }
 
 inline void launch(const Args& a, cudaStream_t stream) {
   if (a.rows <= 0) return;
   require(a.x != a.y, FS2_ERR_INVALID, "fused FFN: output must not alias the input (conv halo rows are re-read)");
+  require(a.partial != nullptr && a.flags != nullptr && a.epoch != 0, FS2_ERR_INVALID, "fused FFN: hand-over workspace missing");
   if (cluster_size_flag() == 2 && a.rows > BM) launch_cl<2>(a, stream);
   else launch_cl<1>(a, stream);
 }

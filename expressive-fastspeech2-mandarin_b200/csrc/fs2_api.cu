@@ -83,6 +83,9 @@ struct fs2_ctx {
   float* pe_long = nullptr;  // generated sinusoid table for sequences beyond max_seq_len
   int pe_long_rows = 0;
   float* splitk_ws = nullptr;  // K-split workspace (tc2::SPLITK_WS_BYTES): partial tiles of single-utterance launches
+  int32_t* ffn_flags = nullptr;  // fused FFN hand-over flags (grow-only, zero-filled when grown) and the launch counter
+  size_t ffn_flags_cap = 0;
+  int32_t ffn_epoch = 0;
   float* split_buf = nullptr;  // FS2_MATH_TF32X3: [rows, hi | lo] copy of the activations of the contraction being launched
   size_t split_cap = 0;
 
@@ -366,6 +369,16 @@ static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSi
     f.x = t2; f.rows = rows; f.w1 = L.w1; f.b1 = L.b1; f.w2 = L.w2; f.b2 = L.b2; f.gamma = L.ln2_g; f.beta = L.ln2_b;
     f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 0;
     f.live_rows = live; f.y = x;
+    // a row-tile group split between two clusters is handed over through the (otherwise unused) hidden buffer
+    if (ffn::flag_count(rows) > c->ffn_flags_cap) {
+      FS2_CUDA_OK(cudaStreamSynchronize(s));
+      cudaFree(c->ffn_flags);
+      c->ffn_flags_cap = ffn::flag_count(rows) * 2;
+      c->ffn_flags = dalloc<int32_t>(c->ffn_flags_cap);
+      FS2_CUDA_OK(cudaMemsetAsync(c->ffn_flags, 0, c->ffn_flags_cap * sizeof(int32_t), s));
+      c->ffn_epoch = 0;
+    }
+    f.partial = pool.hid; f.flags = c->ffn_flags; f.epoch = ++c->ffn_epoch;
     ProfScope ps(c, s, frame ? "dec.ffn_fused" : "enc.ffn_fused");
     ffn::launch(f, s);
     return;
@@ -954,7 +967,7 @@ void fs2_destroy(fs2_ctx* c) {
     cudaFree(p->hidb); cudaFree(p->qkvb); cudaFree(p->melb); cudaFree(p->pnb[0]); cudaFree(p->pnb[1]);
   }
   cudaFree(c->status); cudaFree(c->cum); cudaFree(c->mel_lens32); cudaFree(c->raw_pitch); cudaFree(c->raw_energy);
-  cudaFree(c->cond_spk); cudaFree(c->cond_emo); cudaFree(c->pe_long); cudaFree(c->split_buf); cudaFree(c->splitk_ws); cudaFree(c->raw_pitch_f); cudaFree(c->raw_energy_f);
+  cudaFree(c->cond_spk); cudaFree(c->cond_emo); cudaFree(c->pe_long); cudaFree(c->split_buf); cudaFree(c->splitk_ws); cudaFree(c->ffn_flags); cudaFree(c->raw_pitch_f); cudaFree(c->raw_energy_f);
   cudaFreeHost(c->h_totals);
   delete c;
 }
@@ -1190,7 +1203,18 @@ int fs2_op_ffn_fused(fs2_stream stream, const float* x, int rows, const float* w
     ffn::Args f{};
     f.x = x; f.rows = rows; f.w1 = w1; f.b1 = b1; f.w2 = w2; f.b2 = b2; f.gamma = gamma; f.beta = beta;
     f.row_vpos = row_vpos; f.row_room = row_room; f.extra = extra; f.y = y;
-    ffn::launch(f, static_cast<cudaStream_t>(stream));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float* part = nullptr;
+    int32_t* flags = nullptr;
+    if (rows > 0) {
+      part = dalloc<float>((size_t)rows * D_MODEL);
+      flags = dalloc<int32_t>(ffn::flag_count(rows));
+      FS2_CUDA_OK(cudaMemsetAsync(flags, 0, ffn::flag_count(rows) * sizeof(int32_t), s));
+    }
+    f.partial = part; f.flags = flags; f.epoch = 1;
+    ffn::launch(f, s);
+    FS2_CUDA_OK(cudaStreamSynchronize(s));
+    cudaFree(part); cudaFree(flags);
   });
 }
 
