@@ -69,6 +69,7 @@ struct Args {
   float* partial;
   int32_t* flags;
   int32_t epoch;
+  long long* trace;      // trace builds only (tools/trace_ffn.py): phase stamps of cluster 0's first units
 };
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -80,12 +81,35 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
+#ifdef FS2_TRACE_BUILD   // per-CTA stamps for tools/trace_ffn.py: [cta][entry, after pdl_wait, exit, first unit, units, smid]
+__device__ long long g_ffn_cta_trace[256 * 6];
+#endif
+
 template <int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmP, Args p) {
   extern __shared__ uint8_t smem_raw[];
+  auto stamp = [&](int unit, int k) {
+#ifdef FS2_TRACE_BUILD   // phase timestamps for tools/trace_ffn.py: [unit][issuer: start, conv issued, hidden ready, gemm2 issued |
+                         // epilogue warp 0: conv complete, ReLU done, out complete, segment epilogue done]
+    if (p.trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && unit < 8) {
+      long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      p.trace[unit * 8 + k] = t;
+    }
+#endif
+  };
+  auto cta_stamp = [&](int k, long long v = -1) {
+#ifdef FS2_TRACE_BUILD
+    if (threadIdx.x == 0 && blockIdx.x < 256) {
+      if (v < 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+      g_ffn_cta_trace[blockIdx.x * 6 + k] = v;
+    }
+#endif
+  };
+  cta_stamp(0);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* cst = smem + OFF_CST;
   uint8_t* res = smem + OFF_RES;
@@ -146,6 +170,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int n_cl = min((int)gridDim.x / CL, m_groups), kcl = (int)blockIdx.x / CL;
   const int u0 = kcl < n_cl ? (int)(((long long)kcl * n_units) / n_cl) : 0;
   const int u1 = kcl < n_cl ? (int)(((long long)(kcl + 1) * n_units) / n_cl) : 0;
+  cta_stamp(1);
+  cta_stamp(3, u0);
+  cta_stamp(4, u1 - u0);
+#ifdef FS2_TRACE_BUILD
+  { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); cta_stamp(5, smid); }
+#endif
 
   if (warp == 0) {
     // ---------------- TMA producer
@@ -188,6 +218,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const bool seg_first = u == u0 || c == 0, seg_last = u == u1 - 1 || c == N_CHUNKS - 1;
       // head segment of a group whose last chunks belong to the next cluster: `out` starts from that cluster's partial
       const bool preloaded = c == 0 && u1 - u < N_CHUNKS;
+      stamp(u - u0, 0);
       {
         // conv chunk c -> acc1 (the previous chunk's GEMM2 reads of acc1 precede these writes in the tensor pipe)
         for (int i = 0; i < STEPS1; ++i, ++it) {
@@ -205,11 +236,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         if (leader) umma_commit(hid_full);
         __syncwarp();
+        stamp(u - u0, 1);
         // GEMM2 chunk c: out += ReLU(hidden chunk) (TMEM) x W2 tile (smem)
         mbar_wait(hid_ready, n_h & 1);
         // the previous segment's epilogue has drained `out` (and, for a head segment, loaded the partial into it)
         if (seg_first) mbar_wait(out_empty, (n_seg & 1) ^ 1);
         tc_fence_after();
+        stamp(u - u0, 2);
         for (int i = 0; i < STEPS2; ++i, ++it) {
           const int s = it % STAGES;
           mbar_wait(&full[s], (it / STAGES) & 1);
@@ -224,6 +257,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           __syncwarp();
         }
       }
+      stamp(u - u0, 3);
       if (seg_last) {
         if (leader) umma_commit(out_full);
         __syncwarp();
@@ -312,6 +346,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       {
         mbar_wait(hid_full, n_h & 1);
         tc_fence_after();
+        if (q == 0) stamp(u - u0, 4);
         float va[32], vb[32];
         tmem_ld32_issue(tmem_hid + lane_sel, va);
 #pragma unroll 1
@@ -338,12 +373,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         tc_fence_before();
         mbar_arrive(hid_ready);
+        if (q == 0) stamp(u - u0, 5);
       }
       if (!seg_last) continue;
       // ---- end of this cluster's segment of group w
       mbar_wait(out_full, n_seg & 1);
       ++n_seg;
       tc_fence_after();
+      if (q == 0) stamp(u - u0, 6);
       const uint32_t acc = tmem_out + lane_sel;
       const int seg_c0 = (u - c >= u0) ? 0 : (u0 % N_CHUNKS);     // first chunk of the segment
       // the next segment (if any) starts a new group; it is a HEAD segment when the range ends inside that group: its
@@ -382,6 +419,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(my_flag_base + (size_t)w * CL), "r"(p.epoch) : "memory");
         }
         if (next_is_head) preload_partial(w + 1);
+        if (q == 0) stamp(u - u0, 7);
         continue;
       }
       // ---- HEAD (or whole) segment: LayerNorm(out + b2 + x) -> y   (same two-pass scheme as gemm_tc2.cuh's LN epilogue)
@@ -480,11 +518,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         pass2(vb, cch + 1);
       }
       if (next_is_head) preload_partial(w + 1);
+      if (q == 0) stamp(u - u0, 7);
     }
     if (lane == 0) bulk_wait_read<0>();
   }
   tc_fence_before();
   __syncthreads();
+  cta_stamp(2);
   if (CL > 1) cluster_sync_all();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
 }

@@ -1088,12 +1088,17 @@ int fs2_debug_set_flag(int which, int value) {
   if (which == 1) {
     g_trace_on = value;
     if (value && g_trace_buf == nullptr) cudaMalloc(reinterpret_cast<void**>(&g_trace_buf), 64 * sizeof(long long));
+    if (value) cudaMemset(g_trace_buf, 0, 64 * sizeof(long long));
   }
   return FS2_OK;
 }
 
 int fs2_debug_read_trace(int64_t* host_dst, int n) {
 #ifdef FS2_TRACE_BUILD
+  if (n == 256 * 6) {   // per-CTA stamps of the last fused-FFN launch (tools/trace_ffn.py)
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(host_dst, fs2::ffn::g_ffn_cta_trace, (size_t)n * sizeof(long long)) == cudaSuccess ? FS2_OK : FS2_ERR_CUDA;
+  }
   if (n > 64) {   // per-CTA stamps of the last attention launch (tools/trace_attention_ctas.py)
     cudaDeviceSynchronize();
     return cudaMemcpyFromSymbol(host_dst, fs2::attn_tc::g_attn_cta_trace, std::min<size_t>(n, 2048 * 6) * sizeof(long long)) ==
@@ -1212,6 +1217,7 @@ int fs2_op_ffn_fused(fs2_stream stream, const float* x, int rows, const float* w
       FS2_CUDA_OK(cudaMemsetAsync(flags, 0, ffn::flag_count(rows) * sizeof(int32_t), s));
     }
     f.partial = part; f.flags = flags; f.epoch = 1;
+    if (g_trace_on) f.trace = g_trace_buf;
     ffn::launch(f, s);
     FS2_CUDA_OK(cudaStreamSynchronize(s));
     cudaFree(part); cudaFree(flags);
