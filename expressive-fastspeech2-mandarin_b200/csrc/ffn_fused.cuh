@@ -40,9 +40,14 @@ constexpr int N_CHUNKS = D_INNER / HC;        // 4
 constexpr int KC1 = D_MODEL / 32;             // 8 K chunks of the conv
 constexpr int STEPS1 = FFN_TAPS * KC1;        // 72
 constexpr int STEPS2 = HC / 32;               // 8
-constexpr int STAGES = 3;
-constexpr int A_BYTES = BM * 128, B_BYTES = 256 * 128, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int OFF_CST = STAGES * STAGE_BYTES;
+// CL = 2 (every launch over more than one row tile): the CTA pair issues ONE tcgen05.mma.cta_group::2 (M = 256) per K slice
+// and each CTA keeps only ITS half of the weight tile in shared memory (gemm_tc2.cuh's TWO form): 32 KB stages, four of
+// them, and a third less shared-memory operand traffic per MMA than the 1-SM multicast form (measured on the conv:
+// 25.0 -> XX us per unit).  CL = 1 (a single row tile): 1-SM MMAs, 48 KB stages, three of them.
+constexpr int A_BYTES = BM * 128, B_BYTES = 256 * 128;
+constexpr int RING_BYTES = 3 * (A_BYTES + B_BYTES);
+constexpr int MAX_STAGES = 4;
+constexpr int OFF_CST = RING_BYTES;
 constexpr int OFF_RES = OFF_CST + 8 * WCHUNK;
 constexpr int OFF_PAR = OFF_RES + 8 * WCHUNK;          // b1[1024] | b2[256] | gamma[256] | beta[256]
 constexpr int OFF_BAR = OFF_PAR + 8192;
@@ -72,6 +77,14 @@ struct Args {
   long long* trace;      // trace builds only (tools/trace_ffn.py): phase stamps of cluster 0's first units
 };
 
+__device__ __forceinline__ void umma_tf32_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -117,9 +130,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   float* b2_s = b1_s + D_INNER;
   float* gamma_s = b2_s + 256;
   float* beta_s = gamma_s + 256;
+  constexpr bool TWO = CL == 2;
+  constexpr int BB = TWO ? B_BYTES / 2 : B_BYTES;          // this CTA's part of a weight tile
+  constexpr int STAGE_BYTES = A_BYTES + BB, STAGES = TWO ? 4 : 3;
+  static_assert(STAGES * STAGE_BYTES <= RING_BYTES && STAGES <= MAX_STAGES, "ring");
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* empty = full + STAGES;
-  uint64_t* hid_full = empty + STAGES;    // [1] conv MMAs of a chunk have completed
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* hid_full = empty + MAX_STAGES;    // [1] conv MMAs of a chunk have completed
   uint64_t* hid_ready = hid_full + 1;     // [1] 128 epilogue threads wrote ReLU(hidden) back to TMEM
   uint64_t* out_full = hid_ready + 1;     // [1] the fourth GEMM2 of a tile has completed
   uint64_t* out_empty = out_full + 1;     // [1] 128 epilogue threads have read the out accumulator
@@ -137,19 +154,24 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmP)) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CL);
+      mbar_init(&empty[s], 1);
     }
     mbar_init(hid_full, 1);
-    mbar_init(hid_ready, 128);
+    mbar_init(hid_ready, 128 * CL);    // 2-SM: the issuer (even CTA) waits for the epilogue threads of both CTAs
     mbar_init(out_full, 1);
-    mbar_init(out_empty, 128);
+    mbar_init(out_empty, 128 * CL);
     for (int u = 0; u < 8; ++u) mbar_init(&res_full[u], 1);
     for (int u = 0; u < 8; ++u) mbar_init(&par_full[u], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    if (TWO) {   // the same warp of both CTAs, the same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -190,17 +212,27 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           uint8_t* a_s = smem + s * STAGE_BYTES;
           uint8_t* b_s = a_s + A_BYTES;
           if (leader) {
+            // 2-SM: own activation rows + own half of the weight tile; both CTAs' bytes are counted on the issuer's barrier
             if (i < STEPS1) {     // conv step: activations (tap = row offset) + the chunk's W1 tile
               const int tap = i / KC1, kc = i - tap * KC1;
-              mbar_expect_tx(&full[s], STAGE_BYTES);
-              tma_load_2d(a_s, &tmX, kc * 32, m0 + tap - FFN_TAPS / 2, &full[s]);
-              if (CL == 1) tma_load_2d(b_s, &tmW1, kc * 32, tap * D_INNER + c * HC, &full[s]);
-              else tma_load_2d_mc(b_s + rank * (B_BYTES / 2), &tmW1, kc * 32, tap * D_INNER + c * HC + rank * 128, &full[s], (uint16_t)0x3);
+              if (!TWO) {
+                mbar_expect_tx(&full[s], STAGE_BYTES);
+                tma_load_2d(a_s, &tmX, kc * 32, m0 + tap - FFN_TAPS / 2, &full[s]);
+                tma_load_2d(b_s, &tmW1, kc * 32, tap * D_INNER + c * HC, &full[s]);
+              } else {
+                if (rank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
+                tma_load_2d_2sm(a_s, &tmX, kc * 32, m0 + tap - FFN_TAPS / 2, &full[s]);
+                tma_load_2d_2sm(b_s, &tmW1, kc * 32, tap * D_INNER + c * HC + rank * 128, &full[s]);
+              }
             } else {              // second contraction: only the W2 tile [256 outputs x 32 hidden columns]
               const int kc = i - STEPS1;
-              mbar_expect_tx(&full[s], B_BYTES);
-              if (CL == 1) tma_load_2d(b_s, &tmW2, c * HC + kc * 32, 0, &full[s]);
-              else tma_load_2d_mc(b_s + rank * (B_BYTES / 2), &tmW2, c * HC + kc * 32, rank * 128, &full[s], (uint16_t)0x3);
+              if (!TWO) {
+                mbar_expect_tx(&full[s], BB);
+                tma_load_2d(b_s, &tmW2, c * HC + kc * 32, 0, &full[s]);
+              } else {
+                if (rank == 0) mbar_expect_tx(&full[s], 2 * BB);
+                tma_load_2d_2sm(b_s, &tmW2, c * HC + kc * 32, rank * 128, &full[s]);
+              }
             }
           }
           __syncwarp();
@@ -208,11 +240,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer
+    // ---------------- MMA issuer (2-SM: the even CTA issues for the pair; each CTA's 128 rows of A come from its own shared
+    // or tensor memory, its half of the weight tile from its own shared memory, its 128 accumulator rows are in its own TMEM)
     const bool leader = elect_one();
-    constexpr uint32_t idesc = umma_idesc_tf32(BM, 256);
+    constexpr uint32_t idesc = umma_idesc_tf32(TWO ? 2 * BM : BM, 256);
     int it = 0, n_h = 0, n_seg = 0;
-    for (int u = u0; u < u1; ++u, ++n_h) {
+    for (int u = u0; u < (TWO && rank != 0 ? u0 : u1); ++u, ++n_h) {
       const int c = u % N_CHUNKS;
       // a segment = this cluster's consecutive chunks of one group; `out` is handed over per segment
       const bool seg_first = u == u0 || c == 0, seg_last = u == u1 - 1 || c == N_CHUNKS - 1;
@@ -223,43 +256,49 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         // conv chunk c -> acc1 (the previous chunk's GEMM2 reads of acc1 precede these writes in the tensor pipe)
         for (int i = 0; i < STEPS1; ++i, ++it) {
           const int s = it % STAGES;
-          mbar_wait(&full[s], (it / STAGES) & 1);
+          if (TWO) mbar_wait_cluster(&full[s], (it / STAGES) & 1); else mbar_wait(&full[s], (it / STAGES) & 1);
           tc_fence_after();
           const uint8_t* a_s = smem + s * STAGE_BYTES;
           const uint64_t da = umma_desc(a_s), db = umma_desc(a_s + A_BYTES);
           if (leader) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_tf32(tmem_hid, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
-            if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], (uint16_t)0x3);
+            for (int kk = 0; kk < 4; ++kk) {
+              if (TWO) umma_2sm<false>(tmem_hid, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
+              else umma_tf32(tmem_hid, da + 2 * kk, db + 2 * kk, idesc, (i | kk) != 0 ? 1u : 0u);
+            }
+            if (TWO) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);
           }
           __syncwarp();
         }
-        if (leader) umma_commit(hid_full);
+        if (leader) { if (TWO) umma_commit_2sm(hid_full); else umma_commit(hid_full); }
         __syncwarp();
         stamp(u - u0, 1);
         // GEMM2 chunk c: out += ReLU(hidden chunk) (TMEM) x W2 tile (smem)
-        mbar_wait(hid_ready, n_h & 1);
+        if (TWO) mbar_wait_cluster(hid_ready, n_h & 1); else mbar_wait(hid_ready, n_h & 1);
         // the previous segment's epilogue has drained `out` (and, for a head segment, loaded the partial into it)
-        if (seg_first) mbar_wait(out_empty, (n_seg & 1) ^ 1);
+        if (seg_first) { if (TWO) mbar_wait_cluster(out_empty, (n_seg & 1) ^ 1); else mbar_wait(out_empty, (n_seg & 1) ^ 1); }
         tc_fence_after();
         stamp(u - u0, 2);
         for (int i = 0; i < STEPS2; ++i, ++it) {
           const int s = it % STAGES;
-          mbar_wait(&full[s], (it / STAGES) & 1);
+          if (TWO) mbar_wait_cluster(&full[s], (it / STAGES) & 1); else mbar_wait(&full[s], (it / STAGES) & 1);
           tc_fence_after();
           const uint64_t db = umma_desc(smem + s * STAGE_BYTES + A_BYTES);
           if (leader) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_tf32_ts(tmem_out, tmem_hid + i * 32 + kk * 8, db + 2 * kk, idesc, (!seg_first || preloaded || (i | kk) != 0) ? 1u : 0u);
-            if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], (uint16_t)0x3);
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t accum = (!seg_first || preloaded || (i | kk) != 0) ? 1u : 0u;
+              if (TWO) umma_tf32_ts_2sm(tmem_out, tmem_hid + i * 32 + kk * 8, db + 2 * kk, idesc, accum);
+              else umma_tf32_ts(tmem_out, tmem_hid + i * 32 + kk * 8, db + 2 * kk, idesc, accum);
+            }
+            if (TWO) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);
           }
           __syncwarp();
         }
       }
       stamp(u - u0, 3);
       if (seg_last) {
-        if (leader) umma_commit(out_full);
+        if (leader) { if (TWO) umma_commit_2sm(out_full); else umma_commit(out_full); }
         __syncwarp();
         ++n_seg;
       }
@@ -284,6 +323,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
     epi_barrier();
     int g_res = 0, g_st = 0, g_par = 0, n_h = 0, n_seg = 0;
+    auto arrive_issuer = [&](uint64_t* bar) {   // the issuer lives in the even CTA
+      if (TWO && rank != 0) mbar_arrive_remote(dsmem_addr(bar, 0));
+      else mbar_arrive(bar);
+    };
     uint64_t* my_par_full = par_full + q * 2;
     // groups this cluster FINISHES (LayerNorm + store): those whose first chunk lies in its range
     const int g_fin0 = (u0 + N_CHUNKS - 1) / N_CHUNKS;
@@ -336,7 +379,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       g_par += 8;
       asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
       tc_fence_before();
-      mbar_arrive(out_empty);
+      arrive_issuer(out_empty);
     };
     for (int u = u0; u < u1; ++u, ++n_h) {
       const int w = u / N_CHUNKS, c = u % N_CHUNKS;
@@ -372,7 +415,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         tc_fence_before();
-        mbar_arrive(hid_ready);
+        arrive_issuer(hid_ready);
         if (q == 0) stamp(u - u0, 5);
       }
       if (!seg_last) continue;
@@ -395,7 +438,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tmem_ld32(acc + cc8 * 32, v);
           if (cc8 == 7 && !next_is_head) {
             tc_fence_before();
-            mbar_arrive(out_empty);
+            arrive_issuer(out_empty);
           }
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
@@ -513,7 +556,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tmem_ld32_issue(acc + (cch + 2) * 32, va);
         } else if (!next_is_head) {        // the last read of `out` has landed: hand it back to the issuer
           tc_fence_before();
-          mbar_arrive(out_empty);
+          arrive_issuer(out_empty);
         }
         pass2(vb, cch + 1);
       }
@@ -526,7 +569,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __syncthreads();
   cta_stamp(2);
   if (CL > 1) cluster_sync_all();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
+  if (warp == 1) {
+    if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
 }
 
 // 0 = conv9 + w2/LN as two launches, 1 = always the fused kernel, 2 = automatic (default; FS2_FFN_FUSED overrides).
