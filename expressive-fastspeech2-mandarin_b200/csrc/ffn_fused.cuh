@@ -42,8 +42,11 @@ constexpr int STEPS1 = FFN_TAPS * KC1;        // 72
 constexpr int STEPS2 = HC / 32;               // 8
 // CL = 2 (every launch over more than one row tile): the CTA pair issues ONE tcgen05.mma.cta_group::2 (M = 256) per K slice
 // and each CTA keeps only ITS half of the weight tile in shared memory (gemm_tc2.cuh's TWO form): 32 KB stages, four of
-// them, and a third less shared-memory operand traffic per MMA than the 1-SM multicast form (measured on the conv:
-// 25.0 -> XX us per unit).  CL = 1 (a single row tile): 1-SM MMAs, 48 KB stages, three of them.
+// them, and a third less shared-memory operand traffic per MMA than the 1-SM multicast form (config 2, same box:
+// dec.ffn_fused 1.10 -> 1.08 ms).  CL = 1 (a single row tile): 1-SM MMAs, 48 KB stages, three of them.
+// Tried and dropped: 128-column hidden chunks with TWO hidden buffers in tensor memory and conv(j+1) issued before
+// GEMM2(j), which hides the ReLU hand-over (2.9 of 29.4 us per unit) under the next conv.  The N = 128 conv MMAs run
+// 3 % slower and the forward got slower, not faster (same box, A/B: dec.ffn_fused 1.13-1.17 ms against 1.08).
 constexpr int A_BYTES = BM * 128, B_BYTES = 256 * 128;
 constexpr int RING_BYTES = 3 * (A_BYTES + B_BYTES);
 constexpr int MAX_STAGES = 4;
