@@ -1,10 +1,9 @@
 """One config-2 forward bracketed by cudaProfilerStart/Stop, for `ncu --profile-from-start off` (run on the GPU box).
     python tools/profile_target.py [tf32|bf16]
-Launch order inside the bracket (67 launches at config 2, TF32): 1 row_meta (+ source mask, attention work list, init)
+Launch order inside the bracket (67 launches at config 2, TF32; ncu IDs): 0 layout_scan 1 row_meta (+ source mask, attention work list, init)
 2 embed_pe | 3-22 encoder (4 x [qkv, attention, fc+LN, conv9, w2+LN]) | 23 cond 24 add_cond | 25-26 duration predictor
 27-28 pitch predictor 29 bucket+embed 30-31 energy predictor 32 durations 33 layout_scan | 34 row_meta 35 length regulator
-(+ energy add, PE) | 36-59 decoder (6 x [qkv, attention, fc+LN, fused FFN]) | 60 mel_linear 61-65 PostNet 66 unpack.
-(The first layout_scan of the phoneme side runs before the bracket's first kernel in the same stream: 67 with it.)"""
+(+ energy add, PE) | 36-59 decoder (6 x [qkv, attention, fc+LN, fused FFN]) | 60 mel_linear 61-65 PostNet 66 unpack."""
 import os, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
