@@ -426,7 +426,25 @@ def main():
             torch.cuda.synchronize()
             t_reb = float(np.median(timed_loop(lambda: partition.rebalanced_forward(model, big, parts, rank), steps3, sync_each=True)))
             f_reb = float(r3["mel_lens"].sum()) if r3["ids"] else 0.0
-        v = torch.tensor([t_plain, f_plain, t_reb or 0.0, f_reb or 0.0], dtype=torch.float64, device=dev)
+        # third arm: balance on frames PREDICTED before stage 1 by a speaking-rate prior over the conditioning, learned on
+        # two OTHER batches (config-2 shape, seeds 11 and 12: every rank runs them untimed, so every rank holds the same
+        # prior and plans the same shards without communicating)
+        t_pri, f_pri = None, None
+        if world > 1:
+            prior = partition.RatePrior(len(syn.SPEAKERS), 5, 4, 5)
+            for seed in (11, 12):
+                ob = syn.config2_batch(seed=seed)
+                oo = model(*[ob[k].to(dev) for k in NAMES], ob["max_src_len"])
+                prior.observe({k: ob[k].numpy() for k in NAMES if k != "texts"}, oo[9].cpu().numpy())
+            parts_p = partition.lpt_partition_by_prior({k: big[k].numpy() for k in NAMES if k != "texts"}, world, prior)
+            mine_p = partition.take(big, parts_p[rank])
+            mine_p_args = [mine_p[k].to(dev) for k in NAMES]
+            for _ in range(2):
+                p3 = model(*mine_p_args, mine_p["max_src_len"])
+            torch.cuda.synchronize()
+            t_pri = float(np.median(timed_loop(lambda: model(*mine_p_args, mine_p["max_src_len"]), steps3, sync_each=True)))
+            f_pri = float(p3[9].sum())
+        v = torch.tensor([t_plain, f_plain, t_reb or 0.0, f_reb or 0.0, t_pri or 0.0, f_pri or 0.0], dtype=torch.float64, device=dev)
         if world > 1:
             vmax, vmin, vsum = v.clone(), v.clone(), v.clone()
             dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
@@ -447,6 +465,13 @@ def main():
                 "note": "stage 1 on the phoneme shards, all-gather of mel_lens, LPT on the true stage-2 cost, one NCCL "
                         "all-to-all of the phoneme rows that change owner, stage 2 where the utterance landed "
                         "(partition.rebalanced_forward); the collectives and the host planning are inside the timed step"}
+
+            c3["lpt_by_rate_prior"] = {
+                "ms_per_step": float(vmax[4]), "frames_per_s": float(vsum[5]) / float(vmax[4]) * 1e3,
+                "frames_per_rank_min_max": [float(vmin[5]), float(vmax[5])],
+                "note": "shards balanced on frames predicted before stage 1 by partition.RatePrior (additive speaking-rate "
+                        "model over speaker / emotion / arousal / valence, fitted on 128 utterances of two other batches); "
+                        "no collective, no exchange"}
 
     # p50 single-utterance latency (BASELINE config 1), device-resident inputs, host sync included
     c1 = syn.config1_batch()

@@ -118,3 +118,46 @@ def _worker(rank, world, port, lens):
 def test_gather_over_gloo_world_size_2(syn):
     lens = syn.random_lengths(13, lo=5, hi=40, seed=5)
     mp.spawn(_worker, args=(2, _free_port(), lens), nprocs=2, join=True)
+
+
+def test_rate_prior_learns_the_conditioning_and_balances_frames(syn):
+    """RatePrior: an additive speaking-rate model over (speaker, emotion, arousal, valence) fitted on earlier batches predicts
+    the frames of unseen utterances and the LPT partition on it balances the true frame-side cost where the phoneme counts
+    do not.  Ground truth here is a synthetic rate with the same structure plus noise (the GPU bench measures the real one)."""
+    import numpy as np
+    from fs2_b200 import partition
+    rng = np.random.default_rng(0)
+    eff = [rng.normal(0, s, n) for s, n in ((1.2, 10), (0.6, 5), (0.5, 4), (0.5, 5))]
+
+    def frames_of(batch):
+        rate = 5.0 + sum(e[np.asarray(batch[k])] for e, k in zip(eff, ("speakers", "emotions", "arousals", "valences")))
+        rate = np.maximum(rate + rng.normal(0, 0.15, len(rate)), 1.0)
+        return np.round(rate * np.asarray(batch["src_lens"])).astype(np.int64)
+
+    prior, twin = partition.RatePrior(10, 5, 4, 5), partition.RatePrior(10, 5, 4, 5)
+    fresh = syn.config2_batch(seed=0, batch=512)
+    assert np.allclose(prior.predict_frames(fresh), np.asarray(fresh["src_lens"]) * partition.FRAMES_PER_PHONEME)
+    for seed in (11, 12):
+        b = syn.config2_batch(seed=seed)
+        seen = frames_of(b)
+        prior.observe(b, seen)
+        twin.observe(b, seen)
+    true = frames_of(fresh)
+    pred = prior.predict_frames(fresh)
+    assert np.corrcoef(pred, true)[0, 1] > 0.97
+    lens = np.asarray(fresh["src_lens"]).tolist()
+
+    def worst(parts):
+        cost = [partition.stage2_cost(true[p]).sum() for p in parts]
+        return max(cost) / np.mean(cost)
+
+    by_len = partition.lpt_partition(lens, 8)
+    by_prior = partition.lpt_partition_by_prior(fresh, 8, prior)
+    assert sorted(i for p in by_prior for i in p) == list(range(512))
+    assert worst(by_prior) < 1.015 and worst(by_len) > 1.03
+    # a second prior fed the same observations plans identically (what makes it usable without communication)
+    assert partition.lpt_partition_by_prior(fresh, 8, twin) == by_prior
+    with pytest.raises(ValueError):
+        bad = dict(fresh)
+        bad["speakers"] = np.full(512, 99)
+        prior.predict_frames(bad)
