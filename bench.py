@@ -427,12 +427,12 @@ def main():
             t_reb = float(np.median(timed_loop(lambda: partition.rebalanced_forward(model, big, parts, rank), steps3, sync_each=True)))
             f_reb = float(r3["mel_lens"].sum()) if r3["ids"] else 0.0
         # third arm: balance on frames PREDICTED before stage 1 by a speaking-rate prior over the conditioning, learned on
-        # two OTHER batches (config-2 shape, seeds 11 and 12: every rank runs them untimed, so every rank holds the same
+        # four OTHER batches (config-2 shape, seeds 11-14: every rank runs them untimed, so every rank holds the same
         # prior and plans the same shards without communicating)
         t_pri, f_pri = None, None
         if world > 1:
             prior = partition.RatePrior(len(syn.SPEAKERS), 5, 4, 5)
-            for seed in (11, 12):
+            for seed in (11, 12, 13, 14):
                 ob = syn.config2_batch(seed=seed)
                 oo = model(*[ob[k].to(dev) for k in NAMES], ob["max_src_len"])
                 prior.observe({k: ob[k].numpy() for k in NAMES if k != "texts"}, oo[9].cpu().numpy())
@@ -470,7 +470,7 @@ def main():
                 "ms_per_step": float(vmax[4]), "frames_per_s": float(vsum[5]) / float(vmax[4]) * 1e3,
                 "frames_per_rank_min_max": [float(vmin[5]), float(vmax[5])],
                 "note": "shards balanced on frames predicted before stage 1 by partition.RatePrior (additive speaking-rate "
-                        "model over speaker / emotion / arousal / valence, fitted on 128 utterances of two other batches); "
+                        "model over speaker / emotion / arousal / valence, fitted on 256 utterances of four other batches); "
                         "no collective, no exchange"}
 
     # p50 single-utterance latency (BASELINE config 1), device-resident inputs, host sync included
