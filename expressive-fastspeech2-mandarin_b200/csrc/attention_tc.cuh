@@ -67,7 +67,7 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 #ifdef FS2_TRACE_BUILD   // per-CTA time stamps for tools/trace_attention_ctas.py: [cta][entry, after pdl_wait, first S, exit, smid, tiles]
 __device__ long long g_attn_cta_trace[2048 * 6];
 __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define FS2_CTA_STAMP(k) do { if (threadIdx.x == 64 && blockIdx.x < 2048) g_attn_cta_trace[blockIdx.x * 6 + (k)] = gtimer(); } while (0)
+#define FS2_CTA_STAMP(k) do { if (threadIdx.x == 64 && blockIdx.x < 2048) ::fs2::attn_tc::g_attn_cta_trace[blockIdx.x * 6 + (k)] = ::fs2::attn_tc::gtimer(); } while (0)
 #else
 #define FS2_CTA_STAMP(k) do { } while (0)
 #endif
@@ -489,22 +489,23 @@ inline int work_bound(int64_t total_len, int batch, int max_len, int q_rows = BQ
 // Query rows per work-list entry: 256 = the PAIR form (clusters of two CTAs sharing every K/V tile through multicast), chosen
 // when the batch has enough work to fill the machine with pairs; 128 = one CTA per entry (single utterances: a pair
 // would only add a cluster hand-shake).  The work list must be built with the same value (rowops.cuh).
-inline int& pair_force_flag() {   // -1 automatic (default; FS2_ATTN_PAIR overrides), 0 never, 1 always
+inline int& pair_force_flag() {   // -1 automatic (default; FS2_ATTN_PAIR overrides), 0 never, 1 multicast pair, 2 the 2-SM kernel
   static int f = [] { const char* e = std::getenv("FS2_ATTN_PAIR"); return e != nullptr ? std::atoi(e) : -1; }();
   return f;
 }
 inline int query_rows_per_entry(int64_t total_len, int batch, int max_len) {
   const int force = pair_force_flag();
   if (force == 0) return BQ;
-  if (force == 1) return 2 * BQ;
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  (void)sms; (void)total_len; (void)batch; (void)max_len;
-  // Measured at config 2 (profiles/r02_attention_experiments.txt): the paired form is SLOWER (0.40 vs 0.345 ms per step) --
-  // the two CTAs of a pair advance in lock step through every stage -- so the automatic choice is the unpaired kernel;
-  // the form stays selectable (debug flag 8 / FS2_ATTN_PAIR=1) and is covered by tests/test_gpu_ops.py.
+  if (force >= 1) return 2 * BQ;
+  (void)total_len; (void)batch; (void)max_len;
+  // Automatic: one CTA per 128-query tile.  Both paired forms measured SLOWER at config 2 (same box, per step, six decoder
+  // launches): this file's multicast pair 0.40 ms, the 2-SM kernel of attention_tc2.cuh 0.48 ms, against 0.345 ms --
+  // profiles/r02_attention_experiments.txt has the per-tile and per-CTA traces.  Both stay selectable (FS2_ATTN_PAIR=1 / 2,
+  // debug flag 8) and are covered by tests/test_gpu_ops.py.
   return BQ;
 }
+// which kernel serves 256-row entries
+inline bool use_two_sm(int q_rows) { return q_rows == 2 * BQ && pair_force_flag() != 1; }
 
 template <bool PAIR>
 inline void launch_t(const float* qkv, int rows, const int32_t* starts, const int32_t* lens, const uint32_t* work,

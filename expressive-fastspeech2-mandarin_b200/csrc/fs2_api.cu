@@ -10,6 +10,7 @@
 #include "attention_bf16.cuh"
 #include "common.cuh"
 #include "gemm_tc2.cuh"
+#include "attention_tc2.cuh"
 #include "ffn_fused.cuh"
 #include "rowops.cuh"
 #include "vocoder.cuh"
@@ -303,7 +304,10 @@ static void conv_gemm(fs2_ctx* c, ConvGemmArgs a, cudaStream_t s) {
 static void attention(const float* qkv, int rows, const RowSide& side, int batch, int max_len, float* out, cudaStream_t s,
                       void* out_bf16 = nullptr) {
   (void)batch; (void)max_len;
-  attn_tc::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, side.work_q_rows, out, s, out_bf16);
+  if (attn_tc::use_two_sm(side.work_q_rows))
+    attn2::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, out, s, out_bf16);
+  else
+    attn_tc::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, side.work_q_rows, out, s, out_bf16);
 }
 
 // bf16-operand variant: A and W are bf16 behind the float* fields
@@ -1263,14 +1267,15 @@ int fs2_op_attention(fs2_stream stream, const float* qkv, int rows, const int32_
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // the longest-first work list the forward builds in row_meta_kernel, into a temporary
     // paired (K/V multicast) form when there is enough multi-tile work, exactly as the forward decides
-    const int q_rows = (max_len <= attn_tc::BQ && attn_tc::pair_force_flag() != 1) ? attn_tc::BQ
+    const int q_rows = (max_len <= attn_tc::BQ && attn_tc::pair_force_flag() < 1) ? attn_tc::BQ
                        : attn_tc::query_rows_per_entry((int64_t)batch * max_len, batch, max_len);
     const int cap = attn_tc::work_bound((int64_t)batch * max_len, batch, max_len, q_rows);
     uint32_t* work = dalloc<uint32_t>(cap);
     int32_t* count = dalloc<int32_t>(1);
     attention_work_kernel<<<1, 256, 0, s>>>(lens, batch, work, cap, count, q_rows);
     FS2_LAUNCHED();
-    attn_tc::launch(qkv, rows, starts, lens, work, count, cap, q_rows, out, s);
+    if (attn_tc::use_two_sm(q_rows)) attn2::launch(qkv, rows, starts, lens, work, count, cap, out, s);
+    else attn_tc::launch(qkv, rows, starts, lens, work, count, cap, q_rows, out, s);
     FS2_CUDA_OK(cudaStreamSynchronize(s));
     cudaFree(work);
     cudaFree(count);

@@ -134,12 +134,13 @@ def test_conv_gemm_fused_layernorm(case):
         assert (got[~live] == 0).all()
 
 
-@pytest.mark.parametrize("pair", [0, 1], ids=["one_cta_per_tile", "paired_kv_multicast"])
+@pytest.mark.parametrize("pair", [0, 1, 2], ids=["one_cta_per_tile", "paired_kv_multicast", "two_sm_pair"])
 @pytest.mark.parametrize("lens", [[1], [5, 64, 65, 33], [200, 7, 129, 128, 127], [700], [0, 3, 0, 300, 1],
                                   [37] * 70 + [513, 2, 1024]])
 def test_attention(lens, pair):
-    """Both forms of the kernel: one CTA per 128-query tile, and clusters of two CTAs on adjacent query tiles that share
-    every K/V tile through TMA multicast (odd tile counts leave a loads-only CTA)."""
+    """The forms of the kernel: one CTA per 128-query tile; clusters of two CTAs on adjacent query tiles that share every K/V
+    tile through TMA multicast (odd tile counts leave a loads-only CTA); and the 2-SM kernel (attention_tc2.cuh: M = 256
+    cta_group::2 MMAs, 128-key tiles split between the CTAs; odd tile counts leave a CTA working on nobody's rows)."""
     lib().fs2_debug_set_flag(8, pair)
     try:
         _attention_case(lens)

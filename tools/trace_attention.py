@@ -25,6 +25,7 @@ L.fs2_op_attention(stream(), ptr(qkv), rows, ptr(ds), ptr(dl), len(lens), max(le
 torch.cuda.synchronize()
 L.fs2_debug_set_flag(0, 0)
 t = out[starts[0]].cpu().numpy()[:176].reshape(11, 16)
+print("2-SM kernel (FS2_ATTN_PAIR unset): tile of 128 keys; old kernel (FS2_ATTN_PAIR=0): 64 keys")
 print("tile | sm: wait_s  s_ready  p_arrived acc_done | mma: before_p p_ready v_ready | qk(j): begin k_ready issued committed | pv(j): issued committed")
 for j in range(11):
     print(j, " ".join(f"{int(x):8d}" for x in t[j, :14]))
