@@ -39,7 +39,7 @@ CPU_SAMPLE_UTTS = 64      # the whole config-2 batch per CPU step (about 3-4 s o
 CPU_SAMPLE_STEPS = 3      # cpu_baseline leg of the default run: about 10 s of CPU work
 FLOPS_CONV9_PER_ROW = 2 * 9 * 256 * 1024
 # dram bytes (read + written) of one dec.ffn_fused launch at batch 64, from the ncu --set full capture; None until captured
-DRAM_TRAFFIC_FUSED = {"tf32": 44.37e6}   # 38.68 MB read + 5.69 MB written (profiles/r02_ncu_full_ffn_fused_raw.csv)
+DRAM_TRAFFIC_FUSED = {"tf32": 44.11e6}   # 39.48 MB read + 4.63 MB written (profiles/r02_ncu_full_ffn_fused_final_raw.csv)
 NAMES = ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")
 
 
