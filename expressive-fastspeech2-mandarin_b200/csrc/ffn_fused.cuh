@@ -18,8 +18,11 @@
 // A group whose chunks straddle two clusters is finished by the cluster that owns its FIRST chunks: the other cluster
 // (which meets the group's tail at the very start of its range) writes its partial `out` tile to a global workspace and
 // raises a flag; the owner -- which reaches the group at the end of its range, one to five units later -- loads that
-// partial into its `out` accumulator while the conv of its first chunk runs and accumulates on top of it.  No cluster
-// waits for anything it has not produced except at the end of its own range, on work another cluster does first.
+// partial into its `out` accumulator while the conv of its first chunk runs and accumulates on top of it.
+// Deadlock freedom does not need the whole grid resident: cluster k only ever waits for the FIRST action of cluster k + 1 (its
+// tail dump), which itself waits for nothing.  If fewer clusters fit than the grid has (SMs held by another stream's kernel),
+// clusters are dispatched in blockIdx order, every resident cluster except the last one has its successor resident and
+// finishes, and each SM it frees admits the next cluster, whose first action releases the one that was spinning.
 #pragma once
 
 #include <cstdlib>

@@ -2,6 +2,7 @@
 // One context per device; all work is enqueued on the caller's stream.
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
@@ -379,6 +380,10 @@ static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSi
       cudaFree(c->ffn_flags);
       c->ffn_flags_cap = ffn::flag_count(rows) * 2;
       c->ffn_flags = dalloc<int32_t>(c->ffn_flags_cap);
+      FS2_CUDA_OK(cudaMemsetAsync(c->ffn_flags, 0, c->ffn_flags_cap * sizeof(int32_t), s));
+      c->ffn_epoch = 0;
+    }
+    if (c->ffn_epoch == INT32_MAX) {   // (6 launches per forward: days of continuous serving) restart the epochs behind a clear
       FS2_CUDA_OK(cudaMemsetAsync(c->ffn_flags, 0, c->ffn_flags_cap * sizeof(int32_t), s));
       c->ffn_epoch = 0;
     }
