@@ -57,7 +57,11 @@ def check_phoneme_side(tag, got, want, src_lens, mode="tf32"):
 def check_durations(tag, got, want, d_control):
     """Free-running integer durations: exact, except positions reported at a rounding boundary."""
     g, w = got[5].cpu().numpy(), want["d_rounded"]
-    bad = g != w
+    # d_rounded = round(exp(log_d) - 1) * d_control is an fp32 product on the GPU (as in the reference) and an fp64 one in
+    # the fp64 oracle: compare the integers, and the product to fp32 rounding
+    kg, kw = np.rint(g / d_control), np.rint(np.asarray(w, dtype=np.float64) / d_control)
+    assert np.allclose(g, kg * np.float32(d_control), rtol=3e-7, atol=0)
+    bad = kg != kw
     if bad.any():
         frac = (np.exp(want["log_d"].astype(np.float64)) - 1) % 1.0
         near = np.abs(frac - 0.5) < 0.05
