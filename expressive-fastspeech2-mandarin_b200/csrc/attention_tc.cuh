@@ -85,6 +85,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     __nv_bfloat16* __restrict__ out_b, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   FS2_CTA_STAMP(0);
+#ifdef FS2_TRACE_BUILD
+  const long long c_entry = clock64();
+#endif
   // work item = 128 queries of one (utterance, head), taken from the longest-first work list (rowops.cuh): CTAs are
   // dispatched in blockIdx order, so the expensive items start first and the grid's tail is made of short utterances
   const int rank = PAIR ? (int)(blockIdx.x & 1) : 0;                    // == %cluster_ctarank (cluster of 2 along x)
@@ -464,7 +467,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     g_attn_cta_trace[blockIdx.x * 6 + 3] = gtimer();
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    g_attn_cta_trace[blockIdx.x * 6 + 4] = smid;
+    g_attn_cta_trace[blockIdx.x * 6 + 4] = (long long)smid | ((clock64() - c_entry) << 16);   // SM id | cycles of the CTA's life
     g_attn_cta_trace[blockIdx.x * 6 + 5] = n_tiles;
   }
 #endif

@@ -34,6 +34,13 @@ struct ConvGemmArgs {
   const float* head_b;
   float* head_out;
   const int32_t* slot;
+  // Fused LayerNorm only: y[row] = (y[row] + post_a[u]) + post_b[u] with u = post_utt[row], applied AFTER the row mask on
+  // the rows that are live with post_extra reserved rows -- the speaker / emotion conditioning of
+  // model/fastspeech2.py:101-110 on the last encoder layer's output (the reference adds the vectors on padding rows too).
+  const float* post_a;
+  const float* post_b;
+  const int32_t* post_utt;
+  int post_extra;
   // BF16 operand mode: A is bf16 [rows, lda] and W is bf16 [taps][N][K] (both pointers reinterpret the float*
   // fields); bias, residual and C stay fp32.  C2, when set, receives a bf16 copy of the output [rows, ldc2]
   // (the A operand of the next contraction); C may then be nullptr.

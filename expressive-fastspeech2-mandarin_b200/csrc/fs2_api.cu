@@ -283,7 +283,12 @@ static void tap(fs2_ctx* c, cudaStream_t s, const char* name, const void* ptr, i
 // ---------------------------------------------------------------------------- GEMM entry
 // FS2_MATH_TF32X3: the activations are split into [rows, hi | lo] (both exactly representable in TF32) in the context's
 // scratch buffer and the contraction runs three terms against the [hi ; lo] weight blocks prepared by fs2_prepare.
-static void conv_gemm(fs2_ctx* c, ConvGemmArgs a, cudaStream_t s) {
+static void conv_gemm(fs2_ctx* c, ConvGemmArgs a, cudaStream_t s, const ConvGemmArgs* second = nullptr) {
+  if (second != nullptr) {   // two contractions of one shape in one launch (never in the split-operand mode)
+    a.splitk_ws = c->splitk_ws;
+    tc2::launch(a, s, second);
+    return;
+  }
   if (c->cfg.math_mode == FS2_MATH_TF32X3 && a.rows > 0) {
     const size_t need = (size_t)a.rows * 2 * a.K;
     if (need > c->split_cap) {
@@ -331,8 +336,20 @@ static ConvGemmArgs gemm_args_b(const void* A, int lda, int rows, const float* W
 }
 
 // One FFT block in place on x (transformer/Layers.py:21-30).  t1, t2 are [rows,256] temporaries.
+// Stage-1 fusions (debug flag 9 / FS2_STAGE1_FUSION; default 3): bit 0 = the duration and pitch predictors share their
+// launches, bit 1 = the conditioning add lives in the last encoder layer's LayerNorm epilogue.
+static int& stage1_fusion_flag() {
+  static int f = [] { const char* e = std::getenv("FS2_STAGE1_FUSION"); return e != nullptr ? std::atoi(e) : 3; }();
+  return f;
+}
+
+// cond (last encoder layer only): the speaker / emotion vectors added to the block's output inside the FFN's LayerNorm
+// epilogue (ConvGemmArgs::post_a); the caller keeps the stand-alone add_cond_kernel when this layer runs as the fused FFN.
+struct CondAdd {
+  const float *spk, *emo;
+};
 static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSide& side, Pool& pool, int rows, int batch,
-                      int max_len, float* x, float* t1, float* t2, bool frame) {
+                      int max_len, float* x, float* t1, float* t2, bool frame, const CondAdd* cond = nullptr) {
   const int math = c->cfg.math_mode;
   const int32_t* live = reinterpret_cast<const int32_t*>(side.totals);   // low word of totals[0] (little endian)
   if (math == FS2_MATH_BF16) {
@@ -355,6 +372,7 @@ static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSi
     a = gemm_args_b(pool.hidb, D_INNER, rows, L.w2, L.b2, 1, D_INNER, D_MODEL, ACT_NONE, x, D_MODEL, xb, D_MODEL);
     a.residual = t2; a.ldr = D_MODEL; a.live_rows = live;
     a.ln_gamma = L.ln2_g; a.ln_beta = L.ln2_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
+    if (cond != nullptr) { a.post_a = cond->spk; a.post_b = cond->emo; a.post_utt = side.utt; a.post_extra = 2; }
     { ProfScope ps(c, s, frame ? "dec.gemm_w2_ln" : "enc.gemm_w2_ln"); conv_gemm(c, a, s); }
     return;
   }
@@ -369,6 +387,7 @@ static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSi
   a.ln_gamma = L.ln1_g; a.ln_beta = L.ln1_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
   { ProfScope ps(c, s, frame ? "dec.gemm_fc_ln" : "enc.gemm_fc_ln"); conv_gemm(c, a, s); }
   if (math == FS2_MATH_TF32 && ffn::use_fused(rows)) {
+    require(cond == nullptr, FS2_ERR_INVALID, "the fused FFN has no conditioning add");
     // conv9 -> ReLU -> w2 -> +residual -> LayerNorm -> mask in one kernel; the hidden tensor stays in tensor memory
     ffn::Args f{};
     f.x = t2; f.rows = rows; f.w1 = L.w1; f.b1 = L.b1; f.w2 = L.w2; f.b2 = L.b2; f.gamma = L.ln2_g; f.beta = L.ln2_b;
@@ -398,6 +417,7 @@ static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSi
   a = gemm_args(pool.hid, D_INNER, rows, L.w2, L.b2, 1, D_INNER, D_MODEL, ACT_NONE, x, D_MODEL);
   a.residual = t2; a.ldr = D_MODEL; a.live_rows = live;
   a.ln_gamma = L.ln2_g; a.ln_beta = L.ln2_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
+  if (cond != nullptr) { a.post_a = cond->spk; a.post_b = cond->emo; a.post_utt = side.utt; a.post_extra = 2; }
   { ProfScope ps(c, s, frame ? "dec.gemm_w2_ln" : "enc.gemm_w2_ln"); conv_gemm(c, a, s); }
 }
 
@@ -419,6 +439,36 @@ static void predictor(fs2_ctx* c, cudaStream_t s, const Predictor& P, const RowS
   f.ln_gamma = P.ln2_g; f.ln_beta = P.ln2_b; f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 0;
   f.head_w = P.head_w; f.head_b = P.head_b; f.head_out = head_out; f.slot = side.slot;
   conv_gemm(c, f, s);
+}
+
+// Two predictors that read the SAME rows (duration and pitch, model/modules.py:115-121): each of the two conv + ReLU +
+// LayerNorm layers runs both predictors in one launch (grid.y = 2).  h0 / h1 are the two hidden buffers.
+static void predictor_pair(fs2_ctx* c, cudaStream_t s, const Predictor& P0, const Predictor& P1, const RowSide& side, int rows,
+                           const float* x, float* h0, float* h1, float* head0, float* head1, const __nv_bfloat16* xb,
+                           __nv_bfloat16* h0b, __nv_bfloat16* h1b) {
+  ProfScope ps(c, s, "predictor");
+  const int32_t* live = reinterpret_cast<const int32_t*>(side.totals);
+  const bool bf = c->cfg.math_mode == FS2_MATH_BF16;
+  auto layer1 = [&](const Predictor& P, float* h, __nv_bfloat16* hb) {
+    ConvGemmArgs f = bf ? gemm_args_b(xb, D_MODEL, rows, P.w1, P.b1, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, nullptr, 0, hb, D_MODEL)
+                        : gemm_args(x, D_MODEL, rows, P.w1, P.b1, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, h, D_MODEL);
+    f.live_rows = live;
+    f.ln_gamma = P.ln1_g; f.ln_beta = P.ln1_b; f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 1;
+    return f;
+  };
+  auto layer2 = [&](const Predictor& P, const float* h, const __nv_bfloat16* hb, float* head_out) {
+    ConvGemmArgs f = bf ? gemm_args_b(hb, D_MODEL, rows, P.w2, P.b2, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, nullptr, 0, nullptr, 0)
+                        : gemm_args(h, D_MODEL, rows, P.w2, P.b2, VP_TAPS, D_MODEL, D_MODEL, ACT_RELU, nullptr, D_MODEL);
+    f.live_rows = live;
+    f.ln_gamma = P.ln2_g; f.ln_beta = P.ln2_b; f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 0;
+    f.head_w = P.head_w; f.head_b = P.head_b; f.head_out = head_out; f.slot = side.slot;
+    return f;
+  };
+  ConvGemmArgs a0 = layer1(P0, h0, h0b), a1 = layer1(P1, h1, h1b);
+  conv_gemm(c, a0, s, &a1);
+  a0 = layer2(P0, h0, h0b, head0);
+  a1 = layer2(P1, h1, h1b, head1);
+  conv_gemm(c, a0, s, &a1);
 }
 
 static void ensure_side(RowSide& sd, int batch, int rows, cudaStream_t s, int work_cap = 0) {
@@ -554,49 +604,61 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   }
   tap(c, s, "p_start", ps.starts, 1, B + 1);
   tap(c, s, "enc_in", x, rows, D_MODEL);
-  for (int i = 0; i < ENC_LAYERS; ++i) {
-    fft_block(c, s, c->enc[i], ps, pp, rows, B, L, x, t1, t2, false);
-    if (c->debug) tap(c, s, ("enc_" + std::to_string(i)).c_str(), x, rows, D_MODEL);
-  }
-
-  // ---- conditioning (model/fastspeech2.py:101-110)
+  // ---- conditioning vectors (model/fastspeech2.py:101-110): they depend on the inputs only, so they are computed before
+  // the encoder and added to its output inside the last layer's LayerNorm epilogue.  The stand-alone add remains for the
+  // cases that epilogue does not cover: the last layer running as the fused FFN (large batches), the per-layer debug taps
+  // (which want the unconditioned encoder output), and stage-1 fusion flag bit 1 cleared (A/B tests).
   cond_kernel<<<B, 256, 0, s>>>(in->speakers, in->emotions, in->arousals, in->valences, c->raw.at("speaker_emb.weight").ptr,
                                 c->cfg.n_speaker, c->raw.at("emotion_emb.weight").ptr, c->cfg.n_emotion,
                                 c->raw.at("arousal_emb.weight").ptr, c->cfg.n_arousal, c->raw.at("valence_emb.weight").ptr,
                                 c->cfg.n_valence, c->raw.at("emotion_linear.0.weight").ptr,
                                 c->raw.at("emotion_linear.0.bias").ptr, c->cond_spk, c->cond_emo, c->status);
   FS2_LAUNCHED();
-  float* xc = t3;
-  {
+  const bool cond_fused = (stage1_fusion_flag() & 2) != 0 && !c->debug &&
+                          !(c->cfg.math_mode == FS2_MATH_TF32 && ffn::use_fused(rows));
+  const CondAdd cond{c->cond_spk, c->cond_emo};
+  for (int i = 0; i < ENC_LAYERS; ++i) {
+    fft_block(c, s, c->enc[i], ps, pp, rows, B, L, x, t1, t2, false, cond_fused && i == ENC_LAYERS - 1 ? &cond : nullptr);
+    if (c->debug) tap(c, s, ("enc_" + std::to_string(i)).c_str(), x, rows, D_MODEL);
+  }
+  float* xc = cond_fused ? x : t3;                       // the conditioned rows
+  float* spare = cond_fused ? t3 : x;                    // the other [rows,256] buffer: the pitch add writes there
+  __nv_bfloat16* xcb = cond_fused ? pp.actb[0] : pp.actb[3];
+  __nv_bfloat16* spareb = cond_fused ? pp.actb[3] : pp.actb[0];
+  if (!cond_fused) {
     ProfScope pr(c, s, "add_cond");
-    add_cond_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, ps.meta(), c->cond_spk, c->cond_emo, 2, rows, xc, pp.actb[3]);
+    add_cond_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, ps.meta(), c->cond_spk, c->cond_emo, 2, rows, xc, xcb);
     FS2_LAUNCHED();
   }
   tap(c, s, "cond_x", xc, rows, D_MODEL);
 
   // ---- VarianceAdaptor (model/modules.py:102-135)
-  predictor(c, s, c->pred[0], ps, rows, xc, t1, out->log_d, pp.actb[3], pp.actb[1]);
   // phoneme_level features run here (modules.py:114-125); frame_level ones after the LengthRegulator in stage 2
   const bool pitch_here = !c->cfg.pitch_frame_level, energy_here = !c->cfg.energy_frame_level;
-  float* cur = xc;                       // lives in act[3]
-  __nv_bfloat16* curb = pp.actb[3];
+  // the duration and pitch predictors read the same rows: one launch per layer for both (FS2_PRED_PAIR=0 / the
+  // split-operand mode run them one after the other)
+  const bool paired = pitch_here && (stage1_fusion_flag() & 1) != 0 && c->cfg.math_mode != FS2_MATH_TF32X3;
+  if (paired) predictor_pair(c, s, c->pred[0], c->pred[1], ps, rows, xc, t1, t2, out->log_d, c->raw_pitch, xcb, pp.actb[1], pp.actb[2]);
+  else predictor(c, s, c->pred[0], ps, rows, xc, t1, out->log_d, xcb, pp.actb[1]);
+  float* cur = xc;
+  __nv_bfloat16* curb = xcb;
   if (pitch_here) {
-    predictor(c, s, c->pred[1], ps, rows, cur, t1, c->raw_pitch, curb, pp.actb[1]);
-    float* xe = x;  // encoder output is no longer needed
+    if (!paired) predictor(c, s, c->pred[1], ps, rows, cur, t1, c->raw_pitch, curb, pp.actb[1]);
+    float* xe = spare;
     ProfScope pr(c, s, "bucket_embed_add");
     bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
         cur, ps.meta(), ps.slot, 2, rows, c->raw_pitch, in->p_targets, in->p_control,
         c->raw.at("variance_adaptor.pitch_bins").ptr, N_BINS - 1, c->raw.at("variance_adaptor.pitch_embedding.weight").ptr,
-        out->pitch, nullptr, xe, pp.actb[0]);
+        out->pitch, nullptr, xe, spareb);
     FS2_LAUNCHED();
     cur = xe;
-    curb = pp.actb[0];
+    curb = spareb;
   }
   // phoneme_level energy: only the predictor runs here; its bucketize + embedding add (modules.py:93-100,126) is fused
   // into the length regulator of stage 2, and the returned prediction is written by the durations kernel below
   if (energy_here) predictor(c, s, c->pred[2], ps, rows, cur, t1, c->raw_energy, curb, pp.actb[1]);
   float* xf = cur;
-  c->va_spare = cur == t3 ? x : t3;   // free [rows,256] buffer (debug tap of the fused energy add)
+  c->va_spare = cur == xc ? spare : xc;   // free [rows,256] buffer (debug tap of the fused energy add)
   c->p_targets = in->p_targets;
   c->e_targets = in->e_targets;
   c->p_control = in->p_control;
@@ -1094,6 +1156,7 @@ int fs2_debug_set_flag(int which, int value) {
   if (which == 6) fs2::tc2::two_sm_flag() = value ? 1 : 0;
   if (which == 7) fs2::tc2::k_split_flag() = value ? 1 : 0;
   if (which == 8) fs2::attn_tc::pair_force_flag() = value;   // -1 automatic, 0 never, 1 always
+  if (which == 9) stage1_fusion_flag() = value;
   if (which == 1) {
     g_trace_on = value;
     if (value && g_trace_buf == nullptr) cudaMalloc(reinterpret_cast<void**>(&g_trace_buf), 64 * sizeof(long long));

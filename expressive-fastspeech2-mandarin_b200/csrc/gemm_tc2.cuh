@@ -174,11 +174,9 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on
 // and runs the epilogue.  For a SINGLE row tile (one utterance) with a long K loop the kernel is otherwise one CTA per
 // column tile pulling megabytes of operands through one SM at ~90 GB/s (measured: 17 us for the k = 9 FFN conv of a
 // 56-frame utterance, 72 ring steps); KS = 8 puts 8 SMs on that loop.
-template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1, bool TWO = false, int EW = 4, int KS = 1>
-__global__ void __launch_bounds__(64 + 32 * EW, 1)
-conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-                     const __grid_constant__ CUtensorMap tmC2, ConvGemmArgs p) {
+template <int BN, bool LN, int CL, bool BF, int AR, int NS, bool TWO, int EW, int KS>
+__device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC,
+                                                   const CUtensorMap& tmR, const CUtensorMap& tmC2, const ConvGemmArgs& p) {
   using C = Cfg<BN, AR, NS, TWO>;
   static_assert(!TWO || (CL == 2 && AR == 0 && NS == 1 && BN == 256), "2-SM MMA: CTA pairs, 256 columns");
   static_assert(!(AR && LN), "A-resident mode: plain epilogue");
@@ -592,6 +590,14 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int mr = row >> p.mask_shift;
         live = row_live(p.row_vpos[mr], p.row_room[mr], p.extra);
       }
+      const float *post_a = nullptr, *post_b = nullptr;   // this row's conditioning vectors (fused LayerNorm only)
+      if (LN && p.post_a != nullptr && in_range) {
+        const int pu = p.post_utt[row];
+        if (pu >= 0 && row_live(p.row_vpos[row], p.row_room[row], p.post_extra)) {
+          post_a = p.post_a + (size_t)pu * 256;
+          post_b = p.post_b + (size_t)pu * 256;
+        }
+      }
       mbar_wait(&acc_full[u], (lt >> 1) & 1);
       if (lt == 0 && warp == 2) stamp(4);
       if (lt < 6 && warp == 2) stamp(8 + lt * 4 + 2);
@@ -922,6 +928,15 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
+          if (post_a != nullptr) {   // (x + speaker) + emotion, in the reference's order; 32 consecutive rows mostly share u
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              const float4 a4 = __ldg(reinterpret_cast<const float4*>(post_a + n0 + c * 32 + cc * 4));
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(post_b + n0 + c * 32 + cc * 4));
+              v[cc * 4] = (v[cc * 4] + a4.x) + b4.x; v[cc * 4 + 1] = (v[cc * 4 + 1] + a4.y) + b4.y;
+              v[cc * 4 + 2] = (v[cc * 4 + 2] + a4.z) + b4.z; v[cc * 4 + 3] = (v[cc * 4 + 3] + a4.w) + b4.w;
+            }
+          }
           if (has_out) stage_out(v, c * 32, 32);
           if (has_out2) stage_out_b(v, c * 32, 32);
           if (lt == 0 && warp == 2) stamp(40 + c);
@@ -966,6 +981,28 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1, bool TWO = false, int EW = 4, int KS = 1>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
+conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                     const __grid_constant__ CUtensorMap tmC2, const __grid_constant__ ConvGemmArgs p) {
+  conv_gemm_tc2_body<BN, LN, CL, BF, AR, NS, TWO, EW, KS>(tmA, tmW, tmC, tmR, tmC2, p);
+}
+
+// Two independent contractions of the SAME shape in one launch (grid.y = 2; blockIdx.y picks the operand set): the duration
+// and pitch predictors read the same rows (model/modules.py:115-121), so their conv + LayerNorm layers run side by side
+// instead of back to back -- on the phoneme side a single predictor layer fills a quarter of the machine.
+struct ConvGemmMaps {
+  CUtensorMap A, W, C, R, C2;
+};
+template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1, bool TWO = false, int EW = 4, int KS = 1>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
+conv_gemm_tc2_dual_kernel(const __grid_constant__ ConvGemmMaps m0, const __grid_constant__ ConvGemmArgs p0,
+                          const __grid_constant__ ConvGemmMaps m1, const __grid_constant__ ConvGemmArgs p1) {
+  if (blockIdx.y == 0) conv_gemm_tc2_body<BN, LN, CL, BF, AR, NS, TWO, EW, KS>(m0.A, m0.W, m0.C, m0.R, m0.C2, p0);
+  else conv_gemm_tc2_body<BN, LN, CL, BF, AR, NS, TWO, EW, KS>(m1.A, m1.W, m1.C, m1.R, m1.C2, p1);
+}
+
 inline int sm_count() {
   static int n[64] = {};
   int dev = 0;
@@ -988,13 +1025,13 @@ inline int& epi_warps_flag() {   // 8 (default) = two epilogue warps per TMEM la
 }
 
 template <int BN, bool LN, int CL, bool BF, int AR = 0, int NS = 1, bool TWO = false, int EW = 0, int KS = 1>
-inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
+inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream, const ConvGemmArgs* second = nullptr) {
   if constexpr (EW == 0) {   // pick the epilogue width: 8 warps for the full-width streaming variants
     constexpr bool CAN8 = NS == 1 && AR == 0 && (!LN || BN == 256) && BN >= 64;
     if constexpr (CAN8) {
-      if (epi_warps_flag() == 8) { launch_bn_cl<BN, LN, CL, BF, AR, NS, TWO, 8, KS>(a, stream); return; }
+      if (epi_warps_flag() == 8) { launch_bn_cl<BN, LN, CL, BF, AR, NS, TWO, 8, KS>(a, stream, second); return; }
     }
-    launch_bn_cl<BN, LN, CL, BF, AR, NS, TWO, 4, KS>(a, stream);
+    launch_bn_cl<BN, LN, CL, BF, AR, NS, TWO, 4, KS>(a, stream, second);
     return;
   } else {
   using C = Cfg<BN, AR, NS, TWO>;
@@ -1006,22 +1043,42 @@ inline void launch_bn_cl(const ConvGemmArgs& a, cudaStream_t stream) {
     configured[dev & 63] = true;
   }
   constexpr CUtensorMapSwizzle SW128 = CU_TENSOR_MAP_SWIZZLE_128B;
-  const int split = a.terms > 1 ? 2 : 1;   // 3xTF32: activations [rows, hi | lo], weights [hi block ; lo block]
-  const CUtensorMap tmA = BF ? make_map_any(a.A, a.rows, a.K, a.lda, AR ? AR_ROWS : BM / NS, 64, MAP_BF16, SW128)
-                             : make_map(a.A, a.rows, (int64_t)a.K * split, a.lda, AR ? AR_ROWS : BM / NS, /*round_tf32=*/true, false);
-  const CUtensorMap tmW = BF ? make_map_any(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN / CL, 64, MAP_BF16, SW128)
-                             : make_map(a.W, (int64_t)a.taps * a.N * split, a.K, a.K, BN / CL, false, true);
-  const CUtensorMap tmC = a.C != nullptr ? make_map(a.C, a.rows, a.N, a.ldc, 32, false, false) : tmA;
-  const CUtensorMap tmR = a.residual == nullptr ? tmA
-                          : a.res_bf16 ? make_map_any(a.residual, a.rows, a.N, a.ldr, 32, 32, MAP_BF16, CU_TENSOR_MAP_SWIZZLE_64B)
-                                       : make_map(a.residual, a.rows, a.N, a.ldr, 32, false, false);
-  const CUtensorMap tmC2 =
-      a.C2 != nullptr ? make_map_any(a.C2, a.rows, a.N, a.ldc2, 32, 32, MAP_BF16, CU_TENSOR_MAP_SWIZZLE_64B) : tmA;
+  auto maps_of = [&](const ConvGemmArgs& a) {
+    ConvGemmMaps m;
+    const int split = a.terms > 1 ? 2 : 1;   // 3xTF32: activations [rows, hi | lo], weights [hi block ; lo block]
+    m.A = BF ? make_map_any(a.A, a.rows, a.K, a.lda, AR ? AR_ROWS : BM / NS, 64, MAP_BF16, SW128)
+             : make_map(a.A, a.rows, (int64_t)a.K * split, a.lda, AR ? AR_ROWS : BM / NS, /*round_tf32=*/true, false);
+    m.W = BF ? make_map_any(a.W, (int64_t)a.taps * a.N, a.K, a.K, BN / CL, 64, MAP_BF16, SW128)
+             : make_map(a.W, (int64_t)a.taps * a.N * split, a.K, a.K, BN / CL, false, true);
+    m.C = a.C != nullptr ? make_map(a.C, a.rows, a.N, a.ldc, 32, false, false) : m.A;
+    m.R = a.residual == nullptr ? m.A
+          : a.res_bf16 ? make_map_any(a.residual, a.rows, a.N, a.ldr, 32, 32, MAP_BF16, CU_TENSOR_MAP_SWIZZLE_64B)
+                       : make_map(a.residual, a.rows, a.N, a.ldr, 32, false, false);
+    m.C2 = a.C2 != nullptr ? make_map_any(a.C2, a.rows, a.N, a.ldc2, 32, 32, MAP_BF16, CU_TENSOR_MAP_SWIZZLE_64B) : m.A;
+    return m;
+  };
+  const ConvGemmMaps m = maps_of(a);
   constexpr int CSIZE = CL > 1 ? CL : (NS > 1 ? NS : KS);
   const int items = NS > 1 ? (a.rows + BM - 1) / BM : (((a.rows + BM - 1) / BM + CL - 1) / CL) * ((a.N + BN - 1) / BN);
   const int grid = std::min(items, sm_count() / CSIZE) * CSIZE;
   require(KS == 1 || (items * KS <= sm_count() && a.splitk_ws != nullptr), FS2_ERR_INVALID, "K-split: one resident cluster per tile and a workspace");
-  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS, TWO, EW, KS>, dim3(grid), dim3(64 + 32 * EW), C::TOTAL, stream, CSIZE, tmA, tmW, tmC, tmR, tmC2, a);
+  if (second != nullptr) {
+    if constexpr (LN && KS == 1 && AR == 0) {   // the dual entry point exists for the fused-LayerNorm forms (the predictors)
+      static bool configured2[64] = {};
+      if (!configured2[dev & 63]) {
+        FS2_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_dual_kernel<BN, LN, CL, BF, AR, NS, TWO, EW, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+        configured2[dev & 63] = true;
+      }
+      const ConvGemmMaps m1 = maps_of(*second);
+      launch_pdl(conv_gemm_tc2_dual_kernel<BN, LN, CL, BF, AR, NS, TWO, EW, KS>, dim3(grid, 2), dim3(64 + 32 * EW), C::TOTAL, stream, CSIZE,
+                 m, a, m1, *second);
+      FS2_LAUNCHED();
+      return;
+    } else {
+      throw Error(FS2_ERR_UNSUPPORTED, "paired launch: fused-LayerNorm contractions only");
+    }
+  }
+  launch_pdl(conv_gemm_tc2_kernel<BN, LN, CL, BF, AR, NS, TWO, EW, KS>, dim3(grid), dim3(64 + 32 * EW), C::TOTAL, stream, CSIZE, m.A, m.W, m.C, m.R, m.C2, a);
   FS2_LAUNCHED();
   }
 }
@@ -1070,7 +1127,7 @@ inline int& two_sm_flag() {
 }
 
 template <int BN, bool LN>
-inline void launch_bn(const ConvGemmArgs& a, cudaStream_t stream) {
+inline void launch_bn(const ConvGemmArgs& a, cudaStream_t stream, const ConvGemmArgs* second = nullptr) {
   // a single row tile has no partner to share weights with
   const bool pair = cluster_size_flag() == 2 && a.rows > BM;
   if constexpr (BN == 256 && !LN) {
@@ -1080,13 +1137,20 @@ inline void launch_bn(const ConvGemmArgs& a, cudaStream_t stream) {
     }
   }
   if (a.a_bf16) {
-    if (pair) launch_bn_cl<BN, LN, 2, true>(a, stream); else launch_bn_cl<BN, LN, 1, true>(a, stream);
+    if (pair) launch_bn_cl<BN, LN, 2, true>(a, stream, second); else launch_bn_cl<BN, LN, 1, true>(a, stream, second);
   } else {
-    if (pair) launch_bn_cl<BN, LN, 2, false>(a, stream); else launch_bn_cl<BN, LN, 1, false>(a, stream);
+    if (pair) launch_bn_cl<BN, LN, 2, false>(a, stream, second); else launch_bn_cl<BN, LN, 1, false>(a, stream, second);
   }
 }
 
-inline void launch(const ConvGemmArgs& a, cudaStream_t stream) {   // the operand type travels with the arguments (a_bf16, terms)
+// second: an independent contraction of the same shape and options (fused-LayerNorm forms only) that shares the launch
+inline void launch(const ConvGemmArgs& a, cudaStream_t stream, const ConvGemmArgs* second = nullptr) {   // the operand type travels with the arguments (a_bf16, terms)
+  if (second != nullptr)
+    require(a.ln_gamma != nullptr && second->ln_gamma != nullptr && a.rows == second->rows && a.K == second->K && a.N == second->N &&
+                a.taps == second->taps && a.a_bf16 == second->a_bf16 && a.terms <= 1 && second->terms <= 1 &&
+                (a.head_out != nullptr) == (second->head_out != nullptr) && (a.residual != nullptr) == (second->residual != nullptr) &&
+                (a.C != nullptr) == (second->C != nullptr) && (a.C2 != nullptr) == (second->C2 != nullptr),
+            FS2_ERR_INVALID, "paired launch: two fused-LayerNorm contractions of one shape");
   require(a.terms <= 1 || (a.terms == 3 && !a.a_bf16), FS2_ERR_INVALID, "split-operand contraction: three TF32 terms");
   const int am = a.a_bf16 ? 8 : 4;   // elements per 16 bytes of the A / W rows
   require(a.K % am == 0 && a.lda % am == 0 && (a.C == nullptr || a.ldc % 4 == 0) && (a.residual == nullptr || a.ldr % (a.res_bf16 ? 8 : 4) == 0) &&
@@ -1103,20 +1167,22 @@ inline void launch(const ConvGemmArgs& a, cudaStream_t stream) {   // the operan
     require(a.N == 256 && a.ln_beta != nullptr, FS2_ERR_INVALID, "fused LayerNorm needs N == 256 and both affine vectors");
     require(a.C != nullptr || a.C2 != nullptr || a.head_out != nullptr, FS2_ERR_INVALID, "fused LayerNorm: nothing to write");
     require(a.head_out == nullptr || (a.head_w != nullptr && a.head_b != nullptr), FS2_ERR_INVALID, "head needs weight and bias");
+    require(a.post_a == nullptr || (a.post_b != nullptr && a.post_utt != nullptr && a.row_vpos != nullptr && a.mask_shift == 0),
+            FS2_ERR_INVALID, "post-LayerNorm add needs both vectors and the row metadata");
     // few row tiles (single utterances, the encoder of a small batch): split the 256 columns over a cluster of 4 or 2 CTAs
     const int m_tiles_ln = (a.rows + BM - 1) / BM;
     static const int ns_force = [] { const char* e = std::getenv("FS2_LN_NS"); return e != nullptr ? std::atoi(e) : 0; }();
     int ns = (n_split_flag() == 0 || a.head_out != nullptr) ? 1 : (m_tiles_ln * 4 <= sm_count() ? 4 : (m_tiles_ln * 2 <= sm_count() ? 2 : 1));
     if (ns_force > 0 && a.head_out == nullptr && m_tiles_ln * 2 > sm_count()) ns = ns_force;   // experiment: N-split beyond one wave
     if (ns == 4) {
-      if (a.a_bf16) launch_bn_cl<64, true, 1, true, 0, 4>(a, stream); else launch_bn_cl<64, true, 1, false, 0, 4>(a, stream);
+      if (a.a_bf16) launch_bn_cl<64, true, 1, true, 0, 4>(a, stream, second); else launch_bn_cl<64, true, 1, false, 0, 4>(a, stream, second);
     } else if (ns == 2) {
-      if (a.a_bf16) launch_bn_cl<128, true, 1, true, 0, 2>(a, stream); else launch_bn_cl<128, true, 1, false, 0, 2>(a, stream);
+      if (a.a_bf16) launch_bn_cl<128, true, 1, true, 0, 2>(a, stream, second); else launch_bn_cl<128, true, 1, false, 0, 2>(a, stream, second);
     } else if (two_sm_flag() && cluster_size_flag() == 2 && a.rows > BM && a.taps * a.K >= 512) {
       // long K loop (w2 + LayerNorm, K = 1024): operand-delivery bound; the 2-SM form halves the weight bytes each CTA takes in
-      if (a.a_bf16) launch_bn_cl<256, true, 2, true, 0, 1, true>(a, stream); else launch_bn_cl<256, true, 2, false, 0, 1, true>(a, stream);
+      if (a.a_bf16) launch_bn_cl<256, true, 2, true, 0, 1, true>(a, stream, second); else launch_bn_cl<256, true, 2, false, 0, 1, true>(a, stream, second);
     } else {
-      launch_bn<256, true>(a, stream);
+      launch_bn<256, true>(a, stream, second);
     }
     return;
   }

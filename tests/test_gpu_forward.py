@@ -215,6 +215,30 @@ def test_batch_padding_independence(sd32, syn):
     assert torch.equal(one[0][0, :t1], again[0][1, :t1])
 
 
+@pytest.mark.parametrize("math_mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("lens", [[16], [21, 9, 17, 33, 5], None])
+def test_stage1_fusions_are_bit_exact(sd32, syn, math_mode, lens):
+    """Duration + pitch predictors in shared launches (grid.y = 2) and the speaker / emotion add inside the last encoder
+    layer's LayerNorm epilogue (model/fastspeech2.py:101-110, modules.py:115-121) do the same arithmetic in the same order as
+    the separate launches: every output of the free-running forward is bit-identical with the fusions off (debug flag 9).
+    lens = None is the config-2 batch (35 phoneme row tiles: the N-split LayerNorm forms)."""
+    from gpu_util import lib
+    L = lib()
+    model = model_for(sd32, math_mode=math_mode)
+    batch = syn.config2_batch(seed=0) if lens is None else syn.make_batch(lens, seed=5)
+    fused = [t.clone() for t in run(model, batch, p_control=1.1, d_control=0.9)]
+    n_fused = model.last_launch_count
+    try:
+        L.fs2_debug_set_flag(9, 0)
+        plain = [t.clone() for t in run(model, batch, p_control=1.1, d_control=0.9)]
+        n_plain = model.last_launch_count
+    finally:
+        L.fs2_debug_set_flag(9, 3)
+    assert n_plain - n_fused == 3        # two predictor launches and the stand-alone add
+    for i, (a, b) in enumerate(zip(fused, plain)):
+        assert torch.equal(a, b), i
+
+
 def test_input_validation(sd32, syn):
     model = model_for(sd32)
     batch = syn.make_batch([8, 6], seed=1)

@@ -14,7 +14,7 @@ m.load_state_dict(syn.synthetic_state_dict(0))
 m = m.to(dev)
 b = syn.config2_batch(seed=0)
 args = [b[k].to(dev) for k in ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")]
-for _ in range(3):
+for _ in range(int(os.environ.get("WARM", "200"))):   # sustained load: the SM clock under the bench's conditions
     out = m(*args, b["max_src_len"])
 torch.cuda.synchronize()
 lib = _lib.load_library()
@@ -25,11 +25,17 @@ t = np.array(list(buf), dtype=np.int64).reshape(2048, 6)
 t = t[t[:, 3] > 0]
 t0 = t[:, 0].min()
 ent, dep, first, ex, sm, tiles = (t[:, i] for i in range(6))
+cyc, sm = sm >> 16, sm & 0xFFFF
+t[:, 4] = sm
 print(f"CTAs {len(t)} (real: {(tiles > 0).sum()}), kernel span {(ex.max() - t0) / 1e3:.1f} us, SMs used {len(np.unique(sm))}")
 real = tiles > 0
 life = (ex - ent)[real] / 1e3
 print(f"real CTA lifetime: mean {life.mean():.2f} us, per key tile (lifetime / tiles) mean {(life / tiles[real]).mean():.2f} us")
 print(f"entry -> first S: mean {((first - ent)[real] / 1e3).mean():.2f} us; entry -> dependency wait done: {((dep - ent)[real] / 1e3).mean():.2f} us")
+mhz = cyc[real] / np.maximum((ex - ent)[real], 1) * 1e3
+print(f"effective SM clock over the CTAs' lives (clock64 cycles / globaltimer ns): mean {mhz.mean():.0f} MHz, min {mhz.min():.0f}, max {mhz.max():.0f}")
+fitc = np.polyfit(tiles[real], cyc[real], 1)
+print(f"lifetime ~= {fitc[1]:.0f} cycles + {fitc[0]:.0f} cycles per 64-key tile")
 fit = np.polyfit(tiles[real], life, 1)
 print(f"lifetime ~= {fit[1]:.2f} us + {fit[0]:.3f} us per 64-key tile (least squares over the real CTAs)")
 gaps, busy = [], []
