@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "gemm_tc2.cuh"
 #include "attention_tc2.cuh"
+#include "attention_tcp.cuh"
 #include "ffn_fused.cuh"
 #include "rowops.cuh"
 #include "vocoder.cuh"
@@ -312,6 +313,8 @@ static void attention(const float* qkv, int rows, const RowSide& side, int batch
   (void)batch; (void)max_len;
   if (attn_tc::use_two_sm(side.work_q_rows))
     attn2::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, out, s, out_bf16);
+  else if (side.work_q_rows == attn_tc::BQ && attn_tc::debug_flag() == 0 && attn_p::use_persistent(side.work_cap, tc2::sm_count()))
+    attn_p::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, out, s, tc2::sm_count(), out_bf16);
   else
     attn_tc::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, side.work_q_rows, out, s, out_bf16);
 }
@@ -1157,6 +1160,7 @@ int fs2_debug_set_flag(int which, int value) {
   if (which == 7) fs2::tc2::k_split_flag() = value ? 1 : 0;
   if (which == 8) fs2::attn_tc::pair_force_flag() = value;   // -1 automatic, 0 never, 1 always
   if (which == 9) stage1_fusion_flag() = value;
+  if (which == 10) fs2::attn_p::enabled_flag() = value;
   if (which == 1) {
     g_trace_on = value;
     if (value && g_trace_buf == nullptr) cudaMalloc(reinterpret_cast<void**>(&g_trace_buf), 64 * sizeof(long long));
@@ -1343,6 +1347,8 @@ int fs2_op_attention(fs2_stream stream, const float* qkv, int rows, const int32_
     attention_work_kernel<<<1, 256, 0, s>>>(lens, batch, work, cap, count, q_rows);
     FS2_LAUNCHED();
     if (attn_tc::use_two_sm(q_rows)) attn2::launch(qkv, rows, starts, lens, work, count, cap, out, s);
+    else if (q_rows == attn_tc::BQ && attn_tc::debug_flag() == 0 && attn_p::use_persistent(cap, tc2::sm_count()))
+      attn_p::launch(qkv, rows, starts, lens, work, count, cap, out, s, tc2::sm_count());
     else attn_tc::launch(qkv, rows, starts, lens, work, count, cap, q_rows, out, s);
     FS2_CUDA_OK(cudaStreamSynchronize(s));
     cudaFree(work);

@@ -148,6 +148,32 @@ def test_attention(lens, pair):
         lib().fs2_debug_set_flag(8, -1)
 
 
+def _persistent_lens(kind):
+    g = torch.Generator().manual_seed(11)
+    if kind == "config2_like":
+        return [int(x) for x in torch.randint(80, 701, (64,), generator=g)]
+    if kind == "many_short_with_empties":
+        return [int(x) for x in torch.randint(0, 130, (400,), generator=g)]
+    if kind == "one_item_more_than_sms":       # 75 single-tile utterances -> 150 (tile, head) items on 148 CTAs
+        return [int(x) for x in torch.randint(1, 129, (75,), generator=g)]
+    return [37] * 70 + [513, 2, 1024] + [64, 65, 127, 128, 129, 191, 192, 193] * 3
+
+
+@pytest.mark.parametrize("kind", ["config2_like", "many_short_with_empties", "one_item_more_than_sms", "mixed_boundaries"])
+def test_attention_persistent(kind):
+    """attention_tcp.cuh: one CTA per SM walks the work list with Q travelling through the K ring and the pipelines running
+    across items.  Same products in the same order as the one-CTA-per-item kernel: the outputs are bit-identical to it
+    (debug flag 10 = 0) and within the TF32 tolerance of float64."""
+    lens = _persistent_lens(kind)
+    got = _attention_case(lens)
+    lib().fs2_debug_set_flag(10, 0)
+    try:
+        ref = _attention_case(lens)
+    finally:
+        lib().fs2_debug_set_flag(10, 1)
+    assert torch.equal(got, ref)
+
+
 def _attention_case(lens):
     g = torch.Generator().manual_seed(sum(lens))
     gap = 4
@@ -178,6 +204,7 @@ def _attention_case(lens):
     assert (got[~live] == 0).all(), "rows outside the utterances must not be written"
     err = (got[live] - want[live]).abs().max().item()
     assert err < 5e-3, f"max abs err {err}"   # TF32 operands on unit-variance data, d_k = 128
+    return got
 
 
 X3_CASES = [c for c in CASES if c[-1] in ("qkv", "ffn_conv9", "ffn_w2", "postnet_first", "postnet_last", "w2_many_tiles")]
