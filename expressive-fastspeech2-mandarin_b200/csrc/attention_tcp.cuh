@@ -3,7 +3,7 @@
 // tensor memory, online softmax by 128 row-owner threads -- but ONE CTA per SM walks the longest-first work list and its
 // pipelines run ACROSS items:
 //   * Q travels through the K ring as two 64-row tiles (a Q tile is two K stages), so the producer prefetches the next
-//     item's Q and first K/V tiles while the current item is still in its last key tiles (4 K stages + 3 V stages = 224 KB);
+//     item's Q and first K/V tiles while the current item is still in its last key tiles (3 K stages + 3 V stages);
 //   * the softmax threads move the next item's Q into tensor memory right after the P tile of the current item's LAST key
 //     tile is handed over (every Q K^T of the item has completed by then), i.e. before they drain the last P V product,
 //     normalise and store -- the first S tile of the next item is computed under that tail.
@@ -26,9 +26,16 @@ using attn_tc::umma_tf32_ts;
 
 constexpr int THREADS = 224;                      // producer | Q K^T issuer | 4 softmax warps | P V issuer
 constexpr int TILE_BYTES = BKV * D_HEAD * 4;      // 32 KB: 4 sub-tiles [64 rows x 128 B]
-constexpr int K_STAGES = 4, V_STAGES = 3;
-constexpr int BAR_OFF = (K_STAGES + V_STAGES) * TILE_BYTES;
-constexpr int SMEM_TOTAL = BAR_OFF + 256 + 1024;
+constexpr int K_STAGES = 3, V_STAGES = 3;
+// Output staging: each softmax warp owns two 4 KB buffers [32 rows x 32 columns], 128-byte swizzled, and sends every
+// 32-column piece of its rows with ONE 2-D TMA store (a warp whose 32 rows are not all inside the utterance -- the last
+// query tile of an utterance -- stores from registers instead).  Storing from registers costs the softmax threads
+// ~5,000 cycles per item (each 16-byte store instruction of a warp touches 32 different 128-byte lines), and so do
+// per-row bulk copies (128 descriptors per item through one TMA unit: measured 2,000-2,500 cycles per 64 columns).
+constexpr int STG_CHUNK = 32 * 128;                        // one [32 x 32] fp32 piece
+constexpr int STG_OFF = (K_STAGES + V_STAGES) * TILE_BYTES;
+constexpr int BAR_OFF = STG_OFF + 4 * 2 * STG_CHUNK;       // 4 warps x 2 buffers
+constexpr int SMEM_TOTAL = BAR_OFF + 256;         // (dynamic shared memory starts 1024-byte aligned: checked at entry)
 constexpr int TMEM_COLS = 512;                    // S0,S1: 2 x 64 | O0,O1: 2 x 128 | Q: 128
 
 struct Item {
@@ -37,27 +44,36 @@ struct Item {
 };
 
 #ifdef FS2_TRACE_BUILD
+// per-tile clock64 stamps of ONE CTA (tools/trace_attention_persistent.py): [tile g][0 softmax waits for S, 1 S there, 2 P handed
+// over, 3 iteration done, 4 Q K^T issuer starts waiting, 5 its operands are there, 6 issued + committed, 7 P V issuer's operands there]
+__device__ long long g_attn_p_tile_trace[64 * 8];
+#define FS2_P_TILE(g, k) do { if (blockIdx.x == 5 && (threadIdx.x & 31) == 0 && (g) < 64) ::fs2::attn_p::g_attn_p_tile_trace[(g) * 8 + (k)] = clock64(); } while (0)
+__device__ long long g_attn_p_item_trace[16 * 8];   // per item of that CTA: stamps around the item's tail (see the tool)
+#define FS2_P_ITEM(k, i) do { if (blockIdx.x == 5 && threadIdx.x == 64 && (k) < 16) ::fs2::attn_p::g_attn_p_item_trace[(k) * 8 + (i)] = clock64(); } while (0)
 #define FS2_P_STAMP(k) do { if (threadIdx.x == 64 && blockIdx.x < 2048) ::fs2::attn_tc::g_attn_cta_trace[blockIdx.x * 6 + (k)] = ::fs2::attn_tc::gtimer(); } while (0)
 #else
 #define FS2_P_STAMP(k) do { } while (0)
+#define FS2_P_TILE(g, k) do { } while (0)
+#define FS2_P_ITEM(k, i) do { } while (0)
 #endif
 
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tcp_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
-                     const int32_t* __restrict__ starts, const int32_t* __restrict__ lens, const uint32_t* __restrict__ work,
-                     const int32_t* __restrict__ work_count, float* __restrict__ out, __nv_bfloat16* __restrict__ out_b) {
-  extern __shared__ uint8_t smem_raw[];
+                     const __grid_constant__ CUtensorMap tmO, const int32_t* __restrict__ starts, const int32_t* __restrict__ lens, const uint32_t* __restrict__ work,
+                     const int32_t* __restrict__ work_count, float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   FS2_P_STAMP(0);
 #ifdef FS2_TRACE_BUILD
   const long long c_entry = clock64();
   int traced_tiles = 0;
 #endif
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // the swizzled tiles need 1024-byte alignment and there is no room for slack
   auto k_stage = [&](int s) -> uint8_t* { return smem + s * TILE_BYTES; };
   auto v_stage = [&](int s) -> uint8_t* { return smem + (K_STAGES + s) * TILE_BYTES; };
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
-  uint64_t* k_full = bars;             // [4]  K tile (or half a Q tile) has landed
-  uint64_t* k_empty = bars + 4;        // [4]  free after Q K_j^T (a Q half: after the copy to tensor memory)
+  uint64_t* k_full = bars;             // [3]  K tile (or half a Q tile) has landed
+  uint64_t* k_empty = bars + 4;        // [3]  free after Q K_j^T (a Q half: after the copy to tensor memory)
   uint64_t* v_full = bars + 8;         // [3]
   uint64_t* v_empty = bars + 11;       // [3]  free after P_j V_j
   uint64_t* s_full = bars + 14;        // [2]
@@ -70,6 +86,7 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_cons
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmQK)) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
     for (int u = 0; u < K_STAGES; ++u) {
       mbar_init(&k_full[u], 1);
       mbar_init(&k_empty[u], 1);
@@ -174,8 +191,10 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_cons
       kc += 2;
       for (int j = 0; j < it.n_tiles; ++j, ++g, ++kc) {
         const int u = g & 1, sk = kc % K_STAGES;
+        FS2_P_TILE(g, 4);
         mbar_wait(&k_full[sk], (kc / K_STAGES) & 1);
         if (g >= 2) mbar_wait(&o_full[u], ((g - 2) >> 1) & 1);   // P V_{g-2} has read P from these columns
+        FS2_P_TILE(g, 5);
         tc_fence_after();
         const uint8_t* k_s = k_stage(sk);
         if (leader) {
@@ -190,6 +209,7 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_cons
           umma_commit(&k_empty[sk]);
         }
         __syncwarp();
+        FS2_P_TILE(g, 6);
       }
       it = nx;
     }
@@ -205,6 +225,7 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_cons
         const int u = g & 1, sv = vc % V_STAGES;
         mbar_wait(&v_full[sv], (vc / V_STAGES) & 1);
         mbar_wait(&p_full[u], (g >> 1) & 1);      // P_g written; O buffer u drained
+        FS2_P_TILE(g, 7);
         tc_fence_after();
         const uint64_t dv = umma_desc_mn(v_stage(sv), BKV * 128, 512);
         if (leader) {
@@ -235,17 +256,22 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_cons
       const uint32_t qa = smem_u32(k_stage(sk)) + rr * 128;
       const uint32_t sx = (uint32_t)(rr & 7) << 4;
 #pragma unroll 1
-      for (int dc = 0; dc < 4; ++dc) {
-        float v[32];
+      for (int dc = 0; dc < 4; dc += 2) {   // two 32-column pieces per round: 16 shared-memory loads in flight
+        float va[32], vb[32];
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
-          float4 t4;
+          float4 t4, u4;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
                        : "=f"(t4.x), "=f"(t4.y), "=f"(t4.z), "=f"(t4.w)
                        : "r"(qa + dc * (BKV * 128) + ((cc << 4) ^ sx)));
-          v[cc * 4] = t4.x; v[cc * 4 + 1] = t4.y; v[cc * 4 + 2] = t4.z; v[cc * 4 + 3] = t4.w;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                       : "=f"(u4.x), "=f"(u4.y), "=f"(u4.z), "=f"(u4.w)
+                       : "r"(qa + (dc + 1) * (BKV * 128) + ((cc << 4) ^ sx)));
+          va[cc * 4] = t4.x; va[cc * 4 + 1] = t4.y; va[cc * 4 + 2] = t4.z; va[cc * 4 + 3] = t4.w;
+          vb[cc * 4] = u4.x; vb[cc * 4 + 1] = u4.y; vb[cc * 4 + 2] = u4.z; vb[cc * 4 + 3] = u4.w;
         }
-        tmem_st32(tmem_q + lane_sel + dc * 32, v);
+        tmem_st32(tmem_q + lane_sel + dc * 32, va);
+        tmem_st32(tmem_q + lane_sel + dc * 32 + 32, vb);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads before the TMA overwrites the stage
@@ -253,6 +279,53 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_cons
       mbar_arrive(q_moved);
     };
 
+    uint8_t* stg = smem + STG_OFF;
+    const uint32_t sbuf = smem_u32(stg) + q * (2 * STG_CHUNK);   // this warp's two [32 x 32] staging buffers
+    const uint32_t swz = (uint32_t)(lane & 7) << 4;
+    // two [32 rows x 32 columns] pieces of this warp's rows (columns col .. col + 63): registers -> swizzled staging ->
+    // two 2-D TMA stores behind ONE proxy fence (fence.proxy.async is a MEMBAR.ALL.CTA: a few hundred cycles)
+    auto tma_send2 = [&](const float (&va)[32], const float (&vb)[32], int col, int row) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the previous pair has read both buffers
+      __syncwarp();
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(sbuf + lane * 128 + ((cc << 4) ^ swz)), "f"(va[cc * 4]),
+                     "f"(va[cc * 4 + 1]), "f"(va[cc * 4 + 2]), "f"(va[cc * 4 + 3])
+                     : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(sbuf + STG_CHUNK + lane * 128 + ((cc << 4) ^ swz)),
+                     "f"(vb[cc * 4]), "f"(vb[cc * 4 + 1]), "f"(vb[cc * 4 + 2]), "f"(vb[cc * 4 + 3])
+                     : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes -> visible to the TMA stores
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                         reinterpret_cast<uint64_t>(&tmO)),
+                     "r"(sbuf), "r"(col), "r"(row)
+                     : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                         reinterpret_cast<uint64_t>(&tmO)),
+                     "r"(sbuf + STG_CHUNK), "r"(col + 32), "r"(row)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+      }
+    };
+    // The second 64 columns of an item's output wait in tensor memory (in the O buffer the item's last product was drained
+    // from, which the next item's SECOND key tile is the first to write again) and are sent after the next item's first P
+    // tile has been handed over: sent at once they would wait ~1,000 cycles for the TMA unit to get through the queued
+    // K/V loads and read the two staging buffers.
+    bool parked = false;
+    uint32_t park_t = 0;
+    int park_col = 0, park_row = 0;
+    auto flush_parked = [&]() {
+      float v0[32], v1[32];
+      tmem_ld32_issue(park_t, v0);
+      tmem_ld32_issue(park_t + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      tma_send2(v0, v1, park_col, park_row);
+      parked = false;
+    };
     Item it = load_item(0);
     if (it.valid) move_q(0);
     for (int k = 0; it.valid; ++k) {
@@ -287,7 +360,9 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_cons
       // m is the running row maximum of the RAW scores; exp2 arguments are s*c - m*c (one FFMA each)
       for (int j = 0; j < n_tiles; ++j, ++g) {
         const int u = g & 1;
+        if (warp == 2) FS2_P_TILE(g, 0);
         mbar_wait(&s_full[u], (g >> 1) & 1);
+        if (warp == 2) FS2_P_TILE(g, 1);
 #ifdef FS2_TRACE_BUILD
         if (g == 0) FS2_P_STAMP(2);
         ++traced_tiles;
@@ -341,38 +416,88 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_cons
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         tc_fence_before();
         mbar_arrive(&p_full[u]);
+        if (warp == 2) FS2_P_TILE(g, 2);
+        if (parked) flush_parked();   // (warp-uniform) the previous item's second half
         // The S tile of this item's last key tile has been read, so every Q K^T of the item has completed and the Q
         // columns are free: hand the next item's Q over now, and drain the last two P V products under its first Q K^T.
-        if (j == n_tiles - 1 && nx.valid) move_q(kc + n_tiles);
+        if (j == n_tiles - 1 && nx.valid) { FS2_P_ITEM(k, 6); move_q(kc + n_tiles); FS2_P_ITEM(k, 7); }
         if (j >= 1) accumulate(g - 1, alpha_prev);
+        if (warp == 2) FS2_P_TILE(g, 3);
         alpha_prev = alpha;
       }
-      accumulate(g - 1, alpha_prev);
       kc += n_tiles;
-
-      if (qrow < len) {
-        const float inv = 1.f / l;
-        if (out_b != nullptr) {   // BF16 consumers: the context is only ever the A operand of the fc contraction
-          __nv_bfloat16* dst = out_b + (size_t)(it.row0 + qrow) * D_MODEL + it.h * D_HEAD;
+      {
+        // Drain the last P V product, normalise and send the rows: the second half of the product is loaded from tensor
+        // memory while the first half is staged and handed to the TMA unit.
+        const int u = (g - 1) & 1;
+        FS2_P_ITEM(k, 0);
+        mbar_wait(&o_full[u], ((g - 1) >> 1) & 1);
+        FS2_P_ITEM(k, 1);
+        tc_fence_after();
+        float v0[32], v1[32];
+        tmem_ld32_issue(tmem_o + lane_sel + u * D_HEAD, v0);
+        tmem_ld32_issue(tmem_o + lane_sel + u * D_HEAD + 32, v1);
+        tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < D_HEAD; i += 8) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __nv_bfloat162 hh = __floats2bfloat162_rn(o[i + 2 * e] * inv, o[i + 2 * e + 1] * inv);
-              w[e] = *reinterpret_cast<const uint32_t*>(&hh);
-            }
-            *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-        } else {
-          float* dst = out + (size_t)(it.row0 + qrow) * D_MODEL + it.h * D_HEAD;
-#pragma unroll
-          for (int i = 0; i < D_HEAD; i += 4)
-            *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+        for (int i = 0; i < 32; ++i) {
+          o[i] = fmaf(o[i], alpha_prev, v0[i]);
+          o[32 + i] = fmaf(o[32 + i], alpha_prev, v1[i]);
         }
+        tmem_ld32_issue(tmem_o + lane_sel + u * D_HEAD + 64, v0);
+        tmem_ld32_issue(tmem_o + lane_sel + u * D_HEAD + 96, v1);
+        const float inv = 1.f / l;
+        // rows of this warp inside the utterance: 32 -> TMA stores, 1..31 -> stores from registers, 0 -> nothing
+        const int n_valid = min(max(len - (it.q0 + q * 32), 0), 32);
+        const int o_col = it.h * D_HEAD, o_row = it.row0 + it.q0 + q * 32;
+        auto send64 = [&](int c0) {   // columns [c0, c0 + 64) of this thread's row
+          if (n_valid == 32) {
+            float va[32], vb[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              va[i] = o[c0 + i] * inv;
+              vb[i] = o[c0 + 32 + i] * inv;
+            }
+            tma_send2(va, vb, o_col + c0, o_row);
+          } else if (qrow < len) {
+            float* dst = out + (size_t)(it.row0 + qrow) * D_MODEL + o_col + c0;
+#pragma unroll
+            for (int i = 0; i < 64; i += 4)
+              *reinterpret_cast<float4*>(dst + i) = make_float4(o[c0 + i] * inv, o[c0 + i + 1] * inv, o[c0 + i + 2] * inv, o[c0 + i + 3] * inv);
+          }
+        };
+        FS2_P_ITEM(k, 2);
+        send64(0);
+        FS2_P_ITEM(k, 3);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          o[64 + i] = fmaf(o[64 + i], alpha_prev, v0[i]);
+          o[96 + i] = fmaf(o[96 + i], alpha_prev, v1[i]);
+        }
+        FS2_P_ITEM(k, 4);
+        if (n_valid == 32 && nx.valid) {   // park the second half in the drained O buffer (see flush_parked)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v0[i] = o[64 + i] * inv;
+            v1[i] = o[96 + i] * inv;
+          }
+          park_t = tmem_o + lane_sel + u * D_HEAD;
+          tmem_st32(park_t, v0);
+          tmem_st32(park_t + 32, v1);
+          asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+          park_col = o_col + 64;
+          park_row = o_row;
+          parked = true;
+          tc_fence_before();
+        } else {
+          tc_fence_before();   // ordered before this thread's next p_full arrive, which releases the O buffer
+          send64(64);
+        }
+        FS2_P_ITEM(k, 5);
       }
       it = nx;
     }
+    asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // the stores are COMPLETE before the CTA gives up its shared memory
   }
   tc_fence_before();
   __syncthreads();
@@ -400,7 +525,7 @@ inline int& enabled_flag() {
 inline bool use_persistent(int work_cap, int sms) { return enabled_flag() != 0 && N_HEAD * work_cap > sms; }
 
 inline void launch(const float* qkv, int rows, const int32_t* starts, const int32_t* lens, const uint32_t* work,
-                   const int32_t* work_count, int work_cap, float* out, cudaStream_t stream, int sms, void* out_bf16 = nullptr) {
+                   const int32_t* work_count, int work_cap, float* out, cudaStream_t stream, int sms) {
   if (work_cap <= 0 || rows <= 0) return;
   static bool configured[64] = {};
   int dev = 0;
@@ -411,8 +536,11 @@ inline void launch(const float* qkv, int rows, const int32_t* starts, const int3
   }
   const CUtensorMap tmQK = make_map(qkv, rows, LDQKV, LDQKV, BKV, true, true);
   const CUtensorMap tmV = make_map(qkv, rows, LDQKV, LDQKV, BKV, true, true, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  launch_pdl(attention_tcp_kernel, dim3(std::min(sms, N_HEAD * work_cap)), dim3(THREADS), SMEM_TOTAL, stream, 1, tmQK, tmV, starts,
-             lens, work, work_count, out, static_cast<__nv_bfloat16*>(out_bf16));
+  const CUtensorMap tmO = make_map(out, rows, D_MODEL, D_MODEL, 32, false, false);
+  static const int grid_cap = [] { const char* e = std::getenv("FS2_ATTN_GRID"); return e != nullptr ? std::atoi(e) : 0; }();   // experiment
+  if (grid_cap > 0) sms = std::min(sms, grid_cap);
+  launch_pdl(attention_tcp_kernel, dim3(std::min(sms, N_HEAD * work_cap)), dim3(THREADS), SMEM_TOTAL, stream, 1, tmQK, tmV, tmO, starts,
+             lens, work, work_count, out);
   FS2_LAUNCHED();
 }
 

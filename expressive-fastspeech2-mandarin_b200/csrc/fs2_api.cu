@@ -313,8 +313,9 @@ static void attention(const float* qkv, int rows, const RowSide& side, int batch
   (void)batch; (void)max_len;
   if (attn_tc::use_two_sm(side.work_q_rows))
     attn2::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, out, s, out_bf16);
-  else if (side.work_q_rows == attn_tc::BQ && attn_tc::debug_flag() == 0 && attn_p::use_persistent(side.work_cap, tc2::sm_count()))
-    attn_p::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, out, s, tc2::sm_count(), out_bf16);
+  else if (side.work_q_rows == attn_tc::BQ && attn_tc::debug_flag() == 0 && out_bf16 == nullptr &&
+           attn_p::use_persistent(side.work_cap, tc2::sm_count()))
+    attn_p::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, out, s, tc2::sm_count());
   else
     attn_tc::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, side.work_q_rows, out, s, out_bf16);
 }
@@ -1174,6 +1175,14 @@ int fs2_debug_read_trace(int64_t* host_dst, int n) {
   if (n == 256 * 6) {   // per-CTA stamps of the last fused-FFN launch (tools/trace_ffn.py)
     cudaDeviceSynchronize();
     return cudaMemcpyFromSymbol(host_dst, fs2::ffn::g_ffn_cta_trace, (size_t)n * sizeof(long long)) == cudaSuccess ? FS2_OK : FS2_ERR_CUDA;
+  }
+  if (n == 16 * 8 + 2) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(host_dst, fs2::attn_p::g_attn_p_item_trace, 16 * 8 * sizeof(long long)) == cudaSuccess ? FS2_OK : FS2_ERR_CUDA;
+  }
+  if (n == 64 * 8 + 1) {   // per-tile stamps of one CTA of the last persistent attention launch (tools/trace_attention_persistent.py)
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(host_dst, fs2::attn_p::g_attn_p_tile_trace, 64 * 8 * sizeof(long long)) == cudaSuccess ? FS2_OK : FS2_ERR_CUDA;
   }
   if (n > 64) {   // per-CTA stamps of the last attention launch (tools/trace_attention_ctas.py)
     cudaDeviceSynchronize();
