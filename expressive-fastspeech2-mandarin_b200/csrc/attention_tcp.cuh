@@ -273,8 +273,9 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_cons
         tmem_st32(tmem_q + lane_sel + dc * 32, va);
         tmem_st32(tmem_q + lane_sel + dc * 32 + 32, vb);
       }
+      // (no proxy fence: the shared-memory loads have completed -- their values have been stored to tensor memory -- before
+      // this arrival, and the stage is only rewritten by a TMA load issued after the barrier chain q_moved -> k_empty)
       asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads before the TMA overwrites the stage
       tc_fence_before();
       mbar_arrive(q_moved);
     };
