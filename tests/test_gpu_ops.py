@@ -134,18 +134,20 @@ def test_conv_gemm_fused_layernorm(case):
         assert (got[~live] == 0).all()
 
 
-@pytest.mark.parametrize("pair", [0, 1, 2], ids=["one_cta_per_tile", "paired_kv_multicast", "two_sm_pair"])
+@pytest.mark.parametrize("pair", [0, 1, 2, 3], ids=["one_cta_per_tile", "paired_kv_multicast", "two_sm_pair", "persistent"])
 @pytest.mark.parametrize("lens", [[1], [5, 64, 65, 33], [200, 7, 129, 128, 127], [700], [0, 3, 0, 300, 1],
                                   [37] * 70 + [513, 2, 1024]])
 def test_attention(lens, pair):
-    """The forms of the kernel: one CTA per 128-query tile; clusters of two CTAs on adjacent query tiles that share every K/V
+    """The forms of the kernel: one CTA per 128-query tile; the persistent kernel that walks the work list (the default); clusters of two CTAs on adjacent query tiles that share every K/V
     tile through TMA multicast (odd tile counts leave a loads-only CTA); and the 2-SM kernel (attention_tc2.cuh: M = 256
     cta_group::2 MMAs, 128-key tiles split between the CTAs; odd tile counts leave a CTA working on nobody's rows)."""
-    lib().fs2_debug_set_flag(8, pair)
+    lib().fs2_debug_set_flag(8, 0 if pair == 3 else pair)
+    lib().fs2_debug_set_flag(10, 2 if pair == 3 else 0)      # 3: attention_tcp.cuh (the default form) at every size
     try:
         _attention_case(lens)
     finally:
         lib().fs2_debug_set_flag(8, -1)
+        lib().fs2_debug_set_flag(10, 2)
 
 
 def _persistent_lens(kind):
@@ -170,7 +172,7 @@ def test_attention_persistent(kind):
     try:
         ref = _attention_case(lens)
     finally:
-        lib().fs2_debug_set_flag(10, 1)
+        lib().fs2_debug_set_flag(10, 2)
     assert torch.equal(got, ref)
 
 

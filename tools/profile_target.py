@@ -1,9 +1,10 @@
 """One config-2 forward bracketed by cudaProfilerStart/Stop, for `ncu --profile-from-start off` (run on the GPU box).
     python tools/profile_target.py [tf32|bf16]
-Launch order inside the bracket (67 launches at config 2, TF32; ncu IDs): 0 layout_scan 1 row_meta (+ source mask, attention work list, init)
-2 embed_pe | 3-22 encoder (4 x [qkv, attention, fc+LN, conv9, w2+LN]) | 23 cond 24 add_cond | 25-26 duration predictor
-27-28 pitch predictor 29 bucket+embed 30-31 energy predictor 32 durations 33 layout_scan | 34 row_meta 35 length regulator
-(+ energy add, PE) | 36-59 decoder (6 x [qkv, attention, fc+LN, fused FFN]) | 60 mel_linear 61-65 PostNet 66 unpack."""
+Launch order inside the bracket (64 launches at config 2, TF32; ncu IDs): 0 layout_scan 1 row_meta (+ source mask, attention work list, init)
+2 embed_pe 3 cond | 4-23 encoder (4 x [qkv, attention, fc+LN, conv9, w2+LN]; the last w2+LN adds the conditioning vectors) |
+24-25 duration + pitch predictors (one launch per layer for both) 26 bucket+embed 27-28 energy predictor 29 durations 30 layout_scan |
+31 row_meta 32 length regulator (+ energy add, PE) | 33-56 decoder (6 x [qkv, persistent attention, fc+LN, fused FFN]) |
+57 mel_linear 58-62 PostNet 63 unpack."""
 import os, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
