@@ -517,13 +517,14 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_cons
   }
 }
 
-// 2 (default) = always this kernel (with no more items than SMs it is one CTA per item, with the TMA-store output path);
-// 1 = only when the work list can exceed one item per SM; 0 = never (FS2_ATTN_PERSISTENT / debug flag 10)
+// FS2_ATTN_PERSISTENT / debug flag 10: 3 (default) = the persistent kernel with separate softmax and accumulate warpgroups
+// (attention_tcq.cuh); 2 = this kernel (one group of row threads) at every size; 1 = this kernel only when the work list can
+// exceed one item per SM; 0 = one CTA per item (attention_tc.cuh)
 inline int& enabled_flag() {
-  static int f = [] { const char* e = std::getenv("FS2_ATTN_PERSISTENT"); return e != nullptr ? std::atoi(e) : 2; }();
+  static int f = [] { const char* e = std::getenv("FS2_ATTN_PERSISTENT"); return e != nullptr ? std::atoi(e) : 3; }();
   return f;
 }
-inline bool use_persistent(int work_cap, int sms) { return enabled_flag() == 2 || (enabled_flag() == 1 && N_HEAD * work_cap > sms); }
+inline bool use_persistent(int work_cap, int sms) { return enabled_flag() >= 2 || (enabled_flag() == 1 && N_HEAD * work_cap > sms); }
 
 inline void launch(const float* qkv, int rows, const int32_t* starts, const int32_t* lens, const uint32_t* work,
                    const int32_t* work_count, int work_cap, float* out, cudaStream_t stream, int sms) {

@@ -13,6 +13,7 @@
 #include "gemm_tc2.cuh"
 #include "attention_tc2.cuh"
 #include "attention_tcp.cuh"
+#include "attention_tcq.cuh"
 #include "ffn_fused.cuh"
 #include "rowops.cuh"
 #include "vocoder.cuh"
@@ -314,8 +315,12 @@ static void attention(const float* qkv, int rows, const RowSide& side, int batch
   if (attn_tc::use_two_sm(side.work_q_rows))
     attn2::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, out, s, out_bf16);
   else if (side.work_q_rows == attn_tc::BQ && attn_tc::debug_flag() == 0 && out_bf16 == nullptr &&
-           attn_p::use_persistent(side.work_cap, tc2::sm_count()))
-    attn_p::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, out, s, tc2::sm_count());
+           attn_p::use_persistent(side.work_cap, tc2::sm_count())) {
+    if (attn_p::enabled_flag() == 3)
+      attn_q::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, out, s, tc2::sm_count());
+    else
+      attn_p::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, out, s, tc2::sm_count());
+  }
   else
     attn_tc::launch(qkv, rows, side.starts, side.lens, side.work, side.work_count, side.work_cap, side.work_q_rows, out, s, out_bf16);
 }
@@ -1356,8 +1361,10 @@ int fs2_op_attention(fs2_stream stream, const float* qkv, int rows, const int32_
     attention_work_kernel<<<1, 256, 0, s>>>(lens, batch, work, cap, count, q_rows);
     FS2_LAUNCHED();
     if (attn_tc::use_two_sm(q_rows)) attn2::launch(qkv, rows, starts, lens, work, count, cap, out, s);
-    else if (q_rows == attn_tc::BQ && attn_tc::debug_flag() == 0 && attn_p::use_persistent(cap, tc2::sm_count()))
-      attn_p::launch(qkv, rows, starts, lens, work, count, cap, out, s, tc2::sm_count());
+    else if (q_rows == attn_tc::BQ && attn_tc::debug_flag() == 0 && attn_p::use_persistent(cap, tc2::sm_count())) {
+      if (attn_p::enabled_flag() == 3) attn_q::launch(qkv, rows, starts, lens, work, count, cap, out, s, tc2::sm_count());
+      else attn_p::launch(qkv, rows, starts, lens, work, count, cap, out, s, tc2::sm_count());
+    }
     else attn_tc::launch(qkv, rows, starts, lens, work, count, cap, q_rows, out, s);
     FS2_CUDA_OK(cudaStreamSynchronize(s));
     cudaFree(work);

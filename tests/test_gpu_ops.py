@@ -134,20 +134,21 @@ def test_conv_gemm_fused_layernorm(case):
         assert (got[~live] == 0).all()
 
 
-@pytest.mark.parametrize("pair", [0, 1, 2, 3], ids=["one_cta_per_tile", "paired_kv_multicast", "two_sm_pair", "persistent"])
+@pytest.mark.parametrize("pair", [0, 1, 2, 3, 4],
+                         ids=["one_cta_per_tile", "paired_kv_multicast", "two_sm_pair", "persistent_one_group", "persistent"])
 @pytest.mark.parametrize("lens", [[1], [5, 64, 65, 33], [200, 7, 129, 128, 127], [700], [0, 3, 0, 300, 1],
                                   [37] * 70 + [513, 2, 1024]])
 def test_attention(lens, pair):
     """The forms of the kernel: one CTA per 128-query tile; the persistent kernel that walks the work list (the default); clusters of two CTAs on adjacent query tiles that share every K/V
     tile through TMA multicast (odd tile counts leave a loads-only CTA); and the 2-SM kernel (attention_tc2.cuh: M = 256
     cta_group::2 MMAs, 128-key tiles split between the CTAs; odd tile counts leave a CTA working on nobody's rows)."""
-    lib().fs2_debug_set_flag(8, 0 if pair == 3 else pair)
-    lib().fs2_debug_set_flag(10, 2 if pair == 3 else 0)      # 3: attention_tcp.cuh (the default form) at every size
+    lib().fs2_debug_set_flag(8, 0 if pair >= 3 else pair)
+    lib().fs2_debug_set_flag(10, {3: 2, 4: 3}.get(pair, 0))   # attention_tcp.cuh / attention_tcq.cuh (the default) at every size
     try:
         _attention_case(lens)
     finally:
         lib().fs2_debug_set_flag(8, -1)
-        lib().fs2_debug_set_flag(10, 2)
+        lib().fs2_debug_set_flag(10, 3)
 
 
 def _persistent_lens(kind):
@@ -161,18 +162,21 @@ def _persistent_lens(kind):
     return [37] * 70 + [513, 2, 1024] + [64, 65, 127, 128, 129, 191, 192, 193] * 3
 
 
+@pytest.mark.parametrize("form", [2, 3], ids=["one_group", "softmax_and_accumulate_groups"])
 @pytest.mark.parametrize("kind", ["config2_like", "many_short_with_empties", "one_item_more_than_sms", "mixed_boundaries"])
-def test_attention_persistent(kind):
-    """attention_tcp.cuh: one CTA per SM walks the work list with Q travelling through the K ring and the pipelines running
-    across items.  Same products in the same order as the one-CTA-per-item kernel: the outputs are bit-identical to it
-    (debug flag 10 = 0) and within the TF32 tolerance of float64."""
+def test_attention_persistent(kind, form):
+    """attention_tcp.cuh / attention_tcq.cuh: one CTA per SM walks the work list with Q travelling through the K ring and the
+    pipelines running across items (tcq: the row work split between a softmax and an accumulate warpgroup).  Same products
+    in the same order as the one-CTA-per-item kernel: the outputs are bit-identical to it (debug flag 10 = 0) and within the
+    TF32 tolerance of float64."""
     lens = _persistent_lens(kind)
-    got = _attention_case(lens)
-    lib().fs2_debug_set_flag(10, 0)
     try:
+        lib().fs2_debug_set_flag(10, form)
+        got = _attention_case(lens)
+        lib().fs2_debug_set_flag(10, 0)
         ref = _attention_case(lens)
     finally:
-        lib().fs2_debug_set_flag(10, 2)
+        lib().fs2_debug_set_flag(10, 3)
     assert torch.equal(got, ref)
 
 
