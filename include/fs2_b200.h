@@ -165,7 +165,9 @@ int fs2_debug_fetch(fs2_ctx* ctx, const char* name, void* host_dst, int64_t max_
  * 4 = fused FFN kernel: 0 off, 1 on, 2 automatic (default: on when the row tiles fill the SMs at least four times),
  * 5 = N-split fused-LayerNorm GEMMs for small row counts on/off, 6 = cta_group::2 MMAs on/off,
  * 7 = K-split clusters for single-row-tile contractions on/off, 8 = paired (K/V-multicast) attention kernel:
- * -1 automatic, 0 never, 1 always). */
+ * -1 automatic, 0 never, 1 always, 9 = stage-1 fusions (bit 0: duration + pitch predictors share their launches, bit 1:
+ * conditioning add inside the last encoder LayerNorm epilogue; default 3), 10 = attention kernel form: 3 persistent with
+ * softmax and accumulate warpgroups (default), 2 persistent with one group of row threads, 0 one CTA per work item). */
 int fs2_debug_set_flag(int which, int value);
 /* which = 1: CTA 0 of the next fs2_op_conv_gemm writes globaltimer stamps; read them back here. */
 int fs2_debug_read_trace(int64_t* host_dst, int n);
