@@ -239,6 +239,27 @@ def test_stage1_fusions_are_bit_exact(sd32, syn, math_mode, lens):
         assert torch.equal(a, b), i
 
 
+@pytest.mark.parametrize("lens", [[16], [21, 9, 17, 33, 5], None])
+def test_attention_forms_give_the_same_forward(sd32, syn, lens):
+    """The three attention kernels (one CTA per work item; persistent with one group of row threads; persistent with softmax
+    and accumulate warpgroups, the default) compute the same products in the same order: the whole free-running forward is
+    bit-identical under debug flag 10 = 0 / 2 / 3 (transformer/SubLayers.py:42-52).  lens = None is the config-2 batch."""
+    from gpu_util import lib
+    L = lib()
+    model = model_for(sd32)
+    batch = syn.config2_batch(seed=0) if lens is None else syn.make_batch(lens, seed=7)
+    outs = {}
+    try:
+        for form in (0, 2, 3):
+            L.fs2_debug_set_flag(10, form)
+            outs[form] = [t.clone() for t in run(model, batch)]
+    finally:
+        L.fs2_debug_set_flag(10, 3)
+    for form in (0, 2):
+        for i, (a, b) in enumerate(zip(outs[form], outs[3])):
+            assert torch.equal(a, b), (form, i)
+
+
 def test_input_validation(sd32, syn):
     model = model_for(sd32)
     batch = syn.make_batch([8, 6], seed=1)

@@ -1,5 +1,8 @@
-"""Per-CTA view of the persistent attention kernel (attention_tcp.cuh) in the LAST decoder attention launch of a config-2
-forward under sustained load (trace build): key tiles per CTA (balance of the snake deal), lifetime, cycles per key tile."""
+"""Per-CTA and per-tile view of the persistent attention kernels (attention_tcq.cuh by default; FS2_ATTN_PERSISTENT=2 for the
+one-group attention_tcp.cuh, whose per-item stamps fill the last table) in the LAST decoder attention launch of a config-2
+forward under sustained load (trace build): key tiles per CTA (balance of the snake deal), lifetime, cycles per key tile, and for
+CTA 5 the per-tile timeline.  Column "P->iter end": one-group kernel = the O update of the previous tile; two-group kernel = how
+long after the P hand-over the accumulate group has finished the tile."""
 import os, sys, ctypes, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
