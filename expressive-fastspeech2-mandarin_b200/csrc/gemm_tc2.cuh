@@ -1214,6 +1214,10 @@ inline void launch(const ConvGemmArgs& a, cudaStream_t stream, const ConvGemmArg
       }
     }
   }
+  // experiment (FS2_QKV_BN=128): 128-column tiles for the single-tap K = 256 GEMMs whose 256-column tiles leave a partly
+  // empty last wave (QKV at config 2: 630 tiles = 4.26 waves)
+  static const int qkv_bn = [] { const char* e = std::getenv("FS2_QKV_BN"); return e != nullptr ? std::atoi(e) : 0; }();
+  if (qkv_bn == 128 && a.taps == 1 && a.K == 256 && a.N == 768) { launch_bn<128, false>(a, stream); return; }
   if (a.N % 256 == 0 && m_tiles * (a.N / 256) * 4 <= sms) { launch_bn<64, false>(a, stream); return; }
   if (a.N % 256 == 0 && m_tiles * (a.N / 256) * 2 <= sms) { launch_bn<128, false>(a, stream); return; }
   if (a.N % 256 == 0) launch_bn<256, false>(a, stream);
