@@ -617,7 +617,7 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   // the encoder and added to its output inside the last layer's LayerNorm epilogue.  The stand-alone add remains for the
   // cases that epilogue does not cover: the last layer running as the fused FFN (large batches), the per-layer debug taps
   // (which want the unconditioned encoder output), and stage-1 fusion flag bit 1 cleared (A/B tests).
-  cond_kernel<<<B, 256, 0, s>>>(in->speakers, in->emotions, in->arousals, in->valences, c->raw.at("speaker_emb.weight").ptr,
+  cond_kernel<<<B * COND_PARTS, 256, 0, s>>>(in->speakers, in->emotions, in->arousals, in->valences, c->raw.at("speaker_emb.weight").ptr,
                                 c->cfg.n_speaker, c->raw.at("emotion_emb.weight").ptr, c->cfg.n_emotion,
                                 c->raw.at("arousal_emb.weight").ptr, c->cfg.n_arousal, c->raw.at("valence_emb.weight").ptr,
                                 c->cfg.n_valence, c->raw.at("emotion_linear.0.weight").ptr,

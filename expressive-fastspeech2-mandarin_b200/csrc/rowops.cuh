@@ -239,7 +239,10 @@ __global__ void embed_pe_kernel(const int64_t* __restrict__ texts, int max_src_l
 
 // ---------------------------------------------------------------------------------------
 // Conditioning vectors (model/fastspeech2.py:101-110): spk[b] = speaker_emb[s];
-// emo[b] = ReLU(W . cat(emotion_emb[e], arousal_emb[a], valence_emb[v]) + bias).  Block per utterance.
+// emo[b] = ReLU(W . cat(emotion_emb[e], arousal_emb[a], valence_emb[v]) + bias).  COND_PARTS blocks per utterance, each
+// owning 256 / COND_PARTS output rows (a block per utterance walked eight dependent passes over W: ~5 us on the forward's
+// critical path, and on a single utterance's).
+constexpr int COND_PARTS = 4;
 __global__ void cond_kernel(const int64_t* __restrict__ speakers, const int64_t* __restrict__ emotions,
                             const int64_t* __restrict__ arousals, const int64_t* __restrict__ valences,
                             const float* __restrict__ spk_emb, int n_spk, const float* __restrict__ emo_emb, int n_emo,
@@ -247,10 +250,10 @@ __global__ void cond_kernel(const int64_t* __restrict__ speakers, const int64_t*
                             const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ spk_out,
                             float* __restrict__ emo_out, int32_t* __restrict__ status) {
   __shared__ float e[D_MODEL];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.x / COND_PARTS, part = blockIdx.x % COND_PARTS, tid = threadIdx.x;
   long long s = speakers[b], em = emotions[b], ar = arousals[b], va = valences[b];
   if (s < 0 || s >= n_spk || em < 0 || em >= n_emo || ar < 0 || ar >= n_aro || va < 0 || va >= n_val) {
-    if (tid == 0) atomicOr(status, ERR_BAD_INDEX);
+    if (tid == 0 && part == 0) atomicOr(status, ERR_BAD_INDEX);
     s = min(max(s, 0LL), (long long)n_spk - 1);
     em = min(max(em, 0LL), (long long)n_emo - 1);
     ar = min(max(ar, 0LL), (long long)n_aro - 1);
@@ -259,12 +262,14 @@ __global__ void cond_kernel(const int64_t* __restrict__ speakers, const int64_t*
   if (tid < 128) e[tid] = emo_emb[em * 128 + tid];
   else if (tid < 192) e[tid] = aro_emb[ar * 64 + (tid - 128)];
   else e[tid] = val_emb[va * 64 + (tid - 192)];
-  spk_out[(size_t)b * D_MODEL + tid] = spk_emb[s * D_MODEL + tid];
+  if (part == 0) spk_out[(size_t)b * D_MODEL + tid] = spk_emb[s * D_MODEL + tid];
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
-  // each warp owns 32 output rows; four rows per pass keep 32 independent loads in flight per lane (the row-at-a-time
-  // loop was a chain of 32 dependent L2 round trips: 24 us for 64 tiny blocks)
-  for (int n0 = warp * 32; n0 < warp * 32 + 32; n0 += 4) {
+  // each warp owns 32 / COND_PARTS output rows; four rows per pass keep 32 independent loads in flight per lane (the
+  // row-at-a-time loop was a chain of 32 dependent L2 round trips: 24 us for 64 tiny blocks)
+  constexpr int ROWS_W = 32 / COND_PARTS;
+  const int row_lo = part * (D_MODEL / COND_PARTS) + warp * ROWS_W;
+  for (int n0 = row_lo; n0 < row_lo + ROWS_W; n0 += 4) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = lane; k < D_MODEL; k += 32) {
