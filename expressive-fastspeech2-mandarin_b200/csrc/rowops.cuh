@@ -38,9 +38,12 @@ template <typename LenT>
 __global__ void layout_scan_kernel(const LenT* __restrict__ lens, int batch, int gap, int len_limit,
                                    int forced_max, int32_t* __restrict__ starts, int32_t* __restrict__ lens32,
                                    int64_t* __restrict__ totals, int32_t* __restrict__ status) {
-  __shared__ long long part[1024];
-  __shared__ int maxv[1024];
-  const int tid = threadIdx.x;
+  // 1024 threads = 32 warps: inclusive scan of the per-thread sums by warp shuffles, one exchange of the 32 warp totals through
+  // shared memory, and the maxima / real-length sums reduced the same way (two block barriers; the Hillis-Steele scan over
+  // 1024 shared-memory partials took ~30 of them and 5 us on the critical path of both stages)
+  __shared__ long long w_sum[32], w_real[32];
+  __shared__ int w_max[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int per = (batch + blockDim.x - 1) / blockDim.x;
   const int lo = min(tid * per, batch), hi = min(lo + per, batch);
   long long s = 0;
@@ -56,19 +59,33 @@ __global__ void layout_scan_kernel(const LenT* __restrict__ lens, int batch, int
     real += l;
     mx = max(mx, (int)l);
   }
-  part[tid] = s;
-  maxv[tid] = mx;
-  __syncthreads();
-  // Hillis-Steele inclusive scan over 1024 partials
-  for (int off = 1; off < blockDim.x; off <<= 1) {
-    long long v = tid >= off ? part[tid - off] : 0;
-    int m = tid >= off ? maxv[tid - off] : 0;
-    __syncthreads();
-    part[tid] += v;
-    maxv[tid] = max(maxv[tid], m);
-    __syncthreads();
+  long long incl = s;   // inclusive scan inside the warp
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const long long v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
   }
-  long long run = gap + (tid > 0 ? part[tid - 1] : 0);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    real += __shfl_xor_sync(0xffffffffu, real, off);
+  }
+  if (lane == 31) w_sum[warp] = incl;
+  if (lane == 0) {
+    w_max[warp] = mx;
+    w_real[warp] = real;
+  }
+  __syncthreads();
+  long long before = 0, total_s = 0, total_real = 0;   // sum of the warps before this one; block totals
+  int max_len = 0;
+  for (int w = 0; w < 32; ++w) {
+    const long long v = w_sum[w];
+    if (w < warp) before += v;
+    total_s += v;
+    total_real += w_real[w];
+    max_len = max(max_len, w_max[w]);
+  }
+  long long run = gap + before + (incl - s);
   for (int b = lo; b < hi; ++b) {
     long long l = (long long)lens[b];
     l = l < 0 ? 0 : ((len_limit > 0 && l > len_limit) ? len_limit : l);
@@ -76,17 +93,7 @@ __global__ void layout_scan_kernel(const LenT* __restrict__ lens, int batch, int
     lens32[b] = (int32_t)l;
     run += l + gap;
   }
-  // sum of real lengths: second tiny reduction through shared memory
-  __syncthreads();
-  long long total_rows = gap + part[blockDim.x - 1];
-  int max_len = maxv[blockDim.x - 1];
-  __syncthreads();
-  part[tid] = real;
-  __syncthreads();
-  for (int off = blockDim.x / 2; off > 0; off >>= 1) {
-    if (tid < off) part[tid] += part[tid + off];
-    __syncthreads();
-  }
+  const long long total_rows = gap + total_s;
   if (tid == 0) {
     if (forced_max > 0) {
       if (forced_max < max_len) atomicOr(status, ERR_MAXLEN_SMALL);
@@ -95,7 +102,7 @@ __global__ void layout_scan_kernel(const LenT* __restrict__ lens, int batch, int
     starts[batch] = (int32_t)total_rows;
     totals[0] = total_rows;
     totals[1] = max_len;
-    totals[2] = part[0];
+    totals[2] = total_real;
   }
 }
 
