@@ -39,7 +39,8 @@ CPU_SAMPLE_UTTS = 64      # the whole config-2 batch per CPU step (about 3-4 s o
 CPU_SAMPLE_STEPS = 3      # cpu_baseline leg of the default run: about 10 s of CPU work
 FLOPS_CONV9_PER_ROW = 2 * 9 * 256 * 1024
 # dram bytes (read + written) of one dec.ffn_fused launch at batch 64, from the ncu --set full capture; None until captured
-DRAM_TRAFFIC_FUSED = {"tf32": 44.11e6}   # 39.48 MB read + 4.63 MB written (profiles/r02_ncu_full_ffn_fused_final_raw.csv)
+DRAM_TRAFFIC_FUSED = {"tf32": 46.13e6}   # 39.26 MB read + 6.87 MB written (profiles/r02d_ncu_full_forward_summary.csv, launch 36;
+                                          # 44.11 MB in profiles/r02_ncu_full_ffn_fused_final_raw.csv: the written part varies with what L2 keeps)
 NAMES = ("speakers", "emotions", "arousals", "valences", "texts", "src_lens")
 
 
