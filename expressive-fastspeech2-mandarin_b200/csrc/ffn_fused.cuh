@@ -83,6 +83,12 @@ struct Args {
   const int32_t* row_room;
   int extra;
   const int32_t* live_rows;
+  // optional: y[row] = (y[row] + post_a[u]) + post_b[u], u = post_utt[row], after the row mask, on the rows live with
+  // post_extra reserved rows (the speaker / emotion conditioning on the last encoder layer: ConvGemmArgs::post_a)
+  const float* post_a;
+  const float* post_b;
+  const int32_t* post_utt;
+  int post_extra;
   float* y;              // [rows, 256]
   // hand-over of a row-tile group split between two clusters (stream-K schedule): partial [rows, 256] fp32 and
   // flags [flag_count(rows)] int32, each holding the epoch of the launch that last completed the slot (never reset;
@@ -521,6 +527,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       // ---- HEAD (or whole) segment: LayerNorm(out + b2 + x) -> y   (same two-pass scheme as gemm_tc2.cuh's LN epilogue)
       const int row = m0 + r;
       bool live = row < p.rows;
+      const float *post_a = nullptr, *post_b = nullptr;
+      if (live && p.post_a != nullptr) {
+        const int pu = p.post_utt[row];
+        if (pu >= 0 && row_live(p.row_vpos[row], p.row_room[row], p.post_extra)) {
+          post_a = p.post_a + (size_t)pu * 256;
+          post_b = p.post_b + (size_t)pu * 256;
+        }
+      }
       if (live && p.row_vpos != nullptr) live = row_live(p.row_vpos[row], p.row_room[row], p.extra);
       const int w_next = w + 1;
       auto prefetch_res = [&](int cch) {
@@ -583,6 +597,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[cc * 4 + e] = live ? fmaf((v[cc * 4 + e] - mean) * rstd, gg[e], bb[e]) : 0.f;
+        }
+        if (post_a != nullptr) {   // (x + speaker) + emotion, in the reference's order
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) {
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(post_a + cch * 32 + cc * 4));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(post_b + cch * 32 + cc * 4));
+            v[cc * 4] = (v[cc * 4] + a4.x) + b4.x; v[cc * 4 + 1] = (v[cc * 4 + 1] + a4.y) + b4.y;
+            v[cc * 4 + 2] = (v[cc * 4 + 2] + a4.z) + b4.z; v[cc * 4 + 3] = (v[cc * 4 + 3] + a4.w) + b4.w;
+          }
         }
         if (lane == 0) bulk_wait_read<1>();
         __syncwarp();

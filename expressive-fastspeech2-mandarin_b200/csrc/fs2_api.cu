@@ -353,7 +353,7 @@ static int& stage1_fusion_flag() {
 }
 
 // cond (last encoder layer only): the speaker / emotion vectors added to the block's output inside the FFN's LayerNorm
-// epilogue (ConvGemmArgs::post_a); the caller keeps the stand-alone add_cond_kernel when this layer runs as the fused FFN.
+// epilogue (ConvGemmArgs::post_a / ffn::Args::post_a).
 struct CondAdd {
   const float *spk, *emo;
 };
@@ -396,12 +396,12 @@ static void fft_block(fs2_ctx* c, cudaStream_t s, const FFTLayer& L, const RowSi
   a.ln_gamma = L.ln1_g; a.ln_beta = L.ln1_b; a.row_vpos = side.vpos; a.row_room = side.room; a.extra = 0;
   { ProfScope ps(c, s, frame ? "dec.gemm_fc_ln" : "enc.gemm_fc_ln"); conv_gemm(c, a, s); }
   if (math == FS2_MATH_TF32 && ffn::use_fused(rows)) {
-    require(cond == nullptr, FS2_ERR_INVALID, "the fused FFN has no conditioning add");
     // conv9 -> ReLU -> w2 -> +residual -> LayerNorm -> mask in one kernel; the hidden tensor stays in tensor memory
     ffn::Args f{};
     f.x = t2; f.rows = rows; f.w1 = L.w1; f.b1 = L.b1; f.w2 = L.w2; f.b2 = L.b2; f.gamma = L.ln2_g; f.beta = L.ln2_b;
     f.row_vpos = side.vpos; f.row_room = side.room; f.extra = 0;
     f.live_rows = live; f.y = x;
+    if (cond != nullptr) { f.post_a = cond->spk; f.post_b = cond->emo; f.post_utt = side.utt; f.post_extra = 2; }
     // a row-tile group split between two clusters is handed over through the (otherwise unused) hidden buffer
     if (ffn::flag_count(rows) > c->ffn_flags_cap) {
       FS2_CUDA_OK(cudaStreamSynchronize(s));
@@ -614,17 +614,16 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   tap(c, s, "p_start", ps.starts, 1, B + 1);
   tap(c, s, "enc_in", x, rows, D_MODEL);
   // ---- conditioning vectors (model/fastspeech2.py:101-110): they depend on the inputs only, so they are computed before
-  // the encoder and added to its output inside the last layer's LayerNorm epilogue.  The stand-alone add remains for the
-  // cases that epilogue does not cover: the last layer running as the fused FFN (large batches), the per-layer debug taps
-  // (which want the unconditioned encoder output), and stage-1 fusion flag bit 1 cleared (A/B tests).
+  // the encoder and added to its output inside the last layer's LayerNorm epilogue (of the w2 GEMM, or of the fused FFN
+  // kernel on large batches).  The stand-alone add remains for the per-layer debug taps (which want the unconditioned
+  // encoder output) and for stage-1 fusion flag bit 1 cleared (A/B tests).
   cond_kernel<<<B * COND_PARTS, 256, 0, s>>>(in->speakers, in->emotions, in->arousals, in->valences, c->raw.at("speaker_emb.weight").ptr,
                                 c->cfg.n_speaker, c->raw.at("emotion_emb.weight").ptr, c->cfg.n_emotion,
                                 c->raw.at("arousal_emb.weight").ptr, c->cfg.n_arousal, c->raw.at("valence_emb.weight").ptr,
                                 c->cfg.n_valence, c->raw.at("emotion_linear.0.weight").ptr,
                                 c->raw.at("emotion_linear.0.bias").ptr, c->cond_spk, c->cond_emo, c->status);
   FS2_LAUNCHED();
-  const bool cond_fused = (stage1_fusion_flag() & 2) != 0 && !c->debug &&
-                          !(c->cfg.math_mode == FS2_MATH_TF32 && ffn::use_fused(rows));
+  const bool cond_fused = (stage1_fusion_flag() & 2) != 0 && !c->debug;
   const CondAdd cond{c->cond_spk, c->cond_emo};
   for (int i = 0; i < ENC_LAYERS; ++i) {
     fft_block(c, s, c->enc[i], ps, pp, rows, B, L, x, t1, t2, false, cond_fused && i == ENC_LAYERS - 1 ? &cond : nullptr);

@@ -216,16 +216,19 @@ def test_batch_padding_independence(sd32, syn):
 
 
 @pytest.mark.parametrize("math_mode", ["tf32", "bf16"])
-@pytest.mark.parametrize("lens", [[16], [21, 9, 17, 33, 5], None])
+@pytest.mark.parametrize("lens", [[16], [21, 9, 17, 33, 5], None, "config3"])
 def test_stage1_fusions_are_bit_exact(sd32, syn, math_mode, lens):
     """Duration + pitch predictors in shared launches (grid.y = 2) and the speaker / emotion add inside the last encoder
     layer's LayerNorm epilogue (model/fastspeech2.py:101-110, modules.py:115-121) do the same arithmetic in the same order as
     the separate launches: every output of the free-running forward is bit-identical with the fusions off (debug flag 9).
-    lens = None is the config-2 batch (35 phoneme row tiles: the N-split LayerNorm forms)."""
+    lens = None is the config-2 batch (35 phoneme row tiles: the N-split LayerNorm forms); "config3" is 512 utterances."""
     from gpu_util import lib
     L = lib()
     model = model_for(sd32, math_mode=math_mode)
-    batch = syn.config2_batch(seed=0) if lens is None else syn.make_batch(lens, seed=5)
+    if lens == "config3":    # 512 utterances: the encoder's last layer runs as the fused FFN kernel (TF32), whose epilogue adds
+        batch = syn.config3_batch(seed=0)
+    else:
+        batch = syn.config2_batch(seed=0) if lens is None else syn.make_batch(lens, seed=5)
     fused = [t.clone() for t in run(model, batch, p_control=1.1, d_control=0.9)]
     n_fused = model.last_launch_count
     try:
