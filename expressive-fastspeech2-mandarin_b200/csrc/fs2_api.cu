@@ -345,6 +345,20 @@ static ConvGemmArgs gemm_args_b(const void* A, int lda, int rows, const float* W
 }
 
 // One FFT block in place on x (transformer/Layers.py:21-30).  t1, t2 are [rows,256] temporaries.
+// Launch of a row kernel of the forward (rowops.cuh: the kernels that start with row_pdl_sync()) as a programmatic dependent
+// launch: its blocks become resident under the previous kernel's tail and it lets the next kernel start its prologue.
+// FS2_ROW_PDL=0 launches them the ordinary way (A/B).
+template <typename... KArgs, typename... Args>
+static void launch_row(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t s, Args&&... args) {
+  static const bool pdl = [] { const char* e = std::getenv("FS2_ROW_PDL"); return e == nullptr || std::atoi(e) != 0; }();
+  if (pdl) {
+    tc::launch_pdl(kernel, dim3(grid), dim3(block), 0, s, 1, std::forward<Args>(args)...);
+  } else {
+    kernel<<<grid, block, 0, s>>>(std::forward<Args>(args)...);
+    FS2_CUDA_OK(cudaGetLastError());
+  }
+}
+
 // Stage-1 fusions (debug flag 9 / FS2_STAGE1_FUSION; default 3): bit 0 = the duration and pitch predictors share their
 // launches, bit 1 = the conditioning add lives in the last encoder layer's LayerNorm epilogue.
 static int& stage1_fusion_flag() {
@@ -586,7 +600,7 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   // (the status word is zero on entry: fs2_create clears it and every stage 1 clears it again after reading it back)
   {
     ProfScope pr(c, s, "layout_scan");
-    layout_scan_kernel<int64_t><<<1, 1024, 0, s>>>(in->src_lens, B, GAP_PHON, L, L, ps.starts, ps.lens, ps.totals, c->status);
+    launch_row(layout_scan_kernel<int64_t>, 1, 1024, s, in->src_lens, B, GAP_PHON, L, L, ps.starts, ps.lens, ps.totals, c->status);
     FS2_LAUNCHED();
   }
   // row metadata + attention work list + zero fill of the [B, L] outputs that are written at real positions only
@@ -597,8 +611,8 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   init.n = BL; init.src_mask = out->src_mask; init.src_lens = in->src_lens; init.max_src_len = L;
   {
     ProfScope pr(c, s, "row_meta");
-    row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(ps.starts, ps.lens, B, GAP_PHON, L, nullptr, rows, ps.utt, ps.vpos,
-                                                       ps.room, ps.slot, ps.work, ps.work_cap, ps.work_count, init, ps.work_q_rows);
+    launch_row(row_meta_kernel, (rows + 255) / 256, 256, s, ps.starts, ps.lens, B, GAP_PHON, L, nullptr, rows, ps.utt, ps.vpos,
+               ps.room, ps.slot, ps.work, ps.work_cap, ps.work_count, init, ps.work_q_rows);
     FS2_LAUNCHED();
   }
 
@@ -607,8 +621,8 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   const float* pe = position_rows(c, "encoder.position_enc", L, s);
   {
     ProfScope pr(c, s, "embed_pe");
-    embed_pe_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in->texts, L, c->raw.at("encoder.src_word_emb.weight").ptr,
-                                                   c->cfg.n_src_vocab, pe, ps.meta(), ps.lens, rows, x, c->status, pp.actb[0]);
+    launch_row(embed_pe_kernel, (rows + 7) / 8, 256, s, in->texts, L, c->raw.at("encoder.src_word_emb.weight").ptr,
+               c->cfg.n_src_vocab, pe, ps.meta(), ps.lens, rows, x, c->status, pp.actb[0]);
     FS2_LAUNCHED();
   }
   tap(c, s, "p_start", ps.starts, 1, B + 1);
@@ -617,7 +631,7 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   // the encoder and added to its output inside the last layer's LayerNorm epilogue (of the w2 GEMM, or of the fused FFN
   // kernel on large batches).  The stand-alone add remains for the per-layer debug taps (which want the unconditioned
   // encoder output) and for stage-1 fusion flag bit 1 cleared (A/B tests).
-  cond_kernel<<<B * COND_PARTS, 256, 0, s>>>(in->speakers, in->emotions, in->arousals, in->valences, c->raw.at("speaker_emb.weight").ptr,
+  launch_row(cond_kernel, B * COND_PARTS, 256, s, in->speakers, in->emotions, in->arousals, in->valences, c->raw.at("speaker_emb.weight").ptr,
                                 c->cfg.n_speaker, c->raw.at("emotion_emb.weight").ptr, c->cfg.n_emotion,
                                 c->raw.at("arousal_emb.weight").ptr, c->cfg.n_arousal, c->raw.at("valence_emb.weight").ptr,
                                 c->cfg.n_valence, c->raw.at("emotion_linear.0.weight").ptr,
@@ -654,10 +668,10 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
     if (!paired) predictor(c, s, c->pred[1], ps, rows, cur, t1, c->raw_pitch, curb, pp.actb[1]);
     float* xe = spare;
     ProfScope pr(c, s, "bucket_embed_add");
-    bucket_embed_add_kernel<<<(rows + 7) / 8, 256, 0, s>>>(
-        cur, ps.meta(), ps.slot, 2, rows, c->raw_pitch, in->p_targets, in->p_control,
-        c->raw.at("variance_adaptor.pitch_bins").ptr, N_BINS - 1, c->raw.at("variance_adaptor.pitch_embedding.weight").ptr,
-        out->pitch, nullptr, xe, spareb);
+    launch_row(bucket_embed_add_kernel, (rows + 7) / 8, 256, s,
+               cur, ps.meta(), ps.slot, 2, rows, c->raw_pitch, in->p_targets, in->p_control,
+               c->raw.at("variance_adaptor.pitch_bins").ptr, N_BINS - 1, c->raw.at("variance_adaptor.pitch_embedding.weight").ptr,
+               out->pitch, nullptr, xe, spareb);
     FS2_LAUNCHED();
     cur = xe;
     curb = spareb;
@@ -673,14 +687,14 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   if (!energy_here) tap(c, s, "va_x", xf, rows, D_MODEL);
 
   const bool forced = in->d_targets != nullptr;
-  durations_kernel<<<(B + 7) / 8, 256, 0, s>>>(forced ? in->d_targets : out->log_d, forced ? 1 : 0, in->d_control,
-                                               in->src_lens, B, L, forced ? nullptr : out->d_rounded, c->cum,
-                                               out->mel_lens, c->mel_lens32, energy_here ? c->raw_energy : nullptr,
-                                               in->e_targets != nullptr ? 1.f : in->p_control /* sic: modules.py:123-125 */,
-                                               energy_here ? out->energy : nullptr);
+  launch_row(durations_kernel, (B + 7) / 8, 256, s, forced ? in->d_targets : out->log_d, forced ? 1 : 0, in->d_control,
+             in->src_lens, B, L, forced ? nullptr : out->d_rounded, c->cum,
+             out->mel_lens, c->mel_lens32, energy_here ? c->raw_energy : nullptr,
+             in->e_targets != nullptr ? 1.f : in->p_control /* sic: modules.py:123-125 */,
+             energy_here ? out->energy : nullptr);
   FS2_LAUNCHED();
-  layout_scan_kernel<int32_t><<<1, 1024, 0, s>>>(c->mel_lens32, B, GAP_FRAME, 0, in->max_mel_len, c->fs.starts, c->fs.lens,
-                                                 c->fs.totals, c->status);
+  launch_row(layout_scan_kernel<int32_t>, 1, 1024, s, c->mel_lens32, B, GAP_FRAME, 0, in->max_mel_len, c->fs.starts, c->fs.lens,
+             c->fs.totals, c->status);
   FS2_LAUNCHED();
 
   static const bool timing = std::getenv("FS2_TIMING") != nullptr;
@@ -729,9 +743,8 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
   Pool& fp = c->fp;
 
   if (T > 0) {
-    row_meta_kernel<<<(rows + 255) / 256, 256, 0, s>>>(fsd.starts, fsd.lens, B, GAP_FRAME, T, nullptr, rows, fsd.utt,
-                                                       fsd.vpos, fsd.room, fsd.slot, fsd.work, fsd.work_cap, fsd.work_count, SlotInit{},
-                                                       fsd.work_q_rows);
+    launch_row(row_meta_kernel, (rows + 255) / 256, 256, s, fsd.starts, fsd.lens, B, GAP_FRAME, T, nullptr, rows, fsd.utt,
+               fsd.vpos, fsd.room, fsd.slot, fsd.work, fsd.work_cap, fsd.work_count, SlotInit{}, fsd.work_q_rows);
     FS2_LAUNCHED();
     // ---- LengthRegulator + decoder positional encoding (modules.py:167-194, Models.py:145-162)
     float *x = fp.act[0], *t1 = fp.act[1], *t2 = fp.act[2];
@@ -754,9 +767,9 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
           FS2_CUDA_OK(cudaMemsetAsync(en.va_out, 0, (size_t)rows_p * D_MODEL * sizeof(float), s));
         }
       }
-      length_regulate_scatter_kernel<<<(warps + 7) / 8, 256, 0, s>>>(
-          c->lr_input, c->ps.meta(), c->ps.lens, rows_p, c->cum, L, fsd.starts, fsd.lens, B, GAP_FRAME, fsd.totals,
-          (pitch_f || energy_f) ? nullptr : pe, rows, x, fp.actb[0], en);
+      launch_row(length_regulate_scatter_kernel, (warps + 7) / 8, 256, s,
+                 c->lr_input, c->ps.meta(), c->ps.lens, rows_p, c->cum, L, fsd.starts, fsd.lens, B, GAP_FRAME, fsd.totals,
+                 (pitch_f || energy_f) ? nullptr : pe, rows, x, fp.actb[0], en);
       FS2_LAUNCHED();
       if (en.va_out != nullptr) tap(c, s, "va_x", en.va_out, rows_p, D_MODEL);
     }
@@ -843,8 +856,8 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
     const int64_t out_rows = (int64_t)B * T;
     {
       ProfScope ps(c, s, "unpack");
-      unpack_mel_kernel<<<(unsigned)((out_rows * (N_MEL / 4) + 255) / 256), 256, 0, s>>>(fp.mel, fp.post, fsd.starts, fsd.lens, B, T,
-                                                                       c->mel_b, io->mel, io->postnet, io->mel_mask);
+      launch_row(unpack_mel_kernel, (unsigned)((out_rows * (N_MEL / 4) + 255) / 256), 256, s, fp.mel, fp.post, fsd.starts, fsd.lens, B, T,
+                 c->mel_b, io->mel, io->postnet, io->mel_mask);
       FS2_LAUNCHED();
     }
   }

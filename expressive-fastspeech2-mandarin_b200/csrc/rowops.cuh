@@ -13,6 +13,15 @@ namespace fs2 {
 // device-side status word: nonzero => the host raises after the stage's read-back
 enum { ERR_BAD_LEN = 1, ERR_BAD_ID = 2, ERR_MAXLEN_SMALL = 4, ERR_BAD_INDEX = 8 };
 
+// First statement of the row kernels of the forward: when the kernel is launched with the programmatic-serialization
+// attribute (fs2_api.cu: launch_row) its blocks may become resident while the previous kernel is still running -- nothing is
+// read or written before the wait returns (= the previous kernel has completed and its writes are visible) -- and the next
+// kernel may start its own prologue.  Launched the ordinary way both instructions are no-ops.
+__device__ __forceinline__ void row_pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 // optional bf16 copy of a row (BF16 mode: the copy is the A operand of the next contraction); no-op when p == nullptr
@@ -38,6 +47,7 @@ template <typename LenT>
 __global__ void layout_scan_kernel(const LenT* __restrict__ lens, int batch, int gap, int len_limit,
                                    int forced_max, int32_t* __restrict__ starts, int32_t* __restrict__ lens32,
                                    int64_t* __restrict__ totals, int32_t* __restrict__ status) {
+  row_pdl_sync();
   // 1024 threads = 32 warps: inclusive scan of the per-thread sums by warp shuffles, one exchange of the 32 warp totals through
   // shared memory, and the maxima / real-length sums reduced the same way (two block barriers; the Hillis-Steele scan over
   // 1024 shared-memory partials took ~30 of them and 5 us on the critical path of both stages)
@@ -174,6 +184,7 @@ __global__ void row_meta_kernel(const int32_t* __restrict__ starts, const int32_
                                 int32_t* __restrict__ utt, int32_t* __restrict__ vpos, int32_t* __restrict__ room,
                                 int32_t* __restrict__ slot, uint32_t* __restrict__ work = nullptr, int work_cap = 0,
                                 int32_t* __restrict__ work_count = nullptr, SlotInit init = SlotInit{}, int work_q_rows = 128) {
+  row_pdl_sync();
   if (work != nullptr && blockIdx.x == gridDim.x - 1) {   // the last block also builds the attention work list of this side
     __shared__ int bins[1024];
     build_attention_work(lens, batch, work, work_cap, work_count, bins, work_q_rows);
@@ -214,6 +225,7 @@ __global__ void embed_pe_kernel(const int64_t* __restrict__ texts, int max_src_l
                                 int n_vocab, const float* __restrict__ pe, RowMeta meta, const int32_t* __restrict__ lens,
                                 int rows, float* __restrict__ x, int32_t* __restrict__ status,
                                 __nv_bfloat16* __restrict__ xb = nullptr) {
+  row_pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -256,6 +268,7 @@ __global__ void cond_kernel(const int64_t* __restrict__ speakers, const int64_t*
                             const float* __restrict__ aro_emb, int n_aro, const float* __restrict__ val_emb, int n_val,
                             const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ spk_out,
                             float* __restrict__ emo_out, int32_t* __restrict__ status) {
+  row_pdl_sync();
   __shared__ float e[D_MODEL];
   const int b = blockIdx.x / COND_PARTS, part = blockIdx.x % COND_PARTS, tid = threadIdx.x;
   long long s = speakers[b], em = emotions[b], ar = arousals[b], va = valences[b];
@@ -350,6 +363,7 @@ __global__ void bucket_embed_add_kernel(const float* __restrict__ x, RowMeta met
                                         const float* __restrict__ bins, int n_bins, const float* __restrict__ table,
                                         float* __restrict__ pred_out, int32_t* __restrict__ idx_out,
                                         float* __restrict__ y, __nv_bfloat16* __restrict__ yb = nullptr) {
+  row_pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -395,6 +409,7 @@ __global__ void durations_kernel(const float* __restrict__ d_in, int is_target, 
                                  int64_t* __restrict__ mel_lens, int32_t* __restrict__ mel_lens32,
                                  const float* __restrict__ energy_raw = nullptr, float energy_scale = 1.f,
                                  float* __restrict__ energy_out = nullptr) {
+  row_pdl_sync();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= batch) return;
@@ -509,6 +524,7 @@ __global__ void length_regulate_scatter_kernel(const float* __restrict__ x, RowM
                                                int batch, int gap, const int64_t* __restrict__ f_totals,
                                                const float* __restrict__ pe, int rows_f, float* __restrict__ y,
                                                __nv_bfloat16* __restrict__ yb, EnergyAdd en = EnergyAdd{}) {
+  row_pdl_sync();
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const float4 zero = make_float4(0, 0, 0, 0);
@@ -690,6 +706,7 @@ __global__ void unpack_mel_kernel(const float* __restrict__ mel_p, const float* 
                                   const int32_t* __restrict__ f_starts, const int32_t* __restrict__ f_lens, int batch,
                                   int max_mel_len, const float* __restrict__ bias, float* __restrict__ mel,
                                   float* __restrict__ post, uint8_t* __restrict__ mask) {
+  row_pdl_sync();
   constexpr int Q = N_MEL / 4;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)batch * max_mel_len * Q) return;
