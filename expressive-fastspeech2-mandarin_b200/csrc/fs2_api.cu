@@ -600,7 +600,8 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   // (the status word is zero on entry: fs2_create clears it and every stage 1 clears it again after reading it back)
   {
     ProfScope pr(c, s, "layout_scan");
-    launch_row(layout_scan_kernel<int64_t>, 1, 1024, s, in->src_lens, B, GAP_PHON, L, L, ps.starts, ps.lens, ps.totals, c->status);
+    launch_row(layout_scan_kernel<int64_t>, 1, 1024, s, in->src_lens, B, GAP_PHON, L, L, ps.starts, ps.lens, ps.totals, c->status,
+               nullptr);
     FS2_LAUNCHED();
   }
   // row metadata + attention work list + zero fill of the [B, L] outputs that are written at real positions only
@@ -693,16 +694,14 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
              in->e_targets != nullptr ? 1.f : in->p_control /* sic: modules.py:123-125 */,
              energy_here ? out->energy : nullptr);
   FS2_LAUNCHED();
+  // (the frame side's sizes and the stage's status word go straight to pinned host memory: see the kernel)
   launch_row(layout_scan_kernel<int32_t>, 1, 1024, s, c->mel_lens32, B, GAP_FRAME, 0, in->max_mel_len, c->fs.starts, c->fs.lens,
-             c->fs.totals, c->status);
+             c->fs.totals, c->status, c->h_totals);
   FS2_LAUNCHED();
 
   static const bool timing = std::getenv("FS2_TIMING") != nullptr;
   const auto t_enq = std::chrono::steady_clock::now();
   // ---- the one blocking point: sizes of the frame side
-  FS2_CUDA_OK(cudaMemcpyAsync(c->h_totals, c->fs.totals, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  FS2_CUDA_OK(cudaMemcpyAsync(c->h_totals + 3, c->status, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  FS2_CUDA_OK(cudaMemsetAsync(c->status, 0, sizeof(int32_t), s));   // clean for the next forward
   FS2_CUDA_OK(cudaStreamSynchronize(s));
   if (timing) {
     const auto t_end = std::chrono::steady_clock::now();

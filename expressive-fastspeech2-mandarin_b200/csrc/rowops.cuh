@@ -46,7 +46,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <typename LenT>
 __global__ void layout_scan_kernel(const LenT* __restrict__ lens, int batch, int gap, int len_limit,
                                    int forced_max, int32_t* __restrict__ starts, int32_t* __restrict__ lens32,
-                                   int64_t* __restrict__ totals, int32_t* __restrict__ status) {
+                                   int64_t* __restrict__ totals, int32_t* __restrict__ status,
+                                   int64_t* __restrict__ host_out = nullptr) {
+  // host_out (pinned host memory, device-addressable): the three totals and the accumulated status word are also written
+  // there and the status word is cleared for the next forward -- the caller then needs a stream synchronisation only, not
+  // two device->host copies and a memset behind this kernel.
   row_pdl_sync();
   // 1024 threads = 32 warps: inclusive scan of the per-thread sums by warp shuffles, one exchange of the 32 warp totals through
   // shared memory, and the maxima / real-length sums reduced the same way (two block barriers; the Hillis-Steele scan over
@@ -113,6 +117,13 @@ __global__ void layout_scan_kernel(const LenT* __restrict__ lens, int batch, int
     totals[0] = total_rows;
     totals[1] = max_len;
     totals[2] = total_real;
+    if (host_out != nullptr) {   // (every earlier kernel of the stage has completed; this block's own atomics precede the barriers above)
+      host_out[0] = total_rows;
+      host_out[1] = max_len;
+      host_out[2] = total_real;
+      host_out[3] = (int64_t)atomicExch(status, 0);
+      __threadfence_system();
+    }
   }
 }
 
