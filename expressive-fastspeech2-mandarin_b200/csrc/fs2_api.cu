@@ -105,6 +105,8 @@ struct fs2_ctx {
 
   // state carried from stage 1 to stage 2
   bool stage1_done = false;
+  bool eager_stage2 = false;        // fs2_set_eager_stage2: stage 1 enqueues stage 2 up to the PostNet before it returns
+  bool stage2_body_done = false;    // ... and did so for the current forward: fs2_forward_stage2 only unpacks
   int batch = 0, max_src_len = 0, max_mel_len = 0, phon_rows = 0;
   int64_t frame_rows = 0, total_frames = 0;
   const float* lr_input = nullptr;
@@ -552,6 +554,9 @@ static void check_status(fs2_ctx* c, int32_t st) {
   throw Error(FS2_ERR_INVALID, m);
 }
 
+enum { STAGE2_BODY = 1, STAGE2_UNPACK = 2 };
+static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io, int phases);
+
 static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_out* out) {
   require(c->prepared, FS2_ERR_STATE, "fs2_forward_stage1 called before fs2_prepare");
   require(in && out, FS2_ERR_INVALID, "null argument");
@@ -565,6 +570,7 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   const auto t_begin = std::chrono::steady_clock::now();
   g_launches = 0;
   c->stage1_done = false;
+  c->stage2_body_done = false;
   for (auto& r : c->prof) { c->event_pool.push_back(r.beg); c->event_pool.push_back(r.end); }
   c->prof.clear();
   if (c->debug) {
@@ -722,12 +728,21 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   c->lr_adds_energy = true;
   c->stage1_done = true;
   c->last_launches = g_launches;
+  // Eager stage 2 (fs2_set_eager_stage2): everything of stage 2 but the final unpack needs no caller buffer, so it is enqueued
+  // here, right behind the one host synchronisation -- the device does not wait for the caller to allocate its outputs and
+  // come back (tens of microseconds through a Python facade).  Not with frame_level features (they write caller buffers inside
+  // stage 2) and not with debug taps.
+  if (c->eager_stage2 && !c->debug && !c->cfg.pitch_frame_level && !c->cfg.energy_frame_level) {
+    stage2(c, s, nullptr, STAGE2_BODY);
+    c->stage2_body_done = true;
+  }
 }
 
-static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
+static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io, int phases) {
   require(c->stage1_done, FS2_ERR_STATE, "fs2_forward_stage2 called without a completed fs2_forward_stage1");
   // an all-zero duration batch has max_mel_len == 0: the outputs are empty tensors (null data pointers) and nothing runs
-  require(io && (c->max_mel_len == 0 || (io->mel && io->postnet && io->mel_mask)), FS2_ERR_INVALID, "null stage-2 output");
+  require(!(phases & STAGE2_UNPACK) || (io && (c->max_mel_len == 0 || (io->mel && io->postnet && io->mel_mask))), FS2_ERR_INVALID,
+          "null stage-2 output");
   const auto t_begin2 = std::chrono::steady_clock::now();
   FS2_CUDA_OK(cudaSetDevice(c->device));
   g_launches = 0;
@@ -741,7 +756,7 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
   RowSide& fsd = c->fs;
   Pool& fp = c->fp;
 
-  if (T > 0) {
+  if (T > 0 && (phases & STAGE2_BODY)) {
     launch_row(row_meta_kernel, (rows + 255) / 256, 256, s, fsd.starts, fsd.lens, B, GAP_FRAME, T, nullptr, rows, fsd.utt,
                fsd.vpos, fsd.room, fsd.slot, fsd.work, fsd.work_cap, fsd.work_count, SlotInit{}, fsd.work_q_rows);
     FS2_LAUNCHED();
@@ -852,6 +867,8 @@ static void stage2(fs2_ctx* c, cudaStream_t s, const fs2_stage2_io* io) {
       ld = pc.cout;
     }
     tap(c, s, "post_p", fp.post, rows, N_MEL);
+  }
+  if (T > 0 && (phases & STAGE2_UNPACK)) {
     const int64_t out_rows = (int64_t)B * T;
     {
       ProfScope ps(c, s, "unpack");
@@ -938,6 +955,7 @@ static void import_stage1(fs2_ctx* c, cudaStream_t s, const float* hidden, const
   FS2_CUDA_OK(cudaSetDevice(c->device));
   g_launches = 0;
   c->stage1_done = false;
+  c->stage2_body_done = false;
   const int64_t bound = (int64_t)GAP_PHON + (int64_t)B * (L + GAP_PHON);
   require(bound < (1LL << 30), FS2_ERR_INVALID, "batch * max_src_len too large");
   const int rows = round_up((int)bound, 128);
@@ -1103,7 +1121,17 @@ int fs2_forward_stage1(fs2_ctx* c, fs2_stream stream, const fs2_inputs* in, fs2_
 
 int fs2_forward_stage2(fs2_ctx* c, fs2_stream stream, const fs2_stage2_io* io) {
   if (!c) return FS2_ERR_INVALID;
-  return guarded(c, [&] { stage2(c, static_cast<cudaStream_t>(stream), io); });
+  return guarded(c, [&] {
+    const bool body_done = c->stage2_body_done;
+    c->stage2_body_done = false;
+    stage2(c, static_cast<cudaStream_t>(stream), io, body_done ? STAGE2_UNPACK : (STAGE2_BODY | STAGE2_UNPACK));
+  });
+}
+
+int fs2_set_eager_stage2(fs2_ctx* c, int on) {
+  if (!c) return FS2_ERR_INVALID;
+  c->eager_stage2 = on != 0;
+  return FS2_OK;
 }
 
 int fs2_export_stage1(fs2_ctx* c, fs2_stream stream, float* hidden, int32_t* reps) {

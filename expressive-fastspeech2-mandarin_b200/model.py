@@ -227,7 +227,7 @@ class FastSpeech2B200(nn.Module):
         return t.to(torch.float32).contiguous()
 
     def _stage1(self, speakers, emotions, arousals, valences, texts, src_lens, max_src_len, max_mel_len, p_targets, e_targets,
-                d_targets, p_control, e_control, d_control):
+                d_targets, p_control, e_control, d_control, eager=True):
         """fs2_forward_stage1: masks, encoder, conditioning, variance adaptor up to the durations.  Returns the phoneme-side
         tensors and the frame-side sizes (the call blocks for them)."""
         if self.training:
@@ -270,6 +270,10 @@ class FastSpeech2B200(nn.Module):
         stream = torch.cuda.current_stream(dev).cuda_stream
         # the targets must outlive stage 2 (frame_level features and the fused energy add read them there)
         self._keep = (spk, emo, aro, val, txt, lens, p_t, e_t, d_t)
+        # stage 2 up to the PostNet is enqueued by stage 1 itself (the device does not wait for the output allocations
+        # below) unless an asynchronous host read of the previous call's packed rows is still pending: its event is only
+        # waited for in _stage2, and the stage-2 body overwrites those rows
+        lib.fs2_set_eager_stage2(self._ctx, 1 if eager and getattr(self, "_pending_read", None) is None else 0)
         _lib.check(lib, self._ctx, lib.fs2_forward_stage1(self._ctx, stream, C.byref(inp), C.byref(s1)))
         self.last_total_frames = int(s1.total_frames)
         return dict(B=B, L=L, T=int(s1.max_mel_len), pitch=pitch, energy=energy, log_d=log_d, d_round=d_round,
@@ -322,7 +326,7 @@ class FastSpeech2B200(nn.Module):
         (`pitch`, `energy`, `log_d`, `d_round`, `src_mask`), `mel_lens` [B] (device) and what the length regulator consumes,
         exported for another context: `hidden` [B, L, 256] (x + pitch embedding + energy embedding) and `reps` [B, L] int32."""
         s1 = self._stage1(speakers, emotions, arousals, valences, texts, src_lens, max_src_len, None, None, None, None,
-                          p_control, e_control, d_control)
+                          p_control, e_control, d_control, eager=False)   # (stage 2 runs elsewhere, after the exchange)
         dev = self._device()
         hidden = torch.empty(s1["B"], s1["L"], 256, dtype=torch.float32, device=dev)
         reps = torch.empty(s1["B"], s1["L"], dtype=torch.int32, device=dev)

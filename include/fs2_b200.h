@@ -153,6 +153,14 @@ int fs2_import_stage1(fs2_ctx* ctx, fs2_stream stream, const float* hidden, cons
 /* Number of kernels the last stage1+stage2 pair launched. */
 int fs2_last_launch_count(const fs2_ctx* ctx);
 
+/* on != 0: fs2_forward_stage1 enqueues all of stage 2 except the final unpack into the caller's tensors before it returns (none
+ * of it needs a caller buffer), so the device does not idle while the caller allocates [B, max_mel_len, 80] outputs and calls
+ * fs2_forward_stage2, which then only unpacks.  Same kernels, same results.  Ignored with frame_level features and debug taps.
+ * A caller that still reads the previous forward's packed rows asynchronously (fs2_read_packed_postnet on another stream) must
+ * leave it off for that forward: the stage-2 body overwrites those rows.  (The reference has no such split: its forward is one
+ * call, model/fastspeech2.py:73-149.) */
+int fs2_set_eager_stage2(fs2_ctx* ctx, int on);
+
 /* --- introspection for tests -------------------------------------------------------- */
 /* When enabled, intermediate activations are copied aside after each stage of the forward
  * ("enc_in", "enc_0".."enc_3", "cond_x", "va_x", "lr_out", "dec_in", "dec_0".."dec_5", ...)
