@@ -55,6 +55,7 @@ SIGNATURES = {
                                     C.c_void_p, c_i64p, C.POINTER(C.c_int32)]),
     "fs2_last_launch_count": (C.c_int, [C.c_void_p]),
     "fs2_set_eager_stage2": (C.c_int, [C.c_void_p, C.c_int]),
+    "fs2_set_stage2_wait_event": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fs2_read_packed_postnet": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, c_i64p]),
     "fs2_debug_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "fs2_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, c_i64p, c_i64p]),

@@ -107,6 +107,7 @@ struct fs2_ctx {
   bool stage1_done = false;
   bool eager_stage2 = false;        // fs2_set_eager_stage2: stage 1 enqueues stage 2 up to the PostNet before it returns
   bool stage2_body_done = false;    // ... and did so for the current forward: fs2_forward_stage2 only unpacks
+  cudaEvent_t stage2_wait = nullptr;   // fs2_set_stage2_wait_event: the eager stage-2 body of the next forward waits for it
   int batch = 0, max_src_len = 0, max_mel_len = 0, phon_rows = 0;
   int64_t frame_rows = 0, total_frames = 0;
   const float* lr_input = nullptr;
@@ -732,6 +733,10 @@ static void stage1(fs2_ctx* c, cudaStream_t s, const fs2_inputs* in, fs2_stage1_
   // here, right behind the one host synchronisation -- the device does not wait for the caller to allocate its outputs and
   // come back (tens of microseconds through a Python facade).  Not with frame_level features (they write caller buffers inside
   // stage 2) and not with debug taps.
+  // (an asynchronous read of the previous forward's packed rows, which stage 2 overwrites, finishes first; the event is only
+  // guaranteed to live through this call, so the wait is enqueued here whether or not the body follows)
+  if (c->stage2_wait != nullptr) FS2_CUDA_OK(cudaStreamWaitEvent(s, c->stage2_wait, 0));
+  c->stage2_wait = nullptr;
   if (c->eager_stage2 && !c->debug && !c->cfg.pitch_frame_level && !c->cfg.energy_frame_level) {
     stage2(c, s, nullptr, STAGE2_BODY);
     c->stage2_body_done = true;
@@ -1131,6 +1136,12 @@ int fs2_forward_stage2(fs2_ctx* c, fs2_stream stream, const fs2_stage2_io* io) {
 int fs2_set_eager_stage2(fs2_ctx* c, int on) {
   if (!c) return FS2_ERR_INVALID;
   c->eager_stage2 = on != 0;
+  return FS2_OK;
+}
+
+int fs2_set_stage2_wait_event(fs2_ctx* c, void* event) {
+  if (!c) return FS2_ERR_INVALID;
+  c->stage2_wait = static_cast<cudaEvent_t>(event);
   return FS2_OK;
 }
 

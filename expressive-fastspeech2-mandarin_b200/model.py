@@ -271,9 +271,16 @@ class FastSpeech2B200(nn.Module):
         # the targets must outlive stage 2 (frame_level features and the fused energy add read them there)
         self._keep = (spk, emo, aro, val, txt, lens, p_t, e_t, d_t)
         # stage 2 up to the PostNet is enqueued by stage 1 itself (the device does not wait for the output allocations
-        # below) unless an asynchronous host read of the previous call's packed rows is still pending: its event is only
-        # waited for in _stage2, and the stage-2 body overwrites those rows
-        lib.fs2_set_eager_stage2(self._ctx, 1 if eager and getattr(self, "_pending_read", None) is None else 0)
+        # below).  An asynchronous host read of the previous call's packed rows (synthesize_host_async), which that body
+        # overwrites, is waited for on the device right before the body: the library gets its event.
+        pending = getattr(self, "_pending_read", None)
+        lib.fs2_set_eager_stage2(self._ctx, 1 if eager else 0)
+        if pending is not None and pending.cuda_event:
+            # (the library enqueues the wait at the end of stage 1, whether or not the body follows)
+            lib.fs2_set_stage2_wait_event(self._ctx, C.c_void_p(pending.cuda_event))
+            self._pending_read = None        # consumed by the library; `pending` keeps the event alive through the call
+        elif pending is not None:
+            lib.fs2_set_eager_stage2(self._ctx, 0)      # the wait stays where it was: before stage 2, in _stage2
         _lib.check(lib, self._ctx, lib.fs2_forward_stage1(self._ctx, stream, C.byref(inp), C.byref(s1)))
         self.last_total_frames = int(s1.total_frames)
         return dict(B=B, L=L, T=int(s1.max_mel_len), pitch=pitch, energy=energy, log_d=log_d, d_round=d_round,

@@ -160,6 +160,10 @@ int fs2_last_launch_count(const fs2_ctx* ctx);
  * leave it off for that forward: the stage-2 body overwrites those rows.  (The reference has no such split: its forward is one
  * call, model/fastspeech2.py:73-149.) */
 int fs2_set_eager_stage2(fs2_ctx* ctx, int on);
+/* event: a recorded cudaEvent_t (or NULL) the eager stage-2 body of the NEXT fs2_forward_stage1 waits for on its stream before it
+ * overwrites the frame-side rows -- the completion of an asynchronous fs2_read_packed_postnet of the previous forward.  Consumed
+ * (reset to NULL) by that call; the event must stay alive until it returns. */
+int fs2_set_stage2_wait_event(fs2_ctx* ctx, void* event);
 
 /* --- introspection for tests -------------------------------------------------------- */
 /* When enabled, intermediate activations are copied aside after each stage of the forward
