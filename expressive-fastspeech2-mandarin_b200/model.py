@@ -274,6 +274,7 @@ class FastSpeech2B200(nn.Module):
         # below).  An asynchronous host read of the previous call's packed rows (synthesize_host_async), which that body
         # overwrites, is waited for on the device right before the body: the library gets its event.
         pending = getattr(self, "_pending_read", None)
+        eager = eager and getattr(self, "eager_stage2", True)      # (attribute: tests switch the mode off to compare)
         lib.fs2_set_eager_stage2(self._ctx, 1 if eager else 0)
         if pending is not None and pending.cuda_event:
             # (the library enqueues the wait at the end of stage 1, whether or not the body follows)

@@ -263,6 +263,26 @@ def test_attention_forms_give_the_same_forward(sd32, syn, lens):
             assert torch.equal(a, b), (form, i)
 
 
+@pytest.mark.parametrize("lens", [[16], [21, 9, 17, 33, 5], [1, 4, 2]])
+def test_eager_stage2_is_the_same_forward(sd32, syn, lens):
+    """fs2_set_eager_stage2: stage 1 enqueues stage 2 up to the PostNet itself and fs2_forward_stage2 only unpacks -- the same
+    kernels on the same stream in the same order, so every output is bit-identical to the two-call flow; launch counts too."""
+    model = model_for(sd32)
+    batch = syn.make_batch([max(n, 1) for n in lens], seed=9)
+    try:
+        model.eager_stage2 = True
+        a = [t.clone() for t in run(model, batch, d_control=0.8)]
+        na = model.last_launch_count
+        model.eager_stage2 = False
+        b = [t.clone() for t in run(model, batch, d_control=0.8)]
+        nb = model.last_launch_count
+    finally:
+        model.eager_stage2 = True
+    assert na == nb
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert torch.equal(x, y), i
+
+
 def test_input_validation(sd32, syn):
     model = model_for(sd32)
     batch = syn.make_batch([8, 6], seed=1)
